@@ -1,0 +1,175 @@
+"""CPU: the oracle restatements vs the fixtures produced by the UNMODIFIED
+reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import model_oracle as mo
+from oracle import stitch_oracle as so
+from tests import golden_io as gio
+from tests import synth
+
+GZ = gio.load("graph_cases.npz")
+
+
+@pytest.mark.parametrize("name", gio.graph_case_names(GZ))
+def test_graph_oracle_bit_exact_vs_reference(name):
+    c, ref = gio.graph_case(GZ, name)
+    out = go.build_graph(c["depth"], c["mask"], c["unc"], c["res"], c["conn"])
+    for k in ("x", "edge_index", "edge_attr", "pos", "local_std"):
+        assert out[k].dtype == ref[k].dtype, k
+        assert out[k].shape == ref[k].shape, k
+        assert np.array_equal(out[k], ref[k], equal_nan=True), k
+    if "valid_rows" in ref:
+        assert np.array_equal(out["valid_rows"], ref["valid_rows"])
+        assert np.array_equal(out["valid_cols"], ref["valid_cols"])
+        assert out["num_valid_cells"] == int(ref["num_valid_cells"])
+        assert tuple(out["grid_shape"]) == tuple(ref["grid_shape"])
+    else:
+        assert out["grid_shape"] is None            # reference's empty graph has no grid_shape
+
+
+def test_graph_oracle_c1_digests():
+    """BASELINE config 1 (512^2, reference SyntheticNoiseGenerator seed 42)."""
+    z = gio.load("c1_tile.npz")
+    d = z["depth"]
+    out = go.build_graph(d, np.ones_like(d, bool), None, tuple(z["res"]))
+    assert out["x"].shape[0] == int(z["N"]) and out["edge_index"].shape[1] == int(z["E"])
+    for k in ("x", "edge_index", "edge_attr", "pos", "local_std", "valid_rows", "valid_cols"):
+        digest = hashlib.sha256(np.ascontiguousarray(out[k]).tobytes()).hexdigest()
+        assert digest == str(z["sha_" + k]), k
+
+
+def test_edge_count_formula():
+    # E = 4(n-1)(2n-1) for a full n x n 8-connected tile
+    d = synth.noisy_tile(20, 20)
+    out = go.build_graph(d, None, None)
+    assert out["edge_index"].shape[1] == 4 * 19 * 39
+
+
+def test_graph_to_grid_errors():
+    with pytest.raises(ValueError):
+        go.graph_to_grid((2, 2), np.array([0]), np.array([0]), np.zeros((1, 2)))
+
+
+MZ = gio.load("model_cases.npz")
+
+
+def _model_case(key):
+    F, seed, hidden, heads = (int(v) for v in MZ[key + "/meta"])
+    c, ref = gio.graph_case(GZ, str(MZ[key + "/graph"]))
+    cfg = mo.ModelCfg(in_channels=F, hidden=hidden, heads=heads)
+    sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+    sd["classification_head.mlp.3.bias"] = torch.from_numpy(MZ[key + "/cls_bias"])
+    sd["confidence_head.mlp.3.bias"] = torch.from_numpy(MZ[key + "/conf_bias"])
+    return cfg, sd, ref
+
+
+@pytest.mark.parametrize("key", gio.model_case_keys(MZ))
+def test_model_oracle_vs_reference_module(key):
+    cfg, sd, g = _model_case(key)
+    assert mo.param_count(sd) == int(MZ[key + "/param_count"])
+    out = mo.predict(sd, cfg, g["x"], g["edge_index"], g["edge_attr"])
+    # same torch ops in the same order as the reference module on the restated PyG classes
+    for k in ("class_logits", "class_probs", "confidence", "correction"):
+        np.testing.assert_allclose(out[k].numpy(), MZ[f"{key}/{k}"], rtol=1e-6, atol=1e-6, err_msg=k)
+    for k in ("predicted_class", "action", "needs_review", "auto_correct"):
+        assert np.array_equal(out[k].numpy(), MZ[f"{key}/{k}"]), k
+    assert len(np.unique(MZ[f"{key}/predicted_class"])) == 3     # all three classes occur
+
+
+def test_structural_pins():
+    # docs/QUICK_REFERENCE.md:185 "182K parameters"
+    assert int(MZ["param_count_F8"]) == 182469 and int(MZ["param_count_F7"]) == 182405
+    for F in (7, 8):
+        sd = mo.init_state_dict(mo.ModelCfg(in_channels=F), seed=0)
+        assert mo.param_count(sd) == int(MZ[f"param_count_F{F}"])
+    sd = mo.init_state_dict(mo.ModelCfg(in_channels=7), seed=0)
+    assert sorted(sd.keys()) == [str(k) for k in MZ["state_keys"]]
+
+
+def test_model_oracle_fp64_envelope():
+    """fp32 oracle vs its own fp64 evaluation: the envelope the CUDA tolerance is
+    stated against (~2.5e-6 on logits)."""
+    key = gio.model_case_keys(MZ)[0]
+    cfg, sd, g = _model_case(key)
+    o32 = mo.forward(sd, cfg, g["x"], g["edge_index"], g["edge_attr"], torch.float32)
+    o64 = mo.forward(sd, cfg, g["x"], g["edge_index"], g["edge_attr"], torch.float64)
+    err = (o32["class_logits"].double() - o64["class_logits"]).abs().max().item()
+    assert err < 2e-4, err
+
+
+SZ = gio.load("stitch_cases.npz")
+
+
+def test_tile_specs_vs_reference():
+    i = 0
+    while f"specs{i}/cfg" in SZ.files:
+        H, W, ts, ov = (int(v) for v in SZ[f"specs{i}/cfg"])
+        ntr, ntc, specs = so.tile_specs((H, W), ts, ov)
+        assert [ntr, ntc] == list(SZ[f"specs{i}/n"])
+        assert np.array_equal(np.array(specs, np.int64), SZ[f"specs{i}/specs"])
+        i += 1
+    assert i >= 5
+    with pytest.raises(ValueError):
+        so.tile_specs((10, 10), 16, 16)
+
+
+def test_blend_tables_vs_reference():
+    for k in SZ.files:
+        if k.startswith("blend1d/"):
+            size, ov = (int(v) for v in k.split("/")[1].split("_"))
+            assert np.array_equal(so.blend_1d(size, ov), SZ[k]), k
+    assert np.array_equal(so.blend_2d((50, 64), 16), SZ["blend2d/50x64_16"])
+
+
+def test_merge_vs_reference():
+    H, W, ts, ov = (int(v) for v in SZ["merge/cfg"])
+    _, _, specs = so.tile_specs((H, W), ts, ov)
+    m = so.Merger((H, W), ["cleaned_depth", "classification", "confidence", "correction"], ov)
+    for i in SZ["merge/tile_ids"]:
+        td = {k: SZ[f"merge/tile{i}/{k}"] for k in ("cleaned_depth", "classification", "confidence", "correction")}
+        m.add_tile(specs[int(i)], td)
+    res = m.finalize()
+    for k, v in res.items():
+        assert np.array_equal(v, SZ[f"merge/ref/{k}"], equal_nan=True), k
+    # quirk: outer ring of the survey keeps weight 0 -> stays 0.0
+    assert np.all(res["confidence"][0, :40] == 0.0)
+    with pytest.raises(ValueError):
+        m2 = so.Merger((H, W), ["confidence"], ov)
+        m2.add_tile(specs[0], {"bogus": np.zeros((ts, ts), np.float32)})
+
+
+def test_pipeline_oracle_vs_reference():
+    """graph oracle + model oracle + stitch oracle == reference BathymetricPipeline.process."""
+    z = gio.load("pipeline_case.npz")
+    H, W, ts, ov = (int(v) for v in z["cfg"])
+    depth, nodata = z["depth"], float(z["nodata"])
+    valid = np.isfinite(depth) & (depth != nodata)
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=int(z["seed"]), randomize_bn=True, head_gain=8.0)
+    sd["classification_head.mlp.3.bias"] = torch.from_numpy(z["cls_bias"])
+    sd["confidence_head.mlp.3.bias"] = torch.from_numpy(z["conf_bias"])
+    _, _, specs = so.tile_specs((H, W), ts, ov)
+    chans = ["cleaned_depth", "classification", "confidence", "correction"]
+    m = so.Merger((H, W), chans, ov)
+    for s in specs:
+        r0, c0, r1, c1 = s[:4]
+        td, tm = depth[r0:r1, c0:c1], valid[r0:r1, c0:c1]
+        if tm.sum() / tm.size < float(z["min_valid_ratio"]):
+            continue
+        g = go.build_graph(td, tm, None, tuple(z["res"]))
+        o = mo.predict(sd, cfg, g["x"], g["edge_index"], g["edge_attr"])
+        cls, conf, corr = so.tile_outputs_to_grids(td.shape, g["valid_rows"], g["valid_cols"],
+                                                   o["predicted_class"].numpy(), o["confidence"].numpy(),
+                                                   o["correction"].numpy(), g["local_std"])
+        m.add_tile(s, dict(cleaned_depth=td, classification=cls, confidence=conf, correction=corr))
+    res = so.finish_survey(depth, valid, m.finalize())
+    assert np.array_equal(res["classification"], z["ref/classification"], equal_nan=True)
+    np.testing.assert_allclose(res["confidence"], z["ref/confidence"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["correction"], z["ref/correction"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res["cleaned_depth"], z["ref/cleaned_depth"], rtol=1e-6, atol=1e-5)
+    assert (res["cleaned_depth"] != depth).sum() > 100
