@@ -1,0 +1,11 @@
+"""bathymetric-gnn_b200: B200 (sm_100a) implementation of the Bathymetric-GNN
+per-tile inference hot path (graph build -> GAT forward -> tile stitch).
+
+The directory name carries a hyphen (task layout); import it as
+`bathymetric_gnn_b200` (the sibling shim package extends its __path__ here).
+"""
+from .graph import Data, Batch, GridGraph, GraphBuilder, OFFSETS_4, OFFSETS_8, OFFSETS_24  # noqa: F401
+from .gnn import (BathymetricGNN, LocalFeatureExtractor, GNNBackbone, ClassificationHead,  # noqa: F401
+                  ConfidenceHead, CorrectionHead)
+
+__version__ = "0.1.0"

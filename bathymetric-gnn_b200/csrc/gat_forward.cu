@@ -1,0 +1,695 @@
+// GAT forward on the device (sm_100a).
+//
+// Replaces BathymetricGNN.forward / predict of the reference (models/gnn.py:360-451):
+//   LocalFeatureExtractor (gnn.py:55-68)
+//   -> L x [ PyG GATConv(edge_dim) (gnn.py:125-132, 175-176) -> BatchNorm eval (151-154, 181) -> ReLU (184-186) ]
+//   -> classification / confidence / correction heads (gnn.py:191-260, 392-405) -> thresholds (436-449).
+// GATConv semantics follow SURVEY.md 3.4 (public PyG definition; PyG itself is not vendored).
+//
+// Kernels
+//   gemm_nt          C = A . W^T (+bias, ReLU) with an optional epilogue that reduces
+//                    alpha_src / alpha_dst = sum_c h[n,h,c] * att[h,c] while the tile is in registers
+//   gat_aggregate    one warp per destination node: lane-per-edge scores, warp-shuffle segment
+//                    softmax, weighted gather of the source rows, +bias, BN(eval), ReLU.  Per-edge
+//                    tensors ([E+N, H*C] in PyG) are never materialised; the self-loop edge attribute
+//                    (mean of the incoming edge attributes, fill_value='mean') is reduced on the fly.
+//   heads_finish     second layer of the three heads + softmax / argmax / sigmoid / action
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct LayerDev {
+    int in, H, C, HC, out;
+    float *W, *att_src, *att_dst, *Medge, *bias, *bn_a, *bn_b;
+};
+
+struct bgnn_model {
+    bgnn_model_desc d;
+    int device;
+    int nheads_mlp;          // 2 or 3 first-layer head blocks (cls, conf[, corr])
+    float* blob;             // single device allocation
+    float *feW0, *feb0, *feW1, *feb1;
+    std::vector<LayerDev> layers;
+    float *hW0, *hb0;        // concatenated first layers [nheads_mlp*h2, C]
+    float *Wcls, *bcls, *Wconf, *bconf, *Wcorr, *bcorr;
+    int hc_max;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ GEMM
+constexpr int BM = 128, BK = 16, GEMM_THREADS = 256, PAD = 4;
+
+template <int BN, int CH, bool ALPHA>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K, int64_t M, int N,
+        float* __restrict__ Cout, int ldc, const float* __restrict__ bias, int relu,
+        const float* __restrict__ att_src, const float* __restrict__ att_dst, float* __restrict__ alpha,
+        int Htot) {
+    constexpr int TN = BN / 16;              // columns per thread (8 or 4)
+    constexpr int NG = TN / 4;               // float4 column groups per thread (2 or 1)
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Ws[2][BK][BN + PAD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const bool vec_ok = (K % 4 == 0) && (lda % 4 == 0);
+
+    // global->register staging: A tile 128x16 = 512 float4 (2 per thread); W tile BNx16
+    constexpr int A_F4 = BM * BK / 4 / GEMM_THREADS;          // 2
+    constexpr int W_F4 = (BN * BK / 4 + GEMM_THREADS - 1) / GEMM_THREADS;   // 2 or 1
+    float4 ra[A_F4], rw[W_F4];
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+            const int f = tid + i * GEMM_THREADS;
+            const int row = f >> 2, kq = (f & 3) * 4;
+            const int64_t gm = m0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm < M) {
+                const float* p = A + gm * lda + k0 + kq;
+                if (vec_ok && k0 + kq + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    if (k0 + kq + 0 < K) v.x = __ldg(p + 0);
+                    if (k0 + kq + 1 < K) v.y = __ldg(p + 1);
+                    if (k0 + kq + 2 < K) v.z = __ldg(p + 2);
+                    if (k0 + kq + 3 < K) v.w = __ldg(p + 3);
+                }
+            }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < W_F4; ++i) {
+            const int f = tid + i * GEMM_THREADS;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < BN * BK / 4) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                const int gn = n0 + row;
+                if (gn < N) {
+                    const float* p = W + (int64_t)gn * K + k0 + kq;
+                    if (vec_ok && k0 + kq + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
+                    else {
+                        if (k0 + kq + 0 < K) v.x = __ldg(p + 0);
+                        if (k0 + kq + 1 < K) v.y = __ldg(p + 1);
+                        if (k0 + kq + 2 < K) v.z = __ldg(p + 2);
+                        if (k0 + kq + 3 < K) v.w = __ldg(p + 3);
+                    }
+                }
+            }
+            rw[i] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+            const int f = tid + i * GEMM_THREADS;
+            const int row = f >> 2, kq = (f & 3) * 4;
+            As[buf][kq + 0][row] = ra[i].x; As[buf][kq + 1][row] = ra[i].y;
+            As[buf][kq + 2][row] = ra[i].z; As[buf][kq + 3][row] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < W_F4; ++i) {
+            const int f = tid + i * GEMM_THREADS;
+            if (f < BN * BK / 4) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                Ws[buf][kq + 0][row] = rw[i].x; Ws[buf][kq + 1][row] = rw[i].y;
+                Ws[buf][kq + 2][row] = rw[i].z; Ws[buf][kq + 3][row] = rw[i].w;
+            }
+        }
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nk = (K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    int cur = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+        if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[8], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const float4 bv = *reinterpret_cast<const float4*>(&Ws[cur][k][g * 64 + tx * 4]);
+                b[g * 4 + 0] = bv.x; b[g * 4 + 1] = bv.y; b[g * 4 + 2] = bv.z; b[g * 4 + 3] = bv.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store_tiles(cur ^ 1);
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+
+    // epilogue: thread owns rows m0+ty*8+i, columns n0 + g*64 + tx*4 + j
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t gm = m0 + ty * 8 + i;
+        if (ALPHA) {
+            float ps[NG], pd[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                ps[g] = 0.f; pd[g] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gn = n0 + g * 64 + tx * 4 + j;
+                    if (gn < N) {
+                        ps[g] = fmaf(acc[i][g * 4 + j], __ldg(att_src + gn), ps[g]);
+                        pd[g] = fmaf(acc[i][g * 4 + j], __ldg(att_dst + gn), pd[g]);
+                    }
+                }
+            }
+            if (NG == 2 && CH >= 128) { ps[0] += ps[1]; pd[0] += pd[1]; }
+            constexpr int LG = CH >= 64 ? 16 : CH / 4;       // lanes that share a head within a group
+#pragma unroll
+            for (int o = LG / 2; o; o >>= 1) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    ps[g] += __shfl_xor_sync(0xffffffffu, ps[g], o);
+                    pd[g] += __shfl_xor_sync(0xffffffffu, pd[g], o);
+                }
+            }
+            if ((tx % LG) == 0 && gm < M) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (g == 1 && CH >= 128) break;
+                    const int gn = n0 + g * 64 + tx * 4;
+                    if (gn < N) {
+                        const int h = gn / CH;
+                        alpha[gm * (2 * Htot) + h] = ps[g];
+                        alpha[gm * (2 * Htot) + Htot + h] = pd[g];
+                    }
+                }
+            }
+        }
+        if (gm < M) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int gn = n0 + g * 64 + tx * 4;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = acc[i][g * 4 + j];
+                    if (bias && gn + j < N) v[j] += __ldg(bias + gn + j);
+                    if (relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                float* p = Cout + gm * ldc + gn;
+                if (gn + 3 < N && (ldc % 4 == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                else
+                    for (int j = 0; j < 4; ++j)
+                        if (gn + j < N) p[j] = v[j];
+            }
+        }
+    }
+}
+
+int launch_gemm(const float* A, int lda, const float* W, int K, int64_t M, int N, float* C, int ldc,
+                const float* bias, int relu, int CH, const float* att_src, const float* att_dst,
+                float* alpha, int Htot, cudaStream_t s) {
+    if (M == 0) return BGNN_OK;
+    const bool al = alpha != nullptr;
+    dim3 block(GEMM_THREADS);
+#define GO(BN_, CH_, AL_)                                                                              \
+    do {                                                                                               \
+        dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)((N + BN_ - 1) / BN_));                       \
+        gemm_nt<BN_, CH_, AL_><<<grid, block, 0, s>>>(A, lda, W, K, M, N, C, ldc, bias, relu, att_src, \
+                                                      att_dst, alpha, Htot);                           \
+    } while (0)
+    if (N > 64) {
+        if (!al) GO(128, 64, false);
+        else if (CH == 32) GO(128, 32, true);
+        else if (CH == 64) GO(128, 64, true);
+        else if (CH == 128) GO(128, 128, true);
+        else { bgnn_set_error("unsupported hidden width %d", CH); return BGNN_E_UNSUPPORTED; }
+    } else {
+        if (!al) GO(64, 64, false);
+        else if (CH == 32) GO(64, 32, true);
+        else if (CH == 64) GO(64, 64, true);
+        else { bgnn_set_error("unsupported hidden width %d for a <=64-wide projection", CH); return BGNN_E_UNSUPPORTED; }
+    }
+#undef GO
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ aggregation
+constexpr int AGG_WARPS = 8;
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<1> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
+};
+template <> struct VecIO<2> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct VecIO<4> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecIO<8> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { VecIO<4>::ld(p, v); VecIO<4>::ld(p + 4, v + 4); }
+    static __device__ __forceinline__ void st(float* p, const float* v) { VecIO<4>::st(p, v); VecIO<4>::st(p + 4, v + 4); }
+};
+template <> struct VecIO<16> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { VecIO<8>::ld(p, v); VecIO<8>::ld(p + 8, v + 8); }
+    static __device__ __forceinline__ void st(float* p, const float* v) { VecIO<8>::st(p, v); VecIO<8>::st(p + 8, v + 8); }
+};
+
+// One warp per destination node i.  In-edges e = rowptr[i] .. rowptr[i+1]-1 (reference edge
+// order) plus the self loop as the LAST entry (PyG add_self_loops appends the loops).
+template <int H, int VEC>
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+gat_aggregate(const float* __restrict__ h, const float* __restrict__ alpha, const int32_t* __restrict__ rowptr,
+              const int32_t* __restrict__ csr_src, const float* __restrict__ eattr, int ED,
+              const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
+              const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t N) {
+    constexpr int HC = 32 * VEC;
+    constexpr int C = HC / H;
+    __shared__ float s_a[AGG_WARPS][32][H];     // attention weights of the current chunk
+    __shared__ int s_j[AGG_WARPS][32];          // source ids of the current chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int my_head = (lane * VEC) / C;
+    float M[BGNN_MAX_EDGE_FEATS][H];
+#pragma unroll
+    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) M[d][hh] = d < ED ? __ldg(Medge + d * H + hh) : 0.f;
+
+    for (int64_t i = (int64_t)blockIdx.x * AGG_WARPS + warp; i < N; i += (int64_t)gridDim.x * AGG_WARPS) {
+        const int start = __ldg(rowptr + i);
+        const int deg = __ldg(rowptr + i + 1) - start;
+        const int tot = deg + 1;                                  // + self loop
+        // self-loop attribute = mean of the incoming edge attributes (0 when deg == 0)
+        float lsum[BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = 0.f;
+        if (ED > 0) {
+            for (int e = lane; e < deg; e += 32)
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                    if (d < ED) lsum[d] += __ldg(eattr + (int64_t)(start + e) * ED + d);
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) {
+                for (int o = 16; o; o >>= 1) lsum[d] += __shfl_xor_sync(0xffffffffu, lsum[d], o);
+                lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+            }
+        }
+        float ad[H];
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + i * (2 * H) + H + hh);
+
+        // score of virtual edge e (0..tot-1) for all heads, computed by the calling lane
+        auto score = [&](int e, int& j, float* s) {
+            float ea[BGNN_MAX_EDGE_FEATS];
+            if (e < deg) {
+                j = __ldg(csr_src + start + e);
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[d] = d < ED ? __ldg(eattr + (int64_t)(start + e) * ED + d) : 0.f;
+            } else {
+                j = (int)i;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[d] = lsum[d];
+            }
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) {
+                float ae = 0.f;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[d], M[d][hh], ae);
+                float v = (__ldg(alpha + (int64_t)j * (2 * H) + hh) + ad[hh]) + ae;
+                s[hh] = v > 0.f ? v : v * slope;
+            }
+        };
+
+        // pass 1: per-head max
+        float mx[H];
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) mx[hh] = -CUDART_INF_F;
+        for (int e0 = 0; e0 < tot; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < tot) {
+                int j; float s[H];
+                score(e, j, s);
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) mx[hh] = fmaxf(mx[hh], s[hh]);
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh)
+            for (int o = 16; o; o >>= 1) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
+        // pass 2: per-head sum of exp (single-chunk nodes keep their exps for pass 3)
+        float sm[H], pe[H];
+        int jmine = 0;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) { sm[hh] = 0.f; pe[hh] = 0.f; }
+        for (int e0 = 0; e0 < tot; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < tot) {
+                float s[H];
+                score(e, jmine, s);
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) { pe[hh] = expf(s[hh] - mx[hh]); sm[hh] += pe[hh]; }
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+            for (int o = 16; o; o >>= 1) sm[hh] += __shfl_xor_sync(0xffffffffu, sm[hh], o);
+            sm[hh] += 1e-16f;
+        }
+        // pass 3: aggregate
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int e0 = 0; e0 < tot; e0 += 32) {
+            const int e = e0 + lane;
+            __syncwarp();
+            if (e < tot) {
+                if (tot > 32) {                       // multi-chunk: recompute this chunk's exps
+                    float s[H];
+                    score(e, jmine, s);
+#pragma unroll
+                    for (int hh = 0; hh < H; ++hh) pe[hh] = expf(s[hh] - mx[hh]);
+                }
+                s_j[warp][lane] = jmine;
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) s_a[warp][lane][hh] = pe[hh] / sm[hh];
+            }
+            __syncwarp();
+            const int cnt = min(32, tot - e0);
+            for (int q = 0; q < cnt; ++q) {
+                const int j = s_j[warp][q];
+                const float a = s_a[warp][q][my_head];
+                float hv[VEC];
+                VecIO<VEC>::ld(h + (int64_t)j * HC + lane * VEC, hv);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a, hv[v], acc[v]);
+            }
+        }
+        // epilogue: + bias, BN(eval) as x*a + b, ReLU
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int ch = lane * VEC + v;
+            float y = acc[v] + __ldg(bias + ch);
+            y = fmaf(y, __ldg(bn_a + ch), __ldg(bn_b + ch));
+            o[v] = relu ? fmaxf(y, 0.f) : y;
+        }
+        VecIO<VEC>::st(out + i * HC + lane * VEC, o);
+    }
+}
+
+template <int H, int VEC>
+int launch_agg_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const int32_t* src,
+                 const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s) {
+    int64_t blocks = ceil_div64(N, AGG_WARPS);
+    const int64_t cap = (int64_t)sms * 8 * 4;            // persistent grid: multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    gat_aggregate<H, VEC><<<(unsigned)blocks, AGG_WARPS * 32, 0, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,
+                                                                     L.bn_a, L.bn_b, relu, slope, out, N);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+int launch_agg(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const int32_t* src,
+               const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s) {
+    if (N == 0) return BGNN_OK;
+    const int vec = L.HC / 32;
+#define CASE(H_, V_) if (L.H == H_ && vec == V_) return launch_agg_t<H_, V_>(L, h, alpha, rowptr, src, eattr, ED, relu, slope, out, N, sms, s)
+    CASE(1, 1); CASE(1, 2); CASE(1, 4);
+    CASE(2, 2); CASE(2, 4); CASE(2, 8);
+    CASE(4, 4); CASE(4, 8); CASE(4, 16);
+    CASE(8, 8); CASE(8, 16);
+#undef CASE
+    bgnn_set_error("unsupported attention shape heads=%d hidden=%d", L.H, L.C);
+    return BGNN_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------ heads
+// hh: [N, nblk*h2] = ReLU(first layers).  One warp per node.
+__global__ void __launch_bounds__(256)
+heads_finish(const float* __restrict__ hh, int h2, int nblk, int ncls, const float* __restrict__ Wcls,
+             const float* __restrict__ bcls, const float* __restrict__ Wconf, const float* __restrict__ bconf,
+             const float* __restrict__ Wcorr, const float* __restrict__ bcorr, float* __restrict__ logits,
+             float* __restrict__ probs, int64_t* __restrict__ cls, float* __restrict__ conf, float* __restrict__ corr,
+             int64_t* __restrict__ action, float thr_auto, float thr_review, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t n = wid; n < N; n += nw) {
+        const float* row = hh + n * (int64_t)(nblk * h2);
+        float lg[8];
+        float best = -CUDART_INF_F;
+        for (int k = 0; k < ncls; ++k) {
+            float p = 0.f;
+            for (int u = lane; u < h2; u += 32) p = fmaf(__ldg(row + u), __ldg(Wcls + k * h2 + u), p);
+            for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            lg[k] = p + __ldg(bcls + k);
+            best = fmaxf(best, lg[k]);
+        }
+        float pc = 0.f, pr = 0.f;
+        for (int u = lane; u < h2; u += 32) {
+            pc = fmaf(__ldg(row + h2 + u), __ldg(Wconf + u), pc);
+            if (nblk > 2) pr = fmaf(__ldg(row + 2 * h2 + u), __ldg(Wcorr + u), pr);
+        }
+        for (int o = 16; o; o >>= 1) {
+            pc += __shfl_xor_sync(0xffffffffu, pc, o);
+            pr += __shfl_xor_sync(0xffffffffu, pr, o);
+        }
+        if (lane == 0) {
+            float pb[8], sum = 0.f;
+            for (int k = 0; k < ncls; ++k) { pb[k] = expf(lg[k] - best); sum += pb[k]; }
+            int arg = 0; float pmax = -1.f;
+            for (int k = 0; k < ncls; ++k) {
+                pb[k] = pb[k] / sum;
+                if (pb[k] > pmax) { pmax = pb[k]; arg = k; }      // first max wins (torch.argmax)
+                if (logits) logits[n * ncls + k] = lg[k];
+                if (probs) probs[n * ncls + k] = pb[k];
+            }
+            const float cf = 1.f / (1.f + expf(-(pc + __ldg(bconf))));
+            if (cls) cls[n] = arg;
+            if (conf) conf[n] = cf;
+            if (corr && nblk > 2) corr[n] = pr + __ldg(bcorr);
+            if (action) {
+                int64_t a = (arg == 2 && cf > thr_auto) ? 1 : 0;          // gnn.py:439-441
+                if (cf < thr_review) a = 2;                                // gnn.py:444-445
+                action[n] = a;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ model
+static void layer_shape(const bgnn_model_desc* d, int l, int& in, int& H, int& C, int& HC, int& out) {
+    const bool last = l == d->layers - 1;
+    C = d->hidden;
+    H = last ? 1 : d->heads;
+    HC = H * C;
+    in = l == 0 ? d->hidden : d->hidden * d->heads;
+    out = last ? C : HC;
+}
+
+extern "C" int64_t bgnn_model_param_floats(const bgnn_model_desc* d) {
+    if (!d) return -1;
+    const int64_t C = d->hidden, F = d->in_channels, ED = d->edge_dim, h2 = C / 2;
+    int64_t n = C * F + C + C * C + C;
+    for (int l = 0; l < d->layers; ++l) {
+        int in, H, Cc, HC, out;
+        layer_shape(d, l, in, H, Cc, HC, out);
+        n += (int64_t)HC * in + 2 * HC + (ED > 0 ? (int64_t)HC * ED + HC : 0) + 5 * (int64_t)out;
+    }
+    n += h2 * C + h2 + (int64_t)d->num_classes * h2 + d->num_classes;
+    n += h2 * C + h2 + h2 + 1;
+    if (d->predict_correction) n += h2 * C + h2 + h2 + 1;
+    return n;
+}
+
+extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64_t n_floats, int device,
+                                 bgnn_model** out) {
+    BGNN_CHECK_ARG(d && p && out, "null argument");
+    BGNN_CHECK_ARG(d->layers >= 1 && d->layers <= 16, "layers out of range");
+    BGNN_CHECK_ARG(d->hidden == 32 || d->hidden == 64 || d->hidden == 128, "hidden must be 32, 64 or 128");
+    BGNN_CHECK_ARG(d->heads == 1 || d->heads == 2 || d->heads == 4 || d->heads == 8, "heads must be 1, 2, 4 or 8");
+    BGNN_CHECK_ARG(d->heads * d->hidden <= 512, "heads*hidden > 512 is not compiled");
+    BGNN_CHECK_ARG(d->edge_dim >= 0 && d->edge_dim <= BGNN_MAX_EDGE_FEATS, "edge_dim out of range");
+    BGNN_CHECK_ARG(d->num_classes >= 1 && d->num_classes <= 8, "num_classes out of range");
+    BGNN_CHECK_ARG(d->in_channels >= 1 && d->in_channels <= 64, "in_channels out of range");
+    BGNN_CHECK_ARG(n_floats == bgnn_model_param_floats(d), "parameter blob has %lld floats, expected %lld",
+                   (long long)n_floats, (long long)bgnn_model_param_floats(d));
+    const int C = d->hidden, F = d->in_channels, ED = d->edge_dim, h2 = C / 2;
+    const int nblk = d->predict_correction ? 3 : 2;
+
+    // ---- fold on the host, then one upload
+    std::vector<float> hb;
+    auto push = [&](const float* src, int64_t n) { size_t o = hb.size(); hb.insert(hb.end(), src, src + n); hb.resize(align_up(hb.size(), 4)); return o; };
+    struct LOff { size_t W, as, ad, M, bias, a, b; };
+    std::vector<LOff> lo(d->layers);
+    const float* q = p;
+    size_t oW0 = push(q, (int64_t)C * F); q += (int64_t)C * F;
+    size_t ob0 = push(q, C); q += C;
+    size_t oW1 = push(q, (int64_t)C * C); q += (int64_t)C * C;
+    size_t ob1 = push(q, C); q += C;
+    for (int l = 0; l < d->layers; ++l) {
+        int in, H, Cc, HC, outc;
+        layer_shape(d, l, in, H, Cc, HC, outc);
+        lo[l].W = push(q, (int64_t)HC * in); q += (int64_t)HC * in;
+        lo[l].as = push(q, HC); q += HC;
+        lo[l].ad = push(q, HC); q += HC;
+        std::vector<float> M((size_t)BGNN_MAX_EDGE_FEATS * H, 0.f);
+        if (ED > 0) {
+            const float* We = q; q += (int64_t)HC * ED;        // [HC, ED]
+            const float* ae = q; q += HC;
+            for (int e = 0; e < ED; ++e)
+                for (int hh = 0; hh < H; ++hh) {
+                    double s = 0.0;
+                    for (int c = 0; c < Cc; ++c) s += (double)We[(int64_t)(hh * Cc + c) * ED + e] * (double)ae[hh * Cc + c];
+                    M[(size_t)e * H + hh] = (float)s;
+                }
+        }
+        lo[l].M = push(M.data(), (int64_t)M.size());
+        lo[l].bias = push(q, outc); q += outc;
+        const float *bw = q, *bb = q + outc, *bm = q + 2 * outc, *bv = q + 3 * outc;
+        q += 4 * (int64_t)outc;
+        std::vector<float> a(outc), b(outc);
+        for (int c = 0; c < outc; ++c) {            // torch CPU eval BN: alpha = invstd*w, beta = b - mean*alpha
+            const float invstd = 1.0f / sqrtf(bv[c] + d->bn_eps);
+            a[c] = invstd * bw[c];
+            b[c] = bb[c] - bm[c] * a[c];
+        }
+        lo[l].a = push(a.data(), outc);
+        lo[l].b = push(b.data(), outc);
+    }
+    // heads: first layers concatenated [nblk*h2, C]
+    const float* cW0 = q; q += (int64_t)h2 * C; const float* cb0 = q; q += h2;
+    const float* cW1 = q; q += (int64_t)d->num_classes * h2; const float* cb1 = q; q += d->num_classes;
+    const float* fW0 = q; q += (int64_t)h2 * C; const float* fb0 = q; q += h2;
+    const float* fW1 = q; q += h2; const float* fb1 = q; q += 1;
+    const float *rW0 = nullptr, *rb0 = nullptr, *rW1 = nullptr, *rb1 = nullptr;
+    if (d->predict_correction) { rW0 = q; q += (int64_t)h2 * C; rb0 = q; q += h2; rW1 = q; q += h2; rb1 = q; q += 1; }
+    std::vector<float> hW0((size_t)nblk * h2 * C), hb0((size_t)nblk * h2);
+    memcpy(hW0.data(), cW0, sizeof(float) * h2 * C); memcpy(hb0.data(), cb0, sizeof(float) * h2);
+    memcpy(hW0.data() + (size_t)h2 * C, fW0, sizeof(float) * h2 * C); memcpy(hb0.data() + h2, fb0, sizeof(float) * h2);
+    if (rW0) { memcpy(hW0.data() + (size_t)2 * h2 * C, rW0, sizeof(float) * h2 * C); memcpy(hb0.data() + 2 * h2, rb0, sizeof(float) * h2); }
+    size_t ohW0 = push(hW0.data(), (int64_t)hW0.size()), ohb0 = push(hb0.data(), (int64_t)hb0.size());
+    size_t oWc = push(cW1, (int64_t)d->num_classes * h2), obc = push(cb1, d->num_classes);
+    size_t oWf = push(fW1, h2), obf = push(fb1, 1);
+    size_t oWr = rW1 ? push(rW1, h2) : 0, obr = rb1 ? push(rb1, 1) : 0;
+    if (q - p != n_floats) { bgnn_set_error("internal: parameter walk mismatch"); return BGNN_E_INVALID; }
+
+    int prev = 0;
+    BGNN_CUDA(cudaGetDevice(&prev));
+    BGNN_CUDA(cudaSetDevice(device));
+    bgnn_model* m = new bgnn_model();
+    m->d = *d; m->device = device; m->nheads_mlp = nblk;
+    cudaError_t e = cudaMalloc(&m->blob, hb.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(m->blob, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { bgnn_set_error("model upload failed: %s", cudaGetErrorString(e)); delete m; return BGNN_E_CUDA; }
+    float* B = m->blob;
+    m->feW0 = B + oW0; m->feb0 = B + ob0; m->feW1 = B + oW1; m->feb1 = B + ob1;
+    m->hc_max = C;
+    for (int l = 0; l < d->layers; ++l) {
+        LayerDev L;
+        layer_shape(d, l, L.in, L.H, L.C, L.HC, L.out);
+        L.W = B + lo[l].W; L.att_src = B + lo[l].as; L.att_dst = B + lo[l].ad; L.Medge = B + lo[l].M;
+        L.bias = B + lo[l].bias; L.bn_a = B + lo[l].a; L.bn_b = B + lo[l].b;
+        m->layers.push_back(L);
+        if (L.HC > m->hc_max) m->hc_max = L.HC;
+    }
+    if (nblk * h2 > m->hc_max) m->hc_max = nblk * h2;
+    m->hW0 = B + ohW0; m->hb0 = B + ohb0; m->Wcls = B + oWc; m->bcls = B + obc; m->Wconf = B + oWf; m->bconf = B + obf;
+    m->Wcorr = rW1 ? B + oWr : nullptr; m->bcorr = rb1 ? B + obr : nullptr;
+    *out = m;
+    return BGNN_OK;
+}
+
+extern "C" void bgnn_model_destroy(bgnn_model* m) {
+    if (!m) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->device);
+    cudaFree(m->blob);
+    cudaSetDevice(prev);
+    delete m;
+}
+
+static size_t act_bytes(const bgnn_model* m, int64_t n) { return align_up((size_t)n * m->hc_max * sizeof(float), 256); }
+
+extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes) {
+    if (!m || n_nodes < 0) return 0;
+    return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256;
+}
+
+extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const float* x, const int32_t* rowptr,
+                                const int32_t* csr_src, const float* csr_eattr, void* workspace, size_t workspace_bytes,
+                                float* logits, float* probs, int64_t* cls, float* conf, float* corr, int64_t* action,
+                                float thr_auto, float thr_review, float* hidden_out, void* stream_) {
+    BGNN_CHECK_ARG(m, "model is null");
+    BGNN_CHECK_ARG(N >= 0 && E >= 0, "negative sizes");
+    if (N == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(x && rowptr, "x / rowptr are null");
+    BGNN_CHECK_ARG(E == 0 || csr_src, "csr_src is null");
+    BGNN_CHECK_ARG(m->d.edge_dim == 0 || E == 0 || csr_eattr, "model has edge_dim>0 but csr_eattr is null");
+    BGNN_CHECK_ARG(N < (int64_t)2000000000 && E < (int64_t)2000000000, "graph too large for int32 indices");
+    if (workspace_bytes < bgnn_gat_workspace_bytes(m, N) || !workspace) {
+        bgnn_set_error("workspace too small: %zu < %zu", workspace_bytes, bgnn_gat_workspace_bytes(m, N));
+        return BGNN_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    int dev = 0, sms = 148;
+    BGNN_CUDA(cudaGetDevice(&dev));
+    BGNN_CHECK_ARG(dev == m->device, "model lives on device %d but current device is %d", m->device, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    char* w = (char*)workspace;
+    w = (char*)align_up((size_t)w, 256);
+    float* bufA = (float*)w; w += act_bytes(m, N);
+    float* bufB = (float*)w; w += act_bytes(m, N);
+    float* hbuf = (float*)w; w += act_bytes(m, N);
+    float* alpha = (float*)w;
+    const bgnn_model_desc& d = m->d;
+    const int C = d.hidden, h2 = C / 2;
+    int rc;
+    // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C)
+    if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc;
+    if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc;
+    float* cur = bufB;
+    float* nxt = bufA;
+    for (int l = 0; l < d.layers; ++l) {
+        const LayerDev& L = m->layers[l];
+        if ((rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s))) return rc;
+        const int relu = l < d.layers - 1;
+        if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s))) return rc;
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // heads
+    const int nblk = m->nheads_mlp;
+    if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc;
+    int64_t blocks = ceil_div64(N, 8);
+    if (blocks > (int64_t)sms * 32) blocks = (int64_t)sms * 32;
+    heads_finish<<<(unsigned)blocks, 256, 0, s>>>(hbuf, h2, nblk, d.num_classes, m->Wcls, m->bcls, m->Wconf, m->bconf,
+                                                 m->Wcorr, m->bcorr, logits, probs, cls, conf, corr, action, thr_auto,
+                                                 thr_review, N);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}

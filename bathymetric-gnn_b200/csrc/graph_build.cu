@@ -1,0 +1,443 @@
+// Spatial-graph build on the device (sm_100a).
+//
+// Replaces data/graph_construction.py:91-458 of the reference (GraphBuilder.build_graph and
+// its helpers) and, for ragged batches, the per-grid loop + Batch.from_data_list of
+// scripts/inference_native.py:158-179, 249-269, 312.   See include/bgnn.h for the contract.
+//
+// This translation unit is compiled with -fmad=false: the feature arithmetic has to round
+// exactly like NumPy (separate multiply / add), and the kernels are
+// bound by their output bytes (177 B/cell), not by FLOPs.
+//
+// Pipeline (all thread-per-cell, 256 cells per CTA, cells in cell-space order):
+//   gb_count : classify cell, neighbour bitmask -> per-CTA counts {valid, degree, per-offset}
+//   gb_scan  : exclusive scan of the per-CTA table (one CTA)
+//   gb_ids   : node_id grid, node_cell, rowptr          (needs the scan)
+//   gb_emit  : x, local_std, in-edge CSR (src ids + edge features)   (needs the node_id grid)
+//   gb_coo   : optional reference-ordered COO (offset-major) for the API-visible edge_index
+#include "common.cuh"
+
+namespace {
+
+constexpr int GB_THREADS = 256;
+constexpr int GB_WARPS = GB_THREADS / 32;
+constexpr int GB_MAXCOL = BGNN_MAX_OFFSETS + 2;
+
+struct GraphParams {
+    bgnn_cells cells;
+    int K;
+    int dr[BGNN_MAX_OFFSETS], dc[BGNN_MAX_OFFSETS], neg[BGNN_MAX_OFFSETS];
+    int F, nf[BGNN_MAX_NODE_FEATS];
+    int ED, ef[BGNN_MAX_EDGE_FEATS];
+    int ncol;           // K + 2
+    int64_t nblocks;    // CTAs of GB_THREADS cells
+};
+
+struct Ctx {
+    int H, W, r, c;
+    int64_t dbase, dstride;   // depth/mask/unc index = dbase + r*dstride + c
+    int64_t cbase;            // packed cell index   = cbase + r*W + c
+    double rx, ry;
+};
+
+__device__ __forceinline__ void locate(const bgnn_cells& cs, int64_t t, Ctx& x) {
+    if (cs.n_grids == 1) {
+        x.H = cs.rows; x.W = cs.cols;
+        x.r = (int)(t / cs.cols); x.c = (int)(t - (int64_t)x.r * cs.cols);
+        x.dbase = 0; x.dstride = cs.row_stride; x.cbase = 0;
+        x.rx = cs.rx; x.ry = cs.ry;
+    } else {
+        int lo = 0, hi = cs.n_grids;           // largest g with cell_off[g] <= t
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(cs.cell_off + mid) <= t) lo = mid; else hi = mid;
+        }
+        int64_t off = __ldg(cs.cell_off + lo);
+        x.H = __ldg(cs.grid_rows + lo); x.W = __ldg(cs.grid_cols + lo);
+        int64_t l = t - off;
+        x.r = (int)(l / x.W); x.c = (int)(l - (int64_t)x.r * x.W);
+        x.dbase = off; x.dstride = x.W; x.cbase = off;
+        x.rx = __ldg(cs.grid_res + 2 * lo); x.ry = __ldg(cs.grid_res + 2 * lo + 1);
+    }
+}
+
+__device__ __forceinline__ bool valid_at(const bgnn_cells& cs, int64_t di) {
+    if (cs.mask) return __ldg(cs.mask + di) != 0;
+    float d = __ldg(cs.depth + di);
+    return isfinite(d) && (!cs.use_nodata || d != cs.nodata);
+}
+
+__device__ __forceinline__ bool valid_rc(const bgnn_cells& cs, const Ctx& x, int r, int c) {
+    if (r < 0 || r >= x.H || c < 0 || c >= x.W) return false;
+    return valid_at(cs, x.dbase + (int64_t)r * x.dstride + c);
+}
+
+__device__ __forceinline__ uint32_t neighbour_mask(const GraphParams& P, const Ctx& x) {
+    uint32_t nb = 0;
+    for (int k = 0; k < P.K; ++k)
+        if (valid_rc(P.cells, x, x.r + P.dr[k], x.c + P.dc[k])) nb |= 1u << k;
+    return nb;
+}
+
+// ---------------------------------------------------------------- count / scan / ids
+__global__ void __launch_bounds__(GB_THREADS) gb_count(const GraphParams P, int32_t* __restrict__ table) {
+    __shared__ int s_cnt[GB_WARPS][GB_MAXCOL];
+    const int64_t t = (int64_t)blockIdx.x * GB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool v = false; uint32_t nb = 0;
+    if (t < P.cells.n_cells) {
+        Ctx x; locate(P.cells, t, x);
+        v = valid_rc(P.cells, x, x.r, x.c);
+        if (v) nb = neighbour_mask(P, x);
+    }
+    const unsigned bv = __ballot_sync(0xffffffffu, v);
+    int deg = __popc(nb);
+    for (int o = 16; o; o >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, o);
+    if (lane == 0) { s_cnt[warp][0] = __popc(bv); s_cnt[warp][1] = deg; }
+    for (int k = 0; k < P.K; ++k) {
+        const unsigned bk = __ballot_sync(0xffffffffu, (nb >> k) & 1u);
+        if (lane == 0) s_cnt[warp][2 + k] = __popc(bk);
+    }
+    __syncthreads();
+    if (threadIdx.x < P.ncol) {
+        int sum = 0;
+        for (int w = 0; w < GB_WARPS; ++w) sum += s_cnt[w][threadIdx.x];
+        table[(int64_t)threadIdx.x * (P.nblocks + 1) + blockIdx.x] = sum;
+    }
+}
+
+// one CTA: exclusive scan of each column of table[ncol][nblocks+1]; totals land at [nblocks]
+__global__ void __launch_bounds__(1024) gb_scan(int32_t* __restrict__ table, int64_t nblocks, int ncol) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (nblocks + 1023) / 1024;
+    const int64_t b0 = (int64_t)tid * per, b1 = min(b0 + per, nblocks);
+    for (int col = 0; col < ncol; ++col) {
+        int32_t* colp = table + (int64_t)col * (nblocks + 1);
+        int sum = 0;
+        for (int64_t b = b0; b < b1; ++b) sum += colp[b];
+        s_part[tid] = sum;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan
+            int v = tid >= o ? s_part[tid - o] : 0;
+            __syncthreads();
+            s_part[tid] += v;
+            __syncthreads();
+        }
+        int run = s_part[tid] - sum;
+        for (int64_t b = b0; b < b1; ++b) { int v = colp[b]; colp[b] = run; run += v; }
+        if (tid == 1023) colp[nblocks] = s_part[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS) gb_ids(const GraphParams P, const int32_t* __restrict__ table,
+                                                     int32_t* __restrict__ node_id, int32_t* __restrict__ node_cell,
+                                                     int32_t* __restrict__ rowptr) {
+    __shared__ int s_v[GB_WARPS], s_d[GB_WARPS];
+    const int64_t t = (int64_t)blockIdx.x * GB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool v = false; uint32_t nb = 0;
+    if (t < P.cells.n_cells) {
+        Ctx x; locate(P.cells, t, x);
+        v = valid_rc(P.cells, x, x.r, x.c);
+        if (v) nb = neighbour_mask(P, x);
+    }
+    const unsigned bv = __ballot_sync(0xffffffffu, v);
+    const int pv = __popc(bv & ((1u << lane) - 1u));
+    const int deg = __popc(nb);
+    int incl = deg;
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) { s_v[warp] = __popc(bv); s_d[warp] = incl; }
+    __syncthreads();
+    int wv = 0, wd = 0;
+    for (int w = 0; w < warp; ++w) { wv += s_v[w]; wd += s_d[w]; }
+    const int64_t nb1 = P.nblocks + 1;
+    const int id = table[blockIdx.x] + wv + pv;
+    const int ep = table[nb1 + blockIdx.x] + wd + (incl - deg);
+    if (t < P.cells.n_cells) node_id[t] = v ? id : -1;
+    if (v) {
+        if (node_cell) node_cell[id] = (int32_t)t;
+        if (rowptr) rowptr[id] = ep;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && rowptr) rowptr[table[P.nblocks]] = table[nb1 + P.nblocks];
+}
+
+// ---------------------------------------------------------------- node features
+struct BoxStats { float mean, stdv; };
+
+// graph_construction.py:399-430: masked 5x5 sums in fp64, zero outside the grid
+__device__ BoxStats box_stats(const bgnn_cells& cs, const Ctx& x, int r, int c) {
+    double S = 0.0, Q = 0.0; int C = 0;
+    for (int dr = -2; dr <= 2; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0 || rr >= x.H) continue;
+        for (int dc = -2; dc <= 2; ++dc) {
+            const int cc = c + dc;
+            if (cc < 0 || cc >= x.W) continue;
+            const int64_t di = x.dbase + (int64_t)rr * x.dstride + cc;
+            if (valid_at(cs, di)) {
+                const double d = (double)__ldg(cs.depth + di);
+                S += d; Q += d * d; ++C;
+            }
+        }
+    }
+    const double n = C > 0 ? (double)C : 1.0;
+    const double mu = S / n;
+    double var = Q / n - mu * mu;
+    if (var < 0.0) var = 0.0;                 // np.maximum keeps NaN, so no fmax here
+    BoxStats o; o.mean = (float)mu; o.stdv = (float)sqrt(var);
+    return o;
+}
+
+// depth_filled (:281-282): valid ? depth : local_mean, then nan_to_num
+__device__ __forceinline__ float filled_at(const bgnn_cells& cs, const Ctx& x, int r, int c) {
+    const int64_t di = x.dbase + (int64_t)r * x.dstride + c;
+    float f = valid_at(cs, di) ? __ldg(cs.depth + di) : box_stats(cs, x, r, c).mean;
+    return nan_to_num_f32(f);
+}
+
+__device__ __forceinline__ void edge_attr_write(const GraphParams& P, float* __restrict__ out, int k,
+                                                float dz, double rx, double ry) {
+    // tgt - src == offset k (graph_construction.py:348-362)
+    const double dx = (double)P.dc[k] * rx, dy = (double)P.dr[k] * ry;
+    const double dist = sqrt(dx * dx + dy * dy);
+    for (int e = 0; e < P.ED; ++e) {
+        float v;
+        switch (P.ef[e]) {
+            case BGNN_EF_DISTANCE: { double d = dist; if (isnan(d)) d = 0.0; v = (float)d; break; }
+            case BGNN_EF_DEPTH_DIFF: v = nan_to_num_f32(dz); break;
+            case BGNN_EF_SLOPE: {
+                double s = 0.0;
+                if (dist > 0.0) s = atan((double)dz / dist) * (180.0 / 3.14159265358979323846);
+                if (isnan(s)) s = 0.0;
+                v = (float)s; break;
+            }
+            default: v = 0.0f;
+        }
+        out[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS) gb_emit(const GraphParams P, const int32_t* __restrict__ node_id,
+                                                      const int32_t* __restrict__ rowptr, float* __restrict__ xout,
+                                                      float* __restrict__ local_std, int32_t* __restrict__ csr_src,
+                                                      float* __restrict__ csr_eattr) {
+    const int64_t t = (int64_t)blockIdx.x * GB_THREADS + threadIdx.x;
+    if (t >= P.cells.n_cells) return;
+    const int id = node_id[t];
+    if (id < 0) return;
+    const bgnn_cells& cs = P.cells;
+    Ctx x; locate(cs, t, x);
+    const int r = x.r, c = x.c;
+    const int64_t di = x.dbase + (int64_t)r * x.dstride + c;
+    const float d = __ldg(cs.depth + di);
+
+    if (xout || local_std) {
+        const BoxStats st = box_stats(cs, x, r, c);
+        if (local_std) local_std[id] = nan_to_num_f32(st.stdv);
+        if (xout) {
+            const float f0 = nan_to_num_f32(d);
+            const float up = r > 0 ? filled_at(cs, x, r - 1, c) : f0;
+            const float dn = r < x.H - 1 ? filled_at(cs, x, r + 1, c) : f0;
+            const float lf = c > 0 ? filled_at(cs, x, r, c - 1) : f0;
+            const float rt = c < x.W - 1 ? filled_at(cs, x, r, c + 1) : f0;
+            // np.gradient, unit spacing (:284)
+            float gy = 0.f, gx = 0.f;
+            if (x.H >= 2) gy = r == 0 ? dn - f0 : (r == x.H - 1 ? f0 - up : (dn - up) / 2.0f);
+            if (x.W >= 2) gx = c == 0 ? rt - f0 : (c == x.W - 1 ? f0 - lf : (rt - lf) / 2.0f);
+            const float gm = sqrtf(gx * gx + gy * gy);
+            // ndimage.laplace, mode='reflect' (:447): per axis fp64 c*(-2) + (l + r), rounded to fp32
+            const double t0 = (double)f0 * -2.0 + ((double)up + (double)dn);
+            const double t1 = (double)f0 * -2.0 + ((double)lf + (double)rt);
+            float lap = (float)t0 + (float)t1;
+            int cnt3 = 0;                      // zero-padded 3x3 valid count (:451-456)
+            for (int a = -1; a <= 1; ++a)
+                for (int b = -1; b <= 1; ++b) cnt3 += valid_rc(cs, x, r + a, c + b) ? 1 : 0;
+            if (cnt3 < 3) lap = 0.0f;
+            float* row = xout + (int64_t)id * P.F;
+            for (int j = 0; j < P.F; ++j) {
+                float v;
+                switch (P.nf[j]) {
+                    case BGNN_NF_DEPTH: v = d; break;
+                    case BGNN_NF_LOCAL_MEAN: v = st.mean; break;
+                    case BGNN_NF_LOCAL_STD: v = st.stdv; break;
+                    case BGNN_NF_GRAD_X: v = gx; break;
+                    case BGNN_NF_GRAD_Y: v = gy; break;
+                    case BGNN_NF_GRAD_MAG: v = gm; break;
+                    case BGNN_NF_CURVATURE: v = lap; break;
+                    default: v = cs.unc ? __ldg(cs.unc + di) : 0.0f;
+                }
+                row[j] = nan_to_num_f32(v);
+            }
+        }
+    }
+
+    if (csr_src || csr_eattr) {
+        int ep = rowptr[id];
+        for (int k = 0; k < P.K; ++k) {          // in-edge (j -> i) with j = i - off_k
+            const int kk = P.neg[k];
+            const int jr = r + P.dr[kk], jc = c + P.dc[kk];
+            if (!valid_rc(cs, x, jr, jc)) continue;
+            if (csr_src) csr_src[ep] = node_id[x.cbase + (int64_t)jr * x.W + jc];
+            if (csr_eattr) {
+                const float dj = __ldg(cs.depth + x.dbase + (int64_t)jr * x.dstride + jc);
+                edge_attr_write(P, csr_eattr + (int64_t)ep * P.ED, k, d - dj, x.rx, x.ry);
+            }
+            ++ep;
+        }
+    }
+}
+
+// reference COO: offset-major, node-minor (graph_construction.py:196-241)
+__global__ void __launch_bounds__(GB_THREADS) gb_coo(const GraphParams P, const int32_t* __restrict__ table,
+                                                     const int32_t* __restrict__ node_id, int64_t E,
+                                                     int64_t* __restrict__ edge_index, float* __restrict__ edge_attr) {
+    __shared__ int s_cnt[GB_WARPS][BGNN_MAX_OFFSETS];
+    __shared__ int64_t s_goff[BGNN_MAX_OFFSETS];
+    const int64_t t = (int64_t)blockIdx.x * GB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nb1 = P.nblocks + 1;
+    const bgnn_cells& cs = P.cells;
+    bool v = false; uint32_t nb = 0; Ctx x;
+    if (t < cs.n_cells) {
+        locate(cs, t, x);
+        v = node_id[t] >= 0;
+        if (v) nb = neighbour_mask(P, x);
+    }
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < P.K; ++k) { s_goff[k] = run; run += table[(int64_t)(2 + k) * nb1 + P.nblocks]; }
+    }
+    int rank[BGNN_MAX_OFFSETS];
+    for (int k = 0; k < P.K; ++k) {
+        const unsigned bk = __ballot_sync(0xffffffffu, (nb >> k) & 1u);
+        rank[k] = __popc(bk & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[warp][k] = __popc(bk);
+    }
+    __syncthreads();
+    if (!v) return;
+    const int64_t di = x.dbase + (int64_t)x.r * x.dstride + x.c;
+    const float d = __ldg(cs.depth + di);
+    const int id = node_id[t];
+    for (int k = 0; k < P.K; ++k) {
+        if (!((nb >> k) & 1u)) continue;
+        int wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_cnt[w][k];
+        const int64_t e = s_goff[k] + table[(int64_t)(2 + k) * nb1 + blockIdx.x] + wb + rank[k];
+        const int jr = x.r + P.dr[k], jc = x.c + P.dc[k];
+        if (edge_index) {
+            edge_index[e] = id;
+            edge_index[E + e] = node_id[x.cbase + (int64_t)jr * x.W + jc];
+        }
+        if (edge_attr) {
+            const float dn = __ldg(cs.depth + x.dbase + (int64_t)jr * x.dstride + jc);
+            edge_attr_write(P, edge_attr + e * P.ED, k, dn - d, x.rx, x.ry);
+        }
+    }
+}
+
+int make_params(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, GraphParams& P) {
+    BGNN_CHECK_ARG(cells && cfg, "null cells/cfg");
+    BGNN_CHECK_ARG(cells->n_grids >= 1 && cells->n_cells >= 0, "bad cell space");
+    BGNN_CHECK_ARG(cells->n_cells < (int64_t)2000000000, "cell space too large for int32 node ids");
+    BGNN_CHECK_ARG(cells->depth || cells->n_cells == 0, "depth is null");
+    BGNN_CHECK_ARG(cfg->n_offsets >= 1 && cfg->n_offsets <= BGNN_MAX_OFFSETS, "n_offsets out of range");
+    BGNN_CHECK_ARG(cfg->n_node_feats >= 0 && cfg->n_node_feats <= BGNN_MAX_NODE_FEATS, "n_node_feats out of range");
+    BGNN_CHECK_ARG(cfg->n_edge_feats >= 0 && cfg->n_edge_feats <= BGNN_MAX_EDGE_FEATS, "n_edge_feats out of range");
+    if (cells->n_grids == 1) {
+        BGNN_CHECK_ARG((int64_t)cells->rows * cells->cols == cells->n_cells, "rows*cols != n_cells");
+        BGNN_CHECK_ARG(cells->row_stride >= cells->cols, "row_stride < cols");
+    } else {
+        BGNN_CHECK_ARG(cells->cell_off && cells->grid_rows && cells->grid_cols && cells->grid_res,
+                       "ragged descriptors missing");
+    }
+    P.cells = *cells;
+    P.K = cfg->n_offsets;
+    for (int k = 0; k < P.K; ++k) { P.dr[k] = cfg->off_dr[k]; P.dc[k] = cfg->off_dc[k]; P.neg[k] = -1; }
+    for (int k = 0; k < P.K; ++k)
+        for (int j = 0; j < P.K; ++j)
+            if (P.dr[j] == -P.dr[k] && P.dc[j] == -P.dc[k]) P.neg[k] = j;
+    for (int k = 0; k < P.K; ++k)
+        BGNN_CHECK_ARG(P.neg[k] >= 0 && !(P.dr[k] == 0 && P.dc[k] == 0),
+                       "offset set must be symmetric and exclude (0,0)");
+    P.F = cfg->n_node_feats;
+    for (int j = 0; j < P.F; ++j) P.nf[j] = cfg->node_feats[j];
+    P.ED = cfg->n_edge_feats;
+    for (int j = 0; j < P.ED; ++j) P.ef[j] = cfg->edge_feats[j];
+    P.ncol = P.K + 2;
+    P.nblocks = ceil_div64(cells->n_cells, GB_THREADS);
+    return BGNN_OK;
+}
+
+}  // namespace
+
+extern "C" size_t bgnn_graph_scratch_bytes(int64_t n_cells, int32_t n_offsets) {
+    const int64_t nblocks = ceil_div64(n_cells < 0 ? 0 : n_cells, GB_THREADS);
+    return align_up((size_t)(n_offsets + 2) * (size_t)(nblocks + 1) * sizeof(int32_t), 256);
+}
+
+extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch,
+                                size_t scratch_bytes, int64_t* totals_host, void* stream_) {
+    GraphParams P;
+    int rc = make_params(cells, cfg, P);
+    if (rc) return rc;
+    BGNN_CHECK_ARG(totals_host, "totals_host is null");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (cells->n_cells == 0) { totals_host[0] = totals_host[1] = 0; return BGNN_OK; }
+    BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
+    int32_t* table = (int32_t*)scratch;
+    gb_count<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table);
+    BGNN_LAUNCH_CHECK();
+    gb_scan<<<1, 1024, 0, stream>>>(table, P.nblocks, P.ncol);
+    BGNN_LAUNCH_CHECK();
+    int32_t tot[2];
+    BGNN_CUDA(cudaMemcpyAsync(&tot[0], table + P.nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    BGNN_CUDA(cudaMemcpyAsync(&tot[1], table + (P.nblocks + 1) + P.nblocks, sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, stream));
+    BGNN_CUDA(cudaStreamSynchronize(stream));
+    totals_host[0] = tot[0];
+    totals_host[1] = tot[1];
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch,
+                               size_t scratch_bytes, int32_t* node_id, int32_t* node_cell, float* x,
+                               float* local_std, int32_t* rowptr, int32_t* csr_src, float* csr_eattr,
+                               void* stream_) {
+    GraphParams P;
+    int rc = make_params(cells, cfg, P);
+    if (rc) return rc;
+    if (cells->n_cells == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
+    BGNN_CHECK_ARG(node_id, "node_id is required");
+    BGNN_CHECK_ARG(rowptr || !(csr_src || csr_eattr), "rowptr is required for CSR outputs");
+    BGNN_CHECK_ARG(!(x && P.F == 0), "x requested with zero node features");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int32_t* table = (const int32_t*)scratch;
+    gb_ids<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table, node_id, node_cell, rowptr);
+    BGNN_LAUNCH_CHECK();
+    if (x || local_std || csr_src || csr_eattr) {
+        gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr);
+        BGNN_LAUNCH_CHECK();
+    }
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_graph_coo(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch,
+                              size_t scratch_bytes, const int32_t* node_id, int64_t n_edges,
+                              int64_t* edge_index, float* edge_attr, void* stream_) {
+    GraphParams P;
+    int rc = make_params(cells, cfg, P);
+    if (rc) return rc;
+    if (cells->n_cells == 0 || n_edges == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
+    BGNN_CHECK_ARG(node_id, "node_id is required");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gb_coo<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, (const int32_t*)scratch, node_id, n_edges,
+                                                          edge_index, edge_attr);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}

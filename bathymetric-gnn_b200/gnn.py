@@ -1,0 +1,286 @@
+"""`BathymetricGNN` with the reference's module tree, constructor, `forward` and
+`predict` (models/gnn.py:263-451) whose arithmetic runs in libbgnn.so.
+
+The sub-module names are the reference's, so a reference checkpoint's
+`model_state_dict` loads with `strict=True` (SURVEY.md 8(b) "State-dict
+compatibility"); GATConv parameters use the PyG >= 2.4 names and the PyG <= 2.3
+spelling (`lin_src` / `lin_dst`) is accepted on load.  Only the GAT backbone is
+built (GCN / GraphSAGE / GIN are outside the hot path).
+Inference only: there is no autograd through the kernels and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+from .graph import Data
+
+logger = logging.getLogger(__name__)
+
+
+def _glorot(t: torch.Tensor):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+class _Lin(nn.Module):
+    """Parameter holder for PyG's bias-free `Linear` (glorot init)."""
+
+    def __init__(self, fin: int, fout: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fout, fin))
+        _glorot(self.weight)
+
+
+class GATConvParams(nn.Module):
+    """Holds the parameters of one PyG `GATConv(in, out, heads, concat, edge_dim)`
+    (models/gnn.py:125-132) under PyG's names; the arithmetic lives in the
+    gat_aggregate / gemm_nt kernels."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, edge_dim=None):
+        super().__init__()
+        self.in_channels, self.out_channels, self.heads, self.concat, self.edge_dim = in_channels, out_channels, heads, concat, edge_dim
+        self.lin = _Lin(in_channels, heads * out_channels)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        _glorot(self.att_src)
+        _glorot(self.att_dst)
+        if edge_dim is not None:
+            self.lin_edge = _Lin(edge_dim, heads * out_channels)
+            self.att_edge = nn.Parameter(torch.empty(1, heads, out_channels))
+            _glorot(self.att_edge)
+        else:
+            self.lin_edge = None
+            self.register_parameter("att_edge", None)
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # PyG <= 2.3 stored the shared projection twice, as lin_src and lin_dst
+        src, dst, new = prefix + "lin_src.weight", prefix + "lin_dst.weight", prefix + "lin.weight"
+        if src in state_dict and new not in state_dict:
+            state_dict[new] = state_dict.pop(src)
+            state_dict.pop(dst, None)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class BatchNormParams(nn.Module):
+    """`torch_geometric.nn.BatchNorm` wrapper layout: `.module` is a BatchNorm1d."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.module = nn.BatchNorm1d(channels, eps=1e-5, momentum=0.1)
+
+
+def _mlp(fin, hid, fout, dropout, final=None):
+    layers = [nn.Linear(fin, hid), nn.ReLU(), nn.Dropout(dropout), nn.Linear(hid, fout)]
+    if final is not None:
+        layers.append(final)
+    return nn.Sequential(*layers)
+
+
+class LocalFeatureExtractor(nn.Module):
+    """models/gnn.py:34-71 (instantiated by the model with num_layers=2)."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers: int = 2, dropout: float = 0.1):
+        super().__init__()
+        if num_layers != 2:
+            raise NotImplementedError("the reference model always uses num_layers=2 (models/gnn.py:313-319)")
+        self.mlp = _mlp(in_channels, hidden_channels, out_channels, dropout)
+
+
+class GNNBackbone(nn.Module):
+    """models/gnn.py:74-188, GAT branch."""
+
+    def __init__(self, in_channels, hidden_channels, num_layers, gnn_type="GAT", heads=4, dropout=0.1, edge_dim=None):
+        super().__init__()
+        if gnn_type != "GAT":
+            raise NotImplementedError(f"gnn_type={gnn_type!r}: only the GAT backbone is on the accelerated hot path")
+        self.gnn_type, self.num_layers, self.dropout = gnn_type, num_layers, dropout
+        self.convs, self.norms = nn.ModuleList(), nn.ModuleList()
+        for i in range(num_layers):
+            last = i == num_layers - 1
+            layer_in = in_channels if i == 0 else hidden_channels * heads
+            self.convs.append(GATConvParams(layer_in, hidden_channels, heads=1 if last else heads,
+                                            concat=not last, edge_dim=edge_dim))
+            self.norms.append(BatchNormParams(hidden_channels if last else hidden_channels * heads))
+
+
+class ClassificationHead(nn.Module):
+    def __init__(self, in_channels, hidden_channels, num_classes, dropout=0.1):
+        super().__init__()
+        self.mlp = _mlp(in_channels, hidden_channels, num_classes, dropout)
+
+
+class ConfidenceHead(nn.Module):
+    def __init__(self, in_channels, hidden_channels, dropout=0.1):
+        super().__init__()
+        self.mlp = _mlp(in_channels, hidden_channels, 1, dropout, nn.Sigmoid())
+
+
+class CorrectionHead(nn.Module):
+    def __init__(self, in_channels, hidden_channels, dropout=0.1):
+        super().__init__()
+        self.mlp = _mlp(in_channels, hidden_channels, 1, dropout)
+
+
+class BathymetricGNN(nn.Module):
+    CLASS_SEAFLOOR = 0
+    CLASS_FEATURE = 1
+    CLASS_NOISE = 2
+
+    def __init__(self, in_channels: int, hidden_channels: int = 64, num_gnn_layers: int = 4, gnn_type: str = "GAT",
+                 heads: int = 4, num_classes: int = 3, predict_correction: bool = True, dropout: float = 0.1,
+                 edge_dim: Optional[int] = None):
+        super().__init__()
+        self.predict_correction, self.num_classes = predict_correction, num_classes
+        self.in_channels, self.hidden_channels, self.num_gnn_layers = in_channels, hidden_channels, num_gnn_layers
+        self.heads, self.edge_dim, self.dropout = heads, edge_dim, dropout
+        self.feature_extractor = LocalFeatureExtractor(in_channels, hidden_channels, hidden_channels, 2, dropout)
+        self.gnn = GNNBackbone(hidden_channels, hidden_channels, num_gnn_layers, gnn_type, heads, dropout, edge_dim)
+        self.classification_head = ClassificationHead(hidden_channels, hidden_channels // 2, num_classes, dropout)
+        self.confidence_head = ConfidenceHead(hidden_channels, hidden_channels // 2, dropout)
+        self.correction_head = CorrectionHead(hidden_channels, hidden_channels // 2, dropout) if predict_correction else None
+        self._handle = None
+        self._handle_key = None
+        logger.info("Created BathymetricGNN: %s with %d layers, %d hidden channels", gnn_type, num_gnn_layers, hidden_channels)
+
+    # ------------------------------------------------------------------ packing
+    def _desc(self) -> _lib.ModelDesc:
+        d = _lib.ModelDesc()
+        d.in_channels, d.hidden, d.layers, d.heads = self.in_channels, self.hidden_channels, self.num_gnn_layers, self.heads
+        d.num_classes, d.predict_correction = self.num_classes, int(self.predict_correction)
+        d.edge_dim = int(self.edge_dim or 0)
+        d.bn_eps, d.negative_slope = 1e-5, 0.2
+        return d
+
+    def _flat_params(self) -> torch.Tensor:
+        """Blob in the order include/bgnn.h documents for bgnn_model_create."""
+        fe = self.feature_extractor.mlp
+        parts = [fe[0].weight, fe[0].bias, fe[3].weight, fe[3].bias]
+        for conv, norm in zip(self.gnn.convs, self.gnn.norms):
+            parts += [conv.lin.weight, conv.att_src, conv.att_dst]
+            if conv.edge_dim is not None:
+                parts += [conv.lin_edge.weight, conv.att_edge]
+            bn = norm.module
+            parts += [conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        heads = [self.classification_head, self.confidence_head] + ([self.correction_head] if self.predict_correction else [])
+        for h in heads:
+            parts += [h.mlp[0].weight, h.mlp[0].bias, h.mlp[3].weight, h.mlp[3].bias]
+        return torch.cat([p.detach().reshape(-1).to("cpu", torch.float32) for p in parts]).contiguous()
+
+    def _ensure_handle(self, device: torch.device):
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               tuple(t._version for t in list(self.parameters()) + list(self.buffers())),
+               tuple(t.data_ptr() for t in self.parameters()))
+        if self._handle is not None and self._handle_key == key:
+            return self._handle
+        self._release()
+        flat = self._flat_params()
+        d = self._desc()
+        h = C.c_void_p()
+        check(lib.bgnn_model_create(C.byref(d), C.c_void_p(flat.data_ptr()), flat.numel(), key[0], C.byref(h)))
+        self._handle, self._handle_key = h, key
+        return h
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            lib.bgnn_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def __getstate__(self):            # the device handle is never copied / pickled
+        s = self.__dict__.copy()
+        s["_handle"], s["_handle_key"] = None, None
+        return s
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _csr_from_coo(data: Data, device):
+        """Foreign `Data` (not from the device GraphBuilder): in-edge CSR from the COO,
+        existing self loops removed as GATConv does (plumbing, torch ops)."""
+        ei = data.edge_index.to(device)
+        ea = getattr(data, "edge_attr", None)
+        keep = ei[0] != ei[1]
+        ei = ei[:, keep]
+        order = torch.sort(ei[1], stable=True).indices
+        N = int(data.x.shape[0])
+        rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+        rowptr[1:] = torch.cumsum(torch.bincount(ei[1], minlength=N), 0)
+        src = ei[0][order].to(torch.int32).contiguous()
+        if ea is not None:
+            ea = ea.to(device=device, dtype=torch.float32)
+            if ea.dim() == 1:
+                ea = ea.view(-1, 1)
+            ea = ea[keep][order].contiguous()
+        return rowptr.to(torch.int32), src, ea, int(src.numel())
+
+    def _run(self, data: Data, auto_thr: float, review_thr: float, want_action: bool, return_hidden: bool = False):
+        _lib.require_cuda()
+        if self.training and self.dropout > 0:
+            raise RuntimeError("BathymetricGNN (B200 build) is inference-only: call .eval() first")
+        dg = data.__dict__.get("_dev")
+        x = data.x
+        device = dg.device if dg is not None else (x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        with torch.cuda.device(device):
+            x = x.to(device=device, dtype=torch.float32).contiguous()
+            N = int(x.shape[0])
+            if x.dim() != 2 or x.shape[1] != self.in_channels:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({N}x{x.shape[-1]} and "
+                                   f"{self.in_channels}x{self.hidden_channels})")
+            if dg is not None:
+                rowptr, src, ea, E = dg.rowptr, dg.csr_src, dg.csr_eattr, dg.E
+                ed_have = int(dg.cfg.n_edge_feats)
+            else:
+                rowptr, src, ea, E = self._csr_from_coo(data, device)
+                ed_have = 0 if ea is None else int(ea.shape[1])
+            ED = int(self.edge_dim or 0)
+            if ED > 0 and ed_have != ED:
+                raise RuntimeError(f"model expects edge_dim={ED} but the graph carries {ed_have} edge features")
+            h = self._ensure_handle(device)
+            out = dict(class_logits=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
+                       class_probs=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
+                       predicted_class=torch.empty(N, dtype=torch.int64, device=device),
+                       confidence=torch.empty(N, dtype=torch.float32, device=device))
+            if self.predict_correction:
+                out["correction"] = torch.empty(N, dtype=torch.float32, device=device)
+            action = torch.empty(N, dtype=torch.int64, device=device) if want_action else None
+            hidden = torch.empty((N, self.hidden_channels), dtype=torch.float32, device=device) if return_hidden else None
+            if N > 0:
+                wbytes = int(lib.bgnn_gat_workspace_bytes(h, N))
+                ws = torch.empty(wbytes, dtype=torch.uint8, device=device)
+                check(lib.bgnn_gat_forward(h, N, E, ptr(x), ptr(rowptr), ptr(src) if E > 0 else None,
+                                           ptr(ea) if (ED > 0 and E > 0) else None, ptr(ws), wbytes,
+                                           ptr(out["class_logits"]), ptr(out["class_probs"]), ptr(out["predicted_class"]),
+                                           ptr(out["confidence"]), ptr(out.get("correction")), ptr(action),
+                                           float(auto_thr), float(review_thr), ptr(hidden), stream_ptr()))
+            if want_action:
+                out["action"] = action
+            if return_hidden:
+                out["hidden"] = hidden
+        return out
+
+    def forward(self, data: Data) -> Dict[str, torch.Tensor]:
+        """models/gnn.py:360-408."""
+        return self._run(data, 0.85, 0.6, want_action=False)
+
+    def predict(self, data: Data, auto_correct_threshold: float = 0.85, review_threshold: float = 0.6) -> Dict[str, torch.Tensor]:
+        """models/gnn.py:410-451."""
+        self.eval()
+        with torch.no_grad():
+            out = self._run(data, auto_correct_threshold, review_threshold, want_action=True)
+        out["needs_review"] = out["action"] == 2
+        out["auto_correct"] = out["action"] == 1
+        return out

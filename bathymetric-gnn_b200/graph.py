@@ -1,0 +1,387 @@
+"""Graph containers and the device GraphBuilder.
+
+Mirrors the reference interface of data/graph_construction.py (`GraphBuilder`,
+:29-505) and the `torch_geometric.data.{Data,Batch}` surface the reference touches
+(SURVEY.md 8(b) "Data container"), with every array produced by the sm_100a
+kernels behind include/bgnn.h.  No torch_geometric, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+logger = logging.getLogger(__name__)
+
+OFFSETS_4 = [(-1, 0), (1, 0), (0, -1), (0, 1)]                                   # graph_construction.py:79-81
+OFFSETS_8 = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]   # :83-87
+OFFSETS_24 = [(dr, dc) for dr in range(-2, 3) for dc in range(-2, 3) if (dr, dc) != (0, 0)]
+
+
+class Data:
+    """Attribute bag with the PyG `Data` surface used by the reference."""
+
+    def __init__(self, x=None, edge_index=None, edge_attr=None, pos=None, **kwargs):
+        if x is not None:
+            self.x = x
+        if edge_index is not None:
+            self.edge_index = edge_index
+        if edge_attr is not None:
+            self.edge_attr = edge_attr
+        if pos is not None:
+            self.pos = pos
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self) -> int:
+        x = self.__dict__.get("x")
+        return 0 if x is None else int(x.shape[0])
+
+    @property
+    def num_edges(self) -> int:
+        ei = getattr(self, "edge_index", None)
+        return 0 if ei is None else int(ei.shape[1])
+
+    def _apply(self, fn):
+        out = self.__class__.__new__(self.__class__)
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = fn(v) if isinstance(v, torch.Tensor) and not k.startswith("_") else v
+        return out
+
+    def to(self, device, *a, **k):
+        return self._apply(lambda t: t.to(device, *a, **k))
+
+    def cpu(self):
+        return self._apply(lambda t: t.cpu())
+
+    def cuda(self, device=None):
+        return self._apply(lambda t: t.cuda(device))
+
+    def keys(self):
+        return [k for k in self.__dict__ if not k.startswith("_")]
+
+
+class _DeviceGraph:
+    """Device-resident lean graph (what the forward kernels consume).  Shared by a
+    GridGraph and its `.cpu()` / `.to()` copies."""
+    __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "csr_src",
+                 "csr_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta")
+
+
+class GridGraph(Data):
+    """`Data` built by the device GraphBuilder.  `x`, `local_std` are materialised;
+    `edge_index` (int64 COO, reference order), `edge_attr`, `pos`, `valid_rows`,
+    `valid_cols` are emitted by a kernel on first access (the forward pass itself
+    consumes the in-edge CSR and never needs them)."""
+
+    _LAZY = ("edge_index", "edge_attr", "pos", "valid_rows", "valid_cols")
+
+    def __getattr__(self, name):
+        if name in GridGraph._LAZY and "_dev" in self.__dict__:
+            self._materialise(name)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    @property
+    def num_edges(self) -> int:
+        return int(self._dev.E)
+
+    def _materialise(self, name):
+        dg = self._dev
+        tgt = self.__dict__.get("_target_device", dg.device)
+        with torch.cuda.device(dg.device):
+            if name in ("edge_index", "edge_attr"):
+                ED = dg.cfg.n_edge_feats
+                ei = torch.empty((2, dg.E), dtype=torch.int64, device=dg.device)
+                ea = torch.empty((dg.E, ED), dtype=torch.float32, device=dg.device)
+                check(lib.bgnn_graph_coo(C.byref(dg.cells), C.byref(dg.cfg), ptr(dg.scratch), dg.scratch.numel(),
+                                         ptr(dg.node_id), dg.E, ptr(ei), ptr(ea), stream_ptr()))
+                self.__dict__["edge_index"] = ei.to(tgt)
+                self.__dict__["edge_attr"] = ea.to(tgt)
+            else:
+                cell = dg.node_cell.to(torch.int64)
+                if dg.grid_meta is None:
+                    W = int(dg.cells.cols)
+                    rows, cols = torch.div(cell, W, rounding_mode="floor"), cell % W
+                else:                               # ragged batch: rows/cols local to each grid
+                    off, gcols = dg.grid_meta["cell_off_dev"], dg.grid_meta["cols_dev"]
+                    g = torch.searchsorted(off, cell, right=True) - 1
+                    local = cell - off[g]
+                    W = gcols[g].to(torch.int64)
+                    rows, cols = torch.div(local, W, rounding_mode="floor"), local % W
+                self.__dict__["valid_rows"] = rows.to(tgt)
+                self.__dict__["valid_cols"] = cols.to(tgt)
+                self.__dict__["pos"] = torch.stack([cols, rows], dim=1).to(torch.float32).to(tgt)
+
+    def _apply(self, fn):
+        out = super()._apply(fn)
+        probe = fn(torch.empty(0, device=self._dev.device))
+        out.__dict__["_target_device"] = probe.device
+        return out
+
+
+class Batch(Data):
+    """`torch_geometric.data.Batch.from_data_list` replacement
+    (scripts/inference_native.py:312): block-diagonal concatenation."""
+
+    @classmethod
+    def from_data_list(cls, data_list: List[Data]) -> "Batch":
+        out = cls()
+        offs, cat, batch_vec = 0, {}, []
+        for g, d in enumerate(data_list):
+            n = d.num_nodes
+            keys = list(d.keys())
+            if isinstance(d, GridGraph):
+                keys += [k for k in GridGraph._LAZY if k not in keys]
+            for k in keys:
+                v = getattr(d, k)
+                if isinstance(v, torch.Tensor) and k == "edge_index":
+                    v = v + offs
+                cat.setdefault(k, []).append(v)
+            batch_vec.append(torch.full((n,), g, dtype=torch.long, device=d.x.device))
+            offs += n
+        for k, vs in cat.items():
+            if isinstance(vs[0], torch.Tensor):
+                setattr(out, k, torch.cat(vs, dim=1 if k == "edge_index" else 0))
+            else:
+                setattr(out, k, vs)
+        out.batch = torch.cat(batch_vec) if batch_vec else torch.zeros(0, dtype=torch.long)
+        out.num_graphs = len(data_list)
+        return out
+
+
+def _graph_cfg(offsets, node_feats: Sequence[str], has_unc: bool, edge_feats: Sequence[str]) -> Tuple[_lib.GraphCfg, int]:
+    cfg = _lib.GraphCfg()
+    if len(offsets) > _lib.MAX_OFFSETS:
+        raise ValueError(f"at most {_lib.MAX_OFFSETS} neighbour offsets are supported")
+    cfg.n_offsets = len(offsets)
+    for k, (dr, dc) in enumerate(offsets):
+        cfg.off_dr[k], cfg.off_dc[k] = int(dr), int(dc)
+    # node feature columns exactly as the reference assembles them (:288-316)
+    cols = []
+    for n in node_feats:
+        if n in _lib.NF_CODES and n != "uncertainty":
+            cols.append(_lib.NF_CODES[n])
+        elif n == "uncertainty" and has_unc:
+            cols.append(_lib.NF_CODES["uncertainty"])
+    if has_unc and "uncertainty" not in node_feats:
+        cols.append(_lib.NF_CODES["uncertainty"])
+    if len(cols) > _lib.MAX_NODE_FEATS:
+        raise ValueError(f"at most {_lib.MAX_NODE_FEATS} node features are supported")
+    cfg.n_node_feats = len(cols)
+    for j, c in enumerate(cols):
+        cfg.node_feats[j] = c
+    if len(edge_feats) > _lib.MAX_EDGE_FEATS:
+        raise ValueError(f"at most {_lib.MAX_EDGE_FEATS} edge features are supported")
+    cfg.n_edge_feats = len(edge_feats)
+    for j, n in enumerate(edge_feats):
+        cfg.edge_feats[j] = _lib.EF_CODES.get(n, _lib.EF_ZERO)       # unknown name -> 0.0 (:366-367)
+    return cfg, len(cols)
+
+
+def _as_dev_f32(a, device) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device, dtype=torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device, non_blocking=True)
+    return t
+
+
+class GraphBuilder:
+    """Device drop-in for the reference `GraphBuilder` (graph_construction.py:29-505):
+    same constructor, `build_graph`, `graph_to_grid`; `neighbor_offsets` stays a
+    plain list attribute that may be overridden (e.g. the 24-offset 5x5 stencil)."""
+
+    def __init__(self, connectivity: str = "8-connected", include_self_loops: bool = False,
+                 node_features: Optional[List[str]] = None, edge_features: Optional[List[str]] = None,
+                 device: Optional[torch.device] = None):
+        self.connectivity = connectivity
+        self.include_self_loops = include_self_loops
+        self.node_features = node_features or ["depth", "local_mean", "local_std", "gradient_x", "gradient_y",
+                                               "gradient_magnitude", "curvature"]
+        self.edge_features = edge_features or ["distance", "depth_difference", "slope"]
+        if connectivity == "4-connected":
+            self.neighbor_offsets = list(OFFSETS_4)
+        elif connectivity == "8-connected":
+            self.neighbor_offsets = list(OFFSETS_8)
+        elif connectivity == "24-connected":          # additive: BASELINE config 5 (k=24)
+            self.neighbor_offsets = list(OFFSETS_24)
+        else:
+            raise ValueError(f"Unknown connectivity: {connectivity}")
+        if include_self_loops:
+            raise NotImplementedError("include_self_loops=True is never used by the reference pipelines "
+                                      "(GATConv adds its own self loops); not built")
+        self.device = device
+
+    # ------------------------------------------------------------------ build
+    def _device(self) -> torch.device:
+        _lib.require_cuda()
+        return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def build_graph(self, depth, valid_mask=None, uncertainty=None,
+                    resolution: Tuple[float, float] = (1.0, 1.0), nodata: Optional[float] = None) -> Data:
+        """graph_construction.py:91-174.  `depth` may be a NumPy array or a CUDA
+        tensor (a strided 2-D view of a survey is consumed in place).  `nodata`
+        (additive) makes the kernel derive valid = isfinite & != nodata when no mask
+        is given (scripts/inference_native.py:160)."""
+        dev = self._device()
+        if getattr(depth, "ndim", 0) != 2:
+            raise ValueError("depth must be a 2-D array")
+        H, W = int(depth.shape[0]), int(depth.shape[1])
+        with torch.cuda.device(dev):
+            d = _as_dev_f32(depth, dev)
+            if d.stride(1) != 1:
+                d = d.contiguous()
+            stride = int(d.stride(0)) if H > 1 else W
+            keep = [d]
+            cells = _lib.Cells()
+            cells.n_grids, cells.n_cells, cells.rows, cells.cols, cells.row_stride = 1, H * W, H, W, stride
+            cells.rx, cells.ry = float(resolution[0]), float(resolution[1])
+            cells.depth = d.data_ptr()
+            if valid_mask is not None:
+                m = valid_mask if isinstance(valid_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(valid_mask))
+                m = m.to(dev).to(torch.uint8)
+                if stride != W:                     # mask must share the depth view's stride
+                    mm = torch.zeros((H, stride), dtype=torch.uint8, device=dev)
+                    mm[:, :W] = m
+                    m = mm
+                m = m.contiguous()
+                keep.append(m)
+                cells.mask = m.data_ptr()
+            elif nodata is not None and not np.isnan(nodata):
+                cells.use_nodata, cells.nodata = 1, float(nodata)
+            if uncertainty is not None:
+                u = _as_dev_f32(uncertainty, dev)
+                if stride != W:
+                    uu = torch.zeros((H, stride), dtype=torch.float32, device=dev)
+                    uu[:, :W] = u
+                    u = uu
+                u = u.contiguous()
+                keep.append(u)
+                cells.unc = u.data_ptr()
+            return self._build(cells, keep, uncertainty is not None, (H, W), None, dev)
+
+    def build_graph_batch(self, grids: Sequence[Tuple[np.ndarray, Optional[np.ndarray], Tuple[float, float]]],
+                          nodata: Optional[float] = 1.0e6, use_uncertainty: bool = True) -> Data:
+        """Ragged batch of refinement grids as ONE block-diagonal graph: replaces the
+        per-grid build_graph loop + Batch.from_data_list of
+        scripts/inference_native.py:158-179, 249-269, 312.  valid = (depth != nodata)
+        & isfinite(depth) (:160)."""
+        dev = self._device()
+        G = len(grids)
+        if G == 0:
+            return self._empty()
+        rows = np.array([g[0].shape[0] for g in grids], np.int32)
+        cols = np.array([g[0].shape[1] for g in grids], np.int32)
+        off = np.zeros(G + 1, np.int64)
+        np.cumsum(rows.astype(np.int64) * cols.astype(np.int64), out=off[1:])
+        res = np.array([[float(g[2][0]), float(g[2][1])] for g in grids], np.float64)
+        depth = np.concatenate([np.asarray(g[0], np.float32).ravel() for g in grids]) if off[-1] else np.zeros(0, np.float32)
+        has_unc = use_uncertainty and all(g[1] is not None for g in grids)
+        with torch.cuda.device(dev):
+            d = torch.from_numpy(depth).to(dev)
+            t_off, t_rows, t_cols = (torch.from_numpy(a).to(dev) for a in (off, rows, cols))
+            t_res = torch.from_numpy(res).to(dev)
+            keep = [d, t_off, t_rows, t_cols, t_res]
+            cells = _lib.Cells()
+            cells.n_grids, cells.n_cells = G, int(off[-1])
+            cells.cell_off, cells.grid_rows, cells.grid_cols, cells.grid_res = (t.data_ptr() for t in (t_off, t_rows, t_cols, t_res))
+            cells.depth = d.data_ptr()
+            if nodata is not None and not np.isnan(nodata):
+                cells.use_nodata, cells.nodata = 1, float(nodata)
+            if has_unc:
+                u = torch.from_numpy(np.concatenate([np.asarray(g[1], np.float32).ravel() for g in grids])).to(dev)
+                keep.append(u)
+                cells.unc = u.data_ptr()
+            if G == 1:                                # degenerate: same as a single tile
+                cells.n_grids, cells.rows, cells.cols, cells.row_stride = 1, int(rows[0]), int(cols[0]), int(cols[0])
+                cells.rx, cells.ry = float(res[0, 0]), float(res[0, 1])
+            meta = dict(cell_off=off, rows=rows, cols=cols, cell_off_dev=t_off, cols_dev=t_cols)
+            return self._build(cells, keep, has_unc, None, meta if G > 1 else None, dev,
+                               shapes=[(int(r), int(c)) for r, c in zip(rows, cols)])
+
+    def _empty(self) -> Data:
+        """graph_construction.py:460-469 (note: no grid_shape attribute)."""
+        dev = self._device()
+        g = Data(x=torch.zeros((0, len(self.node_features)), dtype=torch.float32, device=dev),
+                 edge_index=torch.zeros((2, 0), dtype=torch.long, device=dev),
+                 edge_attr=torch.zeros((0, len(self.edge_features)), dtype=torch.float32, device=dev),
+                 pos=torch.zeros((0, 2), dtype=torch.float32, device=dev))
+        g.local_std = torch.zeros(0, dtype=torch.float32, device=dev)
+        return g
+
+    def _build(self, cells, keep, has_unc, grid_shape, meta, dev, shapes=None) -> Data:
+        cfg, F = _graph_cfg(self.neighbor_offsets, self.node_features, has_unc, self.edge_features)
+        n_cells = int(cells.n_cells)
+        scratch = torch.empty(max(int(lib.bgnn_graph_scratch_bytes(n_cells, cfg.n_offsets)), 256), dtype=torch.uint8, device=dev)
+        totals = (C.c_int64 * 2)()
+        st = stream_ptr()
+        check(lib.bgnn_graph_count(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), totals, st))
+        N, E = int(totals[0]), int(totals[1])
+        if N == 0:
+            logger.warning("No valid cells in grid")
+            g = self._empty()
+            if shapes is not None:
+                g._grid_shapes = shapes
+            return g
+        dims = shapes if shapes is not None else [grid_shape]
+        if any(min(s) < 2 for s in dims):
+            # the reference raises here from np.gradient (graph_construction.py:284)
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least (edge_order + 1) elements are required.")
+        ED = cfg.n_edge_feats
+        dg = _DeviceGraph()
+        dg.cells, dg.cfg, dg.scratch, dg.keep, dg.device, dg.grid_meta = cells, cfg, scratch, keep, dev, meta
+        dg.N, dg.E, dg.n_cells = N, E, n_cells
+        dg.node_id = torch.empty(n_cells, dtype=torch.int32, device=dev)
+        dg.node_cell = torch.empty(N, dtype=torch.int32, device=dev)
+        dg.x = torch.empty((N, F), dtype=torch.float32, device=dev)
+        dg.local_std = torch.empty(N, dtype=torch.float32, device=dev)
+        dg.rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        dg.csr_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        dg.csr_eattr = torch.empty((max(E, 1), max(ED, 1)), dtype=torch.float32, device=dev)
+        check(lib.bgnn_graph_emit(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), ptr(dg.node_id),
+                                  ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std), ptr(dg.rowptr), ptr(dg.csr_src),
+                                  ptr(dg.csr_eattr) if ED > 0 else None, st))
+        g = GridGraph()
+        g.__dict__["_dev"] = dg
+        g.x = dg.x
+        g.local_std = dg.local_std
+        g.num_valid_cells = N
+        if grid_shape is not None:
+            g.grid_shape = tuple(grid_shape)
+        if shapes is not None:
+            g._grid_shapes = shapes
+        logger.debug("Built graph: %d nodes, %d edges, %d node features, %d edge features", N, E, F, ED)
+        return g
+
+    # ------------------------------------------------------------------ graph_to_grid
+    def graph_to_grid(self, data: Data, node_values: torch.Tensor, fill_value: float = np.nan) -> np.ndarray:
+        """graph_construction.py:471-505 (returns a host float32 array like the reference)."""
+        if not hasattr(data, "grid_shape"):
+            raise ValueError("Data object missing grid_shape metadata")
+        if node_values.dim() != 1:
+            raise ValueError("For multi-channel node values, call graph_to_grid for each channel")
+        return self.graph_to_grid_device(data, node_values, fill_value).cpu().numpy()
+
+    def graph_to_grid_device(self, data: Data, node_values: torch.Tensor, fill_value: float = np.nan) -> torch.Tensor:
+        dev = self._device() if "_dev" not in data.__dict__ else data._dev.device
+        H, W = data.grid_shape
+        with torch.cuda.device(dev):
+            if "_dev" in data.__dict__:
+                node_id = data._dev.node_id
+            else:                                    # foreign Data: rebuild the index grid (plumbing)
+                node_id = torch.full((H * W,), -1, dtype=torch.int32, device=dev)
+                cell = data.valid_rows.to(dev).long() * W + data.valid_cols.to(dev).long()
+                node_id[cell] = torch.arange(cell.numel(), dtype=torch.int32, device=dev)
+            vals = node_values.detach().to(device=dev, dtype=torch.float32).contiguous()
+            grid = torch.empty((H, W), dtype=torch.float32, device=dev)
+            check(lib.bgnn_graph_to_grid(ptr(node_id), H * W, ptr(vals), float(fill_value), ptr(grid), stream_ptr()))
+        return grid

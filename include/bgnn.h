@@ -1,0 +1,227 @@
+/*
+ * bgnn.h -- C ABI of libbgnn.so: the B200 (sm_100a) implementation of the
+ * Bathymetric-GNN per-tile inference hot path
+ *     spatial-graph build -> 4x edge-aware GAT forward + heads -> tile scatter / stitch.
+ *
+ * The reference (grant-froelich/Bathymetric-GNN) is pure Python and has NO FFI /
+ * plugin interface for this path; the boundary it offers is the
+ * Python class surface.  Each entry point below therefore names the reference
+ * Python function it replaces (file:line under the reference tree); the ctypes
+ * binding a maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer marked [dev] is device memory owned by the CALLER; the library
+ *     allocates nothing on the data path (only the opaque model handle owns memory);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises except the functions documented as "host-synchronous";
+ *   - return value: 0 = ok, negative = error (BGNN_E_*); text via bgnn_last_error()
+ *     (thread-local);
+ *   - inputs are never modified;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails.
+ */
+#ifndef BGNN_H_
+#define BGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGNN_VERSION 100            /* 0.1.0 */
+
+#define BGNN_OK            0
+#define BGNN_E_INVALID    -1        /* bad argument (maps to Python ValueError)   */
+#define BGNN_E_CUDA       -2        /* CUDA runtime error (maps to RuntimeError)  */
+#define BGNN_E_UNSUPPORTED -3       /* configuration outside the compiled kernels */
+#define BGNN_E_WORKSPACE  -4        /* workspace too small                        */
+
+#define BGNN_MAX_OFFSETS   24       /* 4-, 8-connected and the 5x5 (k=24) stencil */
+#define BGNN_MAX_NODE_FEATS 8
+#define BGNN_MAX_EDGE_FEATS 4
+
+/* node feature codes: data/graph_construction.py:60-68, 288-316 */
+enum { BGNN_NF_DEPTH = 0, BGNN_NF_LOCAL_MEAN, BGNN_NF_LOCAL_STD, BGNN_NF_GRAD_X, BGNN_NF_GRAD_Y,
+       BGNN_NF_GRAD_MAG, BGNN_NF_CURVATURE, BGNN_NF_UNCERTAINTY };
+/* edge feature codes: data/graph_construction.py:71-75, 342-369 (unknown name -> ZERO) */
+enum { BGNN_EF_DISTANCE = 0, BGNN_EF_DEPTH_DIFF, BGNN_EF_SLOPE, BGNN_EF_ZERO };
+
+int         bgnn_version(void);
+const char* bgnn_last_error(void);
+/* device properties needed by callers that size launches: writes {sm_count, cc_major, cc_minor} */
+int         bgnn_device_info(int device, int* out3);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial-graph build.  Replaces GraphBuilder.build_graph / _build_edges /
+ * _compute_node_features / _masked_local_stats / _compute_curvature / _compute_edge_features
+ * (data/graph_construction.py:91-174, 176-243, 245-327, 378-432, 434-458, 329-376) and, with
+ * n_grids > 1, the per-refinement-grid loop + Batch.from_data_list of
+ * scripts/inference_native.py:158-179, 249-269, 312.
+ *
+ * A "cell space" is one or more row-major grids laid end to end:
+ *   n_grids == 1 : one tile; `depth` may be a strided view into a survey (row_stride elements
+ *                  between rows), so no tile copy is needed (data/tiling.py:140-178);
+ *   n_grids  > 1 : ragged batch; grids are packed contiguously (row stride == cols), described
+ *                  by the device arrays cell_off / rows / cols / res.
+ * Nodes are the valid cells in cell-space order (== reference raster order per grid, grids in
+ * batch order), node ids are the exclusive prefix count of valid cells (int32).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bgnn_cells {
+    int32_t        n_grids;      /* >= 1 */
+    int64_t        n_cells;      /* total cells (sum rows*cols)                                  */
+    /* n_grids == 1 */
+    int32_t        rows, cols;
+    int64_t        row_stride;   /* elements between consecutive rows of depth / mask / unc      */
+    double         rx, ry;       /* resolution (x, y)                                            */
+    /* n_grids > 1 (all [dev]) */
+    const int64_t* cell_off;     /* [n_grids+1] exclusive prefix of rows*cols                    */
+    const int32_t* grid_rows;    /* [n_grids] */
+    const int32_t* grid_cols;    /* [n_grids] */
+    const double*  grid_res;     /* [n_grids][2] (rx, ry)                                        */
+    /* data [dev] */
+    const float*   depth;
+    const uint8_t* mask;         /* optional; NULL => valid = isfinite(depth) [&& depth != nodata] */
+    const float*   unc;          /* optional uncertainty plane                                   */
+    int32_t        use_nodata;   /* when mask == NULL: also require depth != nodata             */
+    float          nodata;
+} bgnn_cells;
+
+typedef struct bgnn_graph_cfg {
+    int32_t n_offsets;                           /* 4, 8 or 24 */
+    int32_t off_dr[BGNN_MAX_OFFSETS];            /* reference order, graph_construction.py:79-87 */
+    int32_t off_dc[BGNN_MAX_OFFSETS];
+    int32_t n_node_feats;                        /* columns of x (<= 8)                          */
+    int32_t node_feats[BGNN_MAX_NODE_FEATS];     /* BGNN_NF_* per column                         */
+    int32_t n_edge_feats;                        /* columns of edge_attr (<= 4)                  */
+    int32_t edge_feats[BGNN_MAX_EDGE_FEATS];     /* BGNN_EF_* per column                         */
+} bgnn_graph_cfg;
+
+/* bytes of scratch needed by bgnn_graph_count/emit/coo for a cell space of n_cells */
+size_t bgnn_graph_scratch_bytes(int64_t n_cells, int32_t n_offsets);
+
+/* Phase 1 (host-synchronous: returns N and E): classify cells, count nodes and edges, scan.
+ * totals_host[0] = N (nodes), totals_host[1] = E (directed edges, no self loops). */
+int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
+                     void* scratch, size_t scratch_bytes, int64_t* totals_host, void* stream);
+
+/* Phase 2: emit the lean graph used by the forward pass.
+ *   node_id   [dev] int32 [n_cells]   node id per cell, -1 invalid (node_index_grid, :125-126)
+ *   node_cell [dev] int32 [N]         cell-space index of each node (valid_rows/cols = divmod)
+ *   x         [dev] f32   [N, n_node_feats]
+ *   local_std [dev] f32   [N]
+ *   rowptr    [dev] int32 [N+1]       in-edge CSR; row i lists the edges (j -> i) in the
+ *   csr_src   [dev] int32 [E]         reference's edge order (offset k ascending, j = i - off_k)
+ *   csr_eattr [dev] f32   [E, n_edge_feats]
+ * Any of x/local_std/csr_* may be NULL to skip that output. */
+int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
+                    void* scratch, size_t scratch_bytes,
+                    int32_t* node_id, int32_t* node_cell, float* x, float* local_std,
+                    int32_t* rowptr, int32_t* csr_src, float* csr_eattr, void* stream);
+
+/* Optional phase 3: the reference's API-visible COO (offset-major, node-minor; :196-241) and
+ * per-edge features in that order.  edge_index int64 [2,E] (row 0 = src/centre, row 1 = tgt),
+ * edge_attr f32 [E, n_edge_feats].  Needs the scratch of the SAME count call and node_id. */
+int bgnn_graph_coo(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
+                   void* scratch, size_t scratch_bytes, const int32_t* node_id,
+                   int64_t n_edges, int64_t* edge_index, float* edge_attr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GAT forward.  Replaces BathymetricGNN.forward / predict (models/gnn.py:360-451):
+ * LocalFeatureExtractor (:55-68) -> L x [GATConv(edge_dim) -> BatchNorm(eval) -> ReLU]
+ * (:107-154, 173-186; PyG GATConv semantics) -> three heads (:191-260).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bgnn_model_desc {
+    int32_t in_channels;        /* F (7 or 8)                      */
+    int32_t hidden;             /* C, per-head width (64 / 128)    */
+    int32_t layers;             /* L (4)                           */
+    int32_t heads;              /* H (4); last layer uses 1 head   */
+    int32_t num_classes;        /* 3                               */
+    int32_t predict_correction; /* 0/1                             */
+    int32_t edge_dim;           /* 0 (None) .. 4                   */
+    float   bn_eps;             /* 1e-5                            */
+    float   negative_slope;     /* 0.2                             */
+} bgnn_model_desc;
+
+typedef struct bgnn_model bgnn_model;   /* opaque: folded weights resident on one device */
+
+/* number of floats bgnn_model_create expects, in this order (all row-major, fp32):
+ *   feature_extractor.mlp.0.{weight[C,F],bias[C]}, feature_extractor.mlp.3.{weight[C,C],bias[C]},
+ *   per layer l: lin.weight[HC_l,in_l], att_src[HC_l], att_dst[HC_l],
+ *                (edge_dim>0: lin_edge.weight[HC_l,edge_dim], att_edge[HC_l]),
+ *                bias[out_l], norm.weight[out_l], norm.bias[out_l], running_mean[out_l], running_var[out_l]
+ *   classification_head.mlp.0.{weight[C/2,C],bias}, .mlp.3.{weight[num_classes,C/2],bias},
+ *   confidence_head.mlp.0.{..}, .mlp.3.{weight[1,C/2],bias[1]},
+ *   (predict_correction: correction_head.mlp.0.{..}, .mlp.3.{..})
+ * with H_l = heads (l < L-1) or 1 (last), HC_l = H_l*C, in_0 = C, in_l = heads*C, out_l = HC_l
+ * (concat) or C (last layer, mean over its single head). */
+int64_t bgnn_model_param_floats(const bgnn_model_desc* desc);
+/* host-synchronous; params_host is HOST memory */
+int  bgnn_model_create(const bgnn_model_desc* desc, const float* params_host, int64_t n_floats,
+                       int device, bgnn_model** out);
+void bgnn_model_destroy(bgnn_model* m);
+
+size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes);
+
+/* outputs (any may be NULL): logits/probs f32 [N,num_classes], cls int64 [N], conf f32 [N],
+ * corr f32 [N], action int64 [N] (0 keep, 1 auto-correct, 2 review; gnn.py:436-445).
+ * `hidden_out` (optional, f32 [N, C]) receives the backbone output x_L (testing aid). */
+int bgnn_gat_forward(const bgnn_model* m, int64_t n_nodes, int64_t n_edges,
+                     const float* x, const int32_t* rowptr, const int32_t* csr_src,
+                     const float* csr_eattr, void* workspace, size_t workspace_bytes,
+                     float* logits, float* probs, int64_t* cls, float* conf, float* corr,
+                     int64_t* action, float auto_correct_threshold, float review_threshold,
+                     float* hidden_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scatter + stitch.  Replaces GraphBuilder.graph_to_grid (graph_construction.py:471-505) as
+ * used by BathymetricPipeline._process_tile (models/pipeline.py:277-314), TileManager.merge_tile
+ * weighted branch (data/tiling.py:242-258), TileMerger.add_tile discrete branch (:408-420) and
+ * finalize (:274-294, 430-454).
+ * ------------------------------------------------------------------------------------------ */
+/* node values -> dense tile grids (fill 0.0): class as float, confidence,
+ * correction = corr * max(local_std, norm_floor).  node_id is the int32 [rows*cols] grid from
+ * bgnn_graph_emit.  Any output may be NULL. */
+int bgnn_scatter_tile(const int32_t* node_id, int64_t n_cells,
+                      const int64_t* cls, const float* conf, const float* corr,
+                      const float* local_std, float norm_floor,
+                      float* class_grid, float* conf_grid, float* corr_grid, void* stream);
+
+/* generic graph_to_grid: grid[cell] = node_id[cell] >= 0 ? values[node_id[cell]] : fill */
+int bgnn_graph_to_grid(const int32_t* node_id, int64_t n_cells, const float* values, float fill,
+                       float* grid, void* stream);
+
+typedef struct bgnn_survey {
+    int64_t rows, cols;
+    /* all [dev], row-major [rows, cols]; NaN / 0 / -1 initialised by bgnn_stitch_init */
+    float* cont[4];      /* weighted-sum accumulators of up to 4 continuous channels */
+    float* wsum[4];      /* their weight sums (may alias each other when all tiles are finite) */
+    int32_t n_cont;
+    float* discrete;     /* classification (float, NaN = never written) */
+    float* tracker;      /* confidence tracker, init -1 (tiling.py:382) */
+} bgnn_survey;
+
+int bgnn_stitch_init(const bgnn_survey* s, void* stream);
+/* add one tile: region [r0:r0+h, c0:c0+w].  row_w [h], col_w [w] are the 1-D blend tables
+ * (tiling.py:313-330, computed on the host in fp64 exactly as the reference does); the 2-D
+ * weight is their fp32 product.  cont_tiles[k] is the tile grid of channel k ([h,w] f32, may
+ * contain NaN = skipped), discrete_tile / conf_tile drive the arg-max-confidence rule.
+ * Tiles must be added in the reference's iteration order on ONE stream (fp32 sum order). */
+int bgnn_stitch_add_tile(const bgnn_survey* s, int64_t r0, int64_t c0, int32_t h, int32_t w,
+                         const float* row_w, const float* col_w,
+                         const float* const* cont_tiles, const float* discrete_tile,
+                         const float* conf_tile, void* stream);
+/* out = acc / wsum where wsum > 0 (tiling.py:289-292) */
+int bgnn_stitch_finalize(const bgnn_survey* s, void* stream);
+
+/* post-stitch: unprocessed valid cells -> class 0 / conf 0 / corr 0 (pipeline.py:196-207) and
+ * cleaned = depth - corr where class == 2 && conf > thr && valid (pipeline.py:316-349).
+ * cont[] order is the caller's; pass the planes explicitly. */
+int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_cells,
+                           float* classification, float* confidence, float* correction,
+                           float* cleaned, float auto_correct_threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGNN_H_ */
