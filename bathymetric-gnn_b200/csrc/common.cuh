@@ -9,6 +9,13 @@
 #include "bgnn.h"
 
 void bgnn_set_error(const char* fmt, ...);
+void bgnn_prof_start(int slot, cudaStream_t s);
+void bgnn_prof_stop(cudaStream_t s);
+struct ProfScope {          // records an event pair around the kernel launches in its scope (bench aid)
+    cudaStream_t s;
+    ProfScope(int slot, cudaStream_t st) : s(st) { bgnn_prof_start(slot, st); }
+    ~ProfScope() { bgnn_prof_stop(s); }
+};
 
 #define BGNN_CHECK_ARG(cond, ...)                      \
     do {                                               \

@@ -1,6 +1,8 @@
 // Error channel, version and device query of libbgnn.so (see include/bgnn.h).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -23,4 +25,38 @@ extern "C" int bgnn_device_info(int device, int* out3) {
     out3[1] = p.major;
     out3[2] = p.minor;
     return BGNN_OK;
+}
+
+// ---------------------------------------------------------------- per-kernel timing (bench aid)
+struct ProfRec { int slot; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_recs;
+
+void bgnn_prof_start(int slot, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfRec r; r.slot = slot;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_recs.push_back(r);
+}
+void bgnn_prof_stop(cudaStream_t s) {
+    if (!g_prof_on || g_recs.empty()) return;
+    cudaEventRecord(g_recs.back().b, s);
+}
+extern "C" int bgnn_profile_enable(int on) {
+    for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_recs.clear();
+    g_prof_on = on != 0;
+    return BGNN_OK;
+}
+extern "C" int bgnn_profile_collect(int cap, int32_t* slots, float* ms) {
+    int n = 0;
+    for (auto& r : g_recs) {
+        BGNN_CUDA(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        BGNN_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        if (n < cap && slots && ms) { slots[n] = r.slot; ms[n] = t; }
+        ++n;
+    }
+    return n;
 }

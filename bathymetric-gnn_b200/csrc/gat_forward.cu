@@ -670,23 +670,29 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const int C = d.hidden, h2 = C / 2;
     int rc;
     // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C)
-    if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc;
-    if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc;
+    { ProfScope ps(10, s);
+      if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
+    { ProfScope ps(11, s);
+      if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc; }
     float* cur = bufB;
     float* nxt = bufA;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
-        if ((rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s))) return rc;
+        { ProfScope ps(20 + l, s);
+          if ((rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s))) return rc; }
         const int relu = l < d.layers - 1;
-        if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s))) return rc;
+        { ProfScope ps(40 + l, s);
+          if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s))) return rc; }
         float* t = cur; cur = nxt; nxt = t;
     }
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // heads
     const int nblk = m->nheads_mlp;
-    if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc;
+    { ProfScope ps(60, s);
+      if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc; }
     int64_t blocks = ceil_div64(N, 8);
     if (blocks > (int64_t)sms * 32) blocks = (int64_t)sms * 32;
+    ProfScope ps(61, s);
     heads_finish<<<(unsigned)blocks, 256, 0, s>>>(hbuf, h2, nblk, d.num_classes, m->Wcls, m->bcls, m->Wconf, m->bconf,
                                                  m->Wcorr, m->bcorr, logits, probs, cls, conf, corr, action, thr_auto,
                                                  thr_review, N);

@@ -389,9 +389,9 @@ extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* c
     if (cells->n_cells == 0) { totals_host[0] = totals_host[1] = 0; return BGNN_OK; }
     BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
     int32_t* table = (int32_t*)scratch;
-    gb_count<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table);
+    { ProfScope ps(0, stream); gb_count<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table); }
     BGNN_LAUNCH_CHECK();
-    gb_scan<<<1, 1024, 0, stream>>>(table, P.nblocks, P.ncol);
+    { ProfScope ps(1, stream); gb_scan<<<1, 1024, 0, stream>>>(table, P.nblocks, P.ncol); }
     BGNN_LAUNCH_CHECK();
     int32_t tot[2];
     BGNN_CUDA(cudaMemcpyAsync(&tot[0], table + P.nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -417,9 +417,10 @@ extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cf
     BGNN_CHECK_ARG(!(x && P.F == 0), "x requested with zero node features");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int32_t* table = (const int32_t*)scratch;
-    gb_ids<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table, node_id, node_cell, rowptr);
+    { ProfScope ps(2, stream); gb_ids<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table, node_id, node_cell, rowptr); }
     BGNN_LAUNCH_CHECK();
     if (x || local_std || csr_src || csr_eattr) {
+        ProfScope ps(3, stream);
         gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr);
         BGNN_LAUNCH_CHECK();
     }
@@ -436,8 +437,9 @@ extern "C" int bgnn_graph_coo(const bgnn_cells* cells, const bgnn_graph_cfg* cfg
     BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
     BGNN_CHECK_ARG(node_id, "node_id is required");
     cudaStream_t stream = (cudaStream_t)stream_;
-    gb_coo<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, (const int32_t*)scratch, node_id, n_edges,
-                                                          edge_index, edge_attr);
+    { ProfScope ps(4, stream);
+      gb_coo<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, (const int32_t*)scratch, node_id, n_edges,
+                                                            edge_index, edge_attr); }
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }

@@ -124,6 +124,7 @@ extern "C" int bgnn_scatter_tile(const int32_t* node_id, int64_t n_cells, const 
                                  float* conf_grid, float* corr_grid, void* stream) {
     BGNN_CHECK_ARG(node_id || n_cells == 0, "node_id is null");
     if (n_cells <= 0) return BGNN_OK;
+    ProfScope ps(70, (cudaStream_t)stream);
     k_scatter_tile<<<grid_for(n_cells), ST_THREADS, 0, (cudaStream_t)stream>>>(node_id, n_cells, cls, conf, corr, local_std,
                                                                                norm_floor, class_grid, conf_grid, corr_grid);
     BGNN_LAUNCH_CHECK();
@@ -134,6 +135,7 @@ extern "C" int bgnn_graph_to_grid(const int32_t* node_id, int64_t n_cells, const
                                   void* stream) {
     BGNN_CHECK_ARG((node_id && grid) || n_cells == 0, "null argument");
     if (n_cells <= 0) return BGNN_OK;
+    ProfScope ps(74, (cudaStream_t)stream);
     k_to_grid<<<grid_for(n_cells), ST_THREADS, 0, (cudaStream_t)stream>>>(node_id, n_cells, values, fill, grid);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
@@ -172,6 +174,7 @@ extern "C" int bgnn_stitch_add_tile(const bgnn_survey* s, int64_t r0, int64_t c0
             if (k < s->n_cont && a.cont[q] && s->wsum[q] == s->wsum[k]) a.wsum_first[k] = 0;
     }
     a.disc = discrete_tile; a.conf = conf_tile;
+    ProfScope ps(71, (cudaStream_t)stream);
     k_add_tile<<<grid_for((int64_t)h * w), ST_THREADS, 0, (cudaStream_t)stream>>>(a);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
@@ -180,6 +183,7 @@ extern "C" int bgnn_stitch_add_tile(const bgnn_survey* s, int64_t r0, int64_t c0
 extern "C" int bgnn_stitch_finalize(const bgnn_survey* s, void* stream) {
     BGNN_CHECK_ARG(s, "null survey");
     if (s->rows * s->cols == 0 || s->n_cont == 0) return BGNN_OK;
+    ProfScope ps(72, (cudaStream_t)stream);
     k_finalize<<<grid_for(s->rows * s->cols), ST_THREADS, 0, (cudaStream_t)stream>>>(*s);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
@@ -189,6 +193,7 @@ extern "C" int bgnn_apply_corrections(const float* depth, const uint8_t* valid, 
                                       float* confidence, float* correction, float* cleaned, float thr, void* stream) {
     BGNN_CHECK_ARG((depth && valid && classification && confidence && correction) || n_cells == 0, "null argument");
     if (n_cells <= 0) return BGNN_OK;
+    ProfScope ps(73, (cudaStream_t)stream);
     k_apply<<<grid_for(n_cells), ST_THREADS, 0, (cudaStream_t)stream>>>(depth, valid, n_cells, classification, confidence,
                                                                        correction, cleaned, thr);
     BGNN_LAUNCH_CHECK();

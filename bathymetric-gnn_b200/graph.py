@@ -247,7 +247,8 @@ class GraphBuilder:
             cells.depth = d.data_ptr()
             if valid_mask is not None:
                 m = valid_mask if isinstance(valid_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(valid_mask))
-                m = m.to(dev).to(torch.uint8)
+                m = m.to(dev)
+                m = m.view(torch.uint8) if (m.dtype == torch.bool and m.is_contiguous()) else m.to(torch.uint8)
                 if stride != W:                     # mask must share the depth view's stride
                     mm = torch.zeros((H, stride), dtype=torch.uint8, device=dev)
                     mm[:, :W] = m

@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""Benchmark of the Bathymetric-GNN per-tile inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one tile: spatial-graph build
+(count + scan + ids + emit of the lean in-edge CSR and node features) followed by
+the GAT forward + heads (`predict`).  Workload at every N: BASELINE.json
+configs[1] -- a 2048x2048 fp32 tile (8-connected, F=7, hidden 64, 4 heads, 4
+layers) cut from a synthetic 3968^2 field; for N > 1 every rank processes its own
+tile (tiles are independent: no collective on the data path; weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = depth cells/s with the tile resident in
+HBM; `e2e` = the same through the public API (`GraphBuilder.build_graph` +
+`BathymetricGNN.predict`) with pinned HOST buffers, H2D of depth+mask and D2H of
+class / confidence / correction inside the timed region.  `roofline` is measured
+live with CUDA events recorded on the launching stream around every kernel
+(bgnn_profile_*), `cpu_baseline` is the CPU oracle (a port; the Python reference
+cannot travel to the GPU box) timed on a bounded sample of the same tile.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 2048
+FIELD_ORIGIN = (1920, 1920)        # second tile of the 2x2 tiling of a 3968^2 field (tile 2048, overlap 128)
+RES = (0.5, 0.5)
+METRIC = "depth cells/sec (graph build+GNN fwd)"
+UNIT = "cells/s"
+
+SLOT_NAMES = {0: "gb_count", 1: "gb_scan", 2: "gb_ids", 3: "gb_emit", 4: "gb_coo", 10: "mlp0", 11: "mlp1",
+              60: "heads_gemm", 61: "heads_finish", 70: "scatter_tile"}
+for _l in range(16):
+    SLOT_NAMES[20 + _l] = f"proj_l{_l}"
+    SLOT_NAMES[40 + _l] = f"agg_l{_l}"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_tile(rank: int):
+    from tests import synth
+    r0, c0 = FIELD_ORIGIN
+    depth = synth.noisy_tile(TILE, TILE, seed=1234 + rank, r0=r0, c0=c0)
+    mask = synth.blob_mask(TILE, TILE, seed=1234 + rank, invalid_frac=0.02)
+    depth[~mask] = 1.0e6
+    return depth, mask
+
+
+def make_weights(seed=0):
+    from oracle import model_oracle as mo          # weights only (init with the reference's key names)
+    cfg = mo.ModelCfg(in_channels=7)
+    return cfg, mo.init_state_dict(cfg, seed=seed, randomize_bn=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=False):
+    """SURVEY.md 8(d) per-unit figures x the units one launch processes (stated in DESIGN.md)."""
+    b = {}
+    deg = E / max(N, 1)
+    b["graph_build"] = cells * (4 + 1) + N * (4 * F + 4 + 4 + 4) + 4 * cells + E * 4 + E * 4 * ED
+    HC = hidden * heads
+    for l in range(layers):
+        last = l == layers - 1
+        hc = hidden if last else HC
+        H = 1 if last else heads
+        fin = hidden if l == 0 else HC
+        b[f"agg_l{l}"] = N * (4 * hc + 8 * H + 4 + 4 * hc) + E * (4 + 4 * ED) + N * 4 * ED * 0
+        b[f"proj_l{l}"] = N * (4 * fin + 4 * hc + 8 * H)
+    b["mlp0"] = N * (4 * F + 4 * hidden)
+    b["mlp1"] = N * (8 * hidden)
+    b["heads_gemm"] = N * (4 * hidden + 4 * 3 * (hidden // 2))
+    b["heads_finish"] = N * (4 * 3 * (hidden // 2) + 4 * 3 * 2 + 8 + 4 + 4 + 8)
+    return b
+
+
+def run_ours(args):
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    depth_np, mask_np = make_tile(rank)
+    cfg, sd = make_weights(0)
+    model = bg.BathymetricGNN(cfg.in_channels, cfg.hidden, cfg.layers, "GAT", cfg.heads, cfg.num_classes,
+                              cfg.predict_correction, 0.0, cfg.edge_dim)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    builder = bg.GraphBuilder("8-connected")
+
+    depth_dev = torch.from_numpy(depth_np).to(dev)
+    mask_dev = torch.from_numpy(mask_np).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    cells = TILE * TILE
+
+    def step_resident():
+        flush.fill_(1)                                                  # L2 flush, inside the timed region
+        g = builder.build_graph(depth_dev, mask_dev, None, RES)
+        out = model.predict(g)
+        return g, out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        g, out = step_resident()
+    N, E = g.num_nodes, g.num_edges
+    del g, out
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        g, out = step_resident()
+        del g, out
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * cells / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with pinned host buffers
+    depth_pin = torch.from_numpy(depth_np).pin_memory()
+    mask_pin = torch.from_numpy(mask_np).pin_memory()
+    host_cls = torch.empty(N, dtype=torch.int64).pin_memory()
+    host_conf = torch.empty(N, dtype=torch.float32).pin_memory()
+    host_corr = torch.empty(N, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        flush.fill_(1)
+        d = depth_pin.to(dev, non_blocking=True)
+        m = mask_pin.to(dev, non_blocking=True)
+        g = builder.build_graph(d, m, None, RES)
+        out = model.predict(g)
+        host_cls.copy_(out["predicted_class"], non_blocking=True)
+        host_conf.copy_(out["confidence"], non_blocking=True)
+        host_corr.copy_(out["correction"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(host_conf[0])
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * cells / (e2e_ms / args.steps * 1e-3)
+    h2d = depth_np.nbytes + mask_np.nbytes
+    d2h = N * (8 + 4 + 4)
+
+    # ---- per-kernel timing for the roofline (separate pass, same step, events inside the library)
+    roof, kernels, launches_per_step = None, {}, 0
+    if rank == 0:
+        lib.bgnn_profile_enable(1)
+        reps = min(args.steps, 5)
+        for _ in range(reps):
+            g, out = step_resident()
+            del g, out
+        torch.cuda.synchronize()
+        n = lib.bgnn_profile_collect(0, None, None)
+        slots = (C.c_int32 * n)()
+        ms = (C.c_float * n)()
+        lib.bgnn_profile_collect(n, slots, ms)
+        lib.bgnn_profile_enable(0)
+        launches_per_step = n // reps
+        agg = {}
+        for s_, m_ in zip(slots, ms):
+            agg.setdefault(SLOT_NAMES.get(int(s_), str(int(s_))), []).append(float(m_))
+        bytes_ = algorithmic_bytes(N, E, cells)
+        peak, peak_src = peaks()
+        gb_ms = sum(np.mean(agg[k]) for k in ("gb_count", "gb_scan", "gb_ids", "gb_emit") if k in agg)
+        tot_ms = sum(np.mean(v) for v in agg.values())
+        for k, v in agg.items():
+            mean_ms = float(np.mean(v))
+            ent = {"ms": round(mean_ms, 4), "share": round(mean_ms / tot_ms, 4)}
+            if k in bytes_:
+                gbs = bytes_[k] / (mean_ms * 1e-3) / 1e9
+                ent.update({"alg_bytes": int(bytes_[k]), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+            kernels[k] = ent
+        kernels["graph_build_total"] = {"ms": round(gb_ms, 4), "share": round(gb_ms / tot_ms, 4),
+                                        "alg_bytes": int(bytes_["graph_build"]),
+                                        "gbs": round(bytes_["graph_build"] / (gb_ms * 1e-3) / 1e9, 1),
+                                        "frac": round(bytes_["graph_build"] / (gb_ms * 1e-3) / 1e9 / peak, 4)}
+        cand = [k for k in kernels if k.startswith(("agg_", "proj_"))]
+        dom = max(cand, key=lambda k: kernels[k]["ms"])
+        roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
+                "message_passing": {k: kernels[k] for k in sorted(kernels) if k.startswith("agg_")}}
+
+    # ---- CPU baseline (oracle port) on a bounded sample of the same tile, rank 0 / N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=args.cpu_crop)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: one 2048x2048 fp32 tile per GPU, 8-connected, F=7, GAT hidden 64 x 4 heads x 4 layers, "
+                                       "graph build + predict", "tile": TILE, "valid_cells": N, "edges": E,
+                           "cells_per_step_per_gpu": cells, "weights": "random-init (reference key names), BN stats randomised",
+                           "l2": "256 MiB flush write before every step (inside the timed region)",
+                           "parallelism": f"tiles x{world} (independent, no collective)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):
+    """Oracle (numpy/scipy graph build + torch-CPU GAT forward) on a crop x crop corner of the tile."""
+    from oracle import graph_oracle as go
+    from oracle import model_oracle as mo
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    d = np.ascontiguousarray(depth_np[:crop, :crop])
+    m = np.ascontiguousarray(mask_np[:crop, :crop])
+    t0 = time.perf_counter()
+    g = go.build_graph(d, m, None, RES)
+    t1 = time.perf_counter()
+    mo.predict(sd, cfg, g["x"], g["edge_index"], g["edge_attr"])
+    t2 = time.perf_counter()
+    return {"value": crop * crop / (t2 - t0), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{crop}x{crop} corner of the bench tile, one pass; build {t1 - t0:.2f}s (numpy/scipy, 1 thread, "
+                      f"per-edge Python loop of the reference vectorised) + forward {t2 - t1:.2f}s (torch CPU fp32, {threads} threads)",
+            "seconds": t2 - t0}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The Python reference cannot
+    travel to the GPU box (/root/reference is absent there), so this times the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    depth_np, mask_np = make_tile(0)
+    cfg, sd = make_weights(0)
+    crop = args.cpu_crop_ref
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop)
+    dt = time.perf_counter() - t0
+    value = args.steps * crop * crop / dt
+    last["value"] = value
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"configs[1] tile, bounded sample: {crop}x{crop} corner per step (CPU oracle port)"},
+                      "cpu_baseline": last,
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-crop", type=int, default=512)
+    ap.add_argument("--cpu-crop-ref", type=int, default=256)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -221,6 +221,18 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
                            float* classification, float* confidence, float* correction,
                            float* cleaned, float auto_correct_threshold, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement aid (bench.py): per-kernel device timing with CUDA events recorded on the
+ * launching stream around every kernel the library launches.  Not thread-safe; off by default.
+ * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
+ * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
+ * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid.
+ * ------------------------------------------------------------------------------------------ */
+int bgnn_profile_enable(int on);                               /* also clears recorded events */
+/* waits for the recorded events; fills up to `cap` (slot, milliseconds) pairs in launch order;
+ * returns the number of records (may exceed cap) or a negative error */
+int bgnn_profile_collect(int cap, int32_t* slots, float* ms);
+
 #ifdef __cplusplus
 }
 #endif
