@@ -8,4 +8,10 @@ from .graph import Data, Batch, GridGraph, GraphBuilder, OFFSETS_4, OFFSETS_8, O
 from .gnn import (BathymetricGNN, LocalFeatureExtractor, GNNBackbone, ClassificationHead,  # noqa: F401
                   ConfidenceHead, CorrectionHead)
 
+from .config import (Config, TileConfig, GraphConfig, ModelConfig, TrainingConfig, SyntheticNoiseConfig,  # noqa: F401
+                     InferenceConfig, CORRECTION_NORM_FLOOR, CORRECTION_NORM_CAP)
+from .tiling import BathymetricGrid, Tile, TileSpec, TileManager, TileMerger  # noqa: F401
+from .pipeline import BathymetricPipeline, NpzLoader, NpzWriter  # noqa: F401
+from .native_vr import NativeVRProcessor, apply_results  # noqa: F401
+
 __version__ = "0.1.0"

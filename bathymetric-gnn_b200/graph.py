@@ -237,34 +237,47 @@ class GraphBuilder:
         H, W = int(depth.shape[0]), int(depth.shape[1])
         with torch.cuda.device(dev):
             d = _as_dev_f32(depth, dev)
-            if d.stride(1) != 1:
+
+            def same_view(t):       # a CUDA plane that shares the depth view's row stride is consumed in place
+                return (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 2 and t.stride(1) == 1
+                        and (H == 1 or t.stride(0) == d.stride(0)))
+
+            others_ok = all(t is None or same_view(t) or d.is_contiguous() for t in (valid_mask, uncertainty))
+            if d.stride(1) != 1 or not others_ok:
                 d = d.contiguous()
             stride = int(d.stride(0)) if H > 1 else W
+            if stride < W:
+                d = d.contiguous(); stride = W
             keep = [d]
             cells = _lib.Cells()
             cells.n_grids, cells.n_cells, cells.rows, cells.cols, cells.row_stride = 1, H * W, H, W, stride
             cells.rx, cells.ry = float(resolution[0]), float(resolution[1])
             cells.depth = d.data_ptr()
+
+            def plane(t, dtype):
+                if same_view(t) and stride != W:
+                    if t.dtype == dtype:
+                        return t
+                    if t.dtype == torch.bool and dtype == torch.uint8:
+                        return t.view(torch.uint8)
+                if not isinstance(t, torch.Tensor):
+                    t = torch.from_numpy(np.ascontiguousarray(t))
+                t = t.to(dev)
+                if t.dtype == torch.bool and dtype == torch.uint8 and t.is_contiguous():
+                    t = t.view(torch.uint8)
+                t = t.to(dtype).contiguous()
+                if stride != W:
+                    raise ValueError("mask / uncertainty must be views with the same row stride as a strided depth view")
+                return t
+
             if valid_mask is not None:
-                m = valid_mask if isinstance(valid_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(valid_mask))
-                m = m.to(dev)
-                m = m.view(torch.uint8) if (m.dtype == torch.bool and m.is_contiguous()) else m.to(torch.uint8)
-                if stride != W:                     # mask must share the depth view's stride
-                    mm = torch.zeros((H, stride), dtype=torch.uint8, device=dev)
-                    mm[:, :W] = m
-                    m = mm
-                m = m.contiguous()
+                m = plane(valid_mask, torch.uint8)
                 keep.append(m)
                 cells.mask = m.data_ptr()
             elif nodata is not None and not np.isnan(nodata):
                 cells.use_nodata, cells.nodata = 1, float(nodata)
             if uncertainty is not None:
-                u = _as_dev_f32(uncertainty, dev)
-                if stride != W:
-                    uu = torch.zeros((H, stride), dtype=torch.float32, device=dev)
-                    uu[:, :W] = u
-                    u = uu
-                u = u.contiguous()
+                u = plane(uncertainty, torch.float32)
                 keep.append(u)
                 cells.unc = u.data_ptr()
             return self._build(cells, keep, uncertainty is not None, (H, W), None, dev)

@@ -1,0 +1,149 @@
+"""CPU: host-side logic that needs no GPU -- the C-ABI library loads and exports every
+symbol include/bgnn.h declares, tile geometry / blend tables vs the reference goldens,
+config round trip, band partition + seam merge (world_size-2 gloo)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stitch_oracle as so
+from tests import golden_io as gio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import bathymetric_gnn_b200 as bg
+    hdr = open(os.path.join(ROOT, "include", "bgnn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bgnn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(bg._lib.SYMBOLS.keys())
+    for name in declared:
+        assert hasattr(bg._lib.lib, name), name
+    assert bg._lib.lib.bgnn_version() == 100
+
+
+def test_no_cpu_fallback():
+    import bathymetric_gnn_b200 as bg
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bg.GraphBuilder().build_graph(np.zeros((4, 4), np.float32))
+    m = bg.BathymetricGNN(7, edge_dim=3).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(bg.Data(x=torch.zeros(3, 7), edge_index=torch.zeros(2, 0, dtype=torch.long)))
+    with pytest.raises(RuntimeError):
+        bg.BathymetricPipeline(bg.Config())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bathymetric-gnn_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), fn
+
+
+def test_tile_geometry_and_blend_vs_reference_golden():
+    import bathymetric_gnn_b200 as bg
+    z = gio.load("stitch_cases.npz")
+    i = 0
+    while f"specs{i}/cfg" in z.files:
+        H, W, ts, ov = (int(v) for v in z[f"specs{i}/cfg"])
+        ntr, ntc, specs = bg.TileManager(ts, ov, 0.1).compute_tile_grid((H, W))
+        assert [ntr, ntc] == list(z[f"specs{i}/n"])
+        got = np.array([[s.row_start, s.col_start, s.row_end, s.col_end, s.tile_row, s.tile_col] for s in specs], np.int64)
+        assert np.array_equal(got, z[f"specs{i}/specs"])
+        i += 1
+    for k in z.files:
+        if k.startswith("blend1d/"):
+            size, ov = (int(v) for v in k.split("/")[1].split("_"))
+            assert np.array_equal(bg.TileManager(max(size, ov + 1), ov)._create_1d_blend(size), z[k])
+    assert np.array_equal(bg.TileManager(64, 16)._create_blend_weights((50, 64)), z["blend2d/50x64_16"])
+    with pytest.raises(ValueError):
+        bg.TileManager(16, 16)
+
+
+def test_config_roundtrip(tmp_path):
+    import bathymetric_gnn_b200 as bg
+    c = bg.Config()
+    assert (c.tile.tile_size, c.tile.overlap, c.tile.min_valid_ratio) == (1024, 128, 0.1)
+    assert c.graph.connectivity == "8-connected" and c.model.gnn_heads == 4 and c.inference.auto_correct_threshold == 0.85
+    c.tile.tile_size = 512
+    c.noise.blob_size_range = (4, 9)
+    c.save(tmp_path / "c.yaml")
+    d = bg.Config.load(tmp_path / "c.yaml")
+    assert d.tile.tile_size == 512 and d.noise.blob_size_range == (4, 9) and d.graph.edge_features == c.graph.edge_features
+    with pytest.raises(AssertionError):
+        bg.Config(tile=bg.TileConfig(tile_size=100, overlap=80))
+    assert bg.CORRECTION_NORM_FLOOR == 0.01 and bg.CORRECTION_NORM_CAP == 50.0
+
+
+def test_band_partition():
+    from bathymetric_gnn_b200 import parallel as par
+    assert par.band_partition(32, 8) == [(4 * i, 4 * i + 4) for i in range(8)]
+    assert par.band_partition(5, 2) == [(0, 3), (3, 5)]
+    assert par.band_partition(1, 2) == [(0, 1), (1, 1)]
+
+
+def _band_worker(rank, world, port, q):
+    """One rank: stitch its band of tiles with the CPU oracle merger (stands in for the device
+    TileMerger), then gather the unfinalised band planes on rank 0 over gloo."""
+    import torch.distributed as dist
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200 import parallel as par
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    z = gio.load("stitch_cases.npz")
+    H, W, ts, ov = (int(v) for v in z["merge/cfg"])
+    ntr, ntc, specs = bg.TileManager(ts, ov, 0.1).compute_tile_grid((H, W))
+    ids = set(int(i) for i in z["merge/tile_ids"])
+    band = par.band_partition(ntr, world)[rank]
+    mine = par.band_specs(specs, band)
+    r0, r1 = par.band_rows(mine)
+    chans = ["classification", "confidence", "correction"]
+    m = so.Merger((r1 - r0, W), chans, ov)
+    for s, s_local in zip(mine, par.shift_specs(mine, r0)):
+        i = specs.index(s)
+        if i in ids:
+            m.add_tile((s_local.row_start, s_local.col_start, s_local.row_end, s_local.col_end),
+                       {k: z[f"merge/tile{i}/{k}"] for k in chans})
+    part = {"classification": torch.from_numpy(m.out["classification"]), "tracker": torch.from_numpy(m.tracker)}
+    for c in ("confidence", "correction"):
+        part["acc_" + c], part["wsum_" + c] = torch.from_numpy(m.out[c]), torch.from_numpy(m.w[c])
+    gathered = [None] * world
+    dist.gather_object((part, (r0, r1)), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        full = par.merge_band_partials((H, W), [g[0] for g in gathered], [g[1] for g in gathered])
+        res = par.finalize_merged(full)
+        q.put({k: v.numpy() for k, v in res.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_stitch_two_ranks_gloo():
+    """world_size 2 over gloo: banded stitch + seam merge == the single-process reference result
+    (classification bit-exact; continuous channels within 4 eps32 on seam cells, exact off the seams)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    z = gio.load("stitch_cases.npz")
+    assert np.array_equal(res["classification"], z["merge/ref/classification"], equal_nan=True)
+    for c in ("confidence", "correction"):
+        ref = z[f"merge/ref/{c}"]
+        assert np.array_equal(np.isnan(res[c]), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        diff = np.abs(res[c][ok].astype(np.float64) - ref[ok])
+        # seam cells: (A+B)+(C+D) vs ((A+B)+C)+D, then acc/wsum -> a few ulp32 of the term magnitude
+        assert np.all(diff <= 4 * np.finfo(np.float32).eps * np.maximum(1.0, np.abs(ref[ok]))), diff.max()
+        assert (diff == 0).mean() > 0.9
