@@ -205,6 +205,14 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * cells / (ms_step * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_step, "quick": True}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the public API with pinned host buffers
     depth_pin = torch.from_numpy(depth_np).pin_memory()
     mask_pin = torch.from_numpy(mask_np).pin_memory()
@@ -357,6 +365,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="timed loop only (used under ncu): no e2e / per-kernel / cpu legs")
     ap.add_argument("--cpu-crop", type=int, default=512)
     ap.add_argument("--cpu-crop-ref", type=int, default=256)
     args = ap.parse_args()
