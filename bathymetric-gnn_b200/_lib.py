@@ -40,6 +40,11 @@ class ModelDesc(C.Structure):
                 ("bn_eps", C.c_float), ("negative_slope", C.c_float)]
 
 
+class GridTopo(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("node_id", C.c_void_p), ("n_offsets", C.c_int32),
+                ("off_dr", C.c_int32 * MAX_OFFSETS), ("off_dc", C.c_int32 * MAX_OFFSETS)]
+
+
 class Survey(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("cont", C.c_void_p * 4), ("wsum", C.c_void_p * 4),
                 ("n_cont", C.c_int32), ("discrete", C.c_void_p), ("tracker", C.c_void_p)]
@@ -59,7 +64,7 @@ SYMBOLS = {
     "bgnn_model_create": (C.c_int, [C.POINTER(ModelDesc), P, I64, C.c_int, C.POINTER(P)]),
     "bgnn_model_destroy": (None, [P]),
     "bgnn_gat_workspace_bytes": (SZ, [P, I64]),
-    "bgnn_gat_forward": (C.c_int, [P, I64, I64, P, P, P, P, P, SZ, P, P, P, P, P, P, F32, F32, P, P]),
+    "bgnn_gat_forward": (C.c_int, [P, I64, I64, P, P, P, P, P, SZ, P, P, P, P, P, P, F32, F32, P, P, P]),
     "bgnn_scatter_tile": (C.c_int, [P, I64, P, P, P, P, F32, P, P, P, P]),
     "bgnn_graph_to_grid": (C.c_int, [P, I64, P, F32, P, P]),
     "bgnn_stitch_init": (C.c_int, [C.POINTER(Survey), P]),

@@ -442,6 +442,213 @@ int launch_agg(const LayerDev& L, const float* h, const float* alpha, const int3
     return BGNN_E_UNSUPPORTED;
 }
 
+
+// ------------------------------------------------------------------------------------------ tiled aggregation
+// Grid path: one CTA per PH x 16 patch of cells.  Every source row of the (PH+2) x 18 halo is staged ONCE
+// per head in shared memory with cp.async (L2 -> smem, bypassing L1); destinations then read their <= 9
+// neighbour rows from shared memory at fixed stencil offsets.  Thread t owns destination cell t for the
+// score / softmax phase (edge features and the self-loop mean stay in its registers across the head loop),
+// warp w aggregates destinations 32w .. 32w+31 with lane <-> channels.  Same arithmetic and summation order
+// as gat_aggregate (offset k ascending, source = i - off_k, self loop last).
+struct TopoDev {
+    int rows, cols;
+    const int32_t* node_id;
+    int K;
+    int dr[8], dc[8];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int H, int C, int PH> struct TileCfg {
+    static constexpr int PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, NT = PH * PW, AST = 12;
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST) * 4;
+};
+
+template <int H, int C, int PH>
+__global__ void __launch_bounds__(PH * 16, (C <= 64 ? 2 : 1))
+gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha, const TopoDev T,
+                   const int32_t* __restrict__ rowptr, const float* __restrict__ eattr, int ED,
+                   const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
+                   const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out) {
+    using G = TileCfg<H, C, PH>;
+    constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, AST = G::AST;
+    constexpr int VEC = C / 32, HC = H * C, CH16 = C / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
+    int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
+    float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [NSLOT][H]   alpha_src per halo cell
+    float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    attention weights of the current head
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pr0 = blockIdx.y * PH, pc0 = blockIdx.x * 16;
+
+    for (int s = tid; s < NSLOT; s += NT) {
+        const int r = pr0 - 1 + s / HW, c = pc0 - 1 + s % HW;
+        int id = -1;
+        if (r >= 0 && r < T.rows && c >= 0 && c < T.cols) id = __ldg(T.node_id + (int64_t)r * T.cols + c);
+        ids[s] = id;
+        if (id >= 0) {
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) asrc[s * H + hh] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
+        }
+    }
+    __syncthreads();
+
+    // ---- per-destination state (thread t <-> cell t of the patch)
+    const int cs = (tid / 16 + 1) * HW + (tid % 16 + 1);
+    const int myid = ids[cs];
+    float ea[8][BGNN_MAX_EDGE_FEATS], lsum[BGNN_MAX_EDGE_FEATS], ad[H], M[BGNN_MAX_EDGE_FEATS][H];
+    unsigned nbv = 0;
+#pragma unroll
+    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) {
+        lsum[d] = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) M[d][hh] = d < ED ? __ldg(Medge + d * H + hh) : 0.f;
+    }
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
+    if (myid >= 0) {
+        int ep = __ldg(rowptr + myid), deg = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
+            if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {          // in-edge from i - off_k
+                nbv |= 1u << k;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                    if (d < ED) { ea[k][d] = __ldg(eattr + (int64_t)ep * ED + d); lsum[d] += ea[k][d]; }
+                ++ep; ++deg;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
+    }
+
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+        // 1. stage the source rows of head hh (16 B chunks, coalesced per row)
+        for (int q = tid; q < NSLOT * CH16; q += NT) {
+            const int s = q / CH16, part = q % CH16;
+            const int id = ids[s];
+            if (id >= 0) cp_async16(rows + s * C + part * 4, h + (int64_t)id * HC + hh * C + part * 4);
+        }
+        // 2. scores + softmax of this head while the copies are in flight
+        if (myid >= 0) {
+            float sc[9], mx = -CUDART_INF_F;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sc[k] = 0.f;
+                if ((nbv >> k) & 1u) {
+                    float ae = 0.f;
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], M[d][hh], ae);
+                    float v = (asrc[(cs - T.dr[k] * HW - T.dc[k]) * H + hh] + ad[hh]) + ae;
+                    v = v > 0.f ? v : v * slope;
+                    sc[k] = v;
+                    mx = fmaxf(mx, v);
+                }
+            }
+            {
+                float ae = 0.f;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], M[d][hh], ae);
+                float v = (asrc[cs * H + hh] + ad[hh]) + ae;
+                v = v > 0.f ? v : v * slope;
+                sc[8] = v;
+                mx = fmaxf(mx, v);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((nbv >> k) & 1u) { sc[k] = expf(sc[k] - mx); sum += sc[k]; }
+            sc[8] = expf(sc[8] - mx);
+            sum += sc[8];
+            sum += 1e-16f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a_sm[tid * AST + k] = ((nbv >> k) & 1u) ? sc[k] / sum : 0.f;
+            a_sm[tid * AST + 8] = sc[8] / sum;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // 3. aggregate: warp w handles destinations 32w .. 32w+31, lane <-> VEC channels
+        float bs[VEC], ba[VEC], bb[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int ch = hh * C + lane * VEC + v;
+            bs[v] = __ldg(bias + ch); ba[v] = __ldg(bn_a + ch); bb[v] = __ldg(bn_b + ch);
+        }
+        for (int q = 0; q < 32; ++q) {
+            const int t2 = warp * 32 + q;
+            const int cs2 = (t2 / 16 + 1) * HW + (t2 % 16 + 1);
+            const int id2 = ids[cs2];
+            if (id2 < 0) continue;
+            const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
+            const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
+            const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
+            float acc[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (aw[k] != 0.f) {
+                    const int s = k < 8 ? cs2 - T.dr[k] * HW - T.dc[k] : cs2;
+                    float hv[VEC];
+                    if (VEC == 1) hv[0] = rows[s * C + lane];
+                    else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(rows + s * C + lane * 2); hv[0] = t.x; hv[1] = t.y; }
+                    else { const float4 t = *reinterpret_cast<const float4*>(rows + s * C + lane * 4); hv[0] = t.x; hv[1] = t.y; hv[2 % VEC] = t.z; hv[3 % VEC] = t.w; }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[k], hv[v], acc[v]);
+                }
+            }
+            float o[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float y = acc[v] + bs[v];
+                y = fmaf(y, ba[v], bb[v]);
+                o[v] = relu ? fmaxf(y, 0.f) : y;
+            }
+            VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
+        }
+        __syncthreads();
+    }
+}
+
+template <int H, int C, int PH>
+int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
+                      const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
+    using G = TileCfg<H, C, PH>;
+    static bool configured = false;
+    auto kern = gat_aggregate_tile<H, C, PH>;
+    if (!configured) {
+        BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
+    kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, rowptr, eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+// returns 1 if no tiled instantiation fits (caller falls back to the CSR kernel)
+int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
+                    const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
+#define TCASE(H_, C_, PH_) if (L.H == H_ && L.C == C_) return launch_agg_tile_t<H_, C_, PH_>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)
+    TCASE(4, 64, 16); TCASE(1, 64, 16); TCASE(2, 64, 16); TCASE(8, 64, 16);
+    TCASE(1, 32, 16); TCASE(2, 32, 16); TCASE(4, 32, 16); TCASE(8, 32, 16);
+    TCASE(1, 128, 8); TCASE(2, 128, 8); TCASE(4, 128, 8);
+#undef TCASE
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------ heads
 // hh: [N, nblk*h2] = ReLU(first layers).  One warp per node.
 __global__ void __launch_bounds__(256)
@@ -642,7 +849,8 @@ extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes)
 extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const float* x, const int32_t* rowptr,
                                 const int32_t* csr_src, const float* csr_eattr, void* workspace, size_t workspace_bytes,
                                 float* logits, float* probs, int64_t* cls, float* conf, float* corr, int64_t* action,
-                                float thr_auto, float thr_review, float* hidden_out, void* stream_) {
+                                float thr_auto, float thr_review, float* hidden_out, const bgnn_grid_topo* topo,
+                                void* stream_) {
     BGNN_CHECK_ARG(m, "model is null");
     BGNN_CHECK_ARG(N >= 0 && E >= 0, "negative sizes");
     if (N == 0) return BGNN_OK;
@@ -659,6 +867,19 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     BGNN_CUDA(cudaGetDevice(&dev));
     BGNN_CHECK_ARG(dev == m->device, "model lives on device %d but current device is %d", m->device, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    // grid path: radius-1 stencil (4-/8-connected) on a single tile
+    TopoDev T;
+    bool tiled = false;
+    if (topo && topo->node_id && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0) {
+        tiled = true;
+        T.rows = topo->rows; T.cols = topo->cols; T.node_id = topo->node_id; T.K = topo->n_offsets;
+        for (int k = 0; k < 8; ++k) {
+            T.dr[k] = k < T.K ? topo->off_dr[k] : 0;
+            T.dc[k] = k < T.K ? topo->off_dc[k] : 0;
+            if (k < T.K && (abs(T.dr[k]) > 1 || abs(T.dc[k]) > 1)) tiled = false;
+        }
+    }
 
     char* w = (char*)workspace;
     w = (char*)align_up((size_t)w, 256);
@@ -682,7 +903,10 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           if ((rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s))) return rc; }
         const int relu = l < d.layers - 1;
         { ProfScope ps(40 + l, s);
-          if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s))) return rc; }
+          rc = 1;
+          if (tiled) rc = launch_agg_tile(L, hbuf, alpha, T, rowptr, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, s);
+          if (rc == 1) rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s);
+          if (rc) return rc; }
         float* t = cur; cur = nxt; nxt = t;
     }
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -150,6 +150,7 @@ class BathymetricGNN(nn.Module):
         self.correction_head = CorrectionHead(hidden_channels, hidden_channels // 2, dropout) if predict_correction else None
         self._handle = None
         self._handle_key = None
+        self.use_grid_kernel = True      # tiled aggregation when the graph carries its grid topology
         logger.info("Created BathymetricGNN: %s with %d layers, %d hidden channels", gnn_type, num_gnn_layers, hidden_channels)
 
     # ------------------------------------------------------------------ packing
@@ -240,9 +241,16 @@ class BathymetricGNN(nn.Module):
             if x.dim() != 2 or x.shape[1] != self.in_channels:
                 raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({N}x{x.shape[-1]} and "
                                    f"{self.in_channels}x{self.hidden_channels})")
+            topo = None
             if dg is not None:
                 rowptr, src, ea, E = dg.rowptr, dg.csr_src, dg.csr_eattr, dg.E
                 ed_have = int(dg.cfg.n_edge_feats)
+                if dg.grid_meta is None and int(dg.cells.n_grids) == 1 and self.use_grid_kernel:
+                    topo = _lib.GridTopo()
+                    topo.rows, topo.cols, topo.node_id = int(dg.cells.rows), int(dg.cells.cols), dg.node_id.data_ptr()
+                    topo.n_offsets = int(dg.cfg.n_offsets)
+                    for k in range(topo.n_offsets):
+                        topo.off_dr[k], topo.off_dc[k] = dg.cfg.off_dr[k], dg.cfg.off_dc[k]
             else:
                 rowptr, src, ea, E = self._csr_from_coo(data, device)
                 ed_have = 0 if ea is None else int(ea.shape[1])
@@ -265,7 +273,8 @@ class BathymetricGNN(nn.Module):
                                            ptr(ea) if (ED > 0 and E > 0) else None, ptr(ws), wbytes,
                                            ptr(out["class_logits"]), ptr(out["class_probs"]), ptr(out["predicted_class"]),
                                            ptr(out["confidence"]), ptr(out.get("correction")), ptr(action),
-                                           float(auto_thr), float(review_thr), ptr(hidden), stream_ptr()))
+                                           float(auto_thr), float(review_thr), ptr(hidden),
+                                           C.byref(topo) if topo is not None else None, stream_ptr()))
             if want_action:
                 out["action"] = action
             if return_hidden:

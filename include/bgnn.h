@@ -163,6 +163,18 @@ void bgnn_model_destroy(bgnn_model* m);
 
 size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes);
 
+/* Optional grid topology of the node set (single tile, n_grids == 1): when given, and the stencil
+ * has radius 1 (4-/8-connected), the aggregation runs as a shared-memory tiled kernel: one CTA per
+ * 16x16 patch of cells stages every source row of its 18x18 halo ONCE (cp.async) instead of
+ * gathering 9 rows per destination through L1.  The in-edge CSR is still required (edge features). */
+typedef struct bgnn_grid_topo {
+    int32_t        rows, cols;
+    const int32_t* node_id;                      /* [dev] int32 [rows*cols] from bgnn_graph_emit */
+    int32_t        n_offsets;
+    int32_t        off_dr[BGNN_MAX_OFFSETS];
+    int32_t        off_dc[BGNN_MAX_OFFSETS];
+} bgnn_grid_topo;
+
 /* outputs (any may be NULL): logits/probs f32 [N,num_classes], cls int64 [N], conf f32 [N],
  * corr f32 [N], action int64 [N] (0 keep, 1 auto-correct, 2 review; gnn.py:436-445).
  * `hidden_out` (optional, f32 [N, C]) receives the backbone output x_L (testing aid). */
@@ -171,7 +183,7 @@ int bgnn_gat_forward(const bgnn_model* m, int64_t n_nodes, int64_t n_edges,
                      const float* csr_eattr, void* workspace, size_t workspace_bytes,
                      float* logits, float* probs, int64_t* cls, float* conf, float* corr,
                      int64_t* action, float auto_correct_threshold, float review_threshold,
-                     float* hidden_out, void* stream);
+                     float* hidden_out, const bgnn_grid_topo* topo /* may be NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scatter + stitch.  Replaces GraphBuilder.graph_to_grid (graph_construction.py:471-505) as
