@@ -482,7 +482,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
     int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
-    float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [NSLOT][H]   alpha_src per halo cell
+    float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [H][NSLOT]   alpha_src per halo cell
     float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    attention weights of the current head
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -495,7 +495,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
         ids[s] = id;
         if (id >= 0) {
 #pragma unroll
-            for (int hh = 0; hh < H; ++hh) asrc[s * H + hh] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
+            for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
         }
     }
     __syncthreads();
@@ -513,24 +513,50 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
     }
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
-    if (myid >= 0) {
-        int ep = __ldg(rowptr + myid), deg = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
-            if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {          // in-edge from i - off_k
-                nbv |= 1u << k;
-#pragma unroll
-                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
-                    if (d < ED) { ea[k][d] = __ldg(eattr + (int64_t)ep * ED + d); lsum[d] += ea[k][d]; }
-                ++ep; ++deg;
+    {
+        // Edge attributes of a patch row are one contiguous CSR range (consecutive valid cells have consecutive
+        // node ids): stage them with coalesced loads into the (not yet used) row buffer, then each destination
+        // picks its <= 8 x ED values from shared memory.
+        constexpr int STG = 16 * 8 * BGNN_MAX_EDGE_FEATS;            // floats per patch row
+        float* stage = rows;
+        __shared__ int s_e0[PH], s_e1[PH];
+        if (tid < PH) {
+            int first = -1, last = -1;
+            for (int c = 0; c < 16; ++c) {
+                const int id = ids[(tid + 1) * HW + c + 1];
+                if (id >= 0) { if (first < 0) first = id; last = id; }
             }
+            s_e0[tid] = first >= 0 ? __ldg(rowptr + first) : 0;
+            s_e1[tid] = first >= 0 ? __ldg(rowptr + last + 1) : 0;
         }
+        __syncthreads();
+        for (int pr = warp; pr < PH; pr += NT / 32) {
+            const int e0 = s_e0[pr], n = (s_e1[pr] - e0) * ED;
+            const float* src = eattr + (int64_t)e0 * ED;
+            for (int i = lane; i < n; i += 32) stage[pr * STG + i] = __ldg(src + i);
+        }
+        __syncthreads();
+        if (myid >= 0) {
+            const int pr = tid / 16;
+            int off = (__ldg(rowptr + myid) - s_e0[pr]) * ED, deg = 0;
 #pragma unroll
-        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+            for (int k = 0; k < 8; ++k) {
 #pragma unroll
-        for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
+                if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {      // in-edge from i - off_k
+                    nbv |= 1u << k;
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                        if (d < ED) { ea[k][d] = stage[pr * STG + off + d]; lsum[d] += ea[k][d]; }
+                    off += ED; ++deg;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
+        }
+        __syncthreads();                                             // stage aliases rows: done before the copies start
     }
 
 #pragma unroll
@@ -551,7 +577,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                     float ae = 0.f;
 #pragma unroll
                     for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], M[d][hh], ae);
-                    float v = (asrc[(cs - T.dr[k] * HW - T.dc[k]) * H + hh] + ad[hh]) + ae;
+                    float v = (asrc[hh * NSLOT + cs - T.dr[k] * HW - T.dc[k]] + ad[hh]) + ae;
                     v = v > 0.f ? v : v * slope;
                     sc[k] = v;
                     mx = fmaxf(mx, v);
@@ -561,7 +587,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                 float ae = 0.f;
 #pragma unroll
                 for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], M[d][hh], ae);
-                float v = (asrc[cs * H + hh] + ad[hh]) + ae;
+                float v = (asrc[hh * NSLOT + cs] + ad[hh]) + ae;
                 v = v > 0.f ? v : v * slope;
                 sc[8] = v;
                 mx = fmaxf(mx, v);
@@ -597,18 +623,18 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             float acc[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+            float hv[9][VEC];
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                if (aw[k] != 0.f) {
-                    const int s = k < 8 ? cs2 - T.dr[k] * HW - T.dc[k] : cs2;
-                    float hv[VEC];
-                    if (VEC == 1) hv[0] = rows[s * C + lane];
-                    else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(rows + s * C + lane * 2); hv[0] = t.x; hv[1] = t.y; }
-                    else { const float4 t = *reinterpret_cast<const float4*>(rows + s * C + lane * 4); hv[0] = t.x; hv[1] = t.y; hv[2 % VEC] = t.z; hv[3 % VEC] = t.w; }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[k], hv[v], acc[v]);
-                }
+                const int s = (k < 8 && aw[k] != 0.f) ? cs2 - T.dr[k] * HW - T.dc[k] : cs2;   // weight 0 -> safe centre slot
+                if (VEC == 1) hv[k][0] = rows[s * C + lane];
+                else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(rows + s * C + lane * 2); hv[k][0] = t.x; hv[k][1 % VEC] = t.y; }
+                else { const float4 t = *reinterpret_cast<const float4*>(rows + s * C + lane * 4); hv[k][0] = t.x; hv[k][1 % VEC] = t.y; hv[k][2 % VEC] = t.z; hv[k][3 % VEC] = t.w; }
             }
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[k], hv[k][v], acc[v]);
             float o[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
