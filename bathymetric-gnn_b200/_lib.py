@@ -71,6 +71,8 @@ SYMBOLS = {
     "bgnn_stitch_add_tile": (C.c_int, [C.POINTER(Survey), I64, I64, I32, I32, P, P, C.POINTER(P), P, P, P]),
     "bgnn_stitch_finalize": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_apply_corrections": (C.c_int, [P, P, I64, P, P, P, P, F32, P]),
+    "bgnn_set_tensor_cores": (C.c_int, [C.c_int]),
+    "bgnn_test_proj_umma": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_profile_enable": (C.c_int, [C.c_int]),
     "bgnn_profile_collect": (C.c_int, [C.c_int, P, P]),
 }

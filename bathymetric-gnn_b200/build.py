@@ -25,6 +25,7 @@ SOURCES = [
     ("graph_build.cu", ["-fmad=false"]),
     ("stitch.cu", ["-fmad=false"]),
     ("gat_forward.cu", []),
+    ("proj_umma.cu", []),
 ]
 
 

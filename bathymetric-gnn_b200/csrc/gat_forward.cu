@@ -20,10 +20,15 @@
 #include <vector>
 
 #include "common.cuh"
+#include "proj_umma.cuh"
+
+static bool g_use_umma = true;
+extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
 
 struct LayerDev {
     int in, H, C, HC, out;
     float *W, *att_src, *att_dst, *Medge, *bias, *bn_a, *bn_b;
+    uint16_t* Wsplit;        // [3][HC][in] bf16 split of W for the tcgen05 path (nullptr if the shape is not compiled)
 };
 
 struct bgnn_model {
@@ -31,6 +36,7 @@ struct bgnn_model {
     int device;
     int nheads_mlp;          // 2 or 3 first-layer head blocks (cls, conf[, corr])
     float* blob;             // single device allocation
+    uint16_t* blob16;        // bf16 weight splits
     float *feW0, *feb0, *feW1, *feb1;
     std::vector<LayerDev> layers;
     float *hW0, *hb0;        // concatenated first layers [nheads_mlp*h2, C]
@@ -828,13 +834,28 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     size_t oWr = rW1 ? push(rW1, h2) : 0, obr = rb1 ? push(rb1, 1) : 0;
     if (q - p != n_floats) { bgnn_set_error("internal: parameter walk mismatch"); return BGNN_E_INVALID; }
 
+    // bf16x3 splits of the projection weights for the tensor-core path
+    std::vector<uint16_t> h16;
+    std::vector<size_t> o16(d->layers, (size_t)-1);
+    for (int l = 0; l < d->layers; ++l) {
+        int in, H, Cc, HC, outc;
+        layer_shape(d, l, in, H, Cc, HC, outc);
+        if (!proj_umma_supported(HC, in, Cc, true)) continue;
+        o16[l] = h16.size();
+        h16.resize(h16.size() + (size_t)3 * HC * in);
+        proj_umma_split_weights(hb.data() + lo[l].W, HC, in, h16.data() + o16[l]);
+    }
+
     int prev = 0;
     BGNN_CUDA(cudaGetDevice(&prev));
     BGNN_CUDA(cudaSetDevice(device));
     bgnn_model* m = new bgnn_model();
+    m->blob16 = nullptr;
     m->d = *d; m->device = device; m->nheads_mlp = nblk;
     cudaError_t e = cudaMalloc(&m->blob, hb.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->blob, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !h16.empty()) e = cudaMalloc(&m->blob16, h16.size() * sizeof(uint16_t));
+    if (e == cudaSuccess && !h16.empty()) e = cudaMemcpy(m->blob16, h16.data(), h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { bgnn_set_error("model upload failed: %s", cudaGetErrorString(e)); delete m; return BGNN_E_CUDA; }
     float* B = m->blob;
@@ -845,6 +866,7 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         layer_shape(d, l, L.in, L.H, L.C, L.HC, L.out);
         L.W = B + lo[l].W; L.att_src = B + lo[l].as; L.att_dst = B + lo[l].ad; L.Medge = B + lo[l].M;
         L.bias = B + lo[l].bias; L.bn_a = B + lo[l].a; L.bn_b = B + lo[l].b;
+        L.Wsplit = (o16[l] != (size_t)-1 && m->blob16) ? m->blob16 + o16[l] : nullptr;
         m->layers.push_back(L);
         if (L.HC > m->hc_max) m->hc_max = L.HC;
     }
@@ -861,6 +883,7 @@ extern "C" void bgnn_model_destroy(bgnn_model* m) {
     cudaGetDevice(&prev);
     cudaSetDevice(m->device);
     cudaFree(m->blob);
+    if (m->blob16) cudaFree(m->blob16);
     cudaSetDevice(prev);
     delete m;
 }
@@ -926,7 +949,11 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
         { ProfScope ps(20 + l, s);
-          if ((rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s))) return rc; }
+          if (g_use_umma && L.Wsplit)
+              rc = launch_proj_umma(cur, N, L.in, L.Wsplit, L.HC, hbuf, L.att_src, L.att_dst, alpha, L.H, L.C, sms, s);
+          else
+              rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
+          if (rc) return rc; }
         const int relu = l < d.layers - 1;
         { ProfScope ps(40 + l, s);
           rc = 1;

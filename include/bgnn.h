@@ -233,6 +233,16 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
                            float* classification, float* confidence, float* correction,
                            float* cleaned, float auto_correct_threshold, void* stream);
 
+/* Tensor-core projections: on by default.  When on, every `x W^T` whose shape is compiled for the
+ * tcgen05 path (N in {32,64,128,256}, K % 32 == 0) runs as a bf16x3-split GEMM with fp32 accumulation
+ * in TMEM (fp32-grade accuracy); otherwise, or when switched off, the fp32 FMA GEMM is used. */
+int bgnn_set_tensor_cores(int on);
+/* testing aid: C_dev[M,N] = A_dev[M,K] . W_host[N,K]^T through the tcgen05 path (host-synchronous);
+ * alpha_dev (optional) [M, 2*heads] receives the per-head dot products with att_src / att_dst [N]. */
+int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
+                        const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement aid (bench.py): per-kernel device timing with CUDA events recorded on the
  * launching stream around every kernel the library launches.  Not thread-safe; off by default.

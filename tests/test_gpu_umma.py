@@ -1,0 +1,69 @@
+"""GPU: the tcgen05 (bf16x3 split, fp32 accumulate in TMEM) projection GEMM vs an fp64 reference.
+fp32-grade accuracy is required: the error must be of the order of the fp32 FMA GEMM's own error."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run_umma(A, W, att_s=None, att_d=None, heads=0):
+    from bathymetric_gnn_b200._lib import lib, check, ptr
+    M, K = A.shape
+    N = W.shape[0]
+    Cout = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    alpha = torch.empty((M, 2 * heads), dtype=torch.float32, device="cuda") if heads else None
+    Wh = W.cpu().contiguous()
+    check(lib.bgnn_test_proj_umma(ptr(A), M, K, C.c_void_p(Wh.data_ptr()), N, ptr(Cout), ptr(att_s), ptr(att_d), ptr(alpha),
+                                  heads, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return Cout, alpha
+
+
+@pytest.mark.parametrize("M,K,N,heads", [(256, 64, 256, 4), (1000, 256, 256, 4), (70000, 256, 256, 4), (4099, 256, 64, 1),
+                                         (513, 64, 64, 1), (300, 32, 32, 1), (777, 128, 128, 4), (50000, 64, 256, 4)])
+def test_umma_matches_fp64(M, K, N, heads):
+    g = torch.Generator(device="cpu").manual_seed(M + K + N)
+    A = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, 1, generator=g))).cuda()      # rows of varied scale
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
+    att_s, att_d = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda()
+    Cout, alpha = run_umma(A, W, att_s, att_d, heads)
+    ref = A.double() @ W.double().t()
+    fp32 = (A @ W.t()).double()                       # cuBLAS fp32 (may itself use TF32 off: default highest precision)
+    scale = (A.double().abs() @ W.double().abs().t())              # sum |a||b| : the natural error scale
+    err = ((Cout.double() - ref).abs() / scale).max().item()
+    err32 = ((fp32 - ref).abs() / scale).max().item()
+    assert err < 1e-6 and err < 4 * err32 + 2e-7, (err, err32)   # fp32-grade: same order as the cuBLAS fp32 GEMM
+    CH = N // heads
+    a_ref = torch.stack([(ref[:, h * CH:(h + 1) * CH] * att_s.double()[h * CH:(h + 1) * CH]).sum(1) for h in range(heads)]
+                        + [(ref[:, h * CH:(h + 1) * CH] * att_d.double()[h * CH:(h + 1) * CH]).sum(1) for h in range(heads)], 1)
+    a_scale = torch.stack([(scale[:, h * CH:(h + 1) * CH] * att_s.double().abs()[h * CH:(h + 1) * CH]).sum(1) for h in range(heads)]
+                          + [(scale[:, h * CH:(h + 1) * CH] * att_d.double().abs()[h * CH:(h + 1) * CH]).sum(1) for h in range(heads)], 1)
+    assert ((alpha.double() - a_ref).abs() / a_scale).max().item() < 1e-6
+    print(f"M={M} K={K} N={N}: err/sum|a||b| umma={err:.2e} fp32={err32:.2e}")
+
+
+def test_umma_toggle_equivalence_in_forward():
+    """Whole forward with tensor-core projections vs fp32 FMA projections."""
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200._lib import lib
+    from oracle import model_oracle as mo
+    from tests import synth
+    d = synth.noisy_tile(160, 200, seed=3)
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=5)
+    m = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = bg.GraphBuilder().build_graph(d, None, None, (0.5, 0.5))
+    try:
+        lib.bgnn_set_tensor_cores(1)
+        a = m(g)
+        lib.bgnn_set_tensor_cores(0)
+        b = m(g)
+    finally:
+        lib.bgnn_set_tensor_cores(1)
+    np.testing.assert_allclose(a["class_logits"].cpu().numpy(), b["class_logits"].cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(a["predicted_class"], b["predicted_class"]) or (a["predicted_class"] != b["predicted_class"]).float().mean() < 1e-3
