@@ -147,3 +147,17 @@ def test_sharded_stitch_two_ranks_gloo():
         # seam cells: (A+B)+(C+D) vs ((A+B)+C)+D, then acc/wsum -> a few ulp32 of the term magnitude
         assert np.all(diff <= 4 * np.finfo(np.float32).eps * np.maximum(1.0, np.abs(ref[ok]))), diff.max()
         assert (diff == 0).mean() > 0.9
+
+
+def test_dropin_packages_resolve_reference_imports():
+    """The import lines of scripts/inference.py:24-25, models/pipeline.py:21-31 and
+    scripts/inference_native.py:32-36 resolve against the drop-in directory."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from config import Config\nfrom config.constants import CORRECTION_NORM_FLOOR\n"
+            "from data import BathymetricGrid, BathymetricLoader, BathymetricWriter, TileManager, TileMerger, GraphBuilder\n"
+            "from models import BathymetricPipeline\nfrom models.gnn import BathymetricGNN\n"
+            "assert Config().tile.tile_size == 1024 and CORRECTION_NORM_FLOOR == 0.01\n"
+            "assert BathymetricGNN.CLASS_NOISE == 2\nprint('ok')\n") % os.path.join(ROOT, "bathymetric-gnn_b200", "dropin")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
