@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int UM_THREADS = 256;
+constexpr int UM_THREADS = 416;           // 4 epilogue warps + 1 MMA warp + 8 producer warps
 constexpr int KC = 32;                 // K elements per stage (64 B of bf16 = one SWIZZLE_64B row)
 constexpr int STAGES = 3;
 constexpr int TILE_M = 128;
@@ -108,8 +108,24 @@ struct UmmaSmem {
     static constexpr int STAGE_BYTES = MT * 3 * A_TILE_BYTES + 3 * B_TILE_BYTES;
     static constexpr int ACC_COLS = 2 * MT * N;                  // {main, corr} per M tile
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-    static constexpr size_t BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 2 * N * sizeof(float) + 64;
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE_BYTES + 2 * N * sizeof(float) + 128;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float* x) {          // 256-bit store (PTX ISA 8.8, sm_100)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
+                 "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
+}
+
+// warp roles
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8, PROD_GROUPS = 2;
+constexpr int MMA_WARP = EPI_WARPS, PROD_WARP0 = EPI_WARPS + 1;
+constexpr int PROD_GROUP_THREADS = PROD_WARPS / PROD_GROUPS * 32;                  // 128
+static_assert(UM_THREADS == (EPI_WARPS + 1 + PROD_WARPS) * 32, "thread count / role mismatch");
+// barrier slots
+constexpr int BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_TFULL = 2 * STAGES, BAR_TEMPTY = 2 * STAGES + 1, NUM_BARS = 2 * STAGES + 2;
 
 template <int N>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -117,11 +133,11 @@ proj_umma_kernel(const float* __restrict__ A, int64_t M, int K, const uint16_t* 
                  float* __restrict__ Cout, const float* __restrict__ att_src, const float* __restrict__ att_dst,
                  float* __restrict__ alpha, int Htot, int CH) {
     using S = UmmaSmem<N>;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw;                                                      // stage ring (1024 B aligned)
     float* s_att = reinterpret_cast<float*>(base + (size_t)STAGES * S::STAGE_BYTES);      // [2][N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_att + 2 * N);                          // empty[STAGES], done
-    __shared__ uint32_t s_tmem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_att + 2 * N);                          // NUM_BARS
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
     constexpr int MT = S::MT, SUPER_M = S::SUPER_M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,150 +145,167 @@ proj_umma_kernel(const float* __restrict__ A, int64_t M, int K, const uint16_t* 
     const int64_t n_super = (M + SUPER_M - 1) / SUPER_M;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-        mbar_init(&bars[STAGES], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
+        mbar_init(&bars[BAR_TFULL], 1);
+        mbar_init(&bars[BAR_TEMPTY], EPI_WARPS * 32);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (alpha) {
         for (int i = tid; i < N; i += UM_THREADS) { s_att[i] = __ldg(att_src + i); s_att[N + i] = __ldg(att_dst + i); }
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(S::TMEM_COLS) : "memory");
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "n"(S::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = *s_tmem;
 
-    // instruction descriptor: D = F32, A = B = BF16, both K-major, N, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    constexpr int A_F4 = MT * TILE_M * (KC / 4) / UM_THREADS;       // float4 loads per thread and stage (4 or 8)
-
-    uint32_t it = 0;              // stage-use counter (all threads advance it identically)
-    uint32_t done_phase = 0;
-    for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
-        const int64_t row0 = st * SUPER_M;
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-            const int s = it % STAGES;
-            unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
-            // A loads first (long latency), then wait for the stage to be free
-            float4 av[A_F4];
+    if (warp >= PROD_WARP0) {
+        // ===================== PRODUCERS: two groups of 64 threads own alternate K chunks =====================
+        const int grp = (warp - PROD_WARP0) / (PROD_WARPS / PROD_GROUPS);
+        const int ptid = tid - (PROD_WARP0 + grp * (PROD_WARPS / PROD_GROUPS)) * 32;      // 0..63
+        constexpr int A_F4 = MT * TILE_M * (KC / 4) / PROD_GROUP_THREADS;                  // 8 or 16 float4 per thread and chunk
+        uint32_t it = 0;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+            const int64_t row0 = st * SUPER_M;
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                if ((int)(it % PROD_GROUPS) != grp) continue;
+                const int s = it % STAGES;
+                unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
+                // A loads first (long latency, registers only), then wait for the stage to be free
+                float4 av[A_F4];
 #pragma unroll
-            for (int i = 0; i < A_F4; ++i) {
-                const int f = tid + i * UM_THREADS;
-                const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
-                const int64_t gr = row0 + mt * TILE_M + r;
-                av[i] = gr < M ? __ldg(reinterpret_cast<const float4*>(A + gr * K + kc * KC + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (it >= STAGES) mbar_wait(&bars[s], ((it / STAGES) - 1) & 1);
-            // W split chunks: 3 x N rows x 64 B
-            {
-                const uint32_t sB = smem_u32(stage + MT * 3 * A_TILE_BYTES);
-                for (int q = tid; q < 3 * N * 4; q += UM_THREADS) {
-                    const int sp = q / (N * 4), rem = q - sp * (N * 4), n = rem >> 2, c = rem & 3;
-                    cp_async16(sB + sp * S::B_TILE_BYTES + sw64_off(n, c), Wsplit + ((size_t)sp * N + n) * K + kc * KC + c * 8);
+                for (int i = 0; i < A_F4; ++i) {
+                    const int f = ptid + i * PROD_GROUP_THREADS;
+                    const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
+                    const int64_t gr = row0 + mt * TILE_M + r;
+                    av[i] = gr < M ? __ldg(reinterpret_cast<const float4*>(A + gr * K + kc * KC + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                asm volatile("cp.async.commit_group;\n" ::: "memory");
-            }
+                if (it >= STAGES) mbar_wait(&bars[BAR_EMPTY + s], ((it / STAGES) - 1) & 1);
+                {   // W split chunks: 3 x N rows x 64 B, straight to shared memory
+                    const uint32_t sB = smem_u32(stage + MT * 3 * A_TILE_BYTES);
+                    for (int q = ptid; q < 3 * N * 4; q += PROD_GROUP_THREADS) {
+                        const int sp = q / (N * 4), rem = q - sp * (N * 4), n = rem >> 2, c = rem & 3;
+                        cp_async16(sB + sp * S::B_TILE_BYTES + sw64_off(n, c), Wsplit + ((size_t)sp * N + n) * K + kc * KC + c * 8);
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                }
 #pragma unroll
-            for (int i = 0; i < A_F4; ++i) {
-                const int f = tid + i * UM_THREADS;
-                const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
-                uint2 s1, s2, s3;
-                split4(av[i], s1, s2, s3);
-                unsigned char* t0 = stage + (size_t)(mt * 3) * A_TILE_BYTES + sw64_off(r, c4 >> 1) + (c4 & 1) * 8;
-                *reinterpret_cast<uint2*>(t0) = s1;
-                *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = s2;
-                *reinterpret_cast<uint2*>(t0 + 2 * A_TILE_BYTES) = s3;
+                for (int i = 0; i < A_F4; ++i) {                   // 3-way bf16 split -> swizzled STS
+                    const int f = ptid + i * PROD_GROUP_THREADS;
+                    const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
+                    uint2 s1, s2, s3;
+                    split4(av[i], s1, s2, s3);
+                    unsigned char* t0 = stage + (size_t)(mt * 3) * A_TILE_BYTES + sw64_off(r, c4 >> 1) + (c4 & 1) * 8;
+                    *reinterpret_cast<uint2*>(t0) = s1;
+                    *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = s2;
+                    *reinterpret_cast<uint2*>(t0 + 2 * A_TILE_BYTES) = s3;
+                }
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
+                mbar_arrive(&bars[BAR_FULL + s]);
             }
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
-            __syncthreads();
-            if (tid == 0) {
+        }
+    } else if (warp == MMA_WARP) {
+        // ===================== MMA ISSUER (one thread) =====================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            uint32_t it = 0, t = 0;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
+                if (t >= 1) mbar_wait(&bars[BAR_TEMPTY], (t - 1) & 1);            // epilogue drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t sA = smem_u32(stage), sB = smem_u32(stage + MT * 3 * A_TILE_BYTES);
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&bars[BAR_FULL + s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t sA = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB = sA + MT * 3 * A_TILE_BYTES;
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d_main = tmem_base + (uint32_t)(mt * 2 * N), d_corr = d_main + (uint32_t)N;
-                    // p = 0: leading product a1*b1 -> main; p = 1..5: corrections (i + j <= 4), smallest first -> corr
-                    const int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {0, 0, 1, 2, 0, 1};
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d_main = tmem_base + (uint32_t)(mt * 2 * N), d_corr = d_main + (uint32_t)N;
+                        // p = 0: leading product a1*b1 -> main; p = 1..5: corrections (i + j <= 4), smallest first -> corr
+                        const int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {0, 0, 1, 2, 0, 1};
 #pragma unroll
-                    for (int p = 0; p < 6; ++p) {
+                        for (int p = 0; p < 6; ++p) {
 #pragma unroll
-                        for (int ks = 0; ks < KC / 16; ++ks) {
-                            const uint64_t da = make_desc(sA + (mt * 3 + pa[p]) * A_TILE_BYTES + ks * 32);
-                            const uint64_t db = make_desc(sB + pb[p] * S::B_TILE_BYTES + ks * 32);
-                            const bool first = kc == 0 && ks == 0 && (p == 0 || p == 1);
-                            umma_bf16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
+                            for (int ks = 0; ks < KC / 16; ++ks) {
+                                const uint64_t da = make_desc(sA + (mt * 3 + pa[p]) * A_TILE_BYTES + ks * 32);
+                                const uint64_t db = make_desc(sB + pb[p] * S::B_TILE_BYTES + ks * 32);
+                                const bool first = kc == 0 && ks == 0 && (p == 0 || p == 1);
+                                umma_bf16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
+                            }
                         }
                     }
+                    umma_commit(&bars[BAR_EMPTY + s]);                 // stage free when these MMAs retire
                 }
-                umma_commit(&bars[s]);                         // stage free when these MMAs retire
-                if (kc == nkc - 1) umma_commit(&bars[STAGES]); // accumulators complete
+                umma_commit(&bars[BAR_TFULL]);                         // accumulators complete
             }
         }
-        // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..; MT == 1: warps 4-7 take the upper half of the columns
-        mbar_wait(&bars[STAGES], done_phase);
-        done_phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        {
-            const int lq = warp & 3;
-            const int mt = MT == 2 ? (warp >> 2) : 0;
-            const int c_begin = MT == 1 ? (warp >> 2) * (N / 2) : 0;
-            const int c_end = MT == 1 ? c_begin + N / 2 : N;
-            const int64_t row = row0 + mt * TILE_M + lq * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(mt * 2 * N);
-            float as_acc = 0.f, ad_acc = 0.f;
+    } else {
+        // ===================== EPILOGUE: warp w <-> TMEM lanes 32w .. 32w+31 =====================
+        uint32_t t = 0;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
+            const int64_t row0 = st * SUPER_M;
+            mbar_wait(&bars[BAR_TFULL], t & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                uint32_t v[32], u[32];
+            for (int mt = 0; mt < MT; ++mt) {
+                const int64_t row = row0 + mt * TILE_M + warp * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 2 * N);
+                float as_acc = 0.f, ad_acc = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    uint32_t v[32], u[32];
 #define BGNN_TMEM_LD32(arr, addr)                                                                                              \
-                asm volatile(                                                                                                  \
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                \
-                    : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
-                      "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]),    \
-                      "=r"(arr[15]), "=r"(arr[16]), "=r"(arr[17]), "=r"(arr[18]), "=r"(arr[19]), "=r"(arr[20]), "=r"(arr[21]),  \
-                      "=r"(arr[22]), "=r"(arr[23]), "=r"(arr[24]), "=r"(arr[25]), "=r"(arr[26]), "=r"(arr[27]), "=r"(arr[28]),  \
-                      "=r"(arr[29]), "=r"(arr[30]), "=r"(arr[31])                                                              \
-                    : "r"(addr))
-                BGNN_TMEM_LD32(v, taddr + (uint32_t)c0);
-                BGNN_TMEM_LD32(u, taddr + (uint32_t)(N + c0));
+                    asm volatile(                                                                                              \
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"            \
+                        : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
+                          "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), \
+                          "=r"(arr[15]), "=r"(arr[16]), "=r"(arr[17]), "=r"(arr[18]), "=r"(arr[19]), "=r"(arr[20]), "=r"(arr[21]), \
+                          "=r"(arr[22]), "=r"(arr[23]), "=r"(arr[24]), "=r"(arr[25]), "=r"(arr[26]), "=r"(arr[27]), "=r"(arr[28]), \
+                          "=r"(arr[29]), "=r"(arr[30]), "=r"(arr[31])                                                          \
+                        : "r"(addr))
+                    BGNN_TMEM_LD32(v, taddr + (uint32_t)c0);
+                    BGNN_TMEM_LD32(u, taddr + (uint32_t)(N + c0));
 #undef BGNN_TMEM_LD32
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                float x[32];
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    float x[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);     // main + corrections (RN)
-                if (alpha) {
+                    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);     // main + corrections (RN)
+                    if (alpha) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        as_acc = fmaf(x[j], s_att[c0 + j], as_acc);
-                        ad_acc = fmaf(x[j], s_att[N + c0 + j], ad_acc);
-                    }
-                    if (((c0 + 32) % CH) == 0) {          // a head's channels are complete
-                        if (row < M) {
-                            const int h = (c0 + 32) / CH - 1;
-                            alpha[row * (2 * Htot) + h] = as_acc;
-                            alpha[row * (2 * Htot) + Htot + h] = ad_acc;
+                        for (int j = 0; j < 32; ++j) {
+                            as_acc = fmaf(x[j], s_att[c0 + j], as_acc);
+                            ad_acc = fmaf(x[j], s_att[N + c0 + j], ad_acc);
                         }
-                        as_acc = 0.f; ad_acc = 0.f;
+                        if (((c0 + 32) % CH) == 0) {          // a head's channels are complete
+                            if (row < M) {
+                                const int h = (c0 + 32) / CH - 1;
+                                alpha[row * (2 * Htot) + h] = as_acc;
+                                alpha[row * (2 * Htot) + Htot + h] = ad_acc;
+                            }
+                            as_acc = 0.f; ad_acc = 0.f;
+                        }
                     }
-                }
-                if (row < M) {
-                    float4* dst = reinterpret_cast<float4*>(Cout + row * N + c0);
+                    if (row < M) {
+                        float* dst = Cout + row * N + c0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
+                    }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(&bars[BAR_TEMPTY]);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncthreads();                                     // accumulators drained before the next super tile overwrites them
     }
-    // teardown: every issued MMA has been waited for by the epilogue
+    // teardown
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == MMA_WARP) {
+        __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
     }
 }
