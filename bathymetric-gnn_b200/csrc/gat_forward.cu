@@ -42,6 +42,11 @@ struct bgnn_model {
     float *hW0, *hb0;        // concatenated first layers [nheads_mlp*h2, C]
     float *Wcls, *bcls, *Wconf, *bconf, *Wcorr, *bcorr;
     int hc_max;
+    // tensor-core fusions (proj_umma.cu): layer-0 projection with the feature extractor folded in, fused heads
+    uint16_t* Wfold0;        // [3][HC_0][C] bf16 split of W_lin0 . W_fe1 (nullptr if not compiled for this shape)
+    float* bias_fold0;       // [HC_0] = W_lin0 . b_fe1
+    uint16_t* hWsplit;       // [3][hNpad][C] bf16 split of the concatenated head first layers (zero padded)
+    int hNpad;
 };
 
 namespace {
@@ -450,12 +455,14 @@ int launch_agg(const LayerDev& L, const float* h, const float* alpha, const int3
 
 
 // ------------------------------------------------------------------------------------------ tiled aggregation
-// Grid path: one CTA per PH x 16 patch of cells.  Every source row of the (PH+2) x 18 halo is staged ONCE
-// per head in shared memory with cp.async (L2 -> smem, bypassing L1); destinations then read their <= 9
-// neighbour rows from shared memory at fixed stencil offsets.  Thread t owns destination cell t for the
-// score / softmax phase (edge features and the self-loop mean stay in its registers across the head loop),
-// warp w aggregates destinations 32w .. 32w+31 with lane <-> channels.  Same arithmetic and summation order
-// as gat_aggregate (offset k ascending, source = i - off_k, self loop last).
+// Grid path: one CTA per PH x 16 patch of cells.  Every source row of the (PH+2) x 18 halo is staged ONCE per head in
+// shared memory by a bulk async copy (cp.async.bulk, one 4*C-byte copy per halo cell, completion on an mbarrier);
+// destinations then read their neighbour rows from shared memory.  Thread t owns destination cell t for the score /
+// softmax phase (edge features and the self-loop mean stay in its registers across the head loop) and leaves the 3x3
+// attention weights of its cell in shared memory, indexed by source POSITION; warp w then walks its two patch rows with
+// lane <-> channels and a 3x3 sliding register window, so each step loads only the 3 new source rows of the window's
+// right column.  The FMAs run in the reference's edge order (offset k ascending, source = i - off_k, self loop last),
+// i.e. the same arithmetic as gat_aggregate; absent neighbours contribute fma(0, 0, acc) == acc.
 struct TopoDev {
     int rows, cols;
     const int32_t* node_id;
@@ -463,37 +470,46 @@ struct TopoDev {
     int dr[8], dc[8];
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int H, int C, int PH> struct TileCfg {
     static constexpr int PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, NT = PH * PW, AST = 12;
-    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST) * 4;
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST) * 4 + 16;
 };
 
-template <int H, int C, int PH>
+// window position p = dy*3 + dx (dy, dx in 0..2 <-> source at row r-1+dy, column c-1+dx) visited in reference edge order
+template <bool CONN4> struct EdgeOrder {
+    static constexpr int N = CONN4 ? 5 : 9;
+    __host__ __device__ static constexpr int pos(int q) {
+        return CONN4 ? (q == 0 ? 7 : q == 1 ? 1 : q == 2 ? 5 : q == 3 ? 3 : 4)
+                     : (q == 0 ? 8 : q == 1 ? 7 : q == 2 ? 6 : q == 3 ? 5 : q == 4 ? 3 : q == 5 ? 2 : q == 6 ? 1 : q == 7 ? 0 : 4);
+    }
+};
+
+template <int H, int C, int PH, bool CONN4>
 __global__ void __launch_bounds__(PH * 16, (C <= 64 ? 2 : 1))
 gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha, const TopoDev T,
                    const int32_t* __restrict__ rowptr, const float* __restrict__ eattr, int ED,
                    const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
                    const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out) {
     using G = TileCfg<H, C, PH>;
+    using O = EdgeOrder<CONN4>;
     constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, AST = G::AST;
-    constexpr int VEC = C / 32, HC = H * C, CH16 = C / 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int VEC = C / 32, HC = H * C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
     int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
     float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [H][NSLOT]   alpha_src per halo cell
-    float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    attention weights of the current head
+    float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    3x3 attention weights of the current head
+    uint64_t* bar = reinterpret_cast<uint64_t*>(a_sm + NT * AST);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pr0 = blockIdx.y * PH, pc0 = blockIdx.x * 16;
 
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(NT));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     for (int s = tid; s < NSLOT; s += NT) {
         const int r = pr0 - 1 + s / HW, c = pc0 - 1 + s % HW;
         int id = -1;
@@ -564,16 +580,35 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
         }
         __syncthreads();                                             // stage aliases rows: done before the copies start
     }
-
+    // rows of invalid halo cells stay zero for every head (the bulk copies never touch them)
+    for (int s = tid; s < NSLOT; s += NT)
+        if (ids[s] < 0) {
 #pragma unroll
-    for (int hh = 0; hh < H; ++hh) {
-        // 1. stage the source rows of head hh (16 B chunks, coalesced per row)
-        for (int q = tid; q < NSLOT * CH16; q += NT) {
-            const int s = q / CH16, part = q % CH16;
-            const int id = ids[s];
-            if (id >= 0) cp_async16(rows + s * C + part * 4, h + (int64_t)id * HC + hh * C + part * 4);
+            for (int q = 0; q < C / 4; ++q) *reinterpret_cast<float4*>(rows + s * C + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // 2. scores + softmax of this head while the copies are in flight
+    // window position of in-edge k (source = i - off_k)
+    int wpos[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wpos[k] = (1 - T.dr[k]) * 3 + (1 - T.dc[k]);
+
+#pragma unroll 1
+    for (int hh = 0; hh < H; ++hh) {
+        // 1. stage the source rows of head hh: one bulk copy of 4*C bytes per valid halo cell
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic accesses of `rows` before async writes
+        for (int s = tid; s < NSLOT; s += NT) {
+            const int id = ids[s];
+            if (id >= 0) {
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(C * 4) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                             ::"r"(smem_addr(rows + s * C)), "l"(h + (int64_t)id * HC + hh * C), "r"(C * 4), "r"(smem_addr(bar))
+                             : "memory");
+            }
+        }
+        // 2. scores + softmax of this head while the copies are in flight -> a_sm[t][window position]
+        {
+            float4* az = reinterpret_cast<float4*>(a_sm + tid * AST);
+            az[0] = make_float4(0.f, 0.f, 0.f, 0.f); az[1] = make_float4(0.f, 0.f, 0.f, 0.f); az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (myid >= 0) {
             float sc[9], mx = -CUDART_INF_F;
 #pragma unroll
@@ -606,63 +641,90 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             sum += sc[8];
             sum += 1e-16f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a_sm[tid * AST + k] = ((nbv >> k) & 1u) ? sc[k] / sum : 0.f;
-            a_sm[tid * AST + 8] = sc[8] / sum;
+            for (int k = 0; k < 8; ++k)
+                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] / sum;
+            a_sm[tid * AST + 4] = sc[8] / sum;
         }
-        cp_async_wait_all();
-        __syncthreads();
-        // 3. aggregate: warp w handles destinations 32w .. 32w+31, lane <-> VEC channels
+        // 3. all threads arrive (release: a_sm, zero rows), then wait for the arrivals and the copied bytes
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+            uint32_t ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(ok) : "r"(smem_addr(bar)), "r"((uint32_t)(hh & 1)) : "memory");
+            } while (!ok);
+        }
+        // 4. aggregate: warp w walks patch rows 2w, 2w+1; lane <-> VEC channels; 3x3 sliding window in registers
         float bs[VEC], ba[VEC], bb[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int ch = hh * C + lane * VEC + v;
             bs[v] = __ldg(bias + ch); ba[v] = __ldg(bn_a + ch); bb[v] = __ldg(bn_b + ch);
         }
-        for (int q = 0; q < 32; ++q) {
-            const int t2 = warp * 32 + q;
-            const int cs2 = (t2 / 16 + 1) * HW + (t2 % 16 + 1);
-            const int id2 = ids[cs2];
-            if (id2 < 0) continue;
-            const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
-            const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
-            const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
-            float acc[VEC];
+        auto ldrow = [&](const float* p, float* dst) {
+            if (VEC == 1) dst[0] = p[0];
+            else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); dst[0] = t.x; dst[1 % VEC] = t.y; }
+            else { const float4 t = *reinterpret_cast<const float4*>(p); dst[0] = t.x; dst[1 % VEC] = t.y; dst[2 % VEC] = t.z; dst[3 % VEC] = t.w; }
+        };
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int pr = warp * 2 + rr;                                   // patch row; halo rows pr .. pr+2
+            const float* base = rows + (pr * HW) * C + lane * VEC;
+            float win[3][3][VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-            float hv[9][VEC];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int s = (k < 8 && aw[k] != 0.f) ? cs2 - T.dr[k] * HW - T.dc[k] : cs2;   // weight 0 -> safe centre slot
-                if (VEC == 1) hv[k][0] = rows[s * C + lane];
-                else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(rows + s * C + lane * 2); hv[k][0] = t.x; hv[k][1 % VEC] = t.y; }
-                else { const float4 t = *reinterpret_cast<const float4*>(rows + s * C + lane * 4); hv[k][0] = t.x; hv[k][1 % VEC] = t.y; hv[k][2 % VEC] = t.z; hv[k][3 % VEC] = t.w; }
+            for (int dy = 0; dy < 3; ++dy) {
+                ldrow(base + (dy * HW + 0) * C, win[dy][1]);
+                ldrow(base + (dy * HW + 1) * C, win[dy][2]);
             }
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
+            for (int c = 0; c < 16; ++c) {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[k], hv[k][v], acc[v]);
-            float o[VEC];
+                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                float y = acc[v] + bs[v];
-                y = fmaf(y, ba[v], bb[v]);
-                o[v] = relu ? fmaxf(y, 0.f) : y;
+                    for (int v = 0; v < VEC; ++v) { win[dy][0][v] = win[dy][1][v]; win[dy][1][v] = win[dy][2][v]; }
+                    ldrow(base + (dy * HW + c + 2) * C, win[dy][2]);
+                }
+                const int t2 = pr * 16 + c;
+                const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
+                const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
+                const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
+                float acc[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+                for (int q = 0; q < O::N; ++q) {
+                    const int p = O::pos(q);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[p], win[p / 3][p % 3][v], acc[v]);
+                }
+                const int id2 = ids[(pr + 1) * HW + c + 1];
+                if (id2 >= 0) {
+                    float o[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        float y = acc[v] + bs[v];
+                        y = fmaf(y, ba[v], bb[v]);
+                        o[v] = relu ? fmaxf(y, 0.f) : y;
+                    }
+                    VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
+                }
             }
-            VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
         }
-        __syncthreads();
+        __syncthreads();                     // every warp is done with rows / a_sm before the next head overwrites them
     }
 }
 
-template <int H, int C, int PH>
+template <int H, int C, int PH, bool CONN4>
 int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
                       const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
     using G = TileCfg<H, C, PH>;
-    static bool configured = false;
-    auto kern = gat_aggregate_tile<H, C, PH>;
-    if (!configured) {
+    static bool configured[64] = {};                    // the attribute is per device
+    auto kern = gat_aggregate_tile<H, C, PH, CONN4>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
     kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, rowptr, eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out);
@@ -673,7 +735,17 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
 // returns 1 if no tiled instantiation fits (caller falls back to the CSR kernel)
 int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
                     const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
-#define TCASE(H_, C_, PH_) if (L.H == H_ && L.C == C_) return launch_agg_tile_t<H_, C_, PH_>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)
+    // the reference's own offset lists (graph_construction.py:79-87); any other radius-1 list takes the CSR kernel
+    static const int r8[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, c8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    static const int r4[4] = {-1, 1, 0, 0}, c4[4] = {0, 0, -1, 1};
+    bool is8 = T.K == 8, is4 = T.K == 4;
+    for (int k = 0; k < 8 && is8; ++k) is8 = T.dr[k] == r8[k] && T.dc[k] == c8[k];
+    for (int k = 0; k < 4 && is4; ++k) is4 = T.dr[k] == r4[k] && T.dc[k] == c4[k];
+    if (!is8 && !is4) return 1;
+#define TCASE(H_, C_, PH_)                                                                                              \
+    if (L.H == H_ && L.C == C_)                                                                                         \
+        return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)       \
+                   : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)
     TCASE(4, 64, 16); TCASE(1, 64, 16); TCASE(2, 64, 16); TCASE(8, 64, 16);
     TCASE(1, 32, 16); TCASE(2, 32, 16); TCASE(4, 32, 16); TCASE(8, 32, 16);
     TCASE(1, 128, 8); TCASE(2, 128, 8); TCASE(4, 128, 8);
@@ -846,6 +918,43 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         proj_umma_split_weights(hb.data() + lo[l].W, HC, in, h16.data() + o16[l]);
     }
 
+    // layer 0 with LocalFeatureExtractor.mlp[3] folded in: h = (W1 r + b1) Wl^T = r (Wl W1)^T + Wl b1   (fp64 fold)
+    size_t oFold16 = (size_t)-1, oFoldBias = 0;
+    {
+        int in, H, Cc, HC, outc;
+        layer_shape(d, 0, in, H, Cc, HC, outc);
+        if (proj_umma_supported(HC, in, Cc, true) && proj_umma_mlp0_supported(HC, C, F)) {
+            std::vector<float> Wf((size_t)HC * C), bf(HC);
+            const float* Wl = hb.data() + lo[0].W;      // [HC, C]
+            const float* W1 = hb.data() + oW1;          // [C, C]
+            const float* b1 = hb.data() + ob1;
+            for (int n = 0; n < HC; ++n) {
+                for (int k = 0; k < C; ++k) {
+                    double acc = 0.0;
+                    for (int c = 0; c < C; ++c) acc += (double)Wl[(size_t)n * C + c] * (double)W1[(size_t)c * C + k];
+                    Wf[(size_t)n * C + k] = (float)acc;
+                }
+                double acc = 0.0;
+                for (int c = 0; c < C; ++c) acc += (double)Wl[(size_t)n * C + c] * (double)b1[c];
+                bf[n] = (float)acc;
+            }
+            oFoldBias = push(bf.data(), HC);
+            oFold16 = h16.size();
+            h16.resize(h16.size() + (size_t)3 * HC * C);
+            proj_umma_split_weights(Wf.data(), HC, C, h16.data() + oFold16);
+        }
+    }
+    // heads: concatenated first layers, zero padded to the accumulator width
+    size_t oHeads16 = (size_t)-1;
+    int hNpad = 0;
+    if (proj_umma_heads_supported(C, h2, nblk, d->num_classes, &hNpad)) {
+        std::vector<float> Wp((size_t)hNpad * C, 0.f);
+        memcpy(Wp.data(), hW0.data(), sizeof(float) * hW0.size());
+        oHeads16 = h16.size();
+        h16.resize(h16.size() + (size_t)3 * hNpad * C);
+        proj_umma_split_weights(Wp.data(), hNpad, C, h16.data() + oHeads16);
+    }
+
     int prev = 0;
     BGNN_CUDA(cudaGetDevice(&prev));
     BGNN_CUDA(cudaSetDevice(device));
@@ -873,6 +982,10 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     if (nblk * h2 > m->hc_max) m->hc_max = nblk * h2;
     m->hW0 = B + ohW0; m->hb0 = B + ohb0; m->Wcls = B + oWc; m->bcls = B + obc; m->Wconf = B + oWf; m->bconf = B + obf;
     m->Wcorr = rW1 ? B + oWr : nullptr; m->bcorr = rb1 ? B + obr : nullptr;
+    m->Wfold0 = (oFold16 != (size_t)-1 && m->blob16) ? m->blob16 + oFold16 : nullptr;
+    m->bias_fold0 = B + oFoldBias;
+    m->hWsplit = (oHeads16 != (size_t)-1 && m->blob16) ? m->blob16 + oHeads16 : nullptr;
+    m->hNpad = hNpad;
     *out = m;
     return BGNN_OK;
 }
@@ -939,17 +1052,28 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const bgnn_model_desc& d = m->d;
     const int C = d.hidden, h2 = C / 2;
     int rc;
-    // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C)
-    { ProfScope ps(10, s);
-      if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
-    { ProfScope ps(11, s);
-      if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc; }
+    // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C).  On the tensor-core path both are fused into the
+    // layer-0 projection (first Linear computed by its producers, second folded into its weights).
+    const bool fused0 = g_use_umma && m->Wfold0;
+    if (!fused0) {
+        { ProfScope ps(10, s);
+          if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
+        { ProfScope ps(11, s);
+          if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc; }
+    }
     float* cur = bufB;
     float* nxt = bufA;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
         { ProfScope ps(20 + l, s);
-          if (g_use_umma && L.Wsplit)
+          if (l == 0 && fused0) {
+              UmmaArgs a = {};
+              a.M = N; a.K = C; a.Wsplit = m->Wfold0;
+              a.x = x; a.F = d.in_channels; a.W0 = m->feW0; a.b0 = m->feb0;
+              a.Cout = hbuf; a.bias = m->bias_fold0; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha;
+              a.Htot = L.H; a.CH = L.C;
+              rc = launch_umma(a, L.HC, PM_MLP0, EM_PROJ, sms, s);
+          } else if (g_use_umma && L.Wsplit)
               rc = launch_proj_umma(cur, N, L.in, L.Wsplit, L.HC, hbuf, L.att_src, L.att_dst, alpha, L.H, L.C, sms, s);
           else
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
@@ -965,6 +1089,16 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // heads
     const int nblk = m->nheads_mlp;
+    if (g_use_umma && m->hWsplit) {         // one kernel: first layers on the tensor cores, the rest in its epilogue
+        ProfScope ps(60, s);
+        UmmaArgs a = {};
+        a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit;
+        a.hb0 = m->hb0; a.h2 = h2; a.nblk = nblk; a.ncls = d.num_classes;
+        a.Wcls = m->Wcls; a.bcls = m->bcls; a.Wconf = m->Wconf; a.bconf = m->bconf; a.Wcorr = m->Wcorr; a.bcorr = m->bcorr;
+        a.logits = logits; a.probs = probs; a.cls = cls; a.conf = conf; a.corr = corr; a.action = action;
+        a.thr_auto = thr_auto; a.thr_review = thr_review;
+        return launch_umma(a, m->hNpad, PM_PLAIN, EM_HEADS, sms, s);
+    }
     { ProfScope ps(60, s);
       if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc; }
     int64_t blocks = ceil_div64(N, 8);

@@ -117,7 +117,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=False):
+def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=False, fused_mlp=False, fused_heads=False):
     """SURVEY.md 8(d) per-unit figures x the units one launch processes (stated in DESIGN.md)."""
     b = {}
     deg = E / max(N, 1)
@@ -134,6 +134,10 @@ def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=
     b["mlp1"] = N * (8 * hidden)
     b["heads_gemm"] = N * (4 * hidden + 4 * 3 * (hidden // 2))
     b["heads_finish"] = N * (4 * 3 * (hidden // 2) + 4 * 3 * 2 + 8 + 4 + 4 + 8)
+    if fused_mlp:           # feature extractor fused into the layer-0 projection: reads x instead of the MLP output
+        b["proj_l0"] = N * (4 * F + 4 * HC + 8 * heads)
+    if fused_heads:         # one kernel: reads the backbone output, writes logits, probs, class, conf, corr, action
+        b["heads_gemm"] = N * (4 * hidden + 4 * 3 * 2 + 8 + 4 + 4 + 8)
     return b
 
 
@@ -268,7 +272,7 @@ def run_ours(args):
         agg = {}
         for s_, m_ in zip(slots, ms):
             agg.setdefault(SLOT_NAMES.get(int(s_), str(int(s_))), []).append(float(m_))
-        bytes_ = algorithmic_bytes(N, E, cells)
+        bytes_ = algorithmic_bytes(N, E, cells, fused_mlp="mlp0" not in agg, fused_heads="heads_finish" not in agg)
         peak, peak_src = peaks()
         gb_ms = sum(np.mean(agg[k]) for k in ("gb_count", "gb_scan", "gb_ids", "gb_emit") if k in agg)
         tot_ms = sum(np.mean(v) for v in agg.values())
