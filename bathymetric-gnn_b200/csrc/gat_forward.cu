@@ -28,7 +28,9 @@ extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN
 struct LayerDev {
     int in, H, C, HC, out;
     float *W, *att_src, *att_dst, *Medge, *bias, *bn_a, *bn_b;
-    uint16_t* Wsplit;        // [3][HC][in] bf16 split of W for the tcgen05 path (nullptr if the shape is not compiled)
+    uint16_t* Wsplit;        // 2 x fp16 split of W for the tcgen05 path (nullptr if the shape is not compiled)
+    float w_inv;             // 1 / (power-of-two scale applied to W before the split)
+    float out_mul, out_add;  // |layer output| <= out_mul * max|h| + out_add   (BN(eval) after a convex combination + bias)
 };
 
 struct bgnn_model {
@@ -43,9 +45,12 @@ struct bgnn_model {
     float *Wcls, *bcls, *Wconf, *bconf, *Wcorr, *bcorr;
     int hc_max;
     // tensor-core fusions (proj_umma.cu): layer-0 projection with the feature extractor folded in, fused heads
-    uint16_t* Wfold0;        // [3][HC_0][C] bf16 split of W_lin0 . W_fe1 (nullptr if not compiled for this shape)
+    uint16_t* Wfold0;        // fp16 split of W_lin0 . W_fe1 (nullptr if not compiled for this shape)
     float* bias_fold0;       // [HC_0] = W_lin0 . b_fe1
-    uint16_t* hWsplit;       // [3][hNpad][C] bf16 split of the concatenated head first layers (zero padded)
+    float fold0_inv;
+    float mlp0_mul, mlp0_add;   // |relu(x W0^T + b0)| <= mlp0_mul * max|x| + mlp0_add
+    uint16_t* hWsplit;       // fp16 split of the concatenated head first layers (zero padded to hNpad rows)
+    float heads_inv;
     int hNpad;
 };
 
@@ -906,20 +911,22 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     size_t oWr = rW1 ? push(rW1, h2) : 0, obr = rb1 ? push(rb1, 1) : 0;
     if (q - p != n_floats) { bgnn_set_error("internal: parameter walk mismatch"); return BGNN_E_INVALID; }
 
-    // bf16x3 splits of the projection weights for the tensor-core path
+    // fp16 hi/lo splits of the projection weights for the tensor-core path
     std::vector<uint16_t> h16;
     std::vector<size_t> o16(d->layers, (size_t)-1);
+    std::vector<float> winv(d->layers, 1.f);
     for (int l = 0; l < d->layers; ++l) {
         int in, H, Cc, HC, outc;
         layer_shape(d, l, in, H, Cc, HC, outc);
         if (!proj_umma_supported(HC, in, Cc, true)) continue;
         o16[l] = h16.size();
-        h16.resize(h16.size() + (size_t)3 * HC * in);
-        proj_umma_split_weights(hb.data() + lo[l].W, HC, in, h16.data() + o16[l]);
+        h16.resize(h16.size() + (size_t)2 * HC * in);
+        winv[l] = proj_umma_split_weights(hb.data() + lo[l].W, HC, in, h16.data() + o16[l]);
     }
 
     // layer 0 with LocalFeatureExtractor.mlp[3] folded in: h = (W1 r + b1) Wl^T = r (Wl W1)^T + Wl b1   (fp64 fold)
     size_t oFold16 = (size_t)-1, oFoldBias = 0;
+    float fold0_inv = 1.f, heads_inv = 1.f;
     {
         int in, H, Cc, HC, outc;
         layer_shape(d, 0, in, H, Cc, HC, outc);
@@ -940,8 +947,8 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
             }
             oFoldBias = push(bf.data(), HC);
             oFold16 = h16.size();
-            h16.resize(h16.size() + (size_t)3 * HC * C);
-            proj_umma_split_weights(Wf.data(), HC, C, h16.data() + oFold16);
+            h16.resize(h16.size() + (size_t)2 * HC * C);
+            fold0_inv = proj_umma_split_weights(Wf.data(), HC, C, h16.data() + oFold16);
         }
     }
     // heads: concatenated first layers, zero padded to the accumulator width
@@ -951,8 +958,8 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         std::vector<float> Wp((size_t)hNpad * C, 0.f);
         memcpy(Wp.data(), hW0.data(), sizeof(float) * hW0.size());
         oHeads16 = h16.size();
-        h16.resize(h16.size() + (size_t)3 * hNpad * C);
-        proj_umma_split_weights(Wp.data(), hNpad, C, h16.data() + oHeads16);
+        h16.resize(h16.size() + (size_t)2 * hNpad * C);
+        heads_inv = proj_umma_split_weights(Wp.data(), hNpad, C, h16.data() + oHeads16);
     }
 
     int prev = 0;
@@ -976,6 +983,15 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         L.W = B + lo[l].W; L.att_src = B + lo[l].as; L.att_dst = B + lo[l].ad; L.Medge = B + lo[l].M;
         L.bias = B + lo[l].bias; L.bn_a = B + lo[l].a; L.bn_b = B + lo[l].b;
         L.Wsplit = (o16[l] != (size_t)-1 && m->blob16) ? m->blob16 + o16[l] : nullptr;
+        L.w_inv = winv[l];
+        L.out_mul = 0.f; L.out_add = 0.f;
+        {   // |bn_a (agg + bias) + bn_b| <= max|bn_a| * max|h| + max(|bn_a||bias| + |bn_b|)
+            const float *ba = hb.data() + lo[l].a, *bb = hb.data() + lo[l].b, *bi = hb.data() + lo[l].bias;
+            for (int c = 0; c < L.out; ++c) {
+                L.out_mul = fmaxf(L.out_mul, fabsf(ba[c]));
+                L.out_add = fmaxf(L.out_add, fabsf(ba[c]) * fabsf(bi[c]) + fabsf(bb[c]));
+            }
+        }
         m->layers.push_back(L);
         if (L.HC > m->hc_max) m->hc_max = L.HC;
     }
@@ -986,6 +1002,14 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     m->bias_fold0 = B + oFoldBias;
     m->hWsplit = (oHeads16 != (size_t)-1 && m->blob16) ? m->blob16 + oHeads16 : nullptr;
     m->hNpad = hNpad;
+    m->fold0_inv = fold0_inv; m->heads_inv = heads_inv;
+    m->mlp0_mul = 0.f; m->mlp0_add = 0.f;
+    for (int k = 0; k < C; ++k) {       // |relu(x W0^T + b0)| <= max_k sum_f |W0[k,f]| * max|x| + max_k |b0[k]|
+        float rs = 0.f;
+        for (int f = 0; f < F; ++f) rs += fabsf(hb[oW0 + (size_t)k * F + f]);
+        m->mlp0_mul = fmaxf(m->mlp0_mul, rs);
+        m->mlp0_add = fmaxf(m->mlp0_add, fabsf(hb[ob0 + k]));
+    }
     *out = m;
     return BGNN_OK;
 }
@@ -1005,7 +1029,7 @@ static size_t act_bytes(const bgnn_model* m, int64_t n) { return align_up((size_
 
 extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes) {
     if (!m || n_nodes < 0) return 0;
-    return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256;
+    return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256 /*operand maxima*/ + 256;
 }
 
 extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const float* x, const int32_t* rowptr,
@@ -1048,8 +1072,12 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     float* bufA = (float*)w; w += act_bytes(m, N);
     float* bufB = (float*)w; w += act_bytes(m, N);
     float* hbuf = (float*)w; w += act_bytes(m, N);
-    float* alpha = (float*)w;
+    float* alpha = (float*)w; w += align_up((size_t)N * 2 * m->d.heads * sizeof(float), 256);
+    // operand maxima for the fp16-split tensor-core GEMMs: [0] = max|x| (or max|MLP output|), [1+l] = max|h_l|
+    float* amax = (float*)w;
     const bgnn_model_desc& d = m->d;
+    BGNN_CHECK_ARG(d.layers + 1 <= 64, "too many layers");
+    if (g_use_umma) BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
     const int C = d.hidden, h2 = C / 2;
     int rc;
     // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C).  On the tensor-core path both are fused into the
@@ -1067,16 +1095,30 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
         const LayerDev& L = m->layers[l];
         { ProfScope ps(20 + l, s);
           if (l == 0 && fused0) {
+              if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
               UmmaArgs a = {};
-              a.M = N; a.K = C; a.Wsplit = m->Wfold0;
+              a.M = N; a.K = C; a.Wsplit = m->Wfold0; a.w_inv_scale = m->fold0_inv;
+              a.amax_src = amax; a.amax_mul = m->mlp0_mul; a.amax_add = m->mlp0_add; a.cmax_out = amax + 1;
               a.x = x; a.F = d.in_channels; a.W0 = m->feW0; a.b0 = m->feb0;
               a.Cout = hbuf; a.bias = m->bias_fold0; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha;
               a.Htot = L.H; a.CH = L.C;
               rc = launch_umma(a, L.HC, PM_MLP0, EM_PROJ, sms, s);
-          } else if (g_use_umma && L.Wsplit)
-              rc = launch_proj_umma(cur, N, L.in, L.Wsplit, L.HC, hbuf, L.att_src, L.att_dst, alpha, L.H, L.C, sms, s);
-          else
+          } else if (g_use_umma && L.Wsplit) {
+              UmmaArgs a = {};
+              a.A = cur; a.M = N; a.K = L.in; a.Wsplit = L.Wsplit; a.w_inv_scale = L.w_inv;
+              if (l == 0) {               // input = feature-extractor output (unfused): measure it
+                  if ((rc = launch_absmax(cur, N * L.in, amax, sms, s))) return rc;
+                  a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f;
+              } else {
+                  a.amax_src = amax + l; a.amax_mul = m->layers[l - 1].out_mul; a.amax_add = m->layers[l - 1].out_add;
+              }
+              a.cmax_out = amax + 1 + l;
+              a.Cout = hbuf; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha; a.Htot = L.H; a.CH = L.C;
+              rc = launch_umma(a, L.HC, PM_PLAIN, EM_PROJ, sms, s);
+          } else {
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
+              if (!rc && g_use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
+          }
           if (rc) return rc; }
         const int relu = l < d.layers - 1;
         { ProfScope ps(40 + l, s);
@@ -1092,7 +1134,9 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     if (g_use_umma && m->hWsplit) {         // one kernel: first layers on the tensor cores, the rest in its epilogue
         ProfScope ps(60, s);
         UmmaArgs a = {};
-        a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit;
+        a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit; a.w_inv_scale = m->heads_inv;
+        const LayerDev& LL = m->layers[d.layers - 1];
+        a.amax_src = amax + d.layers; a.amax_mul = LL.out_mul; a.amax_add = LL.out_add;
         a.hb0 = m->hb0; a.h2 = h2; a.nblk = nblk; a.ncls = d.num_classes;
         a.Wcls = m->Wcls; a.bcls = m->bcls; a.Wconf = m->Wconf; a.bconf = m->bconf; a.Wcorr = m->Wcorr; a.bcorr = m->bcorr;
         a.logits = logits; a.probs = probs; a.cls = cls; a.conf = conf; a.corr = corr; a.action = action;

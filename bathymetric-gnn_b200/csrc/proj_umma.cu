@@ -1,27 +1,32 @@
 // Projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 //
-//     C[M, N] = A[M, K] . W[N, K]^T      (fp32 in, fp32 out)     + optional alpha epilogue
+//     C[M, N] = A[M, K] . W[N, K]^T      (fp32 in, fp32 out)     + fused epilogues
 //
-// This is the `h = x W^T` of every GATConv layer (PyG GATConv.lin, called from models/gnn.py:175-176),
-// a skinny dense contraction: M = nodes (millions), N, K <= 256.  fp32 parity (atol 2e-5 on logits)
-// rules out plain bf16 / tf32 operands, so both operands are split into three bf16 terms
-// (a = a1 + a2 + a3, exact to 24 bits) and the six products with i + j <= 4 are accumulated in
-// fp32 in TMEM: error ~2^-23 per product, i.e. fp32-grade, at 1/6 of the bf16 tensor rate --
-// still ~8x the fp32 FMA pipe.
+// This is the `h = x W^T` of every GATConv layer (PyG GATConv.lin, called from models/gnn.py:175-176) and the first
+// layers of the output heads (gnn.py:191-260): skinny dense contractions, M = nodes (millions), N, K <= 256.
 //
-// The tensor core accumulates in fp32 with truncation (RZ), so a long accumulation chain biases the
-// result.  Following Ootomo & Yokota (2022) the leading product a1*b1 gets its OWN accumulator (K/16
-// chained MMAs only) and the five correction products go to a second accumulator that is 2^-8 smaller in
-// magnitude; the two are added in fp32 (RN) in the epilogue.
+// Precision.  fp32 parity (atol 2e-5 on the logits) rules out plain fp16 / bf16 / tf32 operands.  Both operands are
+// split into TWO fp16 terms (Ootomo & Yokota 2022, "halfhalf"):  a*s = a_hi + a_lo * 2^-11 with a_hi = fp16(a*s),
+// a_lo = fp16((a*s - a_hi) * 2^11), 22 significant bits in total, and the three products a_hi*b_hi, a_hi*b_lo, a_lo*b_hi
+// are accumulated in fp32 in TMEM -- half the tensor work of a 3-term bf16 split at the same fp32-grade accuracy
+// (dropped terms ~2^-22).  The tensor core accumulates with truncation, so the leading product gets its OWN accumulator
+// (K/16 chained MMAs) and the two correction products a second one; the epilogue adds them in fp32 (RN) as
+// main + corr * 2^-11.  fp16 has 5 exponent bits: each operand is scaled by a power of two `s` so that |a*s| < 1.  For W
+// the host knows the maximum; for A the kernel derives it from a device-side UPPER BOUND of max|A| that the previous
+// kernel left behind (every projection epilogue tracks max|C|; the layer in between is a convex combination followed by
+// an affine map, so |A| <= bn_mul * max|C| + bn_add).  Scaling by powers of two is exact and is undone in the epilogue.
 //
-// One persistent CTA per SM, 256 threads.  A "super tile" is MT x 128 rows (MT = 1 for N = 256, else 2);
-// TMEM holds {main, corr} x MT x N <= 512 columns.
-//   producers (all 8 warps): A chunk [MT*128 x 32] fp32 -> LDG.128 -> 3-way bf16 split -> STS into
-//                            K-major SWIZZLE_64B tiles; W splits (pre-split on the host) via cp.async
-//   MMA issue (one thread):  12 x tcgen05.mma.kind::f16 (M=128, N, K=16) per M tile and chunk,
-//                            tcgen05.commit -> mbarrier frees the stage (3-stage ring)
-//   epilogue (warp w -> TMEM lanes 32*(w%4)..): tcgen05.ld 32x32b.x32 of main and corr, fp32 add,
-//                            alpha_src / alpha_dst dot products per head, fp32 rows to global
+// One persistent CTA per SM, 576 threads, warp-specialised:
+//   loader (1 thread): each fp32 A chunk [MT*128 x 32] is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d,
+//       mbarrier complete_tx) into a raw ring 3-6 chunks ahead: HBM latency is hidden by the async engine, not by registers.
+//   producers (8 warps, two groups owning alternate K chunks): raw chunk -> 2-way fp16 split -> STS into K-major
+//       SWIZZLE_64B tiles; the W chunk (pre-split and pre-swizzled on the host) arrives by ONE cp.async.bulk per chunk,
+//       completing on the stage's mbarrier.
+//   MMA issue (one thread): 6 x tcgen05.mma.kind::f16 (M=128, N, K=16) per M tile and chunk, tcgen05.commit -> mbarrier
+//       frees the stage (4-stage ring).
+//   epilogue (8 warps; warp w <-> TMEM lanes 32*(w%4).., column half w/4 when N = 256): tcgen05.ld 32x32b.x32 of main
+//       and corr, rescale, bias, alpha_src / alpha_dst dot products per head, fp32 rows to global.  For N <= 128 the
+//       accumulators are double-buffered so the epilogue of one tile overlaps the MMAs of the next.
 //
 // Two fusions ride on the same pipeline (template modes):
 //   PM_MLP0   the producers compute the A operand on the fly as relu(x W0^T + b0) -- LocalFeatureExtractor's first
@@ -31,19 +36,32 @@
 //   EM_HEADS  the epilogue applies bias + ReLU to the concatenated first layers of the three heads and finishes them in
 //             registers (second layers, softmax / argmax / sigmoid / action; gnn.py:191-260, 392-405, 436-449): one
 //             thread per node, only the final per-node outputs are written.
-#include <cuda_bf16.h>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
 
 #include "common.cuh"
 #include "proj_umma.cuh"
 
 namespace {
 
-constexpr int UM_THREADS = 416;           // 4 epilogue warps + 1 MMA warp + 8 producer warps
-constexpr int KC = 32;                 // K elements per stage (64 B of bf16 = one SWIZZLE_64B row)
-constexpr int STAGES = 3;
+constexpr int KC = 32;                 // K elements per stage (64 B of fp16 = one SWIZZLE_64B row)
+constexpr int STAGES = 3;              // fp16 operand stages (conversion -> MMA decoupling)
 constexpr int TILE_M = 128;
+constexpr int NSPLIT = 2;              // hi, lo
 constexpr int A_TILE_BYTES = TILE_M * KC * 2;     // 8 KB per split
 constexpr uint32_t SBO_BYTES = 8 * KC * 2;        // 512 B between 8-row groups
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+// warp roles
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8, PROD_GROUPS = 2;
+constexpr int MMA_WARP = EPI_WARPS, LOAD_WARP = EPI_WARPS + 1, PROD_WARP0 = EPI_WARPS + 2;
+constexpr int UM_THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;                      // 576
+constexpr int PROD_GROUP_THREADS = PROD_WARPS / PROD_GROUPS * 32;                  // 128
+constexpr int MAX_RAW = 6;             // raw fp32 A ring (bulk-copied rows): depth chosen per shape
+// barrier slots
+constexpr int BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_TFULL = 2 * STAGES, BAR_TEMPTY = 2 * STAGES + 2, BAR_RFULL = 2 * STAGES + 4,
+              BAR_REMPTY = BAR_RFULL + MAX_RAW, NUM_BARS = BAR_REMPTY + MAX_RAW;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -58,6 +76,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) | version=1 [46,48) | layout=4 [61,64)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -70,7 +92,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -84,23 +106,15 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int c) {
     return (uint32_t)((r >> 3) * SBO_BYTES + (r & 7) * 64 + ((c ^ ((r & 7) >> 1)) << 4));
 }
 
-// Exact 3-way bf16 split of four fp32 values by TRUNCATION: a1 = top 16 bits of a, r1 = a - a1 (exact), a2 = top 16
-// bits of r1, a3 = r1 - a2 (<= 8 significant bits left, so its top 16 bits hold it exactly): a == a1 + a2 + a3.
-// Two integer ANDs + two FADDs per value and one PRMT per packed pair -- the producers are issue-bound.
-__device__ __forceinline__ void split4(const float4 v, uint2& s1, uint2& s2, uint2& s3) {
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    uint32_t h1[4], h2[4], h3[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        h1[i] = __float_as_uint(x[i]);
-        const float r1 = x[i] - __uint_as_float(h1[i] & 0xffff0000u);
-        h2[i] = __float_as_uint(r1);
-        const float r2 = r1 - __uint_as_float(h2[i] & 0xffff0000u);
-        h3[i] = __float_as_uint(r2);
-    }
-    s1.x = __byte_perm(h1[0], h1[1], 0x7632); s1.y = __byte_perm(h1[2], h1[3], 0x7632);
-    s2.x = __byte_perm(h2[0], h2[1], 0x7632); s2.y = __byte_perm(h2[2], h2[3], 0x7632);
-    s3.x = __byte_perm(h3[0], h3[1], 0x7632); s3.y = __byte_perm(h3[2], h3[3], 0x7632);
+// 2-way fp16 split of four scaled fp32 values: hi = fp16(a*s), lo = fp16((a*s - hi) * 2^11)  (a*s - hi is exact)
+__device__ __forceinline__ void split4h(const float4 v, float s, uint2& hi, uint2& lo) {
+    const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
+    const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((a0 - f01.x) * LO_SCALE, (a1 - f01.y) * LO_SCALE);
+    const __half2 l23 = __floats2half2_rn((a2 - f23.x) * LO_SCALE, (a3 - f23.y) * LO_SCALE);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
 
 constexpr int MLP0_MAXK = 128, MLP0_FP = 8;         // PM_MLP0: K <= 128 hidden units, F <= 8 inputs (padded to 8)
@@ -111,27 +125,33 @@ struct UmmaSmem {
     static constexpr int MT = N >= 128 ? 1 : 2;                  // M tiles per super tile
     static constexpr int SUPER_M = MT * TILE_M;
     static constexpr int B_TILE_BYTES = N * KC * 2;
-    static constexpr int STAGE_BYTES = MT * 3 * A_TILE_BYTES + 3 * B_TILE_BYTES;
+    static constexpr int STAGE_BYTES = MT * NSPLIT * A_TILE_BYTES + NSPLIT * B_TILE_BYTES;
     static constexpr int ACC_COLS = 2 * MT * N;                  // {main, corr} per M tile
     static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;   // double-buffered accumulators when TMEM allows:
                                                                   // the epilogue of super tile t overlaps the MMAs of t+1
     static constexpr int TMEM_COLS = ACC_COLS * ACC_STAGES <= 32 ? 32 : ACC_COLS * ACC_STAGES <= 64 ? 64 : ACC_COLS * ACC_STAGES <= 128 ? 128
                                      : ACC_COLS * ACC_STAGES <= 256 ? 256 : 512;
+    static constexpr int EPI_SPLIT = (EMODE == EM_PROJ && N == 256) ? 2 : 1;    // column halves handled by different epilogue warps
     static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * N : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;   // epilogue parameters
     static constexpr int PAR_P = PMODE == PM_MLP0 ? MLP0_MAXK * MLP0_FP + MLP0_MAXK : 0;              // producer parameters
-    static constexpr size_t BYTES = (size_t)STAGES * STAGE_BYTES + (PAR_E + PAR_P) * sizeof(float) + 128;
+    // PM_PLAIN: the A chunk [SUPER_M x 32] fp32 is fetched by TMA into a raw ring, RAW_STAGES chunks ahead
+    static constexpr int RAW_BYTES = PMODE == PM_PLAIN ? SUPER_M * KC * 4 : 0;
+    // The depth must be a multiple of the producer-group count so that a raw slot is always consumed by the SAME group:
+    // TMA copies may complete out of order, and a group that last saw the slot two phases ago would otherwise pass the
+    // parity wait of a phase that has not completed (then over-arrive on the empty barrier -> launch failure).
+    static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? 4 : N == 128 ? 6 : 2);
+    static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)RAW_STAGES * RAW_BYTES + (PAR_E + PAR_P) * sizeof(float) +
+                                    NUM_BARS * 8 + 16;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void st_global_v8(float* p, const float* x) {          // 256-bit store (PTX ISA 8.8, sm_100)
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
                  "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
 }
 
-// main + corrections of 32 accumulator columns of this thread's TMEM lane -> x[32] (fp32 add, RN)
-__device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_corr, float* x) {
+// (main + corr * 2^-11) * scale of 32 accumulator columns of this thread's TMEM lane -> x[32]
+__device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_corr, float scale, float* x) {
     uint32_t v[32], u[32];
 #define BGNN_TMEM_LD32(arr, addr)                                                                                              \
     asm volatile(                                                                                                              \
@@ -148,24 +168,17 @@ __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_
 #undef BGNN_TMEM_LD32
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+    for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j])) * scale;
 }
-
-// warp roles
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8, PROD_GROUPS = 2;
-constexpr int MMA_WARP = EPI_WARPS, PROD_WARP0 = EPI_WARPS + 1;
-constexpr int PROD_GROUP_THREADS = PROD_WARPS / PROD_GROUPS * 32;                  // 128
-static_assert(UM_THREADS == (EPI_WARPS + 1 + PROD_WARPS) * 32, "thread count / role mismatch");
-// barrier slots
-constexpr int BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_TFULL = 2 * STAGES, BAR_TEMPTY = 2 * STAGES + 2, NUM_BARS = 2 * STAGES + 4;
 
 template <int N, int PMODE, int EMODE>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
+proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA) {
     using S = UmmaSmem<N, PMODE, EMODE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw;                                                      // stage ring (1024 B aligned)
-    float* s_par = reinterpret_cast<float*>(base + (size_t)STAGES * S::STAGE_BYTES);      // epilogue parameters
+    unsigned char* raw = base + (size_t)STAGES * S::STAGE_BYTES;                         // raw fp32 A ring
+    float* s_par = reinterpret_cast<float*>(raw + (size_t)S::RAW_STAGES * S::RAW_BYTES);  // epilogue parameters
     float* s_prod = s_par + S::PAR_E;                                                     // producer parameters
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_prod + S::PAR_P);                      // NUM_BARS
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
@@ -177,9 +190,23 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
     const int nkc = K / KC;
     const int64_t n_super = (M + SUPER_M - 1) / SUPER_M;
 
+    // power-of-two operand scale from the upper bound of max|A|: |a * sA| < 1 (exact; undone in the epilogue)
+    float sA = 1.f, out_scale = P.w_inv_scale;
+    {
+        float bound = P.amax_add;
+        if (P.amax_src) bound = fmaf(P.amax_mul, __ldg(P.amax_src), P.amax_add);
+        const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);
+        const int es = 253 - e;                                     // biased exponent of 2^-(floor(log2 bound) + 1)
+        if (e > 0 && e < 255 && es >= 1 && es <= 253) {
+            sA = __uint_as_float((uint32_t)es << 23);
+            out_scale *= __uint_as_float((uint32_t)(254 - es) << 23);
+        }
+    }
+
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars[BAR_TFULL + a], 1); mbar_init(&bars[BAR_TEMPTY + a], EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars[BAR_TFULL + a], 1); mbar_init(&bars[BAR_TEMPTY + a], 4 * 32 * S::EPI_SPLIT); }
+        for (int r = 0; r < MAX_RAW; ++r) { mbar_init(&bars[BAR_RFULL + r], 1); mbar_init(&bars[BAR_REMPTY + r], PROD_GROUP_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (EMODE == EM_PROJ) {          // s_par = att_src [N] | att_dst [N] | bias [N]
@@ -232,38 +259,43 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
                 if ((int)(it % PROD_GROUPS) != grp) continue;
                 const int s = it % STAGES;
                 unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
-                constexpr uint32_t W_BYTES = 3 * S::B_TILE_BYTES;
+                constexpr uint32_t W_BYTES = NSPLIT * S::B_TILE_BYTES;
                 auto issue_w = [&]() {  // W chunk: the host pre-arranged [kc][split] tiles in the swizzled smem layout -> ONE bulk copy
                     const uint32_t bar = smem_u32(&bars[BAR_FULL + s]);
                     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(W_BYTES) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                                 ::"r"(smem_u32(stage + MT * 3 * A_TILE_BYTES)),
+                                 ::"r"(smem_u32(stage + MT * NSPLIT * A_TILE_BYTES)),
                                    "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + (size_t)kc * W_BYTES), "r"(W_BYTES), "r"(bar)
                                  : "memory");
                 };
                 if (PMODE == PM_PLAIN) {
-                    // A values first (long latency, registers only), then wait for the stage to be free
+                    // fp32 rows of this chunk from the raw ring (bulk-copied by the loader warp), then free the slot
+                    constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
+                    const int slot = it % RS;
+                    mbar_wait(&bars[BAR_RFULL + slot], (it / RS) & 1);
+                    const float* rsrc = reinterpret_cast<const float*>(raw + (size_t)slot * S::RAW_BYTES);
                     float4 av[A_F4];
 #pragma unroll
                     for (int i = 0; i < A_F4; ++i) {
-                        const int f = ptid + i * PROD_GROUP_THREADS;
-                        const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
-                        const int64_t gr = row0 + mt * TILE_M + r;
-                        av[i] = gr < M ? __ldg(reinterpret_cast<const float4*>(P.A + gr * K + kc * KC + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int f = ptid + i * PROD_GROUP_THREADS;           // (row, 16 B column) of the [SUPER_M x 32] chunk
+                        av[i] = *reinterpret_cast<const float4*>(rsrc + f * 4);
                     }
                     if (it >= STAGES) mbar_wait(&bars[BAR_EMPTY + s], ((it / STAGES) - 1) & 1);
                     if (ptid == 0) issue_w();
 #pragma unroll
-                    for (int i = 0; i < A_F4; ++i) {                   // 3-way bf16 split -> swizzled STS
+                    for (int i = 0; i < A_F4; ++i) {                   // 2-way fp16 split -> swizzled STS
                         const int f = ptid + i * PROD_GROUP_THREADS;
                         const int mt = f >> 10, rem = f & 1023, r = rem >> 3, c4 = rem & 7;
-                        uint2 s1, s2, s3;
-                        split4(av[i], s1, s2, s3);
-                        unsigned char* t0 = stage + (size_t)(mt * 3) * A_TILE_BYTES + sw64_off(r, c4 >> 1) + (c4 & 1) * 8;
-                        *reinterpret_cast<uint2*>(t0) = s1;
-                        *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = s2;
-                        *reinterpret_cast<uint2*>(t0 + 2 * A_TILE_BYTES) = s3;
+                        uint2 hi, lo;
+                        split4h(av[i], sA, hi, lo);
+                        unsigned char* t0 = stage + (size_t)(mt * NSPLIT) * A_TILE_BYTES + sw64_off(r, c4 >> 1) + (c4 & 1) * 8;
+                        *reinterpret_cast<uint2*>(t0) = hi;
+                        *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = lo;
                     }
+                    // Release the raw slot only AFTER the stores that consumed the loaded values: an arrive issued right
+                    // behind the LDS does not wait for their data, and the next TMA copy then overwrites rows that are still
+                    // being read (seen as scattered wrong rows under load).
+                    mbar_arrive(&bars[BAR_REMPTY + slot]);
                 } else {
                     // thread <-> node: its F inputs are loaded once, then the 32 hidden units of this chunk are
                     // relu(b0 + x W0^T) straight into the split tiles (W0 rows are warp-uniform broadcasts from smem)
@@ -292,12 +324,11 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
                                 a = fmaf(xr[mt][7], w1.w, a);
                                 o[u] = fmaxf(a + s_prod[MLP0_MAXK * MLP0_FP + k0 + u], 0.f);
                             }
-                            uint2 s1, s2, s3;
-                            split4(make_float4(o[0], o[1], o[2], o[3]), s1, s2, s3);
-                            unsigned char* t0 = stage + (size_t)(mt * 3) * A_TILE_BYTES + sw64_off(ptid, c4 >> 1) + (c4 & 1) * 8;
-                            *reinterpret_cast<uint2*>(t0) = s1;
-                            *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = s2;
-                            *reinterpret_cast<uint2*>(t0 + 2 * A_TILE_BYTES) = s3;
+                            uint2 hi, lo;
+                            split4h(make_float4(o[0], o[1], o[2], o[3]), sA, hi, lo);
+                            unsigned char* t0 = stage + (size_t)(mt * NSPLIT) * A_TILE_BYTES + sw64_off(ptid, c4 >> 1) + (c4 & 1) * 8;
+                            *reinterpret_cast<uint2*>(t0) = hi;
+                            *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = lo;
                         }
                     }
                 }
@@ -305,11 +336,30 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
                 mbar_arrive(&bars[BAR_FULL + s]);
             }
         }
+    } else if (warp == LOAD_WARP) {
+        // ===================== LOADER (one thread): A chunk [SUPER_M x 32] fp32 -> raw ring, ONE TMA tensor copy per chunk
+        // (rows past M are zero-filled by the tensor map's bounds check) =====================
+        if (PMODE == PM_PLAIN && lane == 0) {
+            constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
+            uint32_t it = 0;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+                const int row0 = (int)(st * SUPER_M);
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int slot = it % RS;
+                    if (it >= (uint32_t)RS) mbar_wait(&bars[BAR_REMPTY + slot], ((it / RS) - 1) & 1);
+                    const uint32_t bar = smem_u32(&bars[BAR_RFULL + slot]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)S::RAW_BYTES) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(smem_u32(raw + (size_t)slot * S::RAW_BYTES)), "l"(&tmapA), "r"(kc * KC), "r"(row0), "r"(bar)
+                                 : "memory");
+                }
+            }
+        }
     } else if (warp == MMA_WARP) {
         // ===================== MMA ISSUER (one thread) =====================
         if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = BF16, both K-major, N, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             uint32_t it = 0, t = 0;
             for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
                 const uint32_t as = t % S::ACC_STAGES;
@@ -319,20 +369,20 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
                     const int s = it % STAGES;
                     mbar_wait(&bars[BAR_FULL + s], (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint32_t sA = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB = sA + MT * 3 * A_TILE_BYTES;
+                    const uint32_t sA_ = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB_ = sA_ + MT * NSPLIT * A_TILE_BYTES;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         const uint32_t d_main = tmem_base + as * S::ACC_COLS + (uint32_t)(mt * 2 * N), d_corr = d_main + (uint32_t)N;
-                        // p = 0: leading product a1*b1 -> main; p = 1..5: corrections (i + j <= 4), smallest first -> corr
-                        const int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {0, 0, 1, 2, 0, 1};
+                        // p = 0: a_hi*b_hi -> main; p = 1, 2: a_lo*b_hi, a_hi*b_lo (both carry the 2^11 factor) -> corr
+                        const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
 #pragma unroll
-                        for (int p = 0; p < 6; ++p) {
+                        for (int p = 0; p < 3; ++p) {
 #pragma unroll
                             for (int ks = 0; ks < KC / 16; ++ks) {
-                                const uint64_t da = make_desc(sA + (mt * 3 + pa[p]) * A_TILE_BYTES + ks * 32);
-                                const uint64_t db = make_desc(sB + pb[p] * S::B_TILE_BYTES + ks * 32);
+                                const uint64_t da = make_desc(sA_ + (mt * NSPLIT + pa[p]) * A_TILE_BYTES + ks * 32);
+                                const uint64_t db = make_desc(sB_ + pb[p] * S::B_TILE_BYTES + ks * 32);
                                 const bool first = kc == 0 && ks == 0 && (p == 0 || p == 1);
-                                umma_bf16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
+                                umma_f16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
                             }
                         }
                     }
@@ -341,8 +391,12 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
                 umma_commit(&bars[BAR_TFULL + as]);                    // accumulators complete
             }
         }
-    } else {
-        // ===================== EPILOGUE: warp w <-> TMEM lanes 32w .. 32w+31, one thread per output row =====================
+    } else if ((warp >> 2) < S::EPI_SPLIT) {
+        // ===================== EPILOGUE: warp w <-> TMEM lanes 32*(w%4) .., one thread per output row =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        constexpr int NCOL = N / S::EPI_SPLIT;                 // columns owned by this warp
+        const int cbeg = half * NCOL;
+        float cmax = 0.f;
         uint32_t t = 0;
         for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
             const int64_t row0 = st * SUPER_M;
@@ -351,23 +405,34 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
-                const int64_t row = row0 + mt * TILE_M + warp * 32 + lane;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * S::ACC_COLS + (uint32_t)(mt * 2 * N);
+                const int64_t row = row0 + mt * TILE_M + quarter * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * S::ACC_COLS + (uint32_t)(mt * 2 * N);
                 if (EMODE == EM_PROJ) {
                     float as_acc = 0.f, ad_acc = 0.f;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < N; c0 += 32) {
+                    for (int c0 = cbeg; c0 < cbeg + NCOL; c0 += 32) {
                         float x[32];
-                        tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), x);
+                        tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), out_scale, x);
                         if (P.bias) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] += s_par[2 * N + c0 + j];
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(s_par + 2 * N + c0 + j);
+                                x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+                            }
+                        }
+                        if (P.cmax_out) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, fabsf(x[j]));
                         }
                         if (P.alpha) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                as_acc = fmaf(x[j], s_par[c0 + j], as_acc);
-                                ad_acc = fmaf(x[j], s_par[N + c0 + j], ad_acc);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(s_par + c0 + j);
+                                const float4 d4 = *reinterpret_cast<const float4*>(s_par + N + c0 + j);
+                                as_acc = fmaf(x[j], s4.x, as_acc); as_acc = fmaf(x[j + 1], s4.y, as_acc);
+                                as_acc = fmaf(x[j + 2], s4.z, as_acc); as_acc = fmaf(x[j + 3], s4.w, as_acc);
+                                ad_acc = fmaf(x[j], d4.x, ad_acc); ad_acc = fmaf(x[j + 1], d4.y, ad_acc);
+                                ad_acc = fmaf(x[j + 2], d4.z, ad_acc); ad_acc = fmaf(x[j + 3], d4.w, ad_acc);
                             }
                             if (((c0 + 32) % P.CH) == 0) {          // a head's channels are complete
                                 if (row < M) {
@@ -395,23 +460,35 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
 #pragma unroll 1
                     for (int c0 = 0; c0 < real; c0 += 32) {
                         float x[32];
-                        tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), x);
+                        tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), out_scale, x);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j] + s_par[c0 + j], 0.f);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(s_par + c0 + j);
+                            x[j] = fmaxf(x[j] + b.x, 0.f); x[j + 1] = fmaxf(x[j + 1] + b.y, 0.f);
+                            x[j + 2] = fmaxf(x[j + 2] + b.z, 0.f); x[j + 3] = fmaxf(x[j + 3] + b.w, 0.f);
+                        }
                         const int blk = c0 / h2, u0 = c0 - blk * h2;
                         if (blk == 0) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
                                 if (k < ncls) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) lg[k] = fmaf(x[j], w2[k * h2 + u0 + j], lg[k]);
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const float4 w = *reinterpret_cast<const float4*>(w2 + k * h2 + u0 + j);
+                                        lg[k] = fmaf(x[j], w.x, lg[k]); lg[k] = fmaf(x[j + 1], w.y, lg[k]);
+                                        lg[k] = fmaf(x[j + 2], w.z, lg[k]); lg[k] = fmaf(x[j + 3], w.w, lg[k]);
+                                    }
                                 }
-                        } else if (blk == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) pc = fmaf(x[j], w2[ncls * h2 + u0 + j], pc);
                         } else {
+                            const float* wv = w2 + (blk == 1 ? ncls : ncls + 1) * h2 + u0;
+                            float acc = 0.f;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) pr = fmaf(x[j], w2[(ncls + 1) * h2 + u0 + j], pr);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 w = *reinterpret_cast<const float4*>(wv + j);
+                                acc = fmaf(x[j], w.x, acc); acc = fmaf(x[j + 1], w.y, acc);
+                                acc = fmaf(x[j + 2], w.z, acc); acc = fmaf(x[j + 3], w.w, acc);
+                            }
+                            if (blk == 1) pc += acc; else pr += acc;
                         }
                     }
                     if (row < M) {
@@ -447,6 +524,11 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&bars[BAR_TEMPTY + as]);
         }
+        if (EMODE == EM_PROJ && P.cmax_out) {       // max |C| written by this launch (feeds the next kernel's operand scale)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(P.cmax_out), __float_as_uint(cmax));
+        }
     }
     // teardown
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -455,6 +537,31 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
     }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor map over A [M, K] fp32 (row-major) with a [box_rows x 32] box; out-of-range rows read as zero
+int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        BGNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { bgnn_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BGNN_E_CUDA; }
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for A=%p M=%lld K=%d", (int)r, (const void*)A, (long long)M, K); return BGNN_E_CUDA; }
+    return BGNN_OK;
 }
 
 template <int N, int PMODE, int EMODE>
@@ -469,27 +576,74 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
         BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
         configured[dev & 63] = true;
     }
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (PMODE == PM_PLAIN) {
+        BGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.A) & 15) == 0, "A must be 16-byte aligned");
+        int rc = make_tmap_A(a.A, a.M, a.K, S::SUPER_M, &tmap);
+        if (rc) return rc;
+    }
     const int64_t n_super = (a.M + S::SUPER_M - 1) / S::SUPER_M;
     const unsigned grid = (unsigned)(n_super < sms ? n_super : sms);
-    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a);
-    BGNN_LAUNCH_CHECK();
+    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        bgnn_set_error("proj_umma_kernel<N=%d, producer %d, epilogue %d> M=%lld K=%d: %s", N, PMODE, EMODE, (long long)a.M, a.K,
+                       cudaGetErrorString(e));
+        return BGNN_E_CUDA;
+    }
     return BGNN_OK;
 }
 
-uint16_t f32_to_bf16_rn(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);      // NaN
-    const uint32_t lsb = (u >> 16) & 1u;
-    u += 0x7fffu + lsb;
-    return (uint16_t)(u >> 16);
+// max |v| over n floats -> atomicMax on the bit pattern (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+    float m = 0.f;
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? n / 4 : 0;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = gid; i < n4; i += gsz) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(v) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+    }
+    for (int64_t i = n4 * 4 + gid; i < n; i += gsz) m = fmaxf(m, fabsf(__ldg(v + i)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
-float bf16_to_f32(uint16_t b) {
-    uint32_t u = (uint32_t)b << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
+
+// host fp16 conversions (round to nearest even)
+uint16_t f32_to_f16_rn(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | (x > 0x7f800000u ? 0x7e00u : 0x7c00u));
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                 // >= 65520 rounds to inf
+    if (x < 0x33000001u) return sign;                                        // <= 2^-25 rounds to zero
+    if (x < 0x38800000u) {                                                   // subnormal half (< 2^-14): units of 2^-24
+        const int e = (int)(x >> 23);
+        const uint32_t mant = (x & 0x7fffffu) | 0x800000u;
+        const int shift = 126 - e;
+        uint32_t r = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+        return (uint16_t)(sign | r);
+    }
+    const uint32_t e = (x >> 23) - 112u, mant = x & 0x7fffffu;
+    uint32_t r = (e << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
+    return (uint16_t)(sign | r);
 }
+float f16_to_f32(uint16_t h) {
+    const int e = (h >> 10) & 31, m = h & 1023;
+    float v;
+    if (e == 0) v = ldexpf((float)m, -24);
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = ldexpf((float)(m | 1024), e - 25);
+    return (h & 0x8000) ? -v : v;
+}
+
+static size_t sw64_off_host(int r, int c) { return (size_t)(r >> 3) * SBO_BYTES + (r & 7) * 64 + ((c ^ ((r & 7) >> 1)) << 4); }
 
 }  // namespace
 
@@ -501,24 +655,27 @@ bool proj_umma_supported(int N, int K, int CH, bool want_alpha) {
     return true;
 }
 
-// host: W [N,K] fp32 -> bf16 splits w1 + w2 + w3 (round to nearest), arranged as [K/32][3][N x 32 tile] where each tile
-// is ALREADY in the K-major SWIZZLE_64B shared-memory layout the MMA descriptors expect (one bulk copy per K chunk).
-static size_t sw64_off_host(int r, int c) { return (size_t)(r >> 3) * SBO_BYTES + (r & 7) * 64 + ((c ^ ((r & 7) >> 1)) << 4); }
-void proj_umma_split_weights(const float* W, int N, int K, uint16_t* out /*[K/32][3][N*32]*/) {
+// host: W [N,K] fp32 -> fp16 splits of W*s (s = power of two with max|W*s| < 1): hi = fp16(W s), lo = fp16((W s - hi) 2^11),
+// arranged as [K/32][2][N x 32 tile] where each tile is ALREADY in the K-major SWIZZLE_64B shared-memory layout the MMA
+// descriptors expect (one bulk copy per K chunk).  Returns 1/s.
+float proj_umma_split_weights(const float* W, int N, int K, uint16_t* out /*[K/32][2][N*32]*/) {
+    float mx = 0.f;
+    for (size_t i = 0; i < (size_t)N * K; ++i) mx = fmaxf(mx, fabsf(W[i]));
+    int e = 0;
+    if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);          // mx = m * 2^e, m in [0.5, 1)
+    const float s = ldexpf(1.f, -e), inv = ldexpf(1.f, e);
     const size_t tile = (size_t)N * KC;
     for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) {
-            const float w = W[(size_t)n * K + k];
-            const uint16_t b1 = f32_to_bf16_rn(w);
-            const float r1 = w - bf16_to_f32(b1);
-            const uint16_t b2 = f32_to_bf16_rn(r1);
-            const float r2 = r1 - bf16_to_f32(b2);
-            const uint16_t b3 = f32_to_bf16_rn(r2);
+            const float w = W[(size_t)n * K + k] * s;
+            const uint16_t hi = f32_to_f16_rn(w);
+            const uint16_t lo = f32_to_f16_rn((w - f16_to_f32(hi)) * LO_SCALE);
             const int kc = k / KC, kk = k % KC;
-            const size_t e = sw64_off_host(n, kk >> 3) / 2 + (kk & 7);
-            uint16_t* base = out + (size_t)kc * 3 * tile;
-            base[e] = b1; base[tile + e] = b2; base[2 * tile + e] = b3;
+            const size_t el = sw64_off_host(n, kk >> 3) / 2 + (kk & 7);
+            uint16_t* base = out + (size_t)kc * NSPLIT * tile;
+            base[el] = hi; base[tile + el] = lo;
         }
+    return inv;
 }
 
 bool proj_umma_mlp0_supported(int N, int K, int F) {
@@ -530,6 +687,15 @@ bool proj_umma_heads_supported(int K, int h2, int nblk, int ncls, int* Npad) {
     const int np = real <= 128 ? 128 : 256;
     if (Npad) *Npad = np;
     return h2 % 32 == 0 && h2 <= HEADS_MAXH2 && real <= 256 && ncls >= 1 && ncls <= 8 && K % KC == 0 && K >= KC;
+}
+
+int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s) {
+    if (n <= 0) return BGNN_OK;
+    int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(v, n, out);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
 }
 
 int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStream_t s) {
@@ -556,14 +722,6 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
     return BGNN_E_UNSUPPORTED;
 }
 
-int launch_proj_umma(const float* A, int64_t M, int K, const uint16_t* Wsplit, int N, float* C, const float* att_src,
-                     const float* att_dst, float* alpha, int Htot, int CH, int sms, cudaStream_t s) {
-    UmmaArgs a = {};
-    a.A = A; a.M = M; a.K = K; a.Wsplit = Wsplit; a.Cout = C; a.att_src = att_src; a.att_dst = att_dst; a.alpha = alpha;
-    a.Htot = alpha ? Htot : 1; a.CH = alpha ? CH : N;
-    return launch_umma(a, N, PM_PLAIN, EM_PROJ, sms, s);
-}
-
 // ---- test hook (declared in include/bgnn.h): C = A . W^T on the tensor-core path, W given as fp32 on the HOST
 extern "C" int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
                                    const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
@@ -572,16 +730,28 @@ extern "C" int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const f
     const int CH = heads > 0 ? N / heads : N;
     BGNN_CHECK_ARG(proj_umma_supported(N, K, CH, alpha_dev != nullptr), "shape N=%d K=%d not supported by the tcgen05 path", N, K);
     cudaStream_t s = (cudaStream_t)stream_;
-    std::vector<uint16_t> split((size_t)3 * N * K);
-    proj_umma_split_weights(W_host, N, K, split.data());
+    std::vector<uint16_t> split((size_t)NSPLIT * N * K);
+    const float winv = proj_umma_split_weights(W_host, N, K, split.data());
     uint16_t* d = nullptr;
+    float* amax = nullptr;
     BGNN_CUDA(cudaMalloc(&d, split.size() * 2));
+    BGNN_CUDA(cudaMalloc(&amax, 2 * sizeof(float)));
+    BGNN_CUDA(cudaMemsetAsync(amax, 0, 2 * sizeof(float), s));
     BGNN_CUDA(cudaMemcpyAsync(d, split.data(), split.size() * 2, cudaMemcpyHostToDevice, s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int rc = launch_proj_umma(A_dev, M, K, d, N, C_dev, att_src_dev, att_dst_dev, alpha_dev, heads, CH, sms, s);
+    int rc = launch_absmax(A_dev, M * K, amax, sms, s);
+    if (rc == BGNN_OK) {
+        UmmaArgs a = {};
+        a.A = A_dev; a.M = M; a.K = K; a.Wsplit = d; a.w_inv_scale = winv;
+        a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f; a.cmax_out = amax + 1;
+        a.Cout = C_dev; a.att_src = att_src_dev; a.att_dst = att_dst_dev; a.alpha = alpha_dev;
+        a.Htot = alpha_dev ? heads : 1; a.CH = alpha_dev ? CH : N;
+        rc = launch_umma(a, N, PM_PLAIN, EM_PROJ, sms, s);
+    }
     cudaStreamSynchronize(s);
     cudaFree(d);
+    cudaFree(amax);
     return rc;
 }

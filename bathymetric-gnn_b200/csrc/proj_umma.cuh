@@ -9,8 +9,11 @@ enum { PM_PLAIN = 0, PM_MLP0 = 1 };      // producer: A from global memory | A =
 enum { EM_PROJ = 0, EM_HEADS = 1 };      // epilogue: C (+bias) and alpha_src/alpha_dst | finish the three output heads
 
 struct UmmaArgs {
-    // operands: C[M,N] = A[M,K] . W[N,K]^T, W pre-split on the host into [3][N][K] bf16
-    const float* A; int64_t M; int K; const uint16_t* Wsplit;
+    // operands: C[M,N] = A[M,K] . W[N,K]^T, W pre-split (2 x fp16, scaled by 1/w_inv_scale) and pre-swizzled on the host
+    const float* A; int64_t M; int K; const uint16_t* Wsplit; float w_inv_scale;
+    // upper bound of max|A| = amax_mul * (*amax_src) + amax_add (amax_src may be NULL) -> power-of-two operand scale
+    const float* amax_src; float amax_mul, amax_add;
+    float* cmax_out;          // EM_PROJ, optional: atomicMax of |C| over everything this launch writes
     // PM_MLP0: A[m,k] = relu(b0[k] + sum_f x[m,f] W0[k,f]), x [M,F] row-major, F <= 8, K <= 128
     const float* x; int F; const float* W0; const float* b0;
     // EM_PROJ: Cout [M,N] (+ bias [N], optional); alpha (optional) [M, 2*Htot] from att_src / att_dst [N]
@@ -26,10 +29,9 @@ struct UmmaArgs {
 bool proj_umma_supported(int N, int K, int CH, bool want_alpha);
 bool proj_umma_mlp0_supported(int N, int K, int F);               // PM_MLP0 + EM_PROJ
 bool proj_umma_heads_supported(int K, int h2, int nblk, int ncls, int* Npad);   // PM_PLAIN + EM_HEADS
-// host: W [N,K] fp32 -> three bf16 matrices [3][N][K] with W = w1 + w2 + w3 (round-to-nearest splits)
-void proj_umma_split_weights(const float* W, int N, int K, uint16_t* out);
-// C[M,N] = A[M,K] . W^T; alpha (optional) [M, 2*Htot]: per-head dot products with att_src / att_dst
-int launch_proj_umma(const float* A, int64_t M, int K, const uint16_t* Wsplit, int N, float* C, const float* att_src,
-                     const float* att_dst, float* alpha, int Htot, int CH, int sms, cudaStream_t s);
+// host: W [N,K] fp32 -> 2 x fp16 split of W*s, [K/32][2][N x 32 swizzled tile] (2*N*K uint16); returns 1/s
+float proj_umma_split_weights(const float* W, int N, int K, uint16_t* out);
+// max |v| over n floats, atomicMax into *out (float bits; zero it first)
+int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s);
 // general entry: N = accumulator width (for EM_HEADS the padded width)
 int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStream_t s);
