@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbgnn.so")
+LIB_PATH = os.environ.get("BGNN_LIB") or os.path.join(HERE, "libbgnn.so")      # BGNN_LIB: instrumented dev builds (tools/)
 
 MAX_OFFSETS, MAX_NODE_FEATS, MAX_EDGE_FEATS = 24, 8, 4
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3, -4
@@ -42,7 +42,7 @@ class ModelDesc(C.Structure):
 
 class GridTopo(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("node_id", C.c_void_p), ("n_offsets", C.c_int32),
-                ("off_dr", C.c_int32 * MAX_OFFSETS), ("off_dc", C.c_int32 * MAX_OFFSETS)]
+                ("off_dr", C.c_int32 * MAX_OFFSETS), ("off_dc", C.c_int32 * MAX_OFFSETS), ("grid_eattr", C.c_void_p)]
 
 
 class Survey(C.Structure):
@@ -58,13 +58,14 @@ SYMBOLS = {
     "bgnn_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "bgnn_graph_scratch_bytes": (SZ, [I64, I32]),
     "bgnn_graph_count": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, C.POINTER(I64), P]),
-    "bgnn_graph_emit": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, P, P, P, P, P, P, P]),
+    "bgnn_graph_emit": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, P, P, P, P, P, P, P, P]),
     "bgnn_graph_coo": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, I64, P, P, P]),
     "bgnn_model_param_floats": (I64, [C.POINTER(ModelDesc)]),
     "bgnn_model_create": (C.c_int, [C.POINTER(ModelDesc), P, I64, C.c_int, C.POINTER(P)]),
     "bgnn_model_destroy": (None, [P]),
     "bgnn_gat_workspace_bytes": (SZ, [P, I64]),
     "bgnn_gat_forward": (C.c_int, [P, I64, I64, P, P, P, P, P, SZ, P, P, P, P, P, P, F32, F32, P, P, P]),
+    "bgnn_gat_grid_path": (C.c_int, [P, C.POINTER(GridTopo), I64]),
     "bgnn_scatter_tile": (C.c_int, [P, I64, P, P, P, P, F32, P, P, P, P]),
     "bgnn_graph_to_grid": (C.c_int, [P, I64, P, F32, P, P]),
     "bgnn_stitch_init": (C.c_int, [C.POINTER(Survey), P]),

@@ -24,6 +24,9 @@
 
 static bool g_use_umma = true;
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
+#ifdef BGNN_AGG_TIMING
+extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset);
+#endif
 
 struct LayerDev {
     int in, H, C, HC, out;
@@ -226,7 +229,8 @@ gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K
                     if (bias && gn + j < N) v[j] += __ldg(bias + gn + j);
                     if (relu) v[j] = fmaxf(v[j], 0.f);
                 }
-                float* p = Cout + gm * ldc + gn;
+                // projections (ALPHA) store h head-major: [Htot][M][CH], one contiguous plane per head
+                float* p = ALPHA ? Cout + ((int64_t)(gn / CH) * M + gm) * CH + (gn % CH) : Cout + gm * ldc + gn;
                 if (gn + 3 < N && (ldc % 4 == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
                 else
                     for (int j = 0; j < 4; ++j)
@@ -414,7 +418,7 @@ gat_aggregate(const float* __restrict__ h, const float* __restrict__ alpha, cons
                 const int j = s_j[warp][q];
                 const float a = s_a[warp][q][my_head];
                 float hv[VEC];
-                VecIO<VEC>::ld(h + (int64_t)j * HC + lane * VEC, hv);
+                VecIO<VEC>::ld(h + ((int64_t)my_head * N + j) * C + (lane * VEC) % C, hv);       // h is head-major [H][N][C]
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a, hv[v], acc[v]);
             }
@@ -468,6 +472,15 @@ int launch_agg(const LayerDev& L, const float* h, const float* alpha, const int3
 // lane <-> channels and a 3x3 sliding register window, so each step loads only the 3 new source rows of the window's
 // right column.  The FMAs run in the reference's edge order (offset k ascending, source = i - off_k, self loop last),
 // i.e. the same arithmetic as gat_aggregate; absent neighbours contribute fma(0, 0, acc) == acc.
+#ifdef BGNN_AGG_TIMING
+__device__ unsigned long long g_agg_t[8];
+#define AGG_T0() long long t_prev = clock64()
+#define AGG_TICK(slot) do { if (threadIdx.x == 0) { long long t_now = clock64(); atomicAdd(&g_agg_t[slot], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
+#else
+#define AGG_T0()
+#define AGG_TICK(slot)
+#endif
+
 struct TopoDev {
     int rows, cols;
     const int32_t* node_id;
@@ -479,7 +492,10 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 
 template <int H, int C, int PH> struct TileCfg {
     static constexpr int PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, NT = PH * PW, AST = 12;
-    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST) * 4 + 16;
+    // alpha_src / alpha_dst of the halo arrive by bulk copy (one per run) when a node's 2H floats are a 16 B multiple and
+    // the landing area fits the (not yet used) attention-weight buffer; otherwise they are loaded cell by cell
+    static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= NT * AST;
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C) * 4 + 32;
 };
 
 // window position p = dy*3 + dx (dy, dx in 0..2 <-> source at row r-1+dy, column c-1+dx) visited in reference edge order
@@ -491,28 +507,46 @@ template <bool CONN4> struct EdgeOrder {
     }
 };
 
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
 template <int H, int C, int PH, bool CONN4>
 __global__ void __launch_bounds__(PH * 16, (C <= 64 ? 2 : 1))
 gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha, const TopoDev T,
-                   const int32_t* __restrict__ rowptr, const float* __restrict__ eattr, int ED,
+                   const float* __restrict__ grid_eattr, int ED,
                    const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
-                   const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out) {
+                   const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t n_nodes) {
     using G = TileCfg<H, C, PH>;
     using O = EdgeOrder<CONN4>;
-    constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, AST = G::AST;
+    constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, AST = G::AST, HR = G::HR;
     constexpr int VEC = C / 32, HC = H * C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
     int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
     float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [H][NSLOT]   alpha_src per halo cell
     float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    3x3 attention weights of the current head
-    uint64_t* bar = reinterpret_cast<uint64_t*>(a_sm + NT * AST);
+    float* al_sm = a_sm;                                       // [NSLOT][2H]  landing area of the alpha bulk copies (setup only)
+    float* M_s = a_sm + NT * AST;                              // [ED_MAX][H]  folded edge projection
+    float* s_bn = M_s + BGNN_MAX_EDGE_FEATS * H;               // [3][HC]      bias | bn scale | bn shift
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_bn + 3 * HC);// [0] source rows, [1] alpha
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pr0 = blockIdx.y * PH, pc0 = blockIdx.x * 16;
+    AGG_T0();
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(NT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar + 1)), "r"(HR));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int s = tid; s < NSLOT; s += NT) {
@@ -520,70 +554,96 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
         int id = -1;
         if (r >= 0 && r < T.rows && c >= 0 && c < T.cols) id = __ldg(T.node_id + (int64_t)r * T.cols + c);
         ids[s] = id;
-        if (id >= 0) {
+    }
+    for (int i = tid; i < HC; i += NT) { s_bn[i] = __ldg(bias + i); s_bn[HC + i] = __ldg(bn_a + i); s_bn[2 * HC + i] = __ldg(bn_b + i); }
+    if (tid < BGNN_MAX_EDGE_FEATS * H) M_s[tid] = (tid / H) < ED ? __ldg(Medge + tid) : 0.f;
+    // this destination's dense in-edge features (slot k <-> source i - off_k; zeros where the edge is absent): fetched
+    // straight from the per-cell layout, independent of the node ids, so the loads fly during the id round trip
+    const int cs = (tid / 16 + 1) * HW + (tid % 16 + 1);
+    float ea[8][BGNN_MAX_EDGE_FEATS];
 #pragma unroll
-            for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
+    {
+        const int r = pr0 + tid / 16, c = pc0 + tid % 16;
+        if (ED > 0 && r < T.rows && c < T.cols) {
+            const float* ge = grid_eattr + ((int64_t)r * T.cols + c) * (T.K * ED);
+            if (T.K == 8 && ED == 3) {
+                float v[24];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ge) + q);
+                    v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) ea[k][d] = v[k * 3 + d];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                        if (k < T.K && d < ED) ea[k][d] = __ldg(ge + k * ED + d);
+            }
         }
     }
     __syncthreads();
+    AGG_TICK(0);
 
-    // ---- per-destination state (thread t <-> cell t of the patch)
-    const int cs = (tid / 16 + 1) * HW + (tid % 16 + 1);
-    const int myid = ids[cs];
-    float ea[8][BGNN_MAX_EDGE_FEATS], lsum[BGNN_MAX_EDGE_FEATS], ad[H], M[BGNN_MAX_EDGE_FEATS][H];
-    unsigned nbv = 0;
-#pragma unroll
-    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) {
-        lsum[d] = 0.f;
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) M[d][hh] = d < ED ? __ldg(Medge + d * H + hh) : 0.f;
-    }
-#pragma unroll
-    for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
-    {
-        // Edge attributes of a patch row are one contiguous CSR range (consecutive valid cells have consecutive
-        // node ids): stage them with coalesced loads into the (not yet used) row buffer, then each destination
-        // picks its <= 8 x ED values from shared memory.
-        constexpr int STG = 16 * 8 * BGNN_MAX_EDGE_FEATS;            // floats per patch row
-        float* stage = rows;
-        __shared__ int s_e0[PH], s_e1[PH];
-        if (tid < PH) {
-            int first = -1, last = -1;
-            for (int c = 0; c < 16; ++c) {
-                const int id = ids[(tid + 1) * HW + c + 1];
-                if (id >= 0) { if (first < 0) first = id; last = id; }
-            }
-            s_e0[tid] = first >= 0 ? __ldg(rowptr + first) : 0;
-            s_e1[tid] = first >= 0 ? __ldg(rowptr + last + 1) : 0;
-        }
-        __syncthreads();
-        for (int pr = warp; pr < PH; pr += NT / 32) {
-            const int e0 = s_e0[pr], n = (s_e1[pr] - e0) * ED;
-            const float* src = eattr + (int64_t)e0 * ED;
-            for (int i = lane; i < n; i += 32) stage[pr * STG + i] = __ldg(src + i);
-        }
-        __syncthreads();
-        if (myid >= 0) {
-            const int pr = tid / 16;
-            int off = (__ldg(rowptr + myid) - s_e0[pr]) * ED, deg = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
-                if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {      // in-edge from i - off_k
-                    nbv |= 1u << k;
-#pragma unroll
-                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
-                        if (d < ED) { ea[k][d] = stage[pr * STG + off + d]; lsum[d] += ea[k][d]; }
-                    off += ED; ++deg;
+    // ---- bulk copies: every run of valid cells in a halo row is ONE contiguous chunk, because adjacent valid cells of a
+    //      grid row have consecutive node ids, h is head-major ([H][N][C]) and alpha is [N][2H]
+    auto issue_rows = [&](int hh) {
+        if (tid < HR) {
+            const float* hp = h + (int64_t)hh * n_nodes * C;
+            const int s0 = tid * HW;
+            int run = -1;
+            for (int c = 0; c <= HW; ++c) {
+                const int id = c < HW ? ids[s0 + c] : -1;
+                if (id >= 0 && run < 0) run = c;
+                if (id < 0 && run >= 0) {
+                    bulk_g2s(rows + (s0 + run) * C, hp + (int64_t)ids[s0 + run] * C, (uint32_t)(c - run) * C * 4, bar);
+                    run = -1;
                 }
             }
-#pragma unroll
-            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
-#pragma unroll
-            for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
         }
-        __syncthreads();                                             // stage aliases rows: done before the copies start
+    };
+    if (G::ALPHA_BULK && tid < HR) {
+        const int s0 = tid * HW;
+        int run = -1;
+        for (int c = 0; c <= HW; ++c) {
+            const int id = c < HW ? ids[s0 + c] : -1;
+            if (id >= 0 && run < 0) run = c;
+            if (id < 0 && run >= 0) {
+                bulk_g2s(al_sm + (s0 + run) * 2 * H, alpha + (int64_t)ids[s0 + run] * 2 * H, (uint32_t)(c - run) * 2 * H * 4, bar + 1);
+                run = -1;
+            }
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar + 1)) : "memory");
+    }
+    issue_rows(0);
+
+    // ---- per-destination state (thread t <-> cell t of the patch)
+    const int myid = ids[cs];
+    float lsum[BGNN_MAX_EDGE_FEATS], ad[H];
+    unsigned nbv = 0;
+#pragma unroll
+    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
+    if (myid >= 0) {
+        int deg = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {      // in-edge from i - off_k
+                nbv |= 1u << k;
+                ++deg;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] += ea[k][d];
+            }
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
     }
     // rows of invalid halo cells stay zero for every head (the bulk copies never touch them)
     for (int s = tid; s < NSLOT; s += NT)
@@ -591,6 +651,32 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
 #pragma unroll
             for (int q = 0; q < C / 4; ++q) *reinterpret_cast<float4*>(rows + s * C + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    if (G::ALPHA_BULK) {
+        mbar_wait_parity(bar + 1, 0);
+        for (int s = tid; s < NSLOT; s += NT)
+            if (ids[s] >= 0) {
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = al_sm[s * 2 * H + hh];
+            }
+        if (myid >= 0) {
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) ad[hh] = al_sm[cs * 2 * H + H + hh];
+        }
+    } else {
+        for (int s = tid; s < NSLOT; s += NT) {
+            const int id = ids[s];
+            if (id >= 0) {
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
+            }
+        }
+        if (myid >= 0) {
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
+        }
+    }
+    __syncthreads();                 // asrc complete; the alpha landing area (aliases a_sm) is free
+    AGG_TICK(1);
     // window position of in-edge k (source = i - off_k)
     int wpos[8];
 #pragma unroll
@@ -598,16 +684,10 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
 
 #pragma unroll 1
     for (int hh = 0; hh < H; ++hh) {
-        // 1. stage the source rows of head hh: one bulk copy of 4*C bytes per valid halo cell
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic accesses of `rows` before async writes
-        for (int s = tid; s < NSLOT; s += NT) {
-            const int id = ids[s];
-            if (id >= 0) {
-                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(C * 4) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                             ::"r"(smem_addr(rows + s * C)), "l"(h + (int64_t)id * HC + hh * C), "r"(C * 4), "r"(smem_addr(bar))
-                             : "memory");
-            }
+        // 1. stage the source rows of head hh (head 0 was issued during the setup)
+        if (hh > 0) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic accesses of `rows` before async writes
+            issue_rows(hh);
         }
         // 2. scores + softmax of this head while the copies are in flight -> a_sm[t][window position]
         {
@@ -615,6 +695,11 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             az[0] = make_float4(0.f, 0.f, 0.f, 0.f); az[1] = make_float4(0.f, 0.f, 0.f, 0.f); az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (myid >= 0) {
+            float Mh[BGNN_MAX_EDGE_FEATS], adh = ad[0];
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) Mh[d] = M_s[d * H + hh];
+#pragma unroll
+            for (int q = 1; q < H; ++q) adh = (q == hh) ? ad[q] : adh;
             float sc[9], mx = -CUDART_INF_F;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -622,8 +707,8 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                 if ((nbv >> k) & 1u) {
                     float ae = 0.f;
 #pragma unroll
-                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], M[d][hh], ae);
-                    float v = (asrc[hh * NSLOT + cs - T.dr[k] * HW - T.dc[k]] + ad[hh]) + ae;
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], Mh[d], ae);
+                    float v = (asrc[hh * NSLOT + cs - T.dr[k] * HW - T.dc[k]] + adh) + ae;
                     v = v > 0.f ? v : v * slope;
                     sc[k] = v;
                     mx = fmaxf(mx, v);
@@ -632,8 +717,8 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             {
                 float ae = 0.f;
 #pragma unroll
-                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], M[d][hh], ae);
-                float v = (asrc[hh * NSLOT + cs] + ad[hh]) + ae;
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], Mh[d], ae);
+                float v = (asrc[hh * NSLOT + cs] + adh) + ae;
                 v = v > 0.f ? v : v * slope;
                 sc[8] = v;
                 mx = fmaxf(mx, v);
@@ -650,21 +735,17 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                 if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] / sum;
             a_sm[tid * AST + 4] = sc[8] / sum;
         }
+        AGG_TICK(2);
         // 3. all threads arrive (release: a_sm, zero rows), then wait for the arrivals and the copied bytes
-        {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
-            uint32_t ok;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                             : "=r"(ok) : "r"(smem_addr(bar)), "r"((uint32_t)(hh & 1)) : "memory");
-            } while (!ok);
-        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+        mbar_wait_parity(bar, (uint32_t)(hh & 1));
+        AGG_TICK(3);
         // 4. aggregate: warp w walks patch rows 2w, 2w+1; lane <-> VEC channels; 3x3 sliding window in registers
         float bs[VEC], ba[VEC], bb[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int ch = hh * C + lane * VEC + v;
-            bs[v] = __ldg(bias + ch); ba[v] = __ldg(bn_a + ch); bb[v] = __ldg(bn_b + ch);
+            bs[v] = s_bn[ch]; ba[v] = s_bn[HC + ch]; bb[v] = s_bn[2 * HC + ch];
         }
         auto ldrow = [&](const float* p, float* dst) {
             if (VEC == 1) dst[0] = p[0];
@@ -715,14 +796,17 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                 }
             }
         }
+        AGG_TICK(4);
         __syncthreads();                     // every warp is done with rows / a_sm before the next head overwrites them
+        AGG_TICK(5);
     }
 }
 
 template <int H, int C, int PH, bool CONN4>
-int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
-                      const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
+int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const float* grid_eattr,
+                      int ED, int relu, float slope, float* out, int64_t n_nodes, cudaStream_t s) {
     using G = TileCfg<H, C, PH>;
+    static_assert(G::SMEM <= 232448, "shared memory budget exceeded");
     static bool configured[64] = {};                    // the attribute is per device
     auto kern = gat_aggregate_tile<H, C, PH, CONN4>;
     int dev = 0;
@@ -732,25 +816,34 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
         configured[dev & 63] = true;
     }
     dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
-    kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, rowptr, eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out);
+    kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
 
-// returns 1 if no tiled instantiation fits (caller falls back to the CSR kernel)
-int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const int32_t* rowptr,
-                    const float* eattr, int ED, int relu, float slope, float* out, cudaStream_t s) {
-    // the reference's own offset lists (graph_construction.py:79-87); any other radius-1 list takes the CSR kernel
+// the reference's own offset lists (graph_construction.py:79-87) in their order; a tiled instantiation exists for (H, C)
+static bool tile_supported(const TopoDev& T, int H, int C, int ED, const float* grid_eattr, bool* conn4) {
     static const int r8[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, c8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
     static const int r4[4] = {-1, 1, 0, 0}, c4[4] = {0, 0, -1, 1};
     bool is8 = T.K == 8, is4 = T.K == 4;
     for (int k = 0; k < 8 && is8; ++k) is8 = T.dr[k] == r8[k] && T.dc[k] == c8[k];
     for (int k = 0; k < 4 && is4; ++k) is4 = T.dr[k] == r4[k] && T.dc[k] == c4[k];
-    if (!is8 && !is4) return 1;
+    if (!is8 && !is4) return false;
+    if (ED > 0 && !grid_eattr) return false;           // the dense per-cell edge features are required
+    if (conn4) *conn4 = is4;
+    const bool hok = H == 1 || H == 2 || H == 4 || H == 8;
+    return (C == 32 || C == 64) ? hok : (C == 128 ? (H == 1 || H == 2 || H == 4) : false);
+}
+
+// returns 1 if no tiled instantiation fits (caller falls back to the CSR kernel)
+int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const float* grid_eattr,
+                    int ED, int relu, float slope, float* out, int64_t n_nodes, cudaStream_t s) {
+    bool is4 = false;
+    if (!tile_supported(T, L.H, L.C, ED, grid_eattr, &is4)) return 1;
 #define TCASE(H_, C_, PH_)                                                                                              \
     if (L.H == H_ && L.C == C_)                                                                                         \
-        return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)       \
-                   : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, rowptr, eattr, ED, relu, slope, out, s)
+        return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, s)       \
+                   : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, s)
     TCASE(4, 64, 16); TCASE(1, 64, 16); TCASE(2, 64, 16); TCASE(8, 64, 16);
     TCASE(1, 32, 16); TCASE(2, 32, 16); TCASE(4, 32, 16); TCASE(8, 32, 16);
     TCASE(1, 128, 8); TCASE(2, 128, 8); TCASE(4, 128, 8);
@@ -1032,6 +1125,25 @@ extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes)
     return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256 /*operand maxima*/ + 256;
 }
 
+static bool topo_to_dev(const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
+    if (!(topo && topo->node_id && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0)) return false;
+    T.rows = topo->rows; T.cols = topo->cols; T.node_id = topo->node_id; T.K = topo->n_offsets;
+    for (int k = 0; k < 8; ++k) {
+        T.dr[k] = k < T.K ? topo->off_dr[k] : 0;
+        T.dc[k] = k < T.K ? topo->off_dc[k] : 0;
+        if (k < T.K && (abs(T.dr[k]) > 1 || abs(T.dc[k]) > 1)) return false;
+    }
+    return true;
+}
+
+extern "C" int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* topo, int64_t n_edges) {
+    TopoDev T;
+    if (!m || !topo_to_dev(topo, n_edges, T)) return 0;
+    for (const LayerDev& L : m->layers)
+        if (!tile_supported(T, L.H, L.C, m->d.edge_dim, topo->grid_eattr, nullptr)) return 0;
+    return 1;
+}
+
 extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const float* x, const int32_t* rowptr,
                                 const int32_t* csr_src, const float* csr_eattr, void* workspace, size_t workspace_bytes,
                                 float* logits, float* probs, int64_t* cls, float* conf, float* corr, int64_t* action,
@@ -1040,9 +1152,11 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     BGNN_CHECK_ARG(m, "model is null");
     BGNN_CHECK_ARG(N >= 0 && E >= 0, "negative sizes");
     if (N == 0) return BGNN_OK;
-    BGNN_CHECK_ARG(x && rowptr, "x / rowptr are null");
-    BGNN_CHECK_ARG(E == 0 || csr_src, "csr_src is null");
-    BGNN_CHECK_ARG(m->d.edge_dim == 0 || E == 0 || csr_eattr, "model has edge_dim>0 but csr_eattr is null");
+    BGNN_CHECK_ARG(x, "x is null");
+    const bool grid_only = bgnn_gat_grid_path(m, topo, E) == 1;       // every layer tiled: the CSR payload is not read
+    BGNN_CHECK_ARG(grid_only || rowptr, "rowptr is null");
+    BGNN_CHECK_ARG(grid_only || E == 0 || csr_src, "csr_src is null");
+    BGNN_CHECK_ARG(grid_only || m->d.edge_dim == 0 || E == 0 || csr_eattr, "model has edge_dim>0 but csr_eattr is null");
     BGNN_CHECK_ARG(N < (int64_t)2000000000 && E < (int64_t)2000000000, "graph too large for int32 indices");
     if (workspace_bytes < bgnn_gat_workspace_bytes(m, N) || !workspace) {
         bgnn_set_error("workspace too small: %zu < %zu", workspace_bytes, bgnn_gat_workspace_bytes(m, N));
@@ -1056,16 +1170,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
 
     // grid path: radius-1 stencil (4-/8-connected) on a single tile
     TopoDev T;
-    bool tiled = false;
-    if (topo && topo->node_id && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0) {
-        tiled = true;
-        T.rows = topo->rows; T.cols = topo->cols; T.node_id = topo->node_id; T.K = topo->n_offsets;
-        for (int k = 0; k < 8; ++k) {
-            T.dr[k] = k < T.K ? topo->off_dr[k] : 0;
-            T.dc[k] = k < T.K ? topo->off_dc[k] : 0;
-            if (k < T.K && (abs(T.dr[k]) > 1 || abs(T.dc[k]) > 1)) tiled = false;
-        }
-    }
+    const bool tiled = topo_to_dev(topo, E, T);
 
     char* w = (char*)workspace;
     w = (char*)align_up((size_t)w, 256);
@@ -1101,7 +1206,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               a.amax_src = amax; a.amax_mul = m->mlp0_mul; a.amax_add = m->mlp0_add; a.cmax_out = amax + 1;
               a.x = x; a.F = d.in_channels; a.W0 = m->feW0; a.b0 = m->feb0;
               a.Cout = hbuf; a.bias = m->bias_fold0; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha;
-              a.Htot = L.H; a.CH = L.C;
+              a.Htot = L.H; a.CH = L.C; a.head_major = 1;
               rc = launch_umma(a, L.HC, PM_MLP0, EM_PROJ, sms, s);
           } else if (g_use_umma && L.Wsplit) {
               UmmaArgs a = {};
@@ -1114,6 +1219,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               }
               a.cmax_out = amax + 1 + l;
               a.Cout = hbuf; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha; a.Htot = L.H; a.CH = L.C;
+              a.head_major = 1;
               rc = launch_umma(a, L.HC, PM_PLAIN, EM_PROJ, sms, s);
           } else {
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
@@ -1123,7 +1229,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
         const int relu = l < d.layers - 1;
         { ProfScope ps(40 + l, s);
           rc = 1;
-          if (tiled) rc = launch_agg_tile(L, hbuf, alpha, T, rowptr, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, s);
+          if (tiled) rc = launch_agg_tile(L, hbuf, alpha, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, s);
           if (rc == 1) rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s);
           if (rc) return rc; }
         float* t = cur; cur = nxt; nxt = t;
@@ -1154,3 +1260,11 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
+
+#ifdef BGNN_AGG_TIMING
+extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_agg_t, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_agg_t, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -224,7 +224,7 @@ __device__ __forceinline__ void edge_attr_write(const GraphParams& P, float* __r
 __global__ void __launch_bounds__(GB_THREADS) gb_emit(const GraphParams P, const int32_t* __restrict__ node_id,
                                                       const int32_t* __restrict__ rowptr, float* __restrict__ xout,
                                                       float* __restrict__ local_std, int32_t* __restrict__ csr_src,
-                                                      float* __restrict__ csr_eattr) {
+                                                      float* __restrict__ csr_eattr, float* __restrict__ grid_eattr) {
     const int64_t t = (int64_t)blockIdx.x * GB_THREADS + threadIdx.x;
     if (t >= P.cells.n_cells) return;
     const int id = node_id[t];
@@ -275,7 +275,46 @@ __global__ void __launch_bounds__(GB_THREADS) gb_emit(const GraphParams P, const
         }
     }
 
-    if (csr_src || csr_eattr) {
+    if (grid_eattr && P.K <= 8) {
+        // dense per-cell layout (slot k <-> in-edge from i - off_k, zeros when absent), kept in registers and stored as
+        // 16-byte vectors; the CSR payload is written on the way when requested
+        int ep = rowptr ? rowptr[id] : 0;
+        float gev[8 * BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+        for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q) gev[q] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k >= P.K) continue;
+            const int kk = P.neg[k];
+            const int jr = r + P.dr[kk], jc = c + P.dc[kk];
+            if (!valid_rc(cs, x, jr, jc)) continue;
+            if (csr_src) csr_src[ep] = node_id[x.cbase + (int64_t)jr * x.W + jc];
+            const float dj = __ldg(cs.depth + x.dbase + (int64_t)jr * x.dstride + jc);
+            float ev[BGNN_MAX_EDGE_FEATS] = {0.f, 0.f, 0.f, 0.f};
+            edge_attr_write(P, ev, k, d - dj, x.rx, x.ry);
+#pragma unroll
+            for (int e = 0; e < BGNN_MAX_EDGE_FEATS; ++e) {
+                if (e >= P.ED) continue;
+                if (csr_eattr) csr_eattr[(int64_t)ep * P.ED + e] = ev[e];
+                if (P.ED == 3) gev[k * 3 + e] = ev[e];                 // the reference's 3 edge features: static indices
+                else if (P.ED == 4) gev[k * 4 + e] = ev[e];
+                else if (P.ED == 2) gev[k * 2 + e] = ev[e];
+                else gev[k + e] = ev[e];
+            }
+            ++ep;
+        }
+        float* ge = grid_eattr + t * (int64_t)(P.K * P.ED);
+        const int n = P.K * P.ED;                                      // multiple of 4 for K in {4, 8}
+        if ((n & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (4 * q < n) reinterpret_cast<float4*>(ge)[q] = make_float4(gev[4 * q], gev[4 * q + 1], gev[4 * q + 2], gev[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q)
+                if (q < n) ge[q] = gev[q];
+        }
+    } else if (csr_src || csr_eattr) {
         int ep = rowptr[id];
         for (int k = 0; k < P.K; ++k) {          // in-edge (j -> i) with j = i - off_k
             const int kk = P.neg[k];
@@ -406,7 +445,7 @@ extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* c
 extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch,
                                size_t scratch_bytes, int32_t* node_id, int32_t* node_cell, float* x,
                                float* local_std, int32_t* rowptr, int32_t* csr_src, float* csr_eattr,
-                               void* stream_) {
+                               float* grid_eattr, void* stream_) {
     GraphParams P;
     int rc = make_params(cells, cfg, P);
     if (rc) return rc;
@@ -414,14 +453,15 @@ extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cf
     BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
     BGNN_CHECK_ARG(node_id, "node_id is required");
     BGNN_CHECK_ARG(rowptr || !(csr_src || csr_eattr), "rowptr is required for CSR outputs");
+    BGNN_CHECK_ARG(!grid_eattr || (P.K <= 8 && cells->n_grids == 1), "grid_eattr needs a single grid and at most 8 offsets");
     BGNN_CHECK_ARG(!(x && P.F == 0), "x requested with zero node features");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int32_t* table = (const int32_t*)scratch;
     { ProfScope ps(2, stream); gb_ids<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table, node_id, node_cell, rowptr); }
     BGNN_LAUNCH_CHECK();
-    if (x || local_std || csr_src || csr_eattr) {
+    if (x || local_std || csr_src || csr_eattr || grid_eattr) {
         ProfScope ps(3, stream);
-        gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr);
+        gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr, grid_eattr);
         BGNN_LAUNCH_CHECK();
     }
     return BGNN_OK;

@@ -444,7 +444,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             }
                         }
                         if (row < M) {
-                            float* dst = P.Cout + row * N + c0;
+                            float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH)
+                                                      : P.Cout + row * N + c0;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
                         }

@@ -18,6 +18,7 @@ struct UmmaArgs {
     const float* x; int F; const float* W0; const float* b0;
     // EM_PROJ: Cout [M,N] (+ bias [N], optional); alpha (optional) [M, 2*Htot] from att_src / att_dst [N]
     float* Cout; const float* bias; const float* att_src; const float* att_dst; float* alpha; int Htot; int CH;
+    int head_major;           // EM_PROJ: store C as [Htot][M][CH] (one contiguous plane per head) instead of [M][N]
     // EM_HEADS: W = concatenated first layers [nblk*h2 (zero padded to N), K]; hb0 their biases; second layers below
     const float* hb0; int h2, nblk, ncls;
     const float *Wcls, *bcls, *Wconf, *bconf, *Wcorr, *bcorr;

@@ -242,8 +242,9 @@ class BathymetricGNN(nn.Module):
                 raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({N}x{x.shape[-1]} and "
                                    f"{self.in_channels}x{self.hidden_channels})")
             topo = None
+            h = self._ensure_handle(device)
             if dg is not None:
-                rowptr, src, ea, E = dg.rowptr, dg.csr_src, dg.csr_eattr, dg.E
+                E = dg.E
                 ed_have = int(dg.cfg.n_edge_feats)
                 if dg.grid_meta is None and int(dg.cells.n_grids) == 1 and self.use_grid_kernel:
                     topo = _lib.GridTopo()
@@ -251,13 +252,19 @@ class BathymetricGNN(nn.Module):
                     topo.n_offsets = int(dg.cfg.n_offsets)
                     for k in range(topo.n_offsets):
                         topo.off_dr[k], topo.off_dc[k] = dg.cfg.off_dr[k], dg.cfg.off_dc[k]
+                    ge = getattr(dg, "grid_eattr", None)
+                    topo.grid_eattr = ge.data_ptr() if ge is not None else None
+                rowptr = dg.rowptr
+                if topo is not None and lib.bgnn_gat_grid_path(h, C.byref(topo), E) == 1:
+                    src, ea = None, None            # every layer runs the tiled kernel: the CSR payload is never read
+                else:
+                    src, ea = dg.csr_src, dg.csr_eattr
             else:
                 rowptr, src, ea, E = self._csr_from_coo(data, device)
                 ed_have = 0 if ea is None else int(ea.shape[1])
             ED = int(self.edge_dim or 0)
             if ED > 0 and ed_have != ED:
                 raise RuntimeError(f"model expects edge_dim={ED} but the graph carries {ed_have} edge features")
-            h = self._ensure_handle(device)
             out = dict(class_logits=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
                        class_probs=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
                        predicted_class=torch.empty(N, dtype=torch.int64, device=device),
@@ -269,8 +276,8 @@ class BathymetricGNN(nn.Module):
             if N > 0:
                 wbytes = int(lib.bgnn_gat_workspace_bytes(h, N))
                 ws = torch.empty(wbytes, dtype=torch.uint8, device=device)
-                check(lib.bgnn_gat_forward(h, N, E, ptr(x), ptr(rowptr), ptr(src) if E > 0 else None,
-                                           ptr(ea) if (ED > 0 and E > 0) else None, ptr(ws), wbytes,
+                check(lib.bgnn_gat_forward(h, N, E, ptr(x), ptr(rowptr), ptr(src) if (E > 0 and src is not None) else None,
+                                           ptr(ea) if (ED > 0 and E > 0 and ea is not None) else None, ptr(ws), wbytes,
                                            ptr(out["class_logits"]), ptr(out["class_probs"]), ptr(out["predicted_class"]),
                                            ptr(out["confidence"]), ptr(out.get("correction")), ptr(action),
                                            float(auto_thr), float(review_thr), ptr(hidden),

@@ -70,9 +70,33 @@ class Data:
 
 class _DeviceGraph:
     """Device-resident lean graph (what the forward kernels consume).  Shared by a
-    GridGraph and its `.cpu()` / `.to()` copies."""
-    __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "csr_src",
-                 "csr_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta")
+    GridGraph and its `.cpu()` / `.to()` copies.  The in-edge CSR payload (`csr_src`,
+    `csr_eattr`) is emitted on first access: the tiled aggregation of a single tile reads
+    the dense per-cell `grid_eattr` instead and never needs it."""
+    __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "_csr_src",
+                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta")
+
+    def ensure_csr(self):
+        if getattr(self, "_csr_src", None) is not None:
+            return
+        ED = int(self.cfg.n_edge_feats)
+        with torch.cuda.device(self.device):
+            src = torch.empty(max(self.E, 1), dtype=torch.int32, device=self.device)
+            ea = torch.empty((max(self.E, 1), max(ED, 1)), dtype=torch.float32, device=self.device)
+            check(lib.bgnn_graph_emit(C.byref(self.cells), C.byref(self.cfg), ptr(self.scratch), self.scratch.numel(),
+                                      ptr(self.node_id), None, None, None, ptr(self.rowptr), ptr(src),
+                                      ptr(ea) if ED > 0 else None, None, stream_ptr()))
+        self._csr_src, self._csr_eattr = src, ea
+
+    @property
+    def csr_src(self):
+        self.ensure_csr()
+        return self._csr_src
+
+    @property
+    def csr_eattr(self):
+        self.ensure_csr()
+        return self._csr_eattr
 
 
 class GridGraph(Data):
@@ -359,11 +383,18 @@ class GraphBuilder:
         dg.x = torch.empty((N, F), dtype=torch.float32, device=dev)
         dg.local_std = torch.empty(N, dtype=torch.float32, device=dev)
         dg.rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-        dg.csr_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        dg.csr_eattr = torch.empty((max(E, 1), max(ED, 1)), dtype=torch.float32, device=dev)
+        dg._csr_src = dg._csr_eattr = None
+        # single tile with a radius-1 stencil: also emit the dense per-cell edge features the tiled aggregation reads
+        radius1 = all(abs(cfg.off_dr[k]) <= 1 and abs(cfg.off_dc[k]) <= 1 for k in range(cfg.n_offsets))
+        dg.grid_eattr = None
+        if meta is None and int(cells.n_grids) == 1 and radius1 and cfg.n_offsets <= 8 and ED > 0:
+            dg.grid_eattr = torch.empty((n_cells, cfg.n_offsets, ED), dtype=torch.float32, device=dev)
+        if dg.grid_eattr is None:           # no grid path for this graph: the forward needs the CSR payload right away
+            dg._csr_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            dg._csr_eattr = torch.empty((max(E, 1), max(ED, 1)), dtype=torch.float32, device=dev)
         check(lib.bgnn_graph_emit(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), ptr(dg.node_id),
-                                  ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std), ptr(dg.rowptr), ptr(dg.csr_src),
-                                  ptr(dg.csr_eattr) if ED > 0 else None, st))
+                                  ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std), ptr(dg.rowptr), ptr(dg._csr_src),
+                                  ptr(dg._csr_eattr) if ED > 0 else None, ptr(dg.grid_eattr), st))
         g = GridGraph()
         g.__dict__["_dev"] = dg
         g.x = dg.x

@@ -120,15 +120,19 @@ class ClockSampler:
 def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=False, fused_mlp=False, fused_heads=False):
     """SURVEY.md 8(d) per-unit figures x the units one launch processes (stated in DESIGN.md)."""
     b = {}
-    deg = E / max(N, 1)
-    b["graph_build"] = cells * (4 + 1) + N * (4 * F + 4 + 4 + 4) + 4 * cells + E * 4 + E * 4 * ED
+    K = 8                                                  # 8-connected
+    # lean build of the grid path: depth + mask in, node_id grid out (per cell); x, local_std, node_cell, rowptr and the
+    # dense per-cell edge features [K, ED] out (per node).  The CSR payload (csr_src / csr_eattr) is emitted lazily and
+    # not at all on this path.
+    b["graph_build"] = cells * (4 + 1 + 4) + N * (4 * F + 4 + 4 + 4) + N * K * ED * 4
     HC = hidden * heads
     for l in range(layers):
         last = l == layers - 1
         hc = hidden if last else HC
         H = 1 if last else heads
         fin = hidden if l == 0 else HC
-        b[f"agg_l{l}"] = N * (4 * hc + 8 * H + 4 + 4 * hc) + E * (4 + 4 * ED) + N * 4 * ED * 0
+        # h rows counted ONCE (neighbour re-reads must come from shared memory / L2), alpha, node ids, dense edge features
+        b[f"agg_l{l}"] = N * (4 * hc + 8 * H + 4 * hc) + cells * 4 + N * K * ED * 4
         b[f"proj_l{l}"] = N * (4 * fin + 4 * hc + 8 * H)
     b["mlp0"] = N * (4 * F + 4 * hidden)
     b["mlp1"] = N * (8 * hidden)

@@ -113,11 +113,15 @@ int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
  *   rowptr    [dev] int32 [N+1]       in-edge CSR; row i lists the edges (j -> i) in the
  *   csr_src   [dev] int32 [E]         reference's edge order (offset k ascending, j = i - off_k)
  *   csr_eattr [dev] f32   [E, n_edge_feats]
- * Any of x/local_std/csr_* may be NULL to skip that output. */
+ *   grid_eattr [dev] f32  [n_cells, n_offsets, n_edge_feats]  (optional) the same in-edge features in a dense per-cell
+ *                         layout: slot k of cell i holds the features of the edge (i - off_k -> i), zeros when that edge
+ *                         does not exist; rows of invalid cells are not written.  Consumed by the tiled aggregation
+ *                         (bgnn_grid_topo.grid_eattr), which can then fetch them without the rowptr indirection.
+ * Any of x/local_std/csr_* / grid_eattr may be NULL to skip that output. */
 int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
                     void* scratch, size_t scratch_bytes,
                     int32_t* node_id, int32_t* node_cell, float* x, float* local_std,
-                    int32_t* rowptr, int32_t* csr_src, float* csr_eattr, void* stream);
+                    int32_t* rowptr, int32_t* csr_src, float* csr_eattr, float* grid_eattr, void* stream);
 
 /* Optional phase 3: the reference's API-visible COO (offset-major, node-minor; :196-241) and
  * per-edge features in that order.  edge_index int64 [2,E] (row 0 = src/centre, row 1 = tgt),
@@ -173,7 +177,12 @@ typedef struct bgnn_grid_topo {
     int32_t        n_offsets;
     int32_t        off_dr[BGNN_MAX_OFFSETS];
     int32_t        off_dc[BGNN_MAX_OFFSETS];
+    const float*   grid_eattr;                   /* [dev] optional dense edge features from bgnn_graph_emit */
 } bgnn_grid_topo;
+
+/* 1 if bgnn_gat_forward would run EVERY layer of `m` through the tiled grid kernel for this topology (then
+ * csr_src / csr_eattr are never read and may be NULL), 0 otherwise. */
+int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* topo, int64_t n_edges);
 
 /* outputs (any may be NULL): logits/probs f32 [N,num_classes], cls int64 [N], conf f32 [N],
  * corr f32 [N], action int64 [N] (0 keep, 1 auto-correct, 2 review; gnn.py:436-445).

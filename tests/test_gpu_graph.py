@@ -72,6 +72,25 @@ def check_graph(g, ref, depth, has_holes=True):
     ce = dg.csr_eattr.cpu().numpy()[:E]
     assert np.array_equal(ce[:, :2], eattr[:, :2])
     assert np.all(np.abs(ce[:, 2].astype(np.float64) - eattr[:, 2]) <= ulp32(eattr[:, 2]))
+    # the dense per-cell layout the tiled aggregation reads: slot k of cell i == CSR entry of the in-edge from i - off_k
+    # (bit-identical to the CSR payload, zeros where the edge is absent)
+    ge = getattr(dg, "grid_eattr", None)
+    if ge is not None and N:
+        ge = ge.cpu().numpy()                                   # [cells, K, ED]
+        K = ge.shape[1]
+        cell = dg.node_cell.cpu().numpy().astype(np.int64)
+        nid = dg.node_id.cpu().numpy().reshape(ref["grid_shape"])
+        H, W = nid.shape
+        rr, cc = cell // W, cell % W
+        present = np.zeros((N, K), bool)
+        for k in range(K):
+            dr, dc = int(dg.cfg.off_dr[k]), int(dg.cfg.off_dc[k])
+            jr, jc = rr - dr, cc - dc
+            ok = (jr >= 0) & (jr < H) & (jc >= 0) & (jc < W)
+            present[ok, k] = nid[jr[ok], jc[ok]] >= 0
+        gn = ge[cell]                                           # [N, K, ED] in node order
+        assert np.array_equal(gn[present], ce)                  # row-major over (node, k) == CSR order
+        assert not gn[~present].any()
     return (x[:, 3:7] != ref["x"][:, 3:7]).mean(), (ea[:, 2] != ref["edge_attr"][:, 2]).mean()
 
 
