@@ -161,7 +161,18 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     depth_np, mask_np = make_tile(rank)
     cfg, sd = make_weights(0)
@@ -374,8 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (used under ncu): no e2e / per-kernel / cpu legs")
-    ap.add_argument("--cpu-crop", type=int, default=512)
-    ap.add_argument("--cpu-crop-ref", type=int, default=256)
+    ap.add_argument("--cpu-crop", type=int, default=1024, help="cpu_baseline sample: crop x crop corner (about 10-15 s of CPU work)")
+    ap.add_argument("--cpu-crop-ref", type=int, default=512, help="--impl reference: crop x crop corner per step (about 3 s per step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
