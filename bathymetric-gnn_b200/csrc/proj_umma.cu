@@ -25,8 +25,10 @@
 //   MMA issue (one thread): 6 x tcgen05.mma.kind::f16 (M=128, N, K=16) per M tile and chunk, tcgen05.commit -> mbarrier
 //       frees the stage (4-stage ring).
 //   epilogue (8 warps; warp w <-> TMEM lanes 32*(w%4).., column half w/4 when N = 256): tcgen05.ld 32x32b.x32 of main
-//       and corr, rescale, bias, alpha_src / alpha_dst dot products per head, fp32 rows to global.  For N <= 128 the
-//       accumulators are double-buffered so the epilogue of one tile overlaps the MMAs of the next.
+//       and corr, rescale, bias, alpha_src / alpha_dst dot products per head; each [32 x 32] chunk is staged in a
+//       SWIZZLE_128B shared-memory tile and written by ONE TMA tensor store (thread-per-row global stores touch 32
+//       different lines per instruction and made the kernel LSU-bound).  For N <= 128 the accumulators are
+//       double-buffered so the epilogue of one tile overlaps the MMAs of the next.
 //
 // Two fusions ride on the same pipeline (template modes):
 //   PM_MLP0   the producers compute the A operand on the fly as relu(x W0^T + b0) -- LocalFeatureExtractor's first
@@ -43,10 +45,24 @@
 #include "common.cuh"
 #include "proj_umma.cuh"
 
+#ifdef BGNN_AGG_TIMING
+__device__ unsigned long long g_umma_t[8];
+#define UT_DECL() long long ut_prev = clock64()
+#define UT_TICK(slot) do { long long ut_now = clock64(); atomicAdd(&g_umma_t[slot], (unsigned long long)(ut_now - ut_prev)); ut_prev = ut_now; } while (0)
+extern "C" int bgnn_debug_umma_timing(unsigned long long* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_umma_t, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_umma_t, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define UT_DECL()
+#define UT_TICK(slot)
+#endif
+
 namespace {
 
 constexpr int KC = 32;                 // K elements per stage (64 B of fp16 = one SWIZZLE_64B row)
-constexpr int STAGES = 3;              // fp16 operand stages (conversion -> MMA decoupling)
+constexpr int STAGES = 3;              // fp16 operand stages, upper bound (barrier slots); per-shape depth in UmmaSmem
 constexpr int TILE_M = 128;
 constexpr int NSPLIT = 2;              // hi, lo
 constexpr int A_TILE_BYTES = TILE_M * KC * 2;     // 8 KB per split
@@ -132,6 +148,12 @@ struct UmmaSmem {
     static constexpr int TMEM_COLS = ACC_COLS * ACC_STAGES <= 32 ? 32 : ACC_COLS * ACC_STAGES <= 64 ? 64 : ACC_COLS * ACC_STAGES <= 128 ? 128
                                      : ACC_COLS * ACC_STAGES <= 256 ? 256 : 512;
     static constexpr int EPI_SPLIT = (EMODE == EM_PROJ && N == 256) ? 2 : 1;    // column halves handled by different epilogue warps
+    // EM_PROJ: every epilogue warp stages its [32 rows x 32 cols] chunk in a SWIZZLE_128B tile and hands it to a TMA
+    // tensor store (one 4 KB store instead of 128 scattered 32 B sectors through the LSU)
+    static constexpr int STG_WARPS = EMODE == EM_PROJ ? 4 * EPI_SPLIT : 0;
+    static constexpr int STG_BYTES = STG_WARPS * 4096;
+    static constexpr int NSTAGE = (PMODE == PM_PLAIN && N == 256) ? 2 : STAGES;     // fp16 operand ring depth (measured: for
+                                                                                     // N = 256 a deeper raw ring beats a third stage)
     static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * N : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;   // epilogue parameters
     static constexpr int PAR_P = PMODE == PM_MLP0 ? MLP0_MAXK * MLP0_FP + MLP0_MAXK : 0;              // producer parameters
     // PM_PLAIN: the A chunk [SUPER_M x 32] fp32 is fetched by TMA into a raw ring, RAW_STAGES chunks ahead
@@ -141,14 +163,9 @@ struct UmmaSmem {
     // parity wait of a phase that has not completed (then over-arrive on the empty barrier -> launch failure).
     static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? 4 : N == 128 ? 6 : 2);
     static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
-    static constexpr size_t BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)RAW_STAGES * RAW_BYTES + (PAR_E + PAR_P) * sizeof(float) +
-                                    NUM_BARS * 8 + 16;
+    static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)RAW_STAGES * RAW_BYTES + STG_BYTES +
+                                    (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
 };
-
-__device__ __forceinline__ void st_global_v8(float* p, const float* x) {          // 256-bit store (PTX ISA 8.8, sm_100)
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
-                 "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
-}
 
 // (main + corr * 2^-11) * scale of 32 accumulator columns of this thread's TMEM lane -> x[32]
 __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_corr, float scale, float* x) {
@@ -173,12 +190,14 @@ __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_
 
 template <int N, int PMODE, int EMODE>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA) {
+proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA,
+                 const __grid_constant__ CUtensorMap tmapC) {
     using S = UmmaSmem<N, PMODE, EMODE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw;                                                      // stage ring (1024 B aligned)
-    unsigned char* raw = base + (size_t)STAGES * S::STAGE_BYTES;                         // raw fp32 A ring
-    float* s_par = reinterpret_cast<float*>(raw + (size_t)S::RAW_STAGES * S::RAW_BYTES);  // epilogue parameters
+    unsigned char* raw = base + (size_t)S::NSTAGE * S::STAGE_BYTES;                      // raw fp32 A ring
+    unsigned char* stg = raw + (size_t)S::RAW_STAGES * S::RAW_BYTES;                     // epilogue store staging (1024 B aligned)
+    float* s_par = reinterpret_cast<float*>(stg + S::STG_BYTES);                          // epilogue parameters
     float* s_prod = s_par + S::PAR_E;                                                     // producer parameters
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_prod + S::PAR_P);                      // NUM_BARS
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
@@ -257,7 +276,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             const int64_t row0 = st * SUPER_M;
             for (int kc = 0; kc < nkc; ++kc, ++it) {
                 if ((int)(it % PROD_GROUPS) != grp) continue;
-                const int s = it % STAGES;
+                const int s = it % S::NSTAGE;
                 unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
                 constexpr uint32_t W_BYTES = NSPLIT * S::B_TILE_BYTES;
                 auto issue_w = [&]() {  // W chunk: the host pre-arranged [kc][split] tiles in the swizzled smem layout -> ONE bulk copy
@@ -280,7 +299,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         const int f = ptid + i * PROD_GROUP_THREADS;           // (row, 16 B column) of the [SUPER_M x 32] chunk
                         av[i] = *reinterpret_cast<const float4*>(rsrc + f * 4);
                     }
-                    if (it >= STAGES) mbar_wait(&bars[BAR_EMPTY + s], ((it / STAGES) - 1) & 1);
+                    if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
                     if (ptid == 0) issue_w();
 #pragma unroll
                     for (int i = 0; i < A_F4; ++i) {                   // 2-way fp16 split -> swizzled STS
@@ -306,7 +325,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 #pragma unroll
                         for (int q = 0; q < MLP0_FP; ++q) xr[mt][q] = (gr < M && q < P.F) ? __ldg(P.x + gr * P.F + q) : 0.f;
                     }
-                    if (it >= STAGES) mbar_wait(&bars[BAR_EMPTY + s], ((it / STAGES) - 1) & 1);
+                    if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
                     if (ptid == 0) issue_w();
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -361,13 +380,16 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             uint32_t it = 0, t = 0;
+            UT_DECL();
             for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
                 const uint32_t as = t % S::ACC_STAGES;
                 if (t >= (uint32_t)S::ACC_STAGES) mbar_wait(&bars[BAR_TEMPTY + as], (t / S::ACC_STAGES - 1) & 1);   // epilogue drained this stage
+                UT_TICK(0);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&bars[BAR_FULL + s], (it / STAGES) & 1);
+                    const int s = it % S::NSTAGE;
+                    mbar_wait(&bars[BAR_FULL + s], (it / S::NSTAGE) & 1);
+                    UT_TICK(1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t sA_ = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB_ = sA_ + MT * NSPLIT * A_TILE_BYTES;
 #pragma unroll
@@ -387,6 +409,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         }
                     }
                     umma_commit(&bars[BAR_EMPTY + s]);                 // stage free when these MMAs retire
+                    UT_TICK(2);
                 }
                 umma_commit(&bars[BAR_TFULL + as]);                    // accumulators complete
             }
@@ -401,7 +424,13 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
             const int64_t row0 = st * SUPER_M;
             const uint32_t as = t % S::ACC_STAGES;
+#ifdef BGNN_AGG_TIMING
+            long long ut_prev = clock64();
+#endif
             mbar_wait(&bars[BAR_TFULL + as], (t / S::ACC_STAGES) & 1);
+#ifdef BGNN_AGG_TIMING
+            if (warp == 0 && lane == 0) UT_TICK(3);
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
@@ -443,11 +472,23 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                                 as_acc = 0.f; ad_acc = 0.f;
                             }
                         }
-                        if (row < M) {
-                            float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH)
-                                                      : P.Cout + row * N + c0;
+                        {   // chunk [32 rows x 32 cols] -> SWIZZLE_128B staging tile -> one TMA tensor store (rows >= M are clipped)
+                            unsigned char* tile = stg + (size_t)warp * 4096;
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // previous store has read the tile
+                            __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                                    make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                const int cx = P.head_major ? (c0 % P.CH) : c0, cz = P.head_major ? (c0 / P.CH) : 0;
+                                const int cy = (int)(row0 + mt * TILE_M + quarter * 32);
+                                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n"
+                                             ::"l"(&tmapC), "r"(cx), "r"(cy), "r"(cz), "r"(smem_u32(tile)) : "memory");
+                                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                            }
                         }
                     }
                 } else {
@@ -524,7 +565,11 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&bars[BAR_TEMPTY + as]);
+#ifdef BGNN_AGG_TIMING
+            if (warp == 0 && lane == 0) UT_TICK(4);
+#endif
         }
+        if (EMODE == EM_PROJ && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");     // all tensor stores done
         if (EMODE == EM_PROJ && P.cmax_out) {       // max |C| written by this launch (feeds the next kernel's operand scale)
 #pragma unroll
             for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
@@ -545,7 +590,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D tensor map over A [M, K] fp32 (row-major) with a [box_rows x 32] box; out-of-range rows read as zero
-int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
+int get_encode_fn(EncodeTiledFn* out) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -554,6 +599,13 @@ int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out
         if (!p || q != cudaDriverEntryPointSuccess) { bgnn_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BGNN_E_CUDA; }
         fn = (EncodeTiledFn)p;
     }
+    *out = fn;
+    return BGNN_OK;
+}
+
+int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
+    EncodeTiledFn fn = nullptr;
+    { int rc = get_encode_fn(&fn); if (rc) return rc; }
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
     const cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
@@ -562,6 +614,24 @@ int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for A=%p M=%lld K=%d", (int)r, (const void*)A, (long long)M, K); return BGNN_E_CUDA; }
+    return BGNN_OK;
+}
+
+// 3-D tensor map over the projection output with a [32 cols x 32 rows x 1] SWIZZLE_128B box:
+//   head-major  C[Htot][M][CH]: dims {CH, M, Htot}      row-major  C[M][N]: dims {N, M, 1}
+int make_tmap_C(float* C, int64_t M, int N, int CH, int head_major, CUtensorMap* out) {
+    EncodeTiledFn fn = nullptr;
+    int rc = get_encode_fn(&fn);
+    if (rc) return rc;
+    const int Htot = head_major ? N / CH : 1;
+    const int inner = head_major ? CH : N;
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)M, (cuuint64_t)Htot};
+    const cuuint64_t gstr[2] = {(cuuint64_t)inner * sizeof(float), (cuuint64_t)M * inner * sizeof(float)};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, C, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for C=%p M=%lld N=%d", (int)r, (void*)C, (long long)M, N); return BGNN_E_CUDA; }
     return BGNN_OK;
 }
 
@@ -584,9 +654,16 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
         int rc = make_tmap_A(a.A, a.M, a.K, S::SUPER_M, &tmap);
         if (rc) return rc;
     }
+    alignas(64) CUtensorMap tmapC;
+    memset(&tmapC, 0, sizeof(tmapC));
+    if (EMODE == EM_PROJ) {
+        BGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.Cout) & 15) == 0, "C must be 16-byte aligned");
+        int rc = make_tmap_C(a.Cout, a.M, N, a.CH, a.head_major, &tmapC);
+        if (rc) return rc;
+    }
     const int64_t n_super = (a.M + S::SUPER_M - 1) / S::SUPER_M;
     const unsigned grid = (unsigned)(n_super < sms ? n_super : sms);
-    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap);
+    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap, tmapC);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         bgnn_set_error("proj_umma_kernel<N=%d, producer %d, epilogue %d> M=%lld K=%d: %s", N, PMODE, EMODE, (long long)a.M, a.K,
