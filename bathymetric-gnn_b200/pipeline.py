@@ -135,8 +135,12 @@ class BathymetricPipeline:
         H, W = grid.shape
         tm = self.tile_manager
         with torch.cuda.device(dev):
-            depth = torch.from_numpy(np.ascontiguousarray(grid.depth, dtype=np.float32)).to(dev)
-            unc = None if grid.uncertainty is None else torch.from_numpy(np.ascontiguousarray(grid.uncertainty, dtype=np.float32)).to(dev)
+            def to_dev(a):          # host arrays are uploaded once; a survey already resident in HBM is used in place
+                if isinstance(a, torch.Tensor):
+                    return a.to(device=dev, dtype=torch.float32)
+                return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+            depth = to_dev(grid.depth)
+            unc = None if grid.uncertainty is None else to_dev(grid.uncertainty)
             nodata = grid.nodata_value
             use_nodata = nodata is not None and not np.isnan(nodata)
             valid = torch.isfinite(depth)

@@ -332,6 +332,94 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def make_survey_band(r0, r1, W, dev, seed=1234, nodata=1.0e6):
+    """Synthetic survey rows [r0, r1) generated on the device from (seed, row, col): analytic surface + gaussian noise
+    (sigma 0.2 m) + spikes (p = 0.005, +-U(1,5) m) + ~5 % invalid area (a smooth 'coast' field) marked with nodata."""
+    depth = torch.empty((r1 - r0, W), dtype=torch.float32, device=dev)
+    cols = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
+    g = torch.Generator(device=dev)
+    for rs in range(r0, r1, 1024):
+        re_ = min(rs + 1024, r1)
+        g.manual_seed(seed * 1000003 + rs)
+        rows = torch.arange(rs, re_, device=dev, dtype=torch.float32)[:, None]
+        d = 30.0 + 5.0 * torch.sin(cols / 60.0) + 3.0 * torch.cos(rows / 45.0) + 0.01 * cols
+        d += 0.2 * torch.randn(d.shape, device=dev, generator=g)
+        u = torch.rand(d.shape, device=dev, generator=g)
+        amp = 1.0 + 4.0 * torch.rand(d.shape, device=dev, generator=g)
+        d += torch.where(u < 0.0025, amp, torch.zeros_like(d)) - torch.where(u > 0.9975, amp, torch.zeros_like(d))
+        coast = torch.sin(rows / 2900.0) + torch.cos(cols / 2300.0) + 0.3 * torch.sin((rows + cols) / 700.0)
+        d[coast > 1.72] = nodata
+        depth[rs - r0:re_ - r0] = d
+    return depth
+
+
+def run_survey(args):
+    """BASELINE.json configs[2]: an S x S survey, overlapping tiles (2048 / 128) sharded as tile-row bands across the
+    ranks, each band stitched on its own GPU (no data-path collective).  Secondary workload: one JSON line per run,
+    `value` = survey cells / slowest rank's device time for tiles + stitch + finalize of its band."""
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200 import parallel as par
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    S = args.survey_size
+    cfg_m, sd = make_weights(0)
+    model = bg.BathymetricGNN(cfg_m.in_channels, cfg_m.hidden, cfg_m.layers, "GAT", cfg_m.heads, cfg_m.num_classes,
+                              cfg_m.predict_correction, 0.0, cfg_m.edge_dim)
+    model.load_state_dict(sd, strict=True)
+    cfg = bg.Config()
+    cfg.tile.tile_size, cfg.tile.overlap, cfg.tile.min_valid_ratio = args.tile, args.overlap, 0.1
+    pipe = bg.BathymetricPipeline(cfg)
+    pipe.model = model.to(dev).eval()
+    ntr, ntc, specs = pipe.tile_manager.compute_tile_grid((S, S))
+    mine = par.band_specs(specs, par.band_partition(ntr, world)[rank])
+    r0, r1 = par.band_rows(mine)
+    depth = make_survey_band(r0, r1, S, dev)
+    grid = bg.BathymetricGrid(depth=depth, uncertainty=None, nodata_value=1.0e6, resolution=RES)
+    local = par.shift_specs(mine, r0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up on the first tiles of the band (module load, allocator), then the timed pass over the whole band
+    pipe.process_grid(grid, specs=local[:min(3, len(local))], keep_on_device="partial")
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    state = pipe.process_grid(grid, specs=local, keep_on_device="partial" if world > 1 else True)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd+stitch)", "value": S * S / (ms * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": f"configs[2]: {S}x{S} survey, tile {args.tile} / overlap {args.overlap}, "
+                                                 f"{len(specs)} tiles in {ntr} tile-rows, bands of tile-rows per GPU, device stitch",
+                                     "tiles_rank0": len(local), "band_rows_rank0": [r0, r1],
+                                     "note": "survey band resident in HBM; per-band planes stay on the device (the final gather "
+                                             "of band planes and the seam merge are outside the timed region)"}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):
     """Oracle (numpy/scipy graph build + torch-CPU GAT forward) on a crop x crop corner of the tile."""
     from oracle import graph_oracle as go
@@ -385,6 +473,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (used under ncu): no e2e / per-kernel / cpu legs")
+    ap.add_argument("--workload", default="tile", choices=["tile", "survey"],
+                    help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2] (secondary)")
+    ap.add_argument("--survey-size", type=int, default=16384)
+    ap.add_argument("--tile", type=int, default=2048)
+    ap.add_argument("--overlap", type=int, default=128)
     ap.add_argument("--cpu-crop", type=int, default=1024, help="cpu_baseline sample: crop x crop corner (about 10-15 s of CPU work)")
     ap.add_argument("--cpu-crop-ref", type=int, default=512, help="--impl reference: crop x crop corner per step (about 3 s per step)")
     args = ap.parse_args()
@@ -393,7 +486,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-        run_ours(args)
+        if args.workload == "survey":
+            run_survey(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
