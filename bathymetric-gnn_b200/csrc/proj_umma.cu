@@ -16,14 +16,16 @@
 // kernel left behind (every projection epilogue tracks max|C|; the layer in between is a convex combination followed by
 // an affine map, so |A| <= bn_mul * max|C| + bn_add).  Scaling by powers of two is exact and is undone in the epilogue.
 //
-// One persistent CTA per SM, 576 threads, warp-specialised:
-//   loader (1 thread): each fp32 A chunk [MT*128 x 32] is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d,
-//       mbarrier complete_tx) into a raw ring 3-6 chunks ahead: HBM latency is hidden by the async engine, not by registers.
+// One persistent CTA per SM, 608 threads, warp-specialised:
+//   A loader (1 thread): each fp32 A chunk [MT*128 x 32] is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d,
+//       mbarrier complete_tx) into a raw ring 2-6 chunks ahead: HBM latency is hidden by the async engine, not by registers.
+//   W loader (1 thread): the W chunk (pre-split and pre-swizzled on the host) arrives by ONE cp.async.bulk per chunk in
+//       its own 3-deep ring (its ~1000-cycle L2 latency must not sit between "stage free" and "stage full").
 //   producers (8 warps, two groups owning alternate K chunks): raw chunk -> 2-way fp16 split -> STS into K-major
-//       SWIZZLE_64B tiles; the W chunk (pre-split and pre-swizzled on the host) arrives by ONE cp.async.bulk per chunk,
-//       completing on the stage's mbarrier.
-//   MMA issue (one thread): 6 x tcgen05.mma.kind::f16 (M=128, N, K=16) per M tile and chunk, tcgen05.commit -> mbarrier
-//       frees the stage (4-stage ring).
+//       SWIZZLE_64B tiles.
+//   MMA issue (one thread): 6 x tcgen05.mma.kind::f16 (M=128, N, K=16) per M tile and chunk, tcgen05.commit -> mbarriers
+//       free the A stage and the W slot.  For N = K = 256 the 48 MMAs of a tile are 6 500 cycles of tensor time and the
+//       epilogue another 6 200: main + correction accumulators fill all 512 TMEM columns, so the two cannot overlap.
 //   epilogue (8 warps; warp w <-> TMEM lanes 32*(w%4).., column half w/4 when N = 256): tcgen05.ld 32x32b.x32 of main
 //       and corr, rescale, bias, alpha_src / alpha_dst dot products per head; each [32 x 32] chunk is staged in a
 //       SWIZZLE_128B shared-memory tile and written by ONE TMA tensor store (thread-per-row global stores touch 32
@@ -71,13 +73,15 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 // warp roles
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8, PROD_GROUPS = 2;
-constexpr int MMA_WARP = EPI_WARPS, LOAD_WARP = EPI_WARPS + 1, PROD_WARP0 = EPI_WARPS + 2;
-constexpr int UM_THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;                      // 576
+constexpr int MMA_WARP = EPI_WARPS, LOAD_WARP = EPI_WARPS + 1, WLOAD_WARP = EPI_WARPS + 2, PROD_WARP0 = EPI_WARPS + 3;
+constexpr int UM_THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;                      // 608
 constexpr int PROD_GROUP_THREADS = PROD_WARPS / PROD_GROUPS * 32;                  // 128
 constexpr int MAX_RAW = 6;             // raw fp32 A ring (bulk-copied rows): depth chosen per shape
 // barrier slots
+constexpr int NW = 3;                  // W chunk ring (own, deeper ring: the 32 KB copy has ~1000 cycles of L2 latency)
 constexpr int BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_TFULL = 2 * STAGES, BAR_TEMPTY = 2 * STAGES + 2, BAR_RFULL = 2 * STAGES + 4,
-              BAR_REMPTY = BAR_RFULL + MAX_RAW, NUM_BARS = BAR_REMPTY + MAX_RAW;
+              BAR_REMPTY = BAR_RFULL + MAX_RAW, BAR_WFULL = BAR_REMPTY + MAX_RAW, BAR_WEMPTY = BAR_WFULL + NW,
+              NUM_BARS = BAR_WEMPTY + NW;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -141,7 +145,8 @@ struct UmmaSmem {
     static constexpr int MT = N >= 128 ? 1 : 2;                  // M tiles per super tile
     static constexpr int SUPER_M = MT * TILE_M;
     static constexpr int B_TILE_BYTES = N * KC * 2;
-    static constexpr int STAGE_BYTES = MT * NSPLIT * A_TILE_BYTES + NSPLIT * B_TILE_BYTES;
+    static constexpr int STAGE_BYTES = MT * NSPLIT * A_TILE_BYTES;       // A operand stage (hi, lo tiles per M tile)
+    static constexpr int W_SLOT_BYTES = NSPLIT * B_TILE_BYTES;           // W chunk (hi, lo tiles)
     static constexpr int ACC_COLS = 2 * MT * N;                  // {main, corr} per M tile
     static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;   // double-buffered accumulators when TMEM allows:
                                                                   // the epilogue of super tile t overlaps the MMAs of t+1
@@ -150,7 +155,12 @@ struct UmmaSmem {
     static constexpr int EPI_SPLIT = (EMODE == EM_PROJ && N == 256) ? 2 : 1;    // column halves handled by different epilogue warps
     // EM_PROJ: every epilogue warp stages its [32 rows x 32 cols] chunk in a SWIZZLE_128B tile and hands it to a TMA
     // tensor store (one 4 KB store instead of 128 scattered 32 B sectors through the LSU)
-    static constexpr int STG_WARPS = EMODE == EM_PROJ ? 4 * EPI_SPLIT : 0;
+#ifndef BGNN_N256_TMA_STORE
+#define BGNN_N256_TMA_STORE 0
+#endif
+    // N = 256 from global A: shared memory holds either the staging tiles (with a 2-deep raw ring) or a 4-deep raw ring
+    static constexpr bool TMA_STORE = EMODE == EM_PROJ && !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE);
+    static constexpr int STG_WARPS = TMA_STORE ? 4 * EPI_SPLIT : 0;
     static constexpr int STG_BYTES = STG_WARPS * 4096;
     static constexpr int NSTAGE = (PMODE == PM_PLAIN && N == 256) ? 2 : STAGES;     // fp16 operand ring depth (measured: for
                                                                                      // N = 256 a deeper raw ring beats a third stage)
@@ -161,11 +171,16 @@ struct UmmaSmem {
     // The depth must be a multiple of the producer-group count so that a raw slot is always consumed by the SAME group:
     // TMA copies may complete out of order, and a group that last saw the slot two phases ago would otherwise pass the
     // parity wait of a phase that has not completed (then over-arrive on the empty barrier -> launch failure).
-    static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? 4 : N == 128 ? 6 : 2);
+    static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? (BGNN_N256_TMA_STORE ? 2 : 4) : N == 128 ? 6 : 2);
     static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
-    static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)RAW_STAGES * RAW_BYTES + STG_BYTES +
-                                    (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
+    static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)NW * W_SLOT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
+                                    STG_BYTES + (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
 };
+
+__device__ __forceinline__ void st_global_v8(float* p, const float* x) {          // 256-bit store (PTX ISA 8.8, sm_100)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
+                 "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
+}
 
 // (main + corr * 2^-11) * scale of 32 accumulator columns of this thread's TMEM lane -> x[32]
 __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_corr, float scale, float* x) {
@@ -195,7 +210,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     using S = UmmaSmem<N, PMODE, EMODE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw;                                                      // stage ring (1024 B aligned)
-    unsigned char* raw = base + (size_t)S::NSTAGE * S::STAGE_BYTES;                      // raw fp32 A ring
+    unsigned char* wring = base + (size_t)S::NSTAGE * S::STAGE_BYTES;                    // W chunk ring
+    unsigned char* raw = wring + (size_t)NW * S::W_SLOT_BYTES;                           // raw fp32 A ring
     unsigned char* stg = raw + (size_t)S::RAW_STAGES * S::RAW_BYTES;                     // epilogue store staging (1024 B aligned)
     float* s_par = reinterpret_cast<float*>(stg + S::STG_BYTES);                          // epilogue parameters
     float* s_prod = s_par + S::PAR_E;                                                     // producer parameters
@@ -226,6 +242,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bars[BAR_TFULL + a], 1); mbar_init(&bars[BAR_TEMPTY + a], 4 * 32 * S::EPI_SPLIT); }
         for (int r = 0; r < MAX_RAW; ++r) { mbar_init(&bars[BAR_RFULL + r], 1); mbar_init(&bars[BAR_REMPTY + r], PROD_GROUP_THREADS); }
+        for (int w = 0; w < NW; ++w) { mbar_init(&bars[BAR_WFULL + w], 1); mbar_init(&bars[BAR_WEMPTY + w], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (EMODE == EM_PROJ) {          // s_par = att_src [N] | att_dst [N] | bias [N]
@@ -278,15 +295,6 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 if ((int)(it % PROD_GROUPS) != grp) continue;
                 const int s = it % S::NSTAGE;
                 unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
-                constexpr uint32_t W_BYTES = NSPLIT * S::B_TILE_BYTES;
-                auto issue_w = [&]() {  // W chunk: the host pre-arranged [kc][split] tiles in the swizzled smem layout -> ONE bulk copy
-                    const uint32_t bar = smem_u32(&bars[BAR_FULL + s]);
-                    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(W_BYTES) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                                 ::"r"(smem_u32(stage + MT * NSPLIT * A_TILE_BYTES)),
-                                   "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + (size_t)kc * W_BYTES), "r"(W_BYTES), "r"(bar)
-                                 : "memory");
-                };
                 if (PMODE == PM_PLAIN) {
                     // fp32 rows of this chunk from the raw ring (bulk-copied by the loader warp), then free the slot
                     constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
@@ -300,7 +308,6 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         av[i] = *reinterpret_cast<const float4*>(rsrc + f * 4);
                     }
                     if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
-                    if (ptid == 0) issue_w();
 #pragma unroll
                     for (int i = 0; i < A_F4; ++i) {                   // 2-way fp16 split -> swizzled STS
                         const int f = ptid + i * PROD_GROUP_THREADS;
@@ -326,7 +333,6 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         for (int q = 0; q < MLP0_FP; ++q) xr[mt][q] = (gr < M && q < P.F) ? __ldg(P.x + gr * P.F + q) : 0.f;
                     }
                     if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
-                    if (ptid == 0) issue_w();
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll 2
@@ -356,7 +362,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             }
         }
     } else if (warp == LOAD_WARP) {
-        // ===================== LOADER (one thread): A chunk [SUPER_M x 32] fp32 -> raw ring, ONE TMA tensor copy per chunk
+        // ===================== A LOADER (one thread, PM_PLAIN): A [SUPER_M x 32] fp32 -> raw ring, ONE TMA tensor copy per chunk
         // (rows past M are zero-filled by the tensor map's bounds check) =====================
         if (PMODE == PM_PLAIN && lane == 0) {
             constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
@@ -374,6 +380,25 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 }
             }
         }
+    } else if (warp == WLOAD_WARP) {
+        // ===================== W LOADER (one thread): the host pre-arranged [kc][split] tiles in the swizzled smem layout:
+        // ONE bulk copy per chunk into its own ring (an own thread: its waits must not hold up the A loads) =====================
+        if (lane == 0) {
+            constexpr uint32_t W_BYTES = S::W_SLOT_BYTES;
+            uint32_t it = 0;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int w = it % NW;
+                    if (it >= (uint32_t)NW) mbar_wait(&bars[BAR_WEMPTY + w], ((it / NW) - 1) & 1);
+                    const uint32_t wbar = smem_u32(&bars[BAR_WFULL + w]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wbar), "r"(W_BYTES) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 ::"r"(smem_u32(wring + (size_t)w * S::W_SLOT_BYTES)),
+                                   "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + (size_t)kc * W_BYTES), "r"(W_BYTES), "r"(wbar)
+                                 : "memory");
+                }
+            }
+        }
     } else if (warp == MMA_WARP) {
         // ===================== MMA ISSUER (one thread) =====================
         if (lane == 0) {
@@ -387,11 +412,12 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 UT_TICK(0);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
-                    const int s = it % S::NSTAGE;
+                    const int s = it % S::NSTAGE, w = it % NW;
+                    mbar_wait(&bars[BAR_WFULL + w], (it / NW) & 1);
                     mbar_wait(&bars[BAR_FULL + s], (it / S::NSTAGE) & 1);
                     UT_TICK(1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint32_t sA_ = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB_ = sA_ + MT * NSPLIT * A_TILE_BYTES;
+                    const uint32_t sA_ = smem_u32(base + (size_t)s * S::STAGE_BYTES), sB_ = smem_u32(wring + (size_t)w * S::W_SLOT_BYTES);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         const uint32_t d_main = tmem_base + as * S::ACC_COLS + (uint32_t)(mt * 2 * N), d_corr = d_main + (uint32_t)N;
@@ -408,7 +434,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             }
                         }
                     }
-                    umma_commit(&bars[BAR_EMPTY + s]);                 // stage free when these MMAs retire
+                    umma_commit(&bars[BAR_EMPTY + s]);                 // A stage and W slot free when these MMAs retire
+                    umma_commit(&bars[BAR_WEMPTY + w]);
                     UT_TICK(2);
                 }
                 umma_commit(&bars[BAR_TFULL + as]);                    // accumulators complete
@@ -472,7 +499,14 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                                 as_acc = 0.f; ad_acc = 0.f;
                             }
                         }
-                        {   // chunk [32 rows x 32 cols] -> SWIZZLE_128B staging tile -> one TMA tensor store (rows >= M are clipped)
+                        if (!S::TMA_STORE) {         // thread-per-row 256-bit stores (32 different lines per instruction)
+                            if (row < M) {
+                                float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH)
+                                                          : P.Cout + row * N + c0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
+                            }
+                        } else {   // chunk [32 rows x 32 cols] -> SWIZZLE_128B staging tile -> one TMA tensor store (rows >= M are clipped)
                             unsigned char* tile = stg + (size_t)warp * 4096;
                             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // previous store has read the tile
                             __syncwarp();
@@ -569,7 +603,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             if (warp == 0 && lane == 0) UT_TICK(4);
 #endif
         }
-        if (EMODE == EM_PROJ && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");     // all tensor stores done
+        if (S::TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");     // all tensor stores done
         if (EMODE == EM_PROJ && P.cmax_out) {       // max |C| written by this launch (feeds the next kernel's operand scale)
 #pragma unroll
             for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));

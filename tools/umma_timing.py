@@ -1,7 +1,7 @@
 """Dev aid: where the MMA issuer and one epilogue thread of proj_umma_kernel spend their cycles (needs -DBGNN_AGG_TIMING)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["BGNN_LIB"] = os.path.join(ROOT, "tools", "libbgnn_timing.so")
+os.environ.setdefault("BGNN_LIB", os.path.join(ROOT, "tools", "libbgnn_timing.so"))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from bathymetric_gnn_b200._lib import lib, check, ptr
