@@ -345,6 +345,38 @@ class GraphBuilder:
             return self._build(cells, keep, has_unc, None, meta if G > 1 else None, dev,
                                shapes=[(int(r), int(c)) for r, c in zip(rows, cols)])
 
+    def build_graph_packed(self, depth: torch.Tensor, cell_off, rows, cols, res, uncertainty: Optional[torch.Tensor] = None,
+                           nodata: Optional[float] = 1.0e6) -> Data:
+        """Ragged batch from an ALREADY PACKED device buffer (the natural hand-over from a bulk VR-BAG reader:
+        `varres_refinements` + per-grid metadata): `depth` f32 [sum rows*cols] on the device,
+        `cell_off` int64 [G+1], `rows` / `cols` int32 [G], `res` f64 [G,2] (host arrays or tensors)."""
+        dev = self._device()
+        as_np = lambda a, dt: a.cpu().numpy().astype(dt) if isinstance(a, torch.Tensor) else np.ascontiguousarray(a, dtype=dt)
+        off, rows_h, cols_h, res_h = as_np(cell_off, np.int64), as_np(rows, np.int32), as_np(cols, np.int32), as_np(res, np.float64)
+        G = int(rows_h.shape[0])
+        if G == 0:
+            return self._empty()
+        with torch.cuda.device(dev):
+            d = depth.to(device=dev, dtype=torch.float32).contiguous()
+            t_off, t_rows, t_cols, t_res = (torch.from_numpy(a).to(dev) for a in (off, rows_h, cols_h, res_h.reshape(G, 2)))
+            keep = [d, t_off, t_rows, t_cols, t_res]
+            cells = _lib.Cells()
+            cells.n_grids, cells.n_cells = G, int(off[-1])
+            cells.cell_off, cells.grid_rows, cells.grid_cols, cells.grid_res = (t.data_ptr() for t in (t_off, t_rows, t_cols, t_res))
+            cells.depth = d.data_ptr()
+            if nodata is not None and not np.isnan(nodata):
+                cells.use_nodata, cells.nodata = 1, float(nodata)
+            if uncertainty is not None:
+                u = uncertainty.to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(u)
+                cells.unc = u.data_ptr()
+            if G == 1:
+                cells.n_grids, cells.rows, cells.cols, cells.row_stride = 1, int(rows_h[0]), int(cols_h[0]), int(cols_h[0])
+                cells.rx, cells.ry = float(res_h.reshape(G, 2)[0, 0]), float(res_h.reshape(G, 2)[0, 1])
+            meta = dict(cell_off=off, rows=rows_h, cols=cols_h, cell_off_dev=t_off, cols_dev=t_cols)
+            return self._build(cells, keep, uncertainty is not None, None, meta if G > 1 else None, dev,
+                               shapes=[(int(r), int(c)) for r, c in zip(rows_h, cols_h)])
+
     def _empty(self) -> Data:
         """graph_construction.py:460-469 (note: no grid_shape attribute)."""
         dev = self._device()

@@ -420,6 +420,63 @@ def run_survey(args):
         dist.destroy_process_group()
 
 
+def run_ragged(args):
+    """BASELINE.json configs[3]: native VR BAG refinement grids (sides 3..50, 10 % nodata) batched as ONE ragged
+    block-diagonal graph per chunk of <= ~8 M cells; grids are sharded contiguously across ranks (no collective).
+    Secondary workload; `value` = valid cells / slowest rank's device time (packed buffers resident in HBM)."""
+    import bathymetric_gnn_b200 as bg
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rng = np.random.default_rng(7 + rank)
+    G = args.grids // world
+    rows = rng.integers(3, 51, G).astype(np.int32); cols = rng.integers(3, 51, G).astype(np.int32)
+    res = rng.choice([0.5, 1.0, 2.0, 4.0], G)
+    res2 = np.stack([res, res], 1)
+    size = rows.astype(np.int64) * cols
+    cfg_m, sd = make_weights(0)
+    model = bg.BathymetricGNN(cfg_m.in_channels, cfg_m.hidden, cfg_m.layers, "GAT", cfg_m.heads, cfg_m.num_classes,
+                              cfg_m.predict_correction, 0.0, cfg_m.edge_dim)
+    model.load_state_dict(sd, strict=True); model = model.to(dev).eval()
+    builder = bg.GraphBuilder("8-connected")
+    # chunks of consecutive grids with <= args.chunk_cells cells
+    bounds, acc, start = [], 0, 0
+    for g in range(G):
+        if acc + size[g] > args.chunk_cells and g > start:
+            bounds.append((start, g)); start, acc = g, 0
+        acc += size[g]
+    bounds.append((start, G))
+    gen = torch.Generator(device=dev); gen.manual_seed(7 + rank)
+    chunks = []
+    for (a, b) in bounds:
+        off = np.zeros(b - a + 1, np.int64); np.cumsum(size[a:b], out=off[1:])
+        n = int(off[-1])
+        d = 30.0 + 0.5 * torch.randn(n, device=dev, generator=gen)
+        d[torch.rand(n, device=dev, generator=gen) < 0.10] = 1.0e6
+        chunks.append((d, off, rows[a:b], cols[a:b], res2[a:b]))
+
+    def one_pass():
+        nodes = 0
+        for (d, off, r, c, rs) in chunks:
+            g = builder.build_graph_packed(d, off, r, c, rs, nodata=1.0e6)
+            out = model.predict(g)
+            nodes += g.num_nodes
+            del g, out
+        return nodes
+    one_pass()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(); nodes = one_pass(); ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if rank == 0:
+        print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),
+                          "unit": UNIT, "n_gpus": world, "ms_total": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"configs[3]: {args.grids} refinement grids, sides U{{3..50}}, 10% nodata, "
+                                                 f"{len(chunks)} ragged chunks of <= {args.chunk_cells} cells per rank",
+                                     "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"}}))
+
+
 def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):
     """Oracle (numpy/scipy graph build + torch-CPU GAT forward) on a crop x crop corner of the tile."""
     from oracle import graph_oracle as go
@@ -473,8 +530,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (used under ncu): no e2e / per-kernel / cpu legs")
-    ap.add_argument("--workload", default="tile", choices=["tile", "survey"],
-                    help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2] (secondary)")
+    ap.add_argument("--workload", default="tile", choices=["tile", "survey", "ragged"],
+                    help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2], ragged = configs[3] (secondary)")
+    ap.add_argument("--grids", type=int, default=100000)
+    ap.add_argument("--chunk-cells", type=int, default=8000000)
     ap.add_argument("--survey-size", type=int, default=16384)
     ap.add_argument("--tile", type=int, default=2048)
     ap.add_argument("--overlap", type=int, default=128)
@@ -488,6 +547,8 @@ def main():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
         if args.workload == "survey":
             run_survey(args)
+        elif args.workload == "ragged":
+            run_ragged(args)
         else:
             run_ours(args)
 

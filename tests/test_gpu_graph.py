@@ -199,3 +199,25 @@ def test_determinism():
     _, g2 = build(c)
     for k in ("x", "edge_index", "edge_attr", "local_std"):
         assert torch.equal(getattr(g1, k), getattr(g2, k))
+
+
+def test_packed_ragged_entry_equals_batch():
+    """build_graph_packed (device-resident packed buffer + descriptor table) == build_graph_batch (list of host grids)."""
+    import bathymetric_gnn_b200 as bg
+    rng = np.random.default_rng(11)
+    grids = []
+    for _ in range(40):
+        r, c = int(rng.integers(3, 20)), int(rng.integers(3, 20))
+        d = (30 + rng.normal(0, 1, (r, c))).astype(np.float32)
+        d[rng.random((r, c)) < 0.1] = 1.0e6
+        grids.append((d, None, (float(rng.choice([0.5, 1.0, 2.0])),) * 2))
+    b = bg.GraphBuilder("8-connected")
+    ga = b.build_graph_batch(grids, nodata=1.0e6)
+    rows = np.array([g[0].shape[0] for g in grids], np.int32); cols = np.array([g[0].shape[1] for g in grids], np.int32)
+    off = np.zeros(len(grids) + 1, np.int64); np.cumsum(rows.astype(np.int64) * cols, out=off[1:])
+    depth = torch.from_numpy(np.concatenate([g[0].ravel() for g in grids])).cuda()
+    res = np.array([g[2] for g in grids], np.float64)
+    gb = b.build_graph_packed(depth, off, rows, cols, res, nodata=1.0e6)
+    assert ga.num_nodes == gb.num_nodes and ga.num_edges == gb.num_edges
+    for k in ("x", "edge_index", "edge_attr", "local_std", "valid_rows", "valid_cols"):
+        assert torch.equal(getattr(ga, k), getattr(gb, k)), k
