@@ -730,10 +730,11 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             sc[8] = expf(sc[8] - mx);
             sum += sc[8];
             sum += 1e-16f;
+            const float inv = 1.0f / sum;            // one IEEE division, nine multiplies (<= 1 ulp from exp / sum)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] / sum;
-            a_sm[tid * AST + 4] = sc[8] / sum;
+                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] * inv;
+            a_sm[tid * AST + 4] = sc[8] * inv;
         }
         AGG_TICK(2);
         // 3. all threads arrive (release: a_sm, zero rows), then wait for the arrivals and the copied bytes

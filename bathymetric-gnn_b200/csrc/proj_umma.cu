@@ -477,19 +477,27 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             }
                         }
                         if (P.cmax_out) {
+                            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, fabsf(x[j]));
+                            for (int j = 0; j < 32; j += 4) {
+                                m0 = fmaxf(m0, fabsf(x[j])); m1 = fmaxf(m1, fabsf(x[j + 1]));
+                                m2 = fmaxf(m2, fabsf(x[j + 2])); m3 = fmaxf(m3, fabsf(x[j + 3]));
+                            }
+                            cmax = fmaxf(cmax, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                         }
                         if (P.alpha) {
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(s_par + c0 + j);
                                 const float4 d4 = *reinterpret_cast<const float4*>(s_par + N + c0 + j);
-                                as_acc = fmaf(x[j], s4.x, as_acc); as_acc = fmaf(x[j + 1], s4.y, as_acc);
-                                as_acc = fmaf(x[j + 2], s4.z, as_acc); as_acc = fmaf(x[j + 3], s4.w, as_acc);
-                                ad_acc = fmaf(x[j], d4.x, ad_acc); ad_acc = fmaf(x[j + 1], d4.y, ad_acc);
-                                ad_acc = fmaf(x[j + 2], d4.z, ad_acc); ad_acc = fmaf(x[j + 3], d4.w, ad_acc);
+                                s0 = fmaf(x[j], s4.x, s0); s1 = fmaf(x[j + 1], s4.y, s1);
+                                s2 = fmaf(x[j + 2], s4.z, s2); s3 = fmaf(x[j + 3], s4.w, s3);
+                                d0 = fmaf(x[j], d4.x, d0); d1 = fmaf(x[j + 1], d4.y, d1);
+                                d2 = fmaf(x[j + 2], d4.z, d2); d3 = fmaf(x[j + 3], d4.w, d3);
                             }
+                            as_acc += (s0 + s1) + (s2 + s3);
+                            ad_acc += (d0 + d1) + (d2 + d3);
                             if (((c0 + 32) % P.CH) == 0) {          // a head's channels are complete
                                 if (row < M) {
                                     const int h = (c0 + 32) / P.CH - 1;
@@ -544,26 +552,30 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             x[j + 2] = fmaxf(x[j + 2] + b.z, 0.f); x[j + 3] = fmaxf(x[j + 3] + b.w, 0.f);
                         }
                         const int blk = c0 / h2, u0 = c0 - blk * h2;
+                        // four independent partial sums per output: a 32-long serial FMA chain per class is latency-bound
                         if (blk == 0) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
                                 if (k < ncls) {
+                                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
                                     for (int j = 0; j < 32; j += 4) {
                                         const float4 w = *reinterpret_cast<const float4*>(w2 + k * h2 + u0 + j);
-                                        lg[k] = fmaf(x[j], w.x, lg[k]); lg[k] = fmaf(x[j + 1], w.y, lg[k]);
-                                        lg[k] = fmaf(x[j + 2], w.z, lg[k]); lg[k] = fmaf(x[j + 3], w.w, lg[k]);
+                                        p0 = fmaf(x[j], w.x, p0); p1 = fmaf(x[j + 1], w.y, p1);
+                                        p2 = fmaf(x[j + 2], w.z, p2); p3 = fmaf(x[j + 3], w.w, p3);
                                     }
+                                    lg[k] += (p0 + p1) + (p2 + p3);
                                 }
                         } else {
                             const float* wv = w2 + (blk == 1 ? ncls : ncls + 1) * h2 + u0;
-                            float acc = 0.f;
+                            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 w = *reinterpret_cast<const float4*>(wv + j);
-                                acc = fmaf(x[j], w.x, acc); acc = fmaf(x[j + 1], w.y, acc);
-                                acc = fmaf(x[j + 2], w.z, acc); acc = fmaf(x[j + 3], w.w, acc);
+                                p0 = fmaf(x[j], w.x, p0); p1 = fmaf(x[j + 1], w.y, p1);
+                                p2 = fmaf(x[j + 2], w.z, p2); p3 = fmaf(x[j + 3], w.w, p3);
                             }
+                            const float acc = (p0 + p1) + (p2 + p3);
                             if (blk == 1) pc += acc; else pr += acc;
                         }
                     }
