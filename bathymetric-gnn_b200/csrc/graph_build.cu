@@ -105,13 +105,13 @@ __global__ void __launch_bounds__(GB_THREADS) gb_count(const GraphParams P, int3
     }
 }
 
-// one CTA: exclusive scan of each column of table[ncol][nblocks+1]; totals land at [nblocks]
+// one CTA per column: exclusive scan of column blockIdx.x of table[ncol][nblocks+1]; totals land at [nblocks]
 __global__ void __launch_bounds__(1024) gb_scan(int32_t* __restrict__ table, int64_t nblocks, int ncol) {
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int64_t per = (nblocks + 1023) / 1024;
-    const int64_t b0 = (int64_t)tid * per, b1 = min(b0 + per, nblocks);
-    for (int col = 0; col < ncol; ++col) {
+    const int64_t b0 = min((int64_t)tid * per, nblocks), b1 = min(b0 + per, nblocks);
+    for (int col = blockIdx.x; col < ncol; col += gridDim.x) {
         int32_t* colp = table + (int64_t)col * (nblocks + 1);
         int sum = 0;
         for (int64_t b = b0; b < b1; ++b) sum += colp[b];
@@ -330,6 +330,185 @@ __global__ void __launch_bounds__(GB_THREADS) gb_emit(const GraphParams P, const
     }
 }
 
+// ---------------------------------------------------------------- tiled emit (single grid, the reference's 8 offsets)
+// Lean grid path: x, local_std and the dense per-cell edge features from a shared-memory tile of the depth grid.
+// One CTA per 8 x 32 patch; depth + validity staged once with a halo of 3 (5x5 box of a halo-1 cell that needs the
+// local-mean fill); the slope needs one fp64 atan per UNDIRECTED edge: each cell computes it for its 4 forward
+// neighbours ((0,1), (1,-1), (1,0), (1,1) = offsets 4..7), the reverse direction is the exact negation
+// (atan and the fp32 rounding are odd), so in-edge slot k <= 3 of cell i is -S_i[3-k] and slot k >= 4 is S_j[k-4] of
+// the backward neighbour j = i - off_k.  Same arithmetic (and the same fp64 summation order) as gb_emit.
+constexpr int TP_H = 8, TP_W = 32, TP_HALO = 3, TP_SH = TP_H + 2 * TP_HALO, TP_SW = TP_W + 2 * TP_HALO;
+
+__global__ void __launch_bounds__(TP_H * TP_W) gb_emit_tile(const GraphParams P, const int32_t* __restrict__ node_id,
+                                                            float* __restrict__ xout, float* __restrict__ local_std,
+                                                            float* __restrict__ grid_eattr) {
+    __shared__ float s_d[TP_SH][TP_SW];            // depth (0 where outside the grid)
+    __shared__ unsigned char s_v[TP_SH][TP_SW];    // validity
+    __shared__ float s_f[TP_H + 2][TP_W + 2];      // depth_filled on the halo-1 region
+    __shared__ __align__(16) float s_s[TP_H + 1][TP_W + 2][4];   // forward slopes (degrees, fp32) of rows -1..TP_H-1, cols -1..TP_W
+    const bgnn_cells& cs = P.cells;
+    const int H = cs.rows, W = cs.cols;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.y * TP_H, c0 = blockIdx.x * TP_W;
+
+    for (int q = tid; q < TP_SH * TP_SW; q += TP_H * TP_W) {
+        const int lr = q / TP_SW, lc = q % TP_SW;
+        const int r = r0 - TP_HALO + lr, c = c0 - TP_HALO + lc;
+        float d = 0.f; bool v = false;
+        if (r >= 0 && r < H && c >= 0 && c < W) {
+            const int64_t di = (int64_t)r * cs.row_stride + c;
+            d = __ldg(cs.depth + di);
+            v = cs.mask ? (__ldg(cs.mask + di) != 0) : (isfinite(d) && (!cs.use_nodata || d != cs.nodata));
+        }
+        s_d[lr][lc] = d; s_v[lr][lc] = v ? 1 : 0;
+    }
+    __syncthreads();
+
+    // masked 5x5 box sums in fp64 around local cell (lr, lc) (halo coordinates), zero outside the grid (invalid there)
+    auto box = [&](int lr, int lc, float& mean, float& stdv) {
+        double S = 0.0, Q = 0.0; int C = 0;
+#pragma unroll
+        for (int dr = -2; dr <= 2; ++dr)
+#pragma unroll
+            for (int dc = -2; dc <= 2; ++dc)
+                if (s_v[lr + dr][lc + dc]) { const double d = (double)s_d[lr + dr][lc + dc]; S += d; Q += d * d; ++C; }
+        const double n = C > 0 ? (double)C : 1.0;
+        const double mu = S / n;
+        double var = Q / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean = (float)mu; stdv = (float)sqrt(var);
+    };
+    // depth_filled on the halo-1 region (cells outside the grid are never read by the stencils below)
+    for (int q = tid; q < (TP_H + 2) * (TP_W + 2); q += TP_H * TP_W) {
+        const int fr = q / (TP_W + 2), fc = q % (TP_W + 2);
+        const int lr = fr + TP_HALO - 1, lc = fc + TP_HALO - 1;
+        const int r = r0 - 1 + fr, c = c0 - 1 + fc;
+        float f = 0.f;
+        if (r >= 0 && r < H && c >= 0 && c < W) {
+            if (s_v[lr][lc]) f = s_d[lr][lc];
+            else { float m, sd; box(lr, lc, m, sd); f = m; }
+            f = nan_to_num_f32(f);
+        }
+        s_f[fr][fc] = f;
+    }
+    // forward slopes of rows -1..TP_H-1, cols -1..TP_W: S[f] = degrees(atan((d_F - d_B) / dist_f)) for forward offset f
+    const double rx = cs.rx, ry = cs.ry;
+    for (int q = tid; q < (TP_H + 1) * (TP_W + 2); q += TP_H * TP_W) {
+        const int sr = q / (TP_W + 2), sc = q % (TP_W + 2);
+        const int lr = sr + TP_HALO - 1, lc = sc + TP_HALO - 1;
+        float out4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s_v[lr][lc]) {
+            const float dB = s_d[lr][lc];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int dr = P.dr[4 + f], dc = P.dc[4 + f];
+                if (!s_v[lr + dr][lc + dc]) continue;
+                const double dx = (double)dc * rx, dy = (double)dr * ry;
+                const double dist = sqrt(dx * dx + dy * dy);
+                const float dz = s_d[lr + dr][lc + dc] - dB;
+                double sl = 0.0;
+                if (dist > 0.0) sl = atan((double)dz / dist) * (180.0 / 3.14159265358979323846);
+                if (isnan(sl)) sl = 0.0;
+                out4[f] = (float)sl;
+            }
+        }
+        *reinterpret_cast<float4*>(&s_s[sr][sc][0]) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    }
+    __syncthreads();
+
+    const int pr = tid / TP_W, pc = tid % TP_W;
+    const int r = r0 + pr, c = c0 + pc;
+    if (r >= H || c >= W) return;
+    const int lr = pr + TP_HALO, lc = pc + TP_HALO;
+    if (!s_v[lr][lc]) return;
+    const int64_t t = (int64_t)r * W + c;
+    const int id = node_id[t];
+    const float d = s_d[lr][lc];
+
+    if (xout || local_std) {
+        float mean, stdv;
+        box(lr, lc, mean, stdv);
+        if (local_std) local_std[id] = nan_to_num_f32(stdv);
+        if (xout) {
+            const float f0 = nan_to_num_f32(d);
+            const float up = r > 0 ? s_f[pr][pc + 1] : f0;
+            const float dn = r < H - 1 ? s_f[pr + 2][pc + 1] : f0;
+            const float lf = c > 0 ? s_f[pr + 1][pc] : f0;
+            const float rt = c < W - 1 ? s_f[pr + 1][pc + 2] : f0;
+            float gy = 0.f, gx = 0.f;
+            if (H >= 2) gy = r == 0 ? dn - f0 : (r == H - 1 ? f0 - up : (dn - up) / 2.0f);
+            if (W >= 2) gx = c == 0 ? rt - f0 : (c == W - 1 ? f0 - lf : (rt - lf) / 2.0f);
+            const float gm = sqrtf(gx * gx + gy * gy);
+            const double t0 = (double)f0 * -2.0 + ((double)up + (double)dn);
+            const double t1 = (double)f0 * -2.0 + ((double)lf + (double)rt);
+            float lap = (float)t0 + (float)t1;
+            int cnt3 = 0;
+#pragma unroll
+            for (int a = -1; a <= 1; ++a)
+#pragma unroll
+                for (int b = -1; b <= 1; ++b) cnt3 += s_v[lr + a][lc + b];
+            if (cnt3 < 3) lap = 0.0f;
+            float* row = xout + (int64_t)id * P.F;
+            for (int j = 0; j < P.F; ++j) {
+                float v;
+                switch (P.nf[j]) {
+                    case BGNN_NF_DEPTH: v = d; break;
+                    case BGNN_NF_LOCAL_MEAN: v = mean; break;
+                    case BGNN_NF_LOCAL_STD: v = stdv; break;
+                    case BGNN_NF_GRAD_X: v = gx; break;
+                    case BGNN_NF_GRAD_Y: v = gy; break;
+                    case BGNN_NF_GRAD_MAG: v = gm; break;
+                    case BGNN_NF_CURVATURE: v = lap; break;
+                    default: v = cs.unc ? __ldg(cs.unc + (int64_t)r * cs.row_stride + c) : 0.0f;
+                }
+                row[j] = nan_to_num_f32(v);
+            }
+        }
+    }
+    if (grid_eattr) {
+        float gev[8 * BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+        for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q) gev[q] = 0.0f;
+        const float4 mine = *reinterpret_cast<const float4*>(&s_s[pr + 1][pc + 1][0]);
+        const float ms[4] = {mine.x, mine.y, mine.z, mine.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int jr = lr - P.dr[k], jc = lc - P.dc[k];          // source = i - off_k
+            if (!s_v[jr][jc]) continue;
+            const double dx = (double)P.dc[k] * rx, dy = (double)P.dr[k] * ry;
+            double dist = sqrt(dx * dx + dy * dy);
+            const float dz = d - s_d[jr][jc];
+            const float slope = k < 4 ? 0.0f - ms[3 - k] : s_s[pr + 1 - P.dr[k]][pc + 1 - P.dc[k]][k - 4];   // 0 - x: no -0.0
+#pragma unroll
+            for (int e = 0; e < BGNN_MAX_EDGE_FEATS; ++e) {
+                if (e >= P.ED) continue;
+                float v;
+                switch (P.ef[e]) {
+                    case BGNN_EF_DISTANCE: { double dd = dist; if (isnan(dd)) dd = 0.0; v = (float)dd; break; }
+                    case BGNN_EF_DEPTH_DIFF: v = nan_to_num_f32(dz); break;
+                    case BGNN_EF_SLOPE: v = slope; break;
+                    default: v = 0.0f;
+                }
+                if (P.ED == 3) gev[k * 3 + e] = v;
+                else if (P.ED == 4) gev[k * 4 + e] = v;
+                else if (P.ED == 2) gev[k * 2 + e] = v;
+                else gev[k + e] = v;
+            }
+        }
+        float* ge = grid_eattr + t * (int64_t)(8 * P.ED);
+        const int n = 8 * P.ED;
+        if ((n & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (4 * q < n) reinterpret_cast<float4*>(ge)[q] = make_float4(gev[4 * q], gev[4 * q + 1], gev[4 * q + 2], gev[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q)
+                if (q < n) ge[q] = gev[q];
+        }
+    }
+}
+
 // reference COO: offset-major, node-minor (graph_construction.py:196-241)
 __global__ void __launch_bounds__(GB_THREADS) gb_coo(const GraphParams P, const int32_t* __restrict__ table,
                                                      const int32_t* __restrict__ node_id, int64_t E,
@@ -430,7 +609,7 @@ extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* c
     int32_t* table = (int32_t*)scratch;
     { ProfScope ps(0, stream); gb_count<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table); }
     BGNN_LAUNCH_CHECK();
-    { ProfScope ps(1, stream); gb_scan<<<1, 1024, 0, stream>>>(table, P.nblocks, P.ncol); }
+    { ProfScope ps(1, stream); gb_scan<<<P.ncol, 1024, 0, stream>>>(table, P.nblocks, P.ncol); }
     BGNN_LAUNCH_CHECK();
     int32_t tot[2];
     BGNN_CUDA(cudaMemcpyAsync(&tot[0], table + P.nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -461,7 +640,16 @@ extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cf
     BGNN_LAUNCH_CHECK();
     if (x || local_std || csr_src || csr_eattr || grid_eattr) {
         ProfScope ps(3, stream);
-        gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr, grid_eattr);
+        // lean grid path (no CSR payload requested, the reference's 8 offsets in their order): shared-memory tiled kernel
+        static const int r8[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, c8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+        bool std8 = P.K == 8 && cells->n_grids == 1 && !csr_src && !csr_eattr && cells->rows >= 2 && cells->cols >= 2;
+        for (int k = 0; k < 8 && std8; ++k) std8 = P.dr[k] == r8[k] && P.dc[k] == c8[k];
+        if (std8) {
+            dim3 grid((unsigned)((cells->cols + TP_W - 1) / TP_W), (unsigned)((cells->rows + TP_H - 1) / TP_H));
+            gb_emit_tile<<<grid, TP_H * TP_W, 0, stream>>>(P, node_id, x, local_std, grid_eattr);
+        } else {
+            gb_emit<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, node_id, rowptr, x, local_std, csr_src, csr_eattr, grid_eattr);
+        }
         BGNN_LAUNCH_CHECK();
     }
     return BGNN_OK;

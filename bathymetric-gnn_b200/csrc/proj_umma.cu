@@ -152,7 +152,9 @@ struct UmmaSmem {
                                                                   // the epilogue of super tile t overlaps the MMAs of t+1
     static constexpr int TMEM_COLS = ACC_COLS * ACC_STAGES <= 32 ? 32 : ACC_COLS * ACC_STAGES <= 64 ? 64 : ACC_COLS * ACC_STAGES <= 128 ? 128
                                      : ACC_COLS * ACC_STAGES <= 256 ? 256 : 512;
-    static constexpr int EPI_SPLIT = (EMODE == EM_PROJ && N == 256) ? 2 : 1;    // column halves handled by different epilogue warps
+    // epilogue warps 4..7 share the TMEM lanes of warps 0..3 and take the other half of the work: the upper column half
+    // (EM_PROJ, N = 256) or the correction head (EM_HEADS; one warp per scheduler cannot hide its own FMA latency)
+    static constexpr int EPI_SPLIT = ((EMODE == EM_PROJ && N == 256) || EMODE == EM_HEADS) ? 2 : 1;
     // EM_PROJ: every epilogue warp stages its [32 rows x 32 cols] chunk in a SWIZZLE_128B tile and hands it to a TMA
     // tensor store (one 4 KB store instead of 128 scattered 32 B sectors through the LSU)
 #ifndef BGNN_N256_TMA_STORE
@@ -543,6 +545,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     for (int k = 0; k < 8; ++k) lg[k] = 0.f;
 #pragma unroll 1
                     for (int c0 = 0; c0 < real; c0 += 32) {
+                        if (((c0 / h2) >= 2) != (half == 1)) continue;      // half 0: classification + confidence, half 1: correction
                         float x[32];
                         tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), out_scale, x);
 #pragma unroll
@@ -579,7 +582,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             if (blk == 1) pc += acc; else pr += acc;
                         }
                     }
-                    if (row < M) {
+                    if (row < M && half == 1) {
+                        if (P.corr && P.nblk > 2) P.corr[row] = pr + b2[ncls + 1];
+                    } else if (row < M) {
                         float best = -CUDART_INF_F;
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
@@ -600,7 +605,6 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         const float cf = 1.f / (1.f + expf(-(pc + b2[ncls])));
                         if (P.cls) P.cls[row] = arg;
                         if (P.conf) P.conf[row] = cf;
-                        if (P.corr && P.nblk > 2) P.corr[row] = pr + b2[ncls + 1];
                         if (P.action) {
                             int64_t a = (arg == 2 && cf > P.thr_auto) ? 1 : 0;          // gnn.py:439-441
                             if (cf < P.thr_review) a = 2;                                // gnn.py:444-445

@@ -8,7 +8,7 @@ from bathymetric_gnn_b200._lib import lib, check, ptr
 lib.bgnn_debug_umma_timing.argtypes = [C.c_void_p, C.c_int]
 M = 4099615
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for (K, N, heads) in [(256, 256, 4), (256, 64, 1)]:
+for (K, N, heads) in [(256, 256, 4), (256, 64, 1), (64, 128, 4)]:
     A = torch.relu(torch.randn(M, K, device="cuda"))
     W = torch.randn(N, K) / np.sqrt(K)
     att = torch.randn(N, device="cuda")
