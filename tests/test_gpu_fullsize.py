@@ -1,0 +1,114 @@
+"""GPU: BASELINE.json configs[1] at FULL size (one 2048 x 2048 tile, 2 % invalid cells in blobs) through the C ABI.
+
+The CPU oracle needs minutes at this size, so the checks are the size-independent properties of the path plus an
+oracle comparison on windows cut from the interior:
+  * node ids == exclusive prefix count of the mask in raster order (bit-exact vs NumPy), edge count == the in-grid
+    8-neighbour pair count of the mask, rowptr == prefix sum of the per-node in-degree;
+  * graph features of a 300 x 300 window equal the oracle's features of the same window built from the SAME tile
+    (interior nodes whose 5x5 / 3x3 stencils do not touch the window border);
+  * probabilities sum to 1, class == argmax(logits) (first max), confidence == sigmoid range, action rule
+    (models/gnn.py:436-449) holds for every node;
+  * the forward of the big tile restricted to the window's deep interior (> 4 hops from the window border: 4 GAT layers)
+    equals the oracle forward of the window graph within the fp32 tolerance;
+  * two runs are bit-identical (deterministic summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import model_oracle as mo
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 2e-5, 1e-5
+T = 2048
+
+
+@pytest.fixture(scope="module")
+def big():
+    import bathymetric_gnn_b200 as bg
+    depth = synth.noisy_tile(T, T, seed=1234, r0=1920, c0=1920)
+    mask = synth.blob_mask(T, T, seed=1234, invalid_frac=0.02)
+    depth[~mask] = 1.0e6
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=0, randomize_bn=True, head_gain=1.0)
+    # shift the head biases on a small window so that all three classes and both confidence thresholds occur
+    wd, wm = np.ascontiguousarray(depth[700:828, 900:1028]), np.ascontiguousarray(mask[700:828, 900:1028])
+    wg = go.build_graph(wd, wm, None, (0.5, 0.5))
+    mo.calibrate_heads(sd, cfg, wg["x"], wg["edge_index"], wg["edge_attr"])
+    model = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = bg.GraphBuilder("8-connected").build_graph(torch.from_numpy(depth).cuda(), torch.from_numpy(mask).cuda(), None, (0.5, 0.5))
+    out = model.predict(g)
+    return dict(depth=depth, mask=mask, cfg=cfg, sd=sd, model=model, g=g, out=out)
+
+
+def test_ids_and_edge_count_full_tile(big):
+    g, mask = big["g"], big["mask"]
+    dg = g._dev
+    N = int(mask.sum())
+    assert g.num_nodes == N
+    nid = dg.node_id.cpu().numpy().reshape(T, T)
+    ref = np.where(mask, np.cumsum(mask.ravel()).reshape(T, T) - 1, -1)
+    assert np.array_equal(nid, ref)
+    deg = np.zeros((T, T), np.int64)
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            if dr == 0 and dc == 0:
+                continue
+            sh = np.zeros_like(mask)
+            rs, re_ = max(0, dr), T + min(0, dr)
+            cs, ce = max(0, dc), T + min(0, dc)
+            sh[rs:re_, cs:ce] = mask[rs - dr:re_ - dr, cs - dc:ce - dc]
+            deg += (sh & mask)
+    assert g.num_edges == int(deg.sum())
+    rowptr = dg.rowptr.cpu().numpy().astype(np.int64)
+    assert np.array_equal(rowptr, np.concatenate([[0], np.cumsum(deg[mask])]))
+    assert np.array_equal(g.x.cpu().numpy()[:, 0], big["depth"][mask])
+
+
+def test_outputs_are_self_consistent(big):
+    out = big["out"]
+    lg, pr = out["class_logits"], out["class_probs"]
+    assert torch.isfinite(lg).all()
+    assert torch.allclose(pr.sum(1), torch.ones_like(pr[:, 0]), atol=1e-6)
+    assert torch.equal(out["predicted_class"], torch.argmax(pr, dim=1))
+    cf = out["confidence"]
+    assert ((cf >= 0) & (cf <= 1)).all()
+    act = torch.where((out["predicted_class"] == 2) & (cf > 0.85), 1, 0)
+    act = torch.where(cf < 0.6, torch.full_like(act, 2), act)
+    assert torch.equal(out["action"], act)
+    assert torch.equal(out["needs_review"], act == 2) and torch.equal(out["auto_correct"], act == 1)
+
+
+def test_window_matches_oracle(big):
+    r0, c0, S = 700, 900, 300
+    d = np.ascontiguousarray(big["depth"][r0:r0 + S, c0:c0 + S])
+    m = np.ascontiguousarray(big["mask"][r0:r0 + S, c0:c0 + S])
+    ref = go.build_graph(d, m, None, (0.5, 0.5))
+    exp = mo.forward(big["sd"], big["cfg"], ref["x"], ref["edge_index"], ref["edge_attr"])
+    nid = big["g"]._dev.node_id.cpu().numpy().reshape(T, T)[r0:r0 + S, c0:c0 + S]
+    rows, cols = ref["valid_rows"], ref["valid_cols"]
+    big_ids = nid[rows, cols]
+    x_big = big["g"].x.cpu().numpy()[big_ids]
+    feat_in = (rows >= 3) & (rows < S - 3) & (cols >= 3) & (cols < S - 3)        # 5x5 box + filled neighbours inside the window
+    scale = float(np.abs(d[m]).max())
+    assert np.array_equal(x_big[feat_in, 0], ref["x"][feat_in, 0])
+    assert np.all(np.abs(x_big[feat_in, 1:].astype(np.float64) - ref["x"][feat_in, 1:]) <= 4 * np.spacing(np.float32(scale)) + 1e-7 * scale)
+    deep = (rows >= 8) & (rows < S - 8) & (cols >= 8) & (cols < S - 8)          # 4 layers of 1-hop + feature stencils
+    lg = big["out"]["class_logits"].cpu().numpy()[big_ids]
+    np.testing.assert_allclose(lg[deep], exp["class_logits"].numpy()[deep], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(big["out"]["confidence"].cpu().numpy()[big_ids][deep], exp["confidence"].numpy()[deep], rtol=RTOL, atol=ATOL)
+    srt = np.sort(exp["class_logits"].numpy(), axis=1)
+    strict = deep & ((srt[:, -1] - srt[:, -2]) > 2 * (ATOL + RTOL * np.abs(srt[:, -1])))
+    cls = big["out"]["predicted_class"].cpu().numpy()[big_ids]
+    assert np.array_equal(cls[strict], exp["predicted_class"].numpy()[strict])
+    assert len(set(cls[deep].tolist())) == 3            # all three classes occur in the window
+
+
+def test_full_tile_is_deterministic(big):
+    out2 = big["model"].predict(big["g"])
+    for k in ("class_logits", "confidence", "correction", "predicted_class"):
+        assert torch.equal(out2[k], big["out"][k]), k
