@@ -235,29 +235,58 @@ def run_ours(args):
     # ---- end to end through the public API with pinned host buffers
     depth_pin = torch.from_numpy(depth_np).pin_memory()
     mask_pin = torch.from_numpy(mask_np).pin_memory()
-    host_cls = torch.empty(N, dtype=torch.int64).pin_memory()
-    host_conf = torch.empty(N, dtype=torch.float32).pin_memory()
-    host_corr = torch.empty(N, dtype=torch.float32).pin_memory()
+    # Two sets of pinned result buffers and device input buffers: step t's H2D and step t-1's D2H run on a copy stream
+    # while step t-1 / t computes (the way a caller streams tiles through the public API); every step's input upload and
+    # result read-back is inside the timed region, and each step's result is consumed on the host (float(conf[0])).
+    host_out = [(torch.empty(N, dtype=torch.int64).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
+                 torch.empty(N, dtype=torch.float32).pin_memory()) for _ in range(2)]
+    dev_in = [(torch.empty_like(depth_dev), torch.empty_like(mask_dev)) for _ in range(2)]
+    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def step_e2e():
-        flush.fill_(1)
-        d = depth_pin.to(dev, non_blocking=True)
-        m = mask_pin.to(dev, non_blocking=True)
-        g = builder.build_graph(d, m, None, RES)
-        out = model.predict(g)
-        host_cls.copy_(out["predicted_class"], non_blocking=True)
-        host_conf.copy_(out["confidence"], non_blocking=True)
-        host_corr.copy_(out["correction"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(host_conf[0])
+    def run_e2e(steps):
+        keep, acc = [None, None], 0.0
 
-    for _ in range(2):
-        step_e2e()
+        def upload(t):
+            b = t % 2
+            with torch.cuda.stream(copy_s):
+                if t >= 2:
+                    copy_s.wait_event(ev_cmp[b])               # the graph build of step t-2 has consumed this buffer
+                dev_in[b][0].copy_(depth_pin, non_blocking=True)
+                dev_in[b][1].copy_(mask_pin, non_blocking=True)
+                ev_in[b].record(copy_s)
+        upload(0)
+        for t in range(steps):
+            b = t % 2
+            if t + 1 < steps:
+                upload(t + 1)
+            main_s.wait_event(ev_in[b])
+            flush.fill_(1)
+            g = builder.build_graph(dev_in[b][0], dev_in[b][1], None, RES)
+            out = model.predict(g)
+            ev_cmp[b].record(main_s)
+            keep[b] = (g, out)                                  # alive until their read-back has finished
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_cmp[b])
+                host_out[b][0].copy_(out["predicted_class"], non_blocking=True)
+                host_out[b][1].copy_(out["confidence"], non_blocking=True)
+                host_out[b][2].copy_(out["correction"], non_blocking=True)
+                ev_out[b].record(copy_s)
+            if t >= 1:
+                ev_out[1 - b].synchronize()
+                acc += float(host_out[1 - b][1][0])
+                keep[1 - b] = None
+        ev_out[(steps - 1) % 2].synchronize()
+        acc += float(host_out[(steps - 1) % 2][1][0])
+        main_s.wait_event(ev_out[(steps - 1) % 2])
+        return acc
+
+    run_e2e(2)
     barrier()
-    t0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
