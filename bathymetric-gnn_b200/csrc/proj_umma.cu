@@ -43,17 +43,18 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "proj_umma.cuh"
 
 #ifdef BGNN_AGG_TIMING
-__device__ unsigned long long g_umma_t[8];
+__device__ unsigned long long g_umma_t[12];
 #define UT_DECL() long long ut_prev = clock64()
 #define UT_TICK(slot) do { long long ut_now = clock64(); atomicAdd(&g_umma_t[slot], (unsigned long long)(ut_now - ut_prev)); ut_prev = ut_now; } while (0)
 extern "C" int bgnn_debug_umma_timing(unsigned long long* out8, int reset) {
-    if (out8) cudaMemcpyFromSymbol(out8, g_umma_t, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_umma_t, z, sizeof(z)); }
+    if (out8) cudaMemcpyFromSymbol(out8, g_umma_t, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {}; cudaMemcpyToSymbol(g_umma_t, z, sizeof(z)); }
     return 0;
 }
 #else
@@ -140,8 +141,15 @@ __device__ __forceinline__ void split4h(const float4 v, float s, uint2& hi, uint
 constexpr int MLP0_MAXK = 128, MLP0_FP = 8;         // PM_MLP0: K <= 128 hidden units, F <= 8 inputs (padded to 8)
 constexpr int HEADS_MAXOUT = 10, HEADS_MAXH2 = 64;  // EM_HEADS: <= 8 classes + confidence + correction, h2 <= 64
 
-template <int N, int PMODE = PM_PLAIN, int EMODE = EM_PROJ>
+// NH = 2 ("paired CTAs, resident W"): the output is NT = 2 N columns wide; CTA b owns column block b & 1 for the whole launch and
+// walks the M tiles (b >> 1) + k * gridDim.x / 2, so the two CTAs of a pair work on the same A tile at about the same time
+// (the second fetch is an L2 hit).  The CTA's half of the split weights (K <= 256: 8 chunks x 16 KB) is loaded ONCE and
+// stays in shared memory -- with a 128 x 256 tile per CTA the 256 KB of W re-read from L2 for every 128 rows were twice
+// the A traffic and put the kernel against the L2 throughput cap -- and its accumulators fit TMEM twice, so the epilogue
+// of tile t overlaps the MMAs of tile t + 1.
+template <int N, int PMODE = PM_PLAIN, int EMODE = EM_PROJ, int NH = 1>
 struct UmmaSmem {
+    static constexpr int NT = N * NH;                            // total output width
     static constexpr int MT = N >= 128 ? 1 : 2;                  // M tiles per super tile
     static constexpr int SUPER_M = MT * TILE_M;
     static constexpr int B_TILE_BYTES = N * KC * 2;
@@ -154,28 +162,30 @@ struct UmmaSmem {
                                      : ACC_COLS * ACC_STAGES <= 256 ? 256 : 512;
     // epilogue warps 4..7 share the TMEM lanes of warps 0..3 and take the other half of the work: the upper column half
     // (EM_PROJ, N = 256) or the correction head (EM_HEADS; one warp per scheduler cannot hide its own FMA latency)
-    static constexpr int EPI_SPLIT = ((EMODE == EM_PROJ && N == 256) || EMODE == EM_HEADS) ? 2 : 1;
+    static constexpr int EPI_SPLIT = ((EMODE == EM_PROJ && NT == 256) || EMODE == EM_HEADS) ? 2 : 1;
     // EM_PROJ: every epilogue warp stages its [32 rows x 32 cols] chunk in a SWIZZLE_128B tile and hands it to a TMA
     // tensor store (one 4 KB store instead of 128 scattered 32 B sectors through the LSU)
 #ifndef BGNN_N256_TMA_STORE
 #define BGNN_N256_TMA_STORE 0
 #endif
     // N = 256 from global A: shared memory holds either the staging tiles (with a 2-deep raw ring) or a 4-deep raw ring
-    static constexpr bool TMA_STORE = EMODE == EM_PROJ && !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE);
+    static constexpr bool TMA_STORE = EMODE == EM_PROJ && !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE) && NH == 1;
     static constexpr int STG_WARPS = TMA_STORE ? 4 * EPI_SPLIT : 0;
     static constexpr int STG_BYTES = STG_WARPS * 4096;
-    static constexpr int NSTAGE = (PMODE == PM_PLAIN && N == 256) ? 2 : STAGES;     // fp16 operand ring depth (measured: for
+    static constexpr int NSTAGE = ((PMODE == PM_PLAIN && N == 256) || NH > 1) ? 2 : STAGES;     // fp16 operand ring depth (measured: for
                                                                                      // N = 256 a deeper raw ring beats a third stage)
-    static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * N : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;   // epilogue parameters
+    static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * (NH > 1 ? N : NT) : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;  // epilogue parameters
     static constexpr int PAR_P = PMODE == PM_MLP0 ? MLP0_MAXK * MLP0_FP + MLP0_MAXK : 0;              // producer parameters
     // PM_PLAIN: the A chunk [SUPER_M x 32] fp32 is fetched by TMA into a raw ring, RAW_STAGES chunks ahead
     static constexpr int RAW_BYTES = PMODE == PM_PLAIN ? SUPER_M * KC * 4 : 0;
     // The depth must be a multiple of the producer-group count so that a raw slot is always consumed by the SAME group:
     // TMA copies may complete out of order, and a group that last saw the slot two phases ago would otherwise pass the
     // parity wait of a phase that has not completed (then over-arrive on the empty barrier -> launch failure).
-    static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? (BGNN_N256_TMA_STORE ? 2 : 4) : N == 128 ? 6 : 2);
+    static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? (BGNN_N256_TMA_STORE ? 2 : 4) : N == 128 ? (NH > 1 ? 4 : 6) : 2);
+    static constexpr int W_SLOTS = NH > 1 ? 8 : NW;                      // NH = 2: the whole K extent (<= 256) stays resident
+    static constexpr int PARW = NH > 1 ? N : NT;                          // epilogue parameter columns held by this CTA
     static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
-    static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)NW * W_SLOT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
+    static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)W_SLOTS * W_SLOT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
                                     STG_BYTES + (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
 };
 
@@ -205,15 +215,16 @@ __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_
     for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j])) * scale;
 }
 
-template <int N, int PMODE, int EMODE>
+template <int N, int PMODE, int EMODE, int NH>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA,
                  const __grid_constant__ CUtensorMap tmapC) {
-    using S = UmmaSmem<N, PMODE, EMODE>;
+    using S = UmmaSmem<N, PMODE, EMODE, NH>;
+    constexpr int NT = S::NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw;                                                      // stage ring (1024 B aligned)
     unsigned char* wring = base + (size_t)S::NSTAGE * S::STAGE_BYTES;                    // W chunk ring
-    unsigned char* raw = wring + (size_t)NW * S::W_SLOT_BYTES;                           // raw fp32 A ring
+    unsigned char* raw = wring + (size_t)S::W_SLOTS * S::W_SLOT_BYTES;                           // raw fp32 A ring
     unsigned char* stg = raw + (size_t)S::RAW_STAGES * S::RAW_BYTES;                     // epilogue store staging (1024 B aligned)
     float* s_par = reinterpret_cast<float*>(stg + S::STG_BYTES);                          // epilogue parameters
     float* s_prod = s_par + S::PAR_E;                                                     // producer parameters
@@ -226,6 +237,11 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     const int K = P.K;
     const int nkc = K / KC;
     const int64_t n_super = (M + SUPER_M - 1) / SUPER_M;
+    // tile walk of this CTA (NH = 2: pairs of CTAs share the M tiles, each CTA keeps one column block)
+    const int nh = NH > 1 ? (int)(blockIdx.x & 1) : 0;
+    const int64_t st_first = NH > 1 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+    const int64_t st_step = NH > 1 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+    const int cg0 = nh * N;                                    // first global output column of this CTA
 
     // power-of-two operand scale from the upper bound of max|A|: |a * sA| < 1 (exact; undone in the epilogue)
     float sA = 1.f, out_scale = P.w_inv_scale;
@@ -248,10 +264,10 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (EMODE == EM_PROJ) {          // s_par = att_src [N] | att_dst [N] | bias [N]
-        for (int i = tid; i < N; i += UM_THREADS) {
-            s_par[i] = P.alpha ? __ldg(P.att_src + i) : 0.f;
-            s_par[N + i] = P.alpha ? __ldg(P.att_dst + i) : 0.f;
-            s_par[2 * N + i] = P.bias ? __ldg(P.bias + i) : 0.f;
+        for (int i = tid; i < S::PARW; i += UM_THREADS) {
+            s_par[i] = P.alpha ? __ldg(P.att_src + cg0 + i) : 0.f;
+            s_par[S::PARW + i] = P.alpha ? __ldg(P.att_dst + cg0 + i) : 0.f;
+            s_par[2 * S::PARW + i] = P.bias ? __ldg(P.bias + cg0 + i) : 0.f;
         }
     } else {                         // s_par = hb0 [N, zero padded] | W2 [nout][h2] (cls rows, conf, corr) | b2 [nout]
         const int real = P.nblk * P.h2;
@@ -291,7 +307,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         const int ptid = tid - (PROD_WARP0 + grp * (PROD_WARPS / PROD_GROUPS)) * 32;      // 0..127
         constexpr int A_F4 = MT * TILE_M * (KC / 4) / PROD_GROUP_THREADS;                  // 8 or 16 float4 per thread and chunk
         uint32_t it = 0;
-        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int64_t st = st_first; st < n_super; st += st_step) {
             const int64_t row0 = st * SUPER_M;
             for (int kc = 0; kc < nkc; ++kc, ++it) {
                 if ((int)(it % PROD_GROUPS) != grp) continue;
@@ -301,7 +317,13 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     // fp32 rows of this chunk from the raw ring (bulk-copied by the loader warp), then free the slot
                     constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
                     const int slot = it % RS;
+#ifdef BGNN_AGG_TIMING
+                    long long ut_prev = clock64();
+#endif
                     mbar_wait(&bars[BAR_RFULL + slot], (it / RS) & 1);
+#ifdef BGNN_AGG_TIMING
+                    if (ptid == 0 && grp == 0) UT_TICK(5);
+#endif
                     const float* rsrc = reinterpret_cast<const float*>(raw + (size_t)slot * S::RAW_BYTES);
                     float4 av[A_F4];
 #pragma unroll
@@ -310,6 +332,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         av[i] = *reinterpret_cast<const float4*>(rsrc + f * 4);
                     }
                     if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
+#ifdef BGNN_AGG_TIMING
+                    if (ptid == 0 && grp == 0) UT_TICK(6);
+#endif
 #pragma unroll
                     for (int i = 0; i < A_F4; ++i) {                   // 2-way fp16 split -> swizzled STS
                         const int f = ptid + i * PROD_GROUP_THREADS;
@@ -324,6 +349,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     // behind the LDS does not wait for their data, and the next TMA copy then overwrites rows that are still
                     // being read (seen as scattered wrong rows under load).
                     mbar_arrive(&bars[BAR_REMPTY + slot]);
+#ifdef BGNN_AGG_TIMING
+                    if (ptid == 0 && grp == 0) UT_TICK(7);
+#endif
                 } else {
                     // thread <-> node: its F inputs are loaded once, then the 32 hidden units of this chunk are
                     // relu(b0 + x W0^T) straight into the split tiles (W0 rows are warp-uniform broadcasts from smem)
@@ -369,7 +397,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         if (PMODE == PM_PLAIN && lane == 0) {
             constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
             uint32_t it = 0;
-            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+            for (int64_t st = st_first; st < n_super; st += st_step) {
                 const int row0 = (int)(st * SUPER_M);
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int slot = it % RS;
@@ -387,17 +415,33 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         // ONE bulk copy per chunk into its own ring (an own thread: its waits must not hold up the A loads) =====================
         if (lane == 0) {
             constexpr uint32_t W_BYTES = S::W_SLOT_BYTES;
-            uint32_t it = 0;
-            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
-                for (int kc = 0; kc < nkc; ++kc, ++it) {
-                    const int w = it % NW;
-                    if (it >= (uint32_t)NW) mbar_wait(&bars[BAR_WEMPTY + w], ((it / NW) - 1) & 1);
-                    const uint32_t wbar = smem_u32(&bars[BAR_WFULL + w]);
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wbar), "r"(W_BYTES) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                                 ::"r"(smem_u32(wring + (size_t)w * S::W_SLOT_BYTES)),
-                                   "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + (size_t)kc * W_BYTES), "r"(W_BYTES), "r"(wbar)
-                                 : "memory");
+            if (NH > 1) {
+                // resident W: rows [nh*N, (nh+1)*N) of every K-major swizzled [NT x 32] tile are one contiguous block (8-row
+                // groups); all chunks complete on ONE barrier (tx count = nkc * W_SLOT_BYTES <= 128 KB)
+                const uint32_t wbar = smem_u32(&bars[BAR_WFULL]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wbar), "r"((uint32_t)nkc * W_BYTES) : "memory");
+                for (int kc = 0; kc < nkc; ++kc)
+#pragma unroll
+                    for (int sp = 0; sp < NSPLIT; ++sp)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                     ::"r"(smem_u32(wring + (size_t)kc * S::W_SLOT_BYTES + (size_t)sp * S::B_TILE_BYTES)),
+                                       "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) +
+                                           ((size_t)(kc * NSPLIT + sp) * NH + nh) * S::B_TILE_BYTES),
+                                       "r"((uint32_t)S::B_TILE_BYTES), "r"(wbar)
+                                     : "memory");
+            } else {
+                uint32_t it = 0;
+                for (int64_t st = st_first; st < n_super; st += st_step) {
+                    for (int kc = 0; kc < nkc; ++kc, ++it) {
+                        const int w = it % NW;
+                        if (it >= (uint32_t)NW) mbar_wait(&bars[BAR_WEMPTY + w], ((it / NW) - 1) & 1);
+                        const uint32_t wbar = smem_u32(&bars[BAR_WFULL + w]);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wbar), "r"(W_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                     ::"r"(smem_u32(wring + (size_t)w * S::W_SLOT_BYTES)),
+                                       "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + (size_t)kc * W_BYTES), "r"(W_BYTES), "r"(wbar)
+                                     : "memory");
+                    }
                 }
             }
         }
@@ -408,14 +452,20 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             uint32_t it = 0, t = 0;
             UT_DECL();
-            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
+#ifdef BGNN_AGG_TIMING
+            const long long ut_c0 = clock64();
+            unsigned long long ut_g0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ut_g0));
+#endif
+            if (NH > 1) mbar_wait(&bars[BAR_WFULL], 0);                // resident W has landed
+            for (int64_t st = st_first; st < n_super; st += st_step, ++t) {
                 const uint32_t as = t % S::ACC_STAGES;
                 if (t >= (uint32_t)S::ACC_STAGES) mbar_wait(&bars[BAR_TEMPTY + as], (t / S::ACC_STAGES - 1) & 1);   // epilogue drained this stage
                 UT_TICK(0);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
-                    const int s = it % S::NSTAGE, w = it % NW;
-                    mbar_wait(&bars[BAR_WFULL + w], (it / NW) & 1);
+                    const int s = it % S::NSTAGE, w = NH > 1 ? kc : (int)(it % NW);
+                    if (NH == 1) mbar_wait(&bars[BAR_WFULL + w], (it / NW) & 1);
                     mbar_wait(&bars[BAR_FULL + s], (it / S::NSTAGE) & 1);
                     UT_TICK(1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -437,11 +487,19 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         }
                     }
                     umma_commit(&bars[BAR_EMPTY + s]);                 // A stage and W slot free when these MMAs retire
-                    umma_commit(&bars[BAR_WEMPTY + w]);
+                    if (NH == 1) umma_commit(&bars[BAR_WEMPTY + w]);
                     UT_TICK(2);
                 }
                 umma_commit(&bars[BAR_TFULL + as]);                    // accumulators complete
             }
+#ifdef BGNN_AGG_TIMING
+            {
+                unsigned long long ut_g1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ut_g1));
+                atomicAdd(&g_umma_t[8], (unsigned long long)(clock64() - ut_c0));
+                atomicAdd(&g_umma_t[9], ut_g1 - ut_g0);
+            }
+#endif
         }
     } else if ((warp >> 2) < S::EPI_SPLIT) {
         // ===================== EPILOGUE: warp w <-> TMEM lanes 32*(w%4) .., one thread per output row =====================
@@ -450,7 +508,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         const int cbeg = half * NCOL;
         float cmax = 0.f;
         uint32_t t = 0;
-        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++t) {
+        for (int64_t st = st_first; st < n_super; st += st_step, ++t) {
             const int64_t row0 = st * SUPER_M;
             const uint32_t as = t % S::ACC_STAGES;
 #ifdef BGNN_AGG_TIMING
@@ -468,13 +526,15 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 if (EMODE == EM_PROJ) {
                     float as_acc = 0.f, ad_acc = 0.f;
 #pragma unroll 1
-                    for (int c0 = cbeg; c0 < cbeg + NCOL; c0 += 32) {
+                    for (int cl = cbeg; cl < cbeg + NCOL; cl += 32) {
+                        const int c0 = cg0 + cl;               // global output column (cl: column inside the accumulator)
+                        const int pc = NH > 1 ? cl : c0;       // column inside this CTA's epilogue parameters
                         float x[32];
-                        tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), out_scale, x);
+                        tmem_ld_sum32(taddr + (uint32_t)cl, taddr + (uint32_t)(N + cl), out_scale, x);
                         if (P.bias) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float4 b = *reinterpret_cast<const float4*>(s_par + 2 * N + c0 + j);
+                                const float4 b = *reinterpret_cast<const float4*>(s_par + 2 * S::PARW + pc + j);
                                 x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
                             }
                         }
@@ -491,8 +551,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float4 s4 = *reinterpret_cast<const float4*>(s_par + c0 + j);
-                                const float4 d4 = *reinterpret_cast<const float4*>(s_par + N + c0 + j);
+                                const float4 s4 = *reinterpret_cast<const float4*>(s_par + pc + j);
+                                const float4 d4 = *reinterpret_cast<const float4*>(s_par + S::PARW + pc + j);
                                 s0 = fmaf(x[j], s4.x, s0); s1 = fmaf(x[j + 1], s4.y, s1);
                                 s2 = fmaf(x[j + 2], s4.z, s2); s3 = fmaf(x[j + 3], s4.w, s3);
                                 d0 = fmaf(x[j], d4.x, d0); d1 = fmaf(x[j + 1], d4.y, d1);
@@ -512,7 +572,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         if (!S::TMA_STORE) {         // thread-per-row 256-bit stores (32 different lines per instruction)
                             if (row < M) {
                                 float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH)
-                                                          : P.Cout + row * N + c0;
+                                                          : P.Cout + row * NT + c0;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
                             }
@@ -685,12 +745,12 @@ int make_tmap_C(float* C, int64_t M, int N, int CH, int head_major, CUtensorMap*
     return BGNN_OK;
 }
 
-template <int N, int PMODE, int EMODE>
+template <int N, int PMODE, int EMODE, int NH = 1>
 int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
-    using S = UmmaSmem<N, PMODE, EMODE>;
+    using S = UmmaSmem<N, PMODE, EMODE, NH>;
     static_assert(S::BYTES <= 232448, "shared memory budget exceeded");
     static bool configured[64] = {};                    // the attribute is per device
-    auto kern = proj_umma_kernel<N, PMODE, EMODE>;
+    auto kern = proj_umma_kernel<N, PMODE, EMODE, NH>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
@@ -708,15 +768,19 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
     memset(&tmapC, 0, sizeof(tmapC));
     if (EMODE == EM_PROJ) {
         BGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.Cout) & 15) == 0, "C must be 16-byte aligned");
-        int rc = make_tmap_C(a.Cout, a.M, N, a.CH, a.head_major, &tmapC);
+        int rc = make_tmap_C(a.Cout, a.M, S::NT, a.CH, a.head_major, &tmapC);
         if (rc) return rc;
     }
     const int64_t n_super = (a.M + S::SUPER_M - 1) / S::SUPER_M;
-    const unsigned grid = (unsigned)(n_super < sms ? n_super : sms);
+    unsigned grid = (unsigned)(n_super < sms ? n_super : sms);
+    if (NH > 1) {                                   // pairs of CTAs (one per column block) share the M tiles
+        const int64_t pairs = n_super < sms / 2 ? n_super : sms / 2;
+        grid = (unsigned)(2 * (pairs > 0 ? pairs : 1));
+    }
     kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap, tmapC);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        bgnn_set_error("proj_umma_kernel<N=%d, producer %d, epilogue %d> M=%lld K=%d: %s", N, PMODE, EMODE, (long long)a.M, a.K,
+        bgnn_set_error("proj_umma_kernel<N=%d x %d, producer %d, epilogue %d> M=%lld K=%d: %s", N, NH, PMODE, EMODE, (long long)a.M, a.K,
                        cudaGetErrorString(e));
         return BGNN_E_CUDA;
     }
@@ -826,6 +890,9 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
     return BGNN_OK;
 }
 
+static bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
+                                                                         // 2-deep operand ring cannot hide the split latency)
+
 int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStream_t s) {
     if (a.M == 0) return BGNN_OK;
     if (pmode == PM_PLAIN && emode == EM_PROJ) {
@@ -833,7 +900,11 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
             case 32: return launch_t<32, PM_PLAIN, EM_PROJ>(a, sms, s);
             case 64: return launch_t<64, PM_PLAIN, EM_PROJ>(a, sms, s);
             case 128: return launch_t<128, PM_PLAIN, EM_PROJ>(a, sms, s);
-            case 256: return launch_t<256, PM_PLAIN, EM_PROJ>(a, sms, s);
+            case 256:
+                // paired CTAs, one column block of 128 each, resident W, double-buffered accumulators; an epilogue warp then
+                // owns 64 columns, which must hold whole heads
+                if (g_n256_halves && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_PLAIN, EM_PROJ, 2>(a, sms, s);
+                return launch_t<256, PM_PLAIN, EM_PROJ>(a, sms, s);
         }
     } else if (pmode == PM_MLP0 && emode == EM_PROJ) {
         switch (N) {

@@ -246,6 +246,9 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
  * tcgen05 path (N in {32,64,128,256}, K % 32 == 0) runs as a bf16x3-split GEMM with fp32 accumulation
  * in TMEM (fp32-grade accuracy); otherwise, or when switched off, the fp32 FMA GEMM is used. */
 int bgnn_set_tensor_cores(int on);
+/* Fusion of the last-but-one layer's aggregation with the last layer's projection (tcgen05 inside the tiled aggregation
+ * kernel; the [N, heads*C] intermediate then never reaches HBM): on by default, bit-identical results either way. */
+int bgnn_set_fusion(int on);
 /* testing aid: C_dev[M,N] = A_dev[M,K] . W_host[N,K]^T through the tcgen05 path (host-synchronous);
  * alpha_dev (optional) [M, 2*heads] receives the per-head dot products with att_src / att_dst [N]. */
 int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,

@@ -8,7 +8,7 @@ from bathymetric_gnn_b200._lib import lib, check, ptr
 lib.bgnn_debug_umma_timing.argtypes = [C.c_void_p, C.c_int]
 M = 4099615
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for (K, N, heads) in [(256, 256, 4), (256, 64, 1), (64, 128, 4)]:
+for (K, N, heads) in [(256, 256, 4), (256, 64, 1)]:
     A = torch.relu(torch.randn(M, K, device="cuda"))
     W = torch.randn(N, K) / np.sqrt(K)
     att = torch.randn(N, device="cuda")
@@ -18,10 +18,13 @@ for (K, N, heads) in [(256, 256, 4), (256, 64, 1), (64, 128, 4)]:
         lib.bgnn_debug_umma_timing(None, 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         check(lib.bgnn_test_proj_umma(ptr(A), M, K, C.c_void_p(W.data_ptr()), N, ptr(Cout), ptr(att), ptr(att), ptr(alpha), heads, st))
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 12)()
     lib.bgnn_debug_umma_timing(out, 0)
-    names = ["mma: wait TEMPTY (epilogue)", "mma: wait FULL (operands)", "mma: issue", "epi: wait TFULL (MMA)", "epi: drain + store"]
-    print(f"K={K} N={N}: per-CTA average cycles (148 CTAs)")
+    names = ["mma: wait TEMPTY (epilogue)", "mma: wait FULL (operands)", "mma: issue", "epi: wait TFULL (MMA)", "epi: drain + store",
+             "prod g0: wait RFULL (TMA A)", "prod g0: wait EMPTY (MMA frees stage)", "prod g0: split + STS", "mma thread: total cycles", "mma thread: total ns (globaltimer)"]
+    e0.record(); check(lib.bgnn_test_proj_umma(ptr(A), M, K, C.c_void_p(W.data_ptr()), N, ptr(Cout), ptr(att), ptr(att), ptr(alpha), heads, st)); e1.record(); torch.cuda.synchronize()
+    print(f"K={K} N={N}: per-CTA average cycles (148 CTAs); call incl. setup {e0.elapsed_time(e1):.3f} ms; WHOLE={os.environ.get('BGNN_N256_WHOLE')}")
     for i, n in enumerate(names):
         print(f"   {n:30s} {out[i]/148/1e3:10.1f} kcycles")
+    print(f"   SM clock during the kernel = {out[8]/max(out[9],1):.3f} GHz; kernel time per call = {out[9]/148/2/1e6:.3f} ms")
     del A, Cout, alpha
