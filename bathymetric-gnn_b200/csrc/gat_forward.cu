@@ -24,9 +24,11 @@
 #include "proj_umma.cuh"
 
 static bool g_use_umma = true;
+static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
 static bool g_fuse_last = false;      // aggregation of layer L-2 fused with the projection of layer L-1 (tcgen05 in the tiled kernel): correct, but measured slower (3.37 vs 1.80 + 1.03 ms) -> off by default
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
 extern "C" int bgnn_set_fusion(int on) { g_fuse_last = on != 0; return BGNN_OK; }
+extern "C" int bgnn_set_presplit(int on) { g_presplit = on != 0; return BGNN_OK; }
 #ifdef BGNN_AGG_TIMING
 extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset);
 #endif
@@ -523,12 +525,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// Optional output format: instead of fp32 rows, the layer output is written as the two fp16 planes hi / lo [N, H*C] of
+// y * sA that the next layer's tensor-core projection consumes directly (proj_umma.cu, PM_SPLIT): same 4 bytes per element,
+// same split arithmetic and the same power-of-two scale as the projection's own converter warps would apply (bit-identical
+// products), but the projection then needs no conversion stage at all.
+struct SplitOut {
+    uint16_t* hi;                  // nullptr: fp32 output
+    uint16_t* lo;
+    const float* amax_src;         // max|h_l| (device); |y| <= mul * max|h_l| + add
+    float mul, add;
+};
+
+// power-of-two operand scale of the tensor-core GEMM (same rule as proj_umma_kernel): |y * sA| < 1
+__device__ __forceinline__ float operand_scale(const float* amax_src, float mul, float add) {
+    float bound = add;
+    if (amax_src) bound = fmaf(mul, __ldg(amax_src), add);
+    const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);
+    const int es = 253 - e;
+    return (e > 0 && e < 255 && es >= 1 && es <= 253) ? __uint_as_float((uint32_t)es << 23) : 1.f;
+}
+
 template <int H, int C, int PH, bool CONN4>
 __global__ void __launch_bounds__(PH * 16, (C <= 64 ? 2 : 1))
 gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha, const TopoDev T,
                    const float* __restrict__ grid_eattr, int ED,
                    const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
-                   const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t n_nodes) {
+                   const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t n_nodes,
+                   const SplitOut SO) {
     using G = TileCfg<H, C, PH>;
     using O = EdgeOrder<CONN4>;
     constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, AST = G::AST, HR = G::HR;
@@ -546,6 +569,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pr0 = blockIdx.y * PH, pc0 = blockIdx.x * 16;
     AGG_T0();
+    const float sA = SO.hi ? operand_scale(SO.amax_src, SO.mul, SO.add) : 1.f;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(NT));
@@ -749,7 +773,8 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int ch = hh * C + lane * VEC + v;
-            bs[v] = s_bn[ch]; ba[v] = s_bn[HC + ch]; bb[v] = s_bn[2 * HC + ch];
+            // split output: the power-of-two operand scale rides on the BN constants (exact: relu(y) * sA == relu(y * sA))
+            bs[v] = s_bn[ch]; ba[v] = s_bn[HC + ch] * sA; bb[v] = s_bn[2 * HC + ch] * sA;
         }
         auto ldrow = [&](const float* p, float* dst) {
             if (VEC == 1) dst[0] = p[0];
@@ -796,7 +821,20 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                         y = fmaf(y, ba[v], bb[v]);
                         o[v] = relu ? fmaxf(y, 0.f) : y;
                     }
-                    VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
+                    if (VEC % 2 == 0 && SO.hi) {
+                        const int64_t e0 = (int64_t)id2 * HC + hh * C + lane * VEC;
+#pragma unroll
+                        for (int v = 0; v + 1 < VEC; v += 2) {
+                            const float s0v = o[v], s1v = o[v + 1];             // already scaled by sA
+                            const __half2 hi2 = __floats2half2_rn(s0v, s1v);
+                            const float2 hf = __half22float2(hi2);
+                            const __half2 lo2 = __floats2half2_rn((s0v - hf.x) * 2048.f, (s1v - hf.y) * 2048.f);
+                            *reinterpret_cast<__half2*>(SO.hi + e0 + v) = hi2;
+                            *reinterpret_cast<__half2*>(SO.lo + e0 + v) = lo2;
+                        }
+                    } else {
+                        VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
+                    }
                 }
             }
         }
@@ -808,7 +846,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
 
 template <int H, int C, int PH, bool CONN4>
 int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const float* grid_eattr,
-                      int ED, int relu, float slope, float* out, int64_t n_nodes, cudaStream_t s) {
+                      int ED, int relu, float slope, float* out, int64_t n_nodes, const SplitOut& SO, cudaStream_t s) {
     using G = TileCfg<H, C, PH>;
     static_assert(G::SMEM <= 232448, "shared memory budget exceeded");
     static bool configured[64] = {};                    // the attribute is per device
@@ -820,7 +858,7 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
         configured[dev & 63] = true;
     }
     dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
-    kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes);
+    kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes, SO);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
@@ -1315,13 +1353,14 @@ static bool tile_supported(const TopoDev& T, int H, int C, int ED, const float* 
 
 // returns 1 if no tiled instantiation fits (caller falls back to the CSR kernel)
 int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const TopoDev& T, const float* grid_eattr,
-                    int ED, int relu, float slope, float* out, int64_t n_nodes, cudaStream_t s) {
+                    int ED, int relu, float slope, float* out, int64_t n_nodes, const SplitOut& SO, cudaStream_t s) {
     bool is4 = false;
     if (!tile_supported(T, L.H, L.C, ED, grid_eattr, &is4)) return 1;
+    if (SO.hi && L.C % 64 != 0) return 1;              // the split store packs channel pairs
 #define TCASE(H_, C_, PH_)                                                                                              \
     if (L.H == H_ && L.C == C_)                                                                                         \
-        return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, s)       \
-                   : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, s)
+        return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, SO, s)   \
+                   : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, SO, s)
     TCASE(4, 64, 16); TCASE(1, 64, 16); TCASE(2, 64, 16); TCASE(8, 64, 16);
     TCASE(1, 32, 16); TCASE(2, 32, 16); TCASE(4, 32, 16); TCASE(8, 32, 16);
     TCASE(1, 128, 8); TCASE(2, 128, 8); TCASE(4, 128, 8);
@@ -1679,6 +1718,9 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const float* hsrc = hbuf;                  // where h_l and its alpha live
     const float* al = alpha;
     bool proj_done = false;                    // h_l was already produced by the fused kernel of layer l-1
+    bool cur_split = false;                    // `cur` holds fp16 hi / lo planes [N, in] (written by the tiled aggregation)
+    bool is4_ = false;
+    const bool tile_ok0 = tiled && g_use_umma && g_presplit;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
         if (!proj_done) { ProfScope ps(20 + l, s);
@@ -1695,6 +1737,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           } else if (g_use_umma && L.Wsplit) {
               UmmaArgs a = {};
               a.A = cur; a.M = N; a.K = L.in; a.Wsplit = L.Wsplit; a.w_inv_scale = L.w_inv;
+              if (cur_split) { a.A_hi = reinterpret_cast<const uint16_t*>(cur); a.A_lo = a.A_hi + (size_t)N * L.in; }
               if (l == 0) {               // input = feature-extractor output (unfused): measure it
                   if ((rc = launch_absmax(cur, N * L.in, amax, sms, s))) return rc;
                   a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f;
@@ -1704,7 +1747,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               a.cmax_out = amax + 1 + l;
               a.Cout = hbuf; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha; a.Htot = L.H; a.CH = L.C;
               a.head_major = 1;
-              rc = launch_umma(a, L.HC, PM_PLAIN, EM_PROJ, sms, s);
+              rc = launch_umma(a, L.HC, cur_split ? PM_SPLIT : PM_PLAIN, EM_PROJ, sms, s);
           } else {
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
               if (!rc && g_use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
@@ -1725,7 +1768,23 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               rc = launch_agg_tile_proj(L, Ln, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, N, F, s);
               if (rc == 0) { hsrc = nxt; al = alpha_b; proj_done = true; }
           }
-          if (rc == 1 && tiled) rc = launch_agg_tile(L, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, s);
+          // when the next layer's projection runs on the tensor cores, hand it the output as fp16 hi / lo planes
+          SplitOut SO = {};
+          bool want_split = false;
+          if (!proj_done && tile_ok0 && l + 1 < d.layers && L.C % 64 == 0) {
+              const LayerDev& Ln = m->layers[l + 1];
+              want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
+                           tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_);
+              if (want_split) {
+                  SO.hi = reinterpret_cast<uint16_t*>(nxt); SO.lo = SO.hi + (size_t)N * L.HC;
+                  SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
+              }
+          }
+          cur_split = false;
+          if (rc == 1 && tiled) {
+              rc = launch_agg_tile(L, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, SO, s);
+              if (rc == 0 && want_split) cur_split = true;
+          }
           if (rc == 1) rc = launch_agg(L, hsrc, al, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s);
           if (rc) return rc; }
         float* t = cur; cur = nxt; nxt = t;

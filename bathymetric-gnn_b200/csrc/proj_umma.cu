@@ -65,7 +65,7 @@ extern "C" int bgnn_debug_umma_timing(unsigned long long* out8, int reset) {
 namespace {
 
 constexpr int KC = 32;                 // K elements per stage (64 B of fp16 = one SWIZZLE_64B row)
-constexpr int STAGES = 3;              // fp16 operand stages, upper bound (barrier slots); per-shape depth in UmmaSmem
+constexpr int STAGES = 6;              // fp16 operand stages, upper bound (barrier slots); per-shape depth in UmmaSmem
 constexpr int TILE_M = 128;
 constexpr int NSPLIT = 2;              // hi, lo
 constexpr int A_TILE_BYTES = TILE_M * KC * 2;     // 8 KB per split
@@ -169,10 +169,16 @@ struct UmmaSmem {
 #define BGNN_N256_TMA_STORE 0
 #endif
     // N = 256 from global A: shared memory holds either the staging tiles (with a 2-deep raw ring) or a 4-deep raw ring
-    static constexpr bool TMA_STORE = EMODE == EM_PROJ && !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE) && NH == 1;
+#ifndef BGNN_SPLIT_TMA_STORE
+#define BGNN_SPLIT_TMA_STORE 1
+#endif
+    // (PM_SPLIT, measured: the paired N = 2 x 128 variant prefers direct stores and a 6-deep operand ring, 1.71 vs 1.82 ms;
+    //  N = 64 prefers the TMA stores, 0.79 vs 0.85 ms)
+    static constexpr bool TMA_STORE = EMODE == EM_PROJ && (PMODE == PM_SPLIT ? (BGNN_SPLIT_TMA_STORE != 0 && NH == 1)
+                                                          : !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE) && NH == 1);
     static constexpr int STG_WARPS = TMA_STORE ? 4 * EPI_SPLIT : 0;
     static constexpr int STG_BYTES = STG_WARPS * 4096;
-    static constexpr int NSTAGE = ((PMODE == PM_PLAIN && N == 256) || NH > 1) ? 2 : STAGES;     // fp16 operand ring depth (measured: for
+    static constexpr int NSTAGE = PMODE == PM_SPLIT ? (TMA_STORE ? 4 : 6) : ((PMODE == PM_PLAIN && N == 256) || NH > 1) ? 2 : 3;     // fp16 operand ring depth (measured: for
                                                                                      // N = 256 a deeper raw ring beats a third stage)
     static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * (NH > 1 ? N : NT) : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;  // epilogue parameters
     static constexpr int PAR_P = PMODE == PM_MLP0 ? MLP0_MAXK * MLP0_FP + MLP0_MAXK : 0;              // producer parameters
@@ -184,6 +190,7 @@ struct UmmaSmem {
     static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? (BGNN_N256_TMA_STORE ? 2 : 4) : N == 128 ? (NH > 1 ? 4 : 6) : 2);
     static constexpr int W_SLOTS = NH > 1 ? 8 : NW;                      // NH = 2: the whole K extent (<= 256) stays resident
     static constexpr int PARW = NH > 1 ? N : NT;                          // epilogue parameter columns held by this CTA
+    static_assert(NSTAGE <= STAGES, "barrier slots");
     static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
     static constexpr size_t BYTES = (size_t)NSTAGE * STAGE_BYTES + (size_t)W_SLOTS * W_SLOT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
                                     STG_BYTES + (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
@@ -218,7 +225,7 @@ __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_
 template <int N, int PMODE, int EMODE, int NH>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA,
-                 const __grid_constant__ CUtensorMap tmapC) {
+                 const __grid_constant__ CUtensorMap tmapA2, const __grid_constant__ CUtensorMap tmapC) {
     using S = UmmaSmem<N, PMODE, EMODE, NH>;
     constexpr int NT = S::NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -257,7 +264,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     }
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PMODE == PM_SPLIT ? 1 : PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bars[BAR_TFULL + a], 1); mbar_init(&bars[BAR_TEMPTY + a], 4 * 32 * S::EPI_SPLIT); }
         for (int r = 0; r < MAX_RAW; ++r) { mbar_init(&bars[BAR_RFULL + r], 1); mbar_init(&bars[BAR_REMPTY + r], PROD_GROUP_THREADS); }
         for (int w = 0; w < NW; ++w) { mbar_init(&bars[BAR_WFULL + w], 1); mbar_init(&bars[BAR_WEMPTY + w], 1); }
@@ -302,6 +309,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     const uint32_t tmem_base = *s_tmem;
 
     if (warp >= PROD_WARP0) {
+        if constexpr (PMODE != PM_SPLIT) {          // (PM_SPLIT: the operand arrives already split, the TMA fills the stages)
         // ===================== PRODUCERS: two groups of 128 threads own alternate K chunks =====================
         const int grp = (warp - PROD_WARP0) / (PROD_WARPS / PROD_GROUPS);
         const int ptid = tid - (PROD_WARP0 + grp * (PROD_WARPS / PROD_GROUPS)) * 32;      // 0..127
@@ -391,9 +399,29 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 mbar_arrive(&bars[BAR_FULL + s]);
             }
         }
+        }
     } else if (warp == LOAD_WARP) {
         // ===================== A LOADER (one thread, PM_PLAIN): A [SUPER_M x 32] fp32 -> raw ring, ONE TMA tensor copy per chunk
         // (rows past M are zero-filled by the tensor map's bounds check) =====================
+        if (PMODE == PM_SPLIT && lane == 0) {
+            // A was written as fp16 hi / lo planes [M, K] by the previous kernel: two SWIZZLE_64B tensor copies per chunk land
+            // in the K-major layout the MMA descriptors expect ([split][mt] tiles of 128 rows x 64 B)
+            uint32_t it = 0;
+            for (int64_t st = st_first; st < n_super; st += st_step) {
+                const int row0 = (int)(st * SUPER_M);
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int sidx = it % S::NSTAGE;
+                    if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + sidx], ((it / S::NSTAGE) - 1) & 1);
+                    const uint32_t bar = smem_u32(&bars[BAR_FULL + sidx]);
+                    const uint32_t dst = smem_u32(base + (size_t)sidx * S::STAGE_BYTES);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)S::STAGE_BYTES) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(dst), "l"(&tmapA), "r"(kc * KC), "r"(row0), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(dst + (uint32_t)(MT * A_TILE_BYTES)), "l"(&tmapA2), "r"(kc * KC), "r"(row0), "r"(bar) : "memory");
+                }
+            }
+        }
         if (PMODE == PM_PLAIN && lane == 0) {
             constexpr int RS = S::RAW_STAGES > 0 ? S::RAW_STAGES : 1;
             uint32_t it = 0;
@@ -479,7 +507,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         for (int p = 0; p < 3; ++p) {
 #pragma unroll
                             for (int ks = 0; ks < KC / 16; ++ks) {
-                                const uint64_t da = make_desc(sA_ + (mt * NSPLIT + pa[p]) * A_TILE_BYTES + ks * 32);
+                                const uint64_t da = make_desc(sA_ + (PMODE == PM_SPLIT ? pa[p] * MT + mt : mt * NSPLIT + pa[p]) * A_TILE_BYTES + ks * 32);
                                 const uint64_t db = make_desc(sB_ + pb[p] * S::B_TILE_BYTES + ks * 32);
                                 const bool first = kc == 0 && ks == 0 && (p == 0 || p == 1);
                                 umma_f16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
@@ -727,6 +755,22 @@ int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out
     return BGNN_OK;
 }
 
+// 2-D tensor map over one fp16 plane of a pre-split A [M, K] with a [box_rows x 32] SWIZZLE_64B box (64 B inner extent):
+// the box lands as 128-row K-major swizzled tiles, rows past M read as zero
+int make_tmap_A16(const uint16_t* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
+    EncodeTiledFn fn = nullptr;
+    { int rc = get_encode_fn(&fn); if (rc) return rc; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(uint16_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(A), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for split A=%p M=%lld K=%d", (int)r, (const void*)A, (long long)M, K); return BGNN_E_CUDA; }
+    return BGNN_OK;
+}
+
 // 3-D tensor map over the projection output with a [32 cols x 32 rows x 1] SWIZZLE_128B box:
 //   head-major  C[Htot][M][CH]: dims {CH, M, Htot}      row-major  C[M][N]: dims {N, M, 1}
 int make_tmap_C(float* C, int64_t M, int N, int CH, int head_major, CUtensorMap* out) {
@@ -764,6 +808,15 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
         int rc = make_tmap_A(a.A, a.M, a.K, S::SUPER_M, &tmap);
         if (rc) return rc;
     }
+    alignas(64) CUtensorMap tmap2;
+    memset(&tmap2, 0, sizeof(tmap2));
+    if (PMODE == PM_SPLIT) {
+        BGNN_CHECK_ARG(a.A_hi && a.A_lo && ((reinterpret_cast<uintptr_t>(a.A_hi) | reinterpret_cast<uintptr_t>(a.A_lo)) & 15) == 0,
+                       "split A planes must be 16-byte aligned");
+        int rc = make_tmap_A16(a.A_hi, a.M, a.K, S::SUPER_M, &tmap);
+        if (!rc) rc = make_tmap_A16(a.A_lo, a.M, a.K, S::SUPER_M, &tmap2);
+        if (rc) return rc;
+    }
     alignas(64) CUtensorMap tmapC;
     memset(&tmapC, 0, sizeof(tmapC));
     if (EMODE == EM_PROJ) {
@@ -777,7 +830,7 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
         const int64_t pairs = n_super < sms / 2 ? n_super : sms / 2;
         grid = (unsigned)(2 * (pairs > 0 ? pairs : 1));
     }
-    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap, tmapC);
+    kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap, tmap2, tmapC);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         bgnn_set_error("proj_umma_kernel<N=%d x %d, producer %d, epilogue %d> M=%lld K=%d: %s", N, NH, PMODE, EMODE, (long long)a.M, a.K,
@@ -870,6 +923,10 @@ float proj_umma_split_weights(const float* W, int N, int K, uint16_t* out /*[K/3
     return inv;
 }
 
+bool proj_umma_presplit_supported(int N, int K, int CH, bool want_alpha) {
+    return (N == 64 || N == 256) && proj_umma_supported(N, K, CH, want_alpha);
+}
+
 bool proj_umma_mlp0_supported(int N, int K, int F) {
     return (N == 128 || N == 256) && K % KC == 0 && K >= KC && K <= MLP0_MAXK && F >= 1 && F <= MLP0_FP;
 }
@@ -890,6 +947,7 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
     return BGNN_OK;
 }
 
+static bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
 static bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
                                                                          // 2-deep operand ring cannot hide the split latency)
 
@@ -906,6 +964,13 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
                 if (g_n256_halves && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_PLAIN, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_PLAIN, EM_PROJ>(a, sms, s);
         }
+    } else if (pmode == PM_SPLIT && emode == EM_PROJ) {
+        switch (N) {
+            case 64: return launch_t<64, PM_SPLIT, EM_PROJ>(a, sms, s);
+            case 256:
+                if (!g_split_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_SPLIT, EM_PROJ, 2>(a, sms, s);
+                return launch_t<256, PM_SPLIT, EM_PROJ>(a, sms, s);
+        }
     } else if (pmode == PM_MLP0 && emode == EM_PROJ) {
         switch (N) {
             case 128: return launch_t<128, PM_MLP0, EM_PROJ>(a, sms, s);
@@ -921,13 +986,44 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
     return BGNN_E_UNSUPPORTED;
 }
 
-// ---- test hook (declared in include/bgnn.h): C = A . W^T on the tensor-core path, W given as fp32 on the HOST
+// fp32 rows -> fp16 hi / lo planes of a * sA (test aid: what the tiled aggregation writes for PM_SPLIT)
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ A, int64_t n, const float* __restrict__ amax,
+                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const float bound = __ldg(amax);
+    const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu), es = 253 - e;
+    const float sA = (e > 0 && e < 255 && es >= 1 && es <= 253) ? __uint_as_float((uint32_t)es << 23) : 1.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = __ldg(A + i) * sA;
+        const __half h = __float2half_rn(a);
+        const __half l = __float2half_rn((a - __half2float(h)) * LO_SCALE);
+        hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+    }
+}
+
+static int test_proj_umma_impl(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
+                               const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
+                               void* stream_, bool presplit);
+
+// ---- test hooks (declared in include/bgnn.h): C = A . W^T on the tensor-core path, W given as fp32 on the HOST
 extern "C" int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
                                    const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
                                    void* stream_) {
+    return test_proj_umma_impl(A_dev, M, K, W_host, N, C_dev, att_src_dev, att_dst_dev, alpha_dev, heads, stream_, false);
+}
+extern "C" int bgnn_test_proj_umma_presplit(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
+                                            const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
+                                            void* stream_) {
+    return test_proj_umma_impl(A_dev, M, K, W_host, N, C_dev, att_src_dev, att_dst_dev, alpha_dev, heads, stream_, true);
+}
+
+static int test_proj_umma_impl(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
+                               const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
+                               void* stream_, bool presplit) {
     BGNN_CHECK_ARG(A_dev && W_host && C_dev, "null argument");
     const int CH = heads > 0 ? N / heads : N;
     BGNN_CHECK_ARG(proj_umma_supported(N, K, CH, alpha_dev != nullptr), "shape N=%d K=%d not supported by the tcgen05 path", N, K);
+    BGNN_CHECK_ARG(!presplit || proj_umma_presplit_supported(N, K, CH, alpha_dev != nullptr), "shape N=%d K=%d has no pre-split variant", N, K);
     cudaStream_t s = (cudaStream_t)stream_;
     std::vector<uint16_t> split((size_t)NSPLIT * N * K);
     const float winv = proj_umma_split_weights(W_host, N, K, split.data());
@@ -947,7 +1043,15 @@ extern "C" int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const f
         a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f; a.cmax_out = amax + 1;
         a.Cout = C_dev; a.att_src = att_src_dev; a.att_dst = att_dst_dev; a.alpha = alpha_dev;
         a.Htot = alpha_dev ? heads : 1; a.CH = alpha_dev ? CH : N;
-        rc = launch_umma(a, N, PM_PLAIN, EM_PROJ, sms, s);
+        uint16_t* planes = nullptr;
+        if (presplit) {
+            BGNN_CUDA(cudaMalloc(&planes, (size_t)M * K * 4));
+            split_planes_kernel<<<sms * 8, 256, 0, s>>>(A_dev, M * K, amax, planes, planes + (size_t)M * K);
+            a.A_hi = planes; a.A_lo = planes + (size_t)M * K;
+        }
+        rc = launch_umma(a, N, presplit ? PM_SPLIT : PM_PLAIN, EM_PROJ, sms, s);
+        cudaStreamSynchronize(s);
+        if (planes) cudaFree(planes);
     }
     cudaStreamSynchronize(s);
     cudaFree(d);

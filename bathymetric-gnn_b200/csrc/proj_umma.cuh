@@ -5,12 +5,15 @@
 
 #include <vector>
 
-enum { PM_PLAIN = 0, PM_MLP0 = 1 };      // producer: A from global memory | A = relu(x W0^T + b0) computed on the fly
+enum { PM_PLAIN = 0, PM_MLP0 = 1, PM_SPLIT = 2 };   // producer: fp32 A from global memory | A = relu(x W0^T + b0) computed on
+                                                    // the fly | A already split into fp16 hi / lo planes by the previous kernel
 enum { EM_PROJ = 0, EM_HEADS = 1 };      // epilogue: C (+bias) and alpha_src/alpha_dst | finish the three output heads
 
 struct UmmaArgs {
     // operands: C[M,N] = A[M,K] . W[N,K]^T, W pre-split (2 x fp16, scaled by 1/w_inv_scale) and pre-swizzled on the host
     const float* A; int64_t M; int K; const uint16_t* Wsplit; float w_inv_scale;
+    // PM_SPLIT: A_hi / A_lo [M,K] fp16 bit patterns of a*sA (sA from the same amax bound below), written by the aggregation
+    const uint16_t* A_hi; const uint16_t* A_lo;
     // upper bound of max|A| = amax_mul * (*amax_src) + amax_add (amax_src may be NULL) -> power-of-two operand scale
     const float* amax_src; float amax_mul, amax_add;
     float* cmax_out;          // EM_PROJ, optional: atomicMax of |C| over everything this launch writes
@@ -28,6 +31,7 @@ struct UmmaArgs {
 
 // shapes the tensor-core path is compiled for (N in {32,64,128,256}, K multiple of 32)
 bool proj_umma_supported(int N, int K, int CH, bool want_alpha);
+bool proj_umma_presplit_supported(int N, int K, int CH, bool want_alpha);   // PM_SPLIT + EM_PROJ
 bool proj_umma_mlp0_supported(int N, int K, int F);               // PM_MLP0 + EM_PROJ
 bool proj_umma_heads_supported(int K, int h2, int nblk, int ncls, int* Npad);   // PM_PLAIN + EM_HEADS
 // host: W [N,K] fp32 -> 2 x fp16 split of W*s, [K/32][2][N x 32 swizzled tile] (2*N*K uint16); returns 1/s

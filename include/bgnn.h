@@ -249,11 +249,18 @@ int bgnn_set_tensor_cores(int on);
 /* Fusion of the last-but-one layer's aggregation with the last layer's projection (tcgen05 inside the tiled aggregation
  * kernel; the [N, heads*C] intermediate then never reaches HBM): on by default, bit-identical results either way. */
 int bgnn_set_fusion(int on);
+/* Operand hand-over between a tiled aggregation and the next layer's tcgen05 projection as fp16 hi / lo planes (the
+ * projection then has no conversion stage): on by default, bit-identical results either way. */
+int bgnn_set_presplit(int on);
 /* testing aid: C_dev[M,N] = A_dev[M,K] . W_host[N,K]^T through the tcgen05 path (host-synchronous);
  * alpha_dev (optional) [M, 2*heads] receives the per-head dot products with att_src / att_dst [N]. */
 int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
                         const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
                         void* stream);
+/* same, with A handed over as fp16 hi / lo planes (the PM_SPLIT variant; N in {64, 256}) */
+int bgnn_test_proj_umma_presplit(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
+                                 const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement aid (bench.py): per-kernel device timing with CUDA events recorded on the

@@ -9,14 +9,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def run_umma(A, W, att_s=None, att_d=None, heads=0):
+def run_umma(A, W, att_s=None, att_d=None, heads=0, presplit=False):
     from bathymetric_gnn_b200._lib import lib, check, ptr
     M, K = A.shape
     N = W.shape[0]
     Cout = torch.empty((M, N), dtype=torch.float32, device="cuda")
     alpha = torch.empty((M, 2 * heads), dtype=torch.float32, device="cuda") if heads else None
     Wh = W.cpu().contiguous()
-    check(lib.bgnn_test_proj_umma(ptr(A), M, K, C.c_void_p(Wh.data_ptr()), N, ptr(Cout), ptr(att_s), ptr(att_d), ptr(alpha),
+    fn = lib.bgnn_test_proj_umma_presplit if presplit else lib.bgnn_test_proj_umma
+    check(fn(ptr(A), M, K, C.c_void_p(Wh.data_ptr()), N, ptr(Cout), ptr(att_s), ptr(att_d), ptr(alpha),
                                   heads, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     return Cout, alpha
@@ -91,5 +92,44 @@ def test_fused_last_projection_is_bit_identical():
         b = m._run(g, 0.85, 0.6, True, return_hidden=True)
     finally:
         lib.bgnn_set_fusion(1)
+    for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
+        assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("M,K,N,heads", [(256, 256, 256, 4), (1000, 256, 256, 4), (70001, 256, 256, 4), (4099, 256, 64, 1),
+                                         (513, 64, 64, 1), (50000, 64, 256, 4), (333, 128, 256, 8)])
+def test_umma_presplit_is_bit_identical(M, K, N, heads):
+    """A handed over as fp16 hi / lo planes (what the tiled aggregation writes) vs the in-kernel split of fp32 A: the same
+    operands reach the tensor cores in the same order, so C and alpha must match bit for bit."""
+    g = torch.Generator(device="cpu").manual_seed(M + K + N)
+    A = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, 1, generator=g))).cuda()
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
+    att_s, att_d = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda()
+    C0, a0 = run_umma(A, W, att_s, att_d, heads)
+    C1, a1 = run_umma(A, W, att_s, att_d, heads, presplit=True)
+    assert torch.equal(C0, C1) and torch.equal(a0, a1)
+
+
+def test_presplit_handover_is_bit_identical_in_forward():
+    """Whole forward with the fp16 hi / lo hand-over between aggregation and projection vs fp32 intermediates."""
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200._lib import lib
+    from oracle import model_oracle as mo
+    from tests import synth
+    d = synth.noisy_tile(300, 333, seed=9)
+    mask = synth.blob_mask(300, 333, seed=9, invalid_frac=0.05)
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=7, randomize_bn=True)
+    m = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = bg.GraphBuilder().build_graph(d, mask, None, (0.5, 0.5))
+    try:
+        lib.bgnn_set_presplit(1)
+        a = m._run(g, 0.85, 0.6, True, return_hidden=True)
+        lib.bgnn_set_presplit(0)
+        b = m._run(g, 0.85, 0.6, True, return_hidden=True)
+    finally:
+        lib.bgnn_set_presplit(1)
     for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
         assert torch.equal(a[k], b[k]), k
