@@ -500,7 +500,8 @@ template <int H, int C, int PH> struct TileCfg {
     // alpha_src / alpha_dst of the halo arrive by bulk copy (one per run) when a node's 2H floats are a 16 B multiple and
     // the landing area fits the (not yet used) attention-weight buffer; otherwise they are loaded cell by cell
     static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= NT * AST;
-    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C) * 4 + 32;
+    static constexpr int RT = 2 * (HW / 2) + 2;      // run table per halo row: count, then (start << 16 | length, node id) pairs
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C + HR * RT) * 4 + 32;
 };
 
 // window position p = dy*3 + dx (dy, dx in 0..2 <-> source at row r-1+dy, column c-1+dx) visited in reference edge order
@@ -525,13 +526,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
-// Optional output format: instead of fp32 rows, the layer output is written as the two fp16 planes hi / lo [N, H*C] of
+// Optional output format: instead of fp32 rows, the layer output is written as fp16 rows [N][2][H*C] = hi | lo of
 // y * sA that the next layer's tensor-core projection consumes directly (proj_umma.cu, PM_SPLIT): same 4 bytes per element,
 // same split arithmetic and the same power-of-two scale as the projection's own converter warps would apply (bit-identical
 // products), but the projection then needs no conversion stage at all.
 struct SplitOut {
-    uint16_t* hi;                  // nullptr: fp32 output
-    uint16_t* lo;
+    uint16_t* hi;                  // nullptr: fp32 output; else row n = hi[H*C] | lo[H*C]  (lo of a row at + H*C elements)
     const float* amax_src;         // max|h_l| (device); |y| <= mul * max|h_l| + add
     float mul, add;
 };
@@ -564,7 +564,8 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
     float* al_sm = a_sm;                                       // [NSLOT][2H]  landing area of the alpha bulk copies (setup only)
     float* M_s = a_sm + NT * AST;                              // [ED_MAX][H]  folded edge projection
     float* s_bn = M_s + BGNN_MAX_EDGE_FEATS * H;               // [3][HC]      bias | bn scale | bn shift
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_bn + 3 * HC);// [0] source rows, [1] alpha
+    int* run_tab = reinterpret_cast<int*>(s_bn + 3 * HC);      // [HR][RT]     runs of valid cells per halo row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(run_tab + HR * G::RT);   // [0] source rows, [1] alpha
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pr0 = blockIdx.y * PH, pc0 = blockIdx.x * 16;
@@ -621,31 +622,38 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
 
     // ---- bulk copies: every run of valid cells in a halo row is ONE contiguous chunk, because adjacent valid cells of a
     //      grid row have consecutive node ids, h is head-major ([H][N][C]) and alpha is [N][2H]
-    auto issue_rows = [&](int hh) {
-        if (tid < HR) {
-            const float* hp = h + (int64_t)hh * n_nodes * C;
-            const int s0 = tid * HW;
-            int run = -1;
-            for (int c = 0; c <= HW; ++c) {
-                const int id = c < HW ? ids[s0 + c] : -1;
-                if (id >= 0 && run < 0) run = c;
-                if (id < 0 && run >= 0) {
-                    bulk_g2s(rows + (s0 + run) * C, hp + (int64_t)ids[s0 + run] * C, (uint32_t)(c - run) * C * 4, bar);
-                    run = -1;
-                }
-            }
-        }
-    };
-    if (G::ALPHA_BULK && tid < HR) {
+    // The runs of a halo row are the same for alpha and for every head: thread t < HR finds those of row t ONCE (the
+    // 18-cell scan is a serial chain on the critical path of warp 0) and replays its own table afterwards.
+    if (tid < HR) {
         const int s0 = tid * HW;
-        int run = -1;
+        int run = -1, n = 0;
         for (int c = 0; c <= HW; ++c) {
             const int id = c < HW ? ids[s0 + c] : -1;
             if (id >= 0 && run < 0) run = c;
             if (id < 0 && run >= 0) {
-                bulk_g2s(al_sm + (s0 + run) * 2 * H, alpha + (int64_t)ids[s0 + run] * 2 * H, (uint32_t)(c - run) * 2 * H * 4, bar + 1);
+                run_tab[tid * G::RT + 1 + 2 * n] = (run << 16) | (c - run);
+                run_tab[tid * G::RT + 2 + 2 * n] = ids[s0 + run];
+                ++n;
                 run = -1;
             }
+        }
+        run_tab[tid * G::RT] = n;
+    }
+    auto issue_rows = [&](int hh) {
+        if (tid < HR) {
+            const float* hp = h + (int64_t)hh * n_nodes * C;
+            const int s0 = tid * HW, n = run_tab[tid * G::RT];
+            for (int i = 0; i < n; ++i) {
+                const int sl = run_tab[tid * G::RT + 1 + 2 * i], id = run_tab[tid * G::RT + 2 + 2 * i];
+                bulk_g2s(rows + (s0 + (sl >> 16)) * C, hp + (int64_t)id * C, (uint32_t)(sl & 0xffff) * C * 4, bar);
+            }
+        }
+    };
+    if (G::ALPHA_BULK && tid < HR) {
+        const int s0 = tid * HW, n = run_tab[tid * G::RT];
+        for (int i = 0; i < n; ++i) {
+            const int sl = run_tab[tid * G::RT + 1 + 2 * i], id = run_tab[tid * G::RT + 2 + 2 * i];
+            bulk_g2s(al_sm + (s0 + (sl >> 16)) * 2 * H, alpha + (int64_t)id * 2 * H, (uint32_t)(sl & 0xffff) * 2 * H * 4, bar + 1);
         }
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar + 1)) : "memory");
     }
@@ -822,15 +830,15 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                         o[v] = relu ? fmaxf(y, 0.f) : y;
                     }
                     if (VEC % 2 == 0 && SO.hi) {
-                        const int64_t e0 = (int64_t)id2 * HC + hh * C + lane * VEC;
+                        uint16_t* prow = SO.hi + (int64_t)id2 * (2 * HC) + hh * C + lane * VEC;
 #pragma unroll
                         for (int v = 0; v + 1 < VEC; v += 2) {
                             const float s0v = o[v], s1v = o[v + 1];             // already scaled by sA
                             const __half2 hi2 = __floats2half2_rn(s0v, s1v);
                             const float2 hf = __half22float2(hi2);
                             const __half2 lo2 = __floats2half2_rn((s0v - hf.x) * 2048.f, (s1v - hf.y) * 2048.f);
-                            *reinterpret_cast<__half2*>(SO.hi + e0 + v) = hi2;
-                            *reinterpret_cast<__half2*>(SO.lo + e0 + v) = lo2;
+                            *reinterpret_cast<__half2*>(prow + v) = hi2;
+                            *reinterpret_cast<__half2*>(prow + HC + v) = lo2;
                         }
                     } else {
                         VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
@@ -1737,7 +1745,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           } else if (g_use_umma && L.Wsplit) {
               UmmaArgs a = {};
               a.A = cur; a.M = N; a.K = L.in; a.Wsplit = L.Wsplit; a.w_inv_scale = L.w_inv;
-              if (cur_split) { a.A_hi = reinterpret_cast<const uint16_t*>(cur); a.A_lo = a.A_hi + (size_t)N * L.in; }
+              if (cur_split) { a.A_hi = reinterpret_cast<const uint16_t*>(cur); a.A_lo = a.A_hi + L.in; a.a_ld = 2 * L.in; }
               if (l == 0) {               // input = feature-extractor output (unfused): measure it
                   if ((rc = launch_absmax(cur, N * L.in, amax, sms, s))) return rc;
                   a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f;
@@ -1776,7 +1784,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
                            tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_);
               if (want_split) {
-                  SO.hi = reinterpret_cast<uint16_t*>(nxt); SO.lo = SO.hi + (size_t)N * L.HC;
+                  SO.hi = reinterpret_cast<uint16_t*>(nxt);
                   SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
               }
           }

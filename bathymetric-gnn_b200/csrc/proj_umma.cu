@@ -757,11 +757,11 @@ int make_tmap_A(const float* A, int64_t M, int K, int box_rows, CUtensorMap* out
 
 // 2-D tensor map over one fp16 plane of a pre-split A [M, K] with a [box_rows x 32] SWIZZLE_64B box (64 B inner extent):
 // the box lands as 128-row K-major swizzled tiles, rows past M read as zero
-int make_tmap_A16(const uint16_t* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
+int make_tmap_A16(const uint16_t* A, int64_t M, int K, int64_t ld, int box_rows, CUtensorMap* out) {
     EncodeTiledFn fn = nullptr;
     { int rc = get_encode_fn(&fn); if (rc) return rc; }
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-    const cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(uint16_t)};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(uint16_t)};
     const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(A), gdim, gstr, box, estr,
@@ -813,8 +813,9 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
     if (PMODE == PM_SPLIT) {
         BGNN_CHECK_ARG(a.A_hi && a.A_lo && ((reinterpret_cast<uintptr_t>(a.A_hi) | reinterpret_cast<uintptr_t>(a.A_lo)) & 15) == 0,
                        "split A planes must be 16-byte aligned");
-        int rc = make_tmap_A16(a.A_hi, a.M, a.K, S::SUPER_M, &tmap);
-        if (!rc) rc = make_tmap_A16(a.A_lo, a.M, a.K, S::SUPER_M, &tmap2);
+        const int64_t ld = a.a_ld > 0 ? a.a_ld : a.K;
+        int rc = make_tmap_A16(a.A_hi, a.M, a.K, ld, S::SUPER_M, &tmap);
+        if (!rc) rc = make_tmap_A16(a.A_lo, a.M, a.K, ld, S::SUPER_M, &tmap2);
         if (rc) return rc;
     }
     alignas(64) CUtensorMap tmapC;
@@ -947,6 +948,7 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
     return BGNN_OK;
 }
 
+static bool g_mlp0_whole = getenv("BGNN_MLP0_PAIRED") == nullptr;      // dev switch; the paired variant measured slower here (1.72 vs 1.36 ms)
 static bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
 static bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
                                                                          // 2-deep operand ring cannot hide the split latency)
@@ -974,7 +976,10 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
     } else if (pmode == PM_MLP0 && emode == EM_PROJ) {
         switch (N) {
             case 128: return launch_t<128, PM_MLP0, EM_PROJ>(a, sms, s);
-            case 256: return launch_t<256, PM_MLP0, EM_PROJ>(a, sms, s);
+            case 256:
+                // dev variant (BGNN_MLP0_PAIRED): paired CTAs, N = 2 x 128, epilogue overlapping the next tile
+                if (!g_mlp0_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_MLP0, EM_PROJ, 2>(a, sms, s);
+                return launch_t<256, PM_MLP0, EM_PROJ>(a, sms, s);
         }
     } else if (pmode == PM_PLAIN && emode == EM_HEADS) {
         switch (N) {

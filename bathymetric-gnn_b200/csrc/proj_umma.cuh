@@ -13,7 +13,7 @@ struct UmmaArgs {
     // operands: C[M,N] = A[M,K] . W[N,K]^T, W pre-split (2 x fp16, scaled by 1/w_inv_scale) and pre-swizzled on the host
     const float* A; int64_t M; int K; const uint16_t* Wsplit; float w_inv_scale;
     // PM_SPLIT: A_hi / A_lo [M,K] fp16 bit patterns of a*sA (sA from the same amax bound below), written by the aggregation
-    const uint16_t* A_hi; const uint16_t* A_lo;
+    const uint16_t* A_hi; const uint16_t* A_lo; int64_t a_ld;     // a_ld: row stride in elements (0 = K)
     // upper bound of max|A| = amax_mul * (*amax_src) + amax_add (amax_src may be NULL) -> power-of-two operand scale
     const float* amax_src; float amax_mul, amax_add;
     float* cmax_out;          // EM_PROJ, optional: atomicMax of |C| over everything this launch writes
