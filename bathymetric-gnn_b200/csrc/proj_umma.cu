@@ -51,7 +51,10 @@
 #ifdef BGNN_AGG_TIMING
 __device__ unsigned long long g_umma_t[12];
 #define UT_DECL() long long ut_prev = clock64()
-#define UT_TICK(slot) do { long long ut_now = clock64(); atomicAdd(&g_umma_t[slot], (unsigned long long)(ut_now - ut_prev)); ut_prev = ut_now; } while (0)
+#ifndef BGNN_UT_FILTER
+#define BGNN_UT_FILTER true            // e.g. -DBGNN_UT_FILTER="(PMODE==PM_MLP0)": count only that instantiation
+#endif
+#define UT_TICK(slot) do { long long ut_now = clock64(); if (BGNN_UT_FILTER) atomicAdd(&g_umma_t[slot], (unsigned long long)(ut_now - ut_prev)); ut_prev = ut_now; } while (0)
 extern "C" int bgnn_debug_umma_timing(unsigned long long* out8, int reset) {
     if (out8) cudaMemcpyFromSymbol(out8, g_umma_t, sizeof(unsigned long long) * 12);
     if (reset) { unsigned long long z[12] = {}; cudaMemcpyToSymbol(g_umma_t, z, sizeof(z)); }
@@ -175,7 +178,7 @@ struct UmmaSmem {
     // (PM_SPLIT, measured: the paired N = 2 x 128 variant prefers direct stores and a 6-deep operand ring, 1.71 vs 1.82 ms;
     //  N = 64 prefers the TMA stores, 0.79 vs 0.85 ms)
     static constexpr bool TMA_STORE = EMODE == EM_PROJ && (PMODE == PM_SPLIT ? (BGNN_SPLIT_TMA_STORE != 0 && NH == 1)
-                                                          : !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE) && NH == 1);
+                                                          : !(PMODE == PM_PLAIN && N == 256 && !BGNN_N256_TMA_STORE) && (NH == 1 || PMODE == PM_MLP0));
     static constexpr int STG_WARPS = TMA_STORE ? 4 * EPI_SPLIT : 0;
     static constexpr int STG_BYTES = STG_WARPS * 4096;
     static constexpr int NSTAGE = PMODE == PM_SPLIT ? (TMA_STORE ? 4 : 6) : ((PMODE == PM_PLAIN && N == 256) || NH > 1) ? 2 : 3;     // fp16 operand ring depth (measured: for
@@ -188,7 +191,7 @@ struct UmmaSmem {
     // TMA copies may complete out of order, and a group that last saw the slot two phases ago would otherwise pass the
     // parity wait of a phase that has not completed (then over-arrive on the empty barrier -> launch failure).
     static constexpr int RAW_STAGES = PMODE != PM_PLAIN ? 0 : (N == 256 ? (BGNN_N256_TMA_STORE ? 2 : 4) : N == 128 ? (NH > 1 ? 4 : 6) : 2);
-    static constexpr int W_SLOTS = NH > 1 ? 8 : NW;                      // NH = 2: the whole K extent (<= 256) stays resident
+    static constexpr int W_SLOTS = NH > 1 ? (PMODE == PM_MLP0 ? MLP0_MAXK / KC : 8) : NW;   // NH = 2: the whole K extent stays resident
     static constexpr int PARW = NH > 1 ? N : NT;                          // epilogue parameter columns held by this CTA
     static_assert(NSTAGE <= STAGES, "barrier slots");
     static_assert(RAW_STAGES % PROD_GROUPS == 0, "raw ring depth must be a multiple of the producer group count");
@@ -196,10 +199,23 @@ struct UmmaSmem {
                                     STG_BYTES + (PAR_E + PAR_P) * sizeof(float) + NUM_BARS * 8 + 16;
 };
 
+#ifndef BGNN_EPI_PACKED
+#define BGNN_EPI_PACKED 1
+#endif
+
 __device__ __forceinline__ void st_global_v8(float* p, const float* x) {          // 256-bit store (PTX ISA 8.8, sm_100)
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
                  "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
 }
+
+// packed fp32 pairs (sm_100 fma/add/mul.rn.f32x2 = two IEEE operations per issue slot; the epilogue is one long dependent
+// instruction stream per warp, so halving its length shortens the critical path)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // (main + corr * 2^-11) * scale of 32 accumulator columns of this thread's TMEM lane -> x[32]
 __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_corr, float scale, float* x) {
@@ -218,8 +234,14 @@ __device__ __forceinline__ void tmem_ld_sum32(uint32_t addr_main, uint32_t addr_
     BGNN_TMEM_LD32(u, addr_corr);
 #undef BGNN_TMEM_LD32
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#if BGNN_EPI_PACKED
+    const uint64_t inv2 = pk2(LO_INV, LO_INV), sc2 = pk2(scale, scale);
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) unpk2(fmul2(ffma2(pk2u(u[j], u[j + 1]), inv2, pk2u(v[j], v[j + 1])), sc2), x[j], x[j + 1]);
+#else
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j])) * scale;
+#endif
 }
 
 template <int N, int PMODE, int EMODE, int NH>
@@ -363,6 +385,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 } else {
                     // thread <-> node: its F inputs are loaded once, then the 32 hidden units of this chunk are
                     // relu(b0 + x W0^T) straight into the split tiles (W0 rows are warp-uniform broadcasts from smem)
+#ifdef BGNN_AGG_TIMING
+                    long long ut_prev = clock64();
+#endif
                     float xr[MT][MLP0_FP];
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -371,6 +396,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         for (int q = 0; q < MLP0_FP; ++q) xr[mt][q] = (gr < M && q < P.F) ? __ldg(P.x + gr * P.F + q) : 0.f;
                     }
                     if (it >= (uint32_t)S::NSTAGE) mbar_wait(&bars[BAR_EMPTY + s], ((it / S::NSTAGE) - 1) & 1);
+#ifdef BGNN_AGG_TIMING
+                    if (ptid == 0 && grp == 0) UT_TICK(6);
+#endif
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll 2
@@ -394,6 +422,9 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             *reinterpret_cast<uint2*>(t0 + A_TILE_BYTES) = lo;
                         }
                     }
+#ifdef BGNN_AGG_TIMING
+                    if (ptid == 0 && grp == 0) UT_TICK(7);
+#endif
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
                 mbar_arrive(&bars[BAR_FULL + s]);
@@ -524,8 +555,10 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             {
                 unsigned long long ut_g1;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ut_g1));
-                atomicAdd(&g_umma_t[8], (unsigned long long)(clock64() - ut_c0));
-                atomicAdd(&g_umma_t[9], ut_g1 - ut_g0);
+                if (BGNN_UT_FILTER) {
+                    atomicAdd(&g_umma_t[8], (unsigned long long)(clock64() - ut_c0));
+                    atomicAdd(&g_umma_t[9], ut_g1 - ut_g0);
+                }
             }
 #endif
         }
@@ -562,8 +595,14 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         if (P.bias) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
+#if BGNN_EPI_PACKED
+                                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_par + 2 * S::PARW + pc + j);
+                                unpk2(fadd2(pk2(x[j], x[j + 1]), b.x), x[j], x[j + 1]);
+                                unpk2(fadd2(pk2(x[j + 2], x[j + 3]), b.y), x[j + 2], x[j + 3]);
+#else
                                 const float4 b = *reinterpret_cast<const float4*>(s_par + 2 * S::PARW + pc + j);
                                 x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+#endif
                             }
                         }
                         if (P.cmax_out) {
@@ -577,6 +616,18 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         }
                         if (P.alpha) {
                             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#if BGNN_EPI_PACKED
+                            uint64_t s01 = 0ull, s23 = 0ull, d01 = 0ull, d23 = 0ull;       // the same four partial sums, as pairs
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(s_par + pc + j);
+                                const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(s_par + S::PARW + pc + j);
+                                const uint64_t x01 = pk2(x[j], x[j + 1]), x23 = pk2(x[j + 2], x[j + 3]);
+                                s01 = ffma2(x01, s4.x, s01); s23 = ffma2(x23, s4.y, s23);
+                                d01 = ffma2(x01, d4.x, d01); d23 = ffma2(x23, d4.y, d23);
+                            }
+                            unpk2(s01, s0, s1); unpk2(s23, s2, s3); unpk2(d01, d0, d1); unpk2(d23, d2, d3);
+#else
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(s_par + pc + j);
@@ -586,6 +637,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                                 d0 = fmaf(x[j], d4.x, d0); d1 = fmaf(x[j + 1], d4.y, d1);
                                 d2 = fmaf(x[j + 2], d4.z, d2); d3 = fmaf(x[j + 3], d4.w, d3);
                             }
+#endif
                             as_acc += (s0 + s1) + (s2 + s3);
                             ad_acc += (d0 + d1) + (d2 + d3);
                             if (((c0 + 32) % P.CH) == 0) {          // a head's channels are complete
@@ -948,7 +1000,7 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
     return BGNN_OK;
 }
 
-static bool g_mlp0_whole = getenv("BGNN_MLP0_PAIRED") == nullptr;      // dev switch; the paired variant measured slower here (1.72 vs 1.36 ms)
+static bool g_mlp0_whole = getenv("BGNN_MLP0_WHOLE") != nullptr;       // dev switch: one 128 x 256 tile per CTA (1.30 vs 1.25 ms paired)
 static bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
 static bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
                                                                          // 2-deep operand ring cannot hide the split latency)
@@ -977,7 +1029,7 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
         switch (N) {
             case 128: return launch_t<128, PM_MLP0, EM_PROJ>(a, sms, s);
             case 256:
-                // dev variant (BGNN_MLP0_PAIRED): paired CTAs, N = 2 x 128, epilogue overlapping the next tile
+                // paired CTAs, N = 2 x 128 (TMA stores): the epilogue, which dominates at K = 64, overlaps the next tile's MLP + MMAs
                 if (!g_mlp0_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_MLP0, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_MLP0, EM_PROJ>(a, sms, s);
         }

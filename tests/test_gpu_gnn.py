@@ -184,3 +184,24 @@ def test_tiled_aggregation_matches_csr_kernel(case, hidden, heads):
     exp = mo.forward(sd, cfg, g.x.cpu().numpy(), ref["edge_index"], ref["edge_attr"])
     for out in (a, b):
         np.testing.assert_allclose(out["class_logits"].cpu().numpy(), exp["class_logits"].numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_forward_wide_variant_k24_hidden128():
+    """BASELINE configs[4] at oracle-sized scale: 5x5 neighbourhood (k = 24), hidden 128 x 4 heads x 4 layers, F = 8
+    (uncertainty plane), holes in the grid -- graph bit-exact on the integer paths, forward within the fp32 tolerance."""
+    import bathymetric_gnn_b200 as bg
+    d = synth.noisy_tile(72, 60, seed=24)
+    mask = synth.blob_mask(72, 60, seed=24, invalid_frac=0.08)
+    unc = (0.1 + 0.05 * np.abs(np.sin(np.arange(72 * 60, dtype=np.float32).reshape(72, 60)))).astype(np.float32)
+    cfg = mo.ModelCfg(in_channels=8, hidden=128)
+    sd = mo.init_state_dict(cfg, seed=11, randomize_bn=True, head_gain=1.0)
+    og = go.build_graph(d, mask, unc, (0.5, 0.5), connectivity="24-connected")
+    mo.calibrate_heads(sd, cfg, og["x"], og["edge_index"], og["edge_attr"])
+    model = make_model(cfg, sd)
+    g = bg.GraphBuilder("24-connected").build_graph(d, mask, unc, (0.5, 0.5))
+    assert np.array_equal(g.edge_index.cpu().numpy(), og["edge_index"])
+    assert g.x.shape[1] == 8 and g.num_edges == og["edge_index"].shape[1]
+    out = model.predict(g)
+    ref = mo.forward(sd, cfg, g.x.cpu().numpy(), og["edge_index"], og["edge_attr"], torch.float32)
+    n_exempt, n_flip = compare(out, {k: v.numpy() for k, v in ref.items()}, n_exempt_max_frac=0.05)
+    print(f"k24 / hidden 128: N={g.num_nodes} E={g.num_edges} exempt={n_exempt} flips={n_flip}")
