@@ -117,6 +117,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(slot_name):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel behind `slot_name`, from the
+    committed `ncu --set full` capture of this same workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py);
+    None when no capture is on record."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        ent = t["kernels"].get(slot_name)
+        return (int(ent["dram_bytes"]), t.get("capture")) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
 def algorithmic_bytes(N, E, cells, F=7, hidden=64, heads=4, layers=4, ED=3, unc=False, fused_mlp=False, fused_heads=False):
     """SURVEY.md 8(d) per-unit figures x the units one launch processes (stated in DESIGN.md)."""
     b = {}
@@ -333,8 +346,9 @@ def run_ours(args):
                                         "frac": round(bytes_["graph_build"] / (gb_ms * 1e-3) / 1e9 / peak, 4)}
         cand = [k for k in kernels if k.startswith(("agg_", "proj_"))]
         dom = max(cand, key=lambda k: kernels[k]["ms"])
+        traffic, capture = ncu_traffic(dom)
         roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": capture, "peak_source": peak_src,
                 "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
                 "message_passing": {k: kernels[k] for k in sorted(kernels) if k.startswith("agg_")}}
 
