@@ -183,7 +183,7 @@ struct UmmaSmem {
     static constexpr int STG_BYTES = STG_WARPS * 4096;
     static constexpr int NSTAGE = PMODE == PM_SPLIT ? (TMA_STORE ? 4 : 6) : ((PMODE == PM_PLAIN && N == 256) || NH > 1) ? 2 : 3;     // fp16 operand ring depth (measured: for
                                                                                      // N = 256 a deeper raw ring beats a third stage)
-    static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * (NH > 1 ? N : NT) : N + HEADS_MAXOUT * HEADS_MAXH2 + 16;  // epilogue parameters
+    static constexpr int PAR_E = EMODE == EM_PROJ ? 3 * (NH > 1 ? N : NT) : N + HEADS_MAXOUT * HEADS_MAXH2 + 16 + 2 * TILE_M;  // epilogue parameters (+ class hand-over)
     static constexpr int PAR_P = PMODE == PM_MLP0 ? MLP0_MAXK * MLP0_FP + MLP0_MAXK : 0;              // producer parameters
     // PM_PLAIN: the A chunk [SUPER_M x 32] fp32 is fetched by TMA into a raw ring, RAW_STAGES chunks ahead
     static constexpr int RAW_BYTES = PMODE == PM_PLAIN ? SUPER_M * KC * 4 : 0;
@@ -680,12 +680,19 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     const float* w2 = s_par + N;
                     const float* b2 = w2 + HEADS_MAXOUT * HEADS_MAXH2;
                     const int h2 = P.h2, ncls = P.ncls, real = P.nblk * h2;
+                    // Work split between the two epilogue halves (warps q and q + 4 share TMEM lanes 32q ..): half 0 takes the
+                    // classification block (ncls dot products, softmax, argmax), half 1 the confidence and correction blocks
+                    // and the action, for which it receives the class through shared memory (one 64-thread named barrier
+                    // per tile; the hand-over slot alternates with the tile parity, so a slot is rewritten only after the
+                    // barrier of the following tile, i.e. after its reader is done with it).
                     float lg[8], pc = 0.f, pr = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) lg[k] = 0.f;
+                    int* s_arg = reinterpret_cast<int*>(s_par + N + HEADS_MAXOUT * HEADS_MAXH2 + 16) + (t & 1u) * TILE_M;
 #pragma unroll 1
                     for (int c0 = 0; c0 < real; c0 += 32) {
-                        if (((c0 / h2) >= 2) != (half == 1)) continue;      // half 0: classification + confidence, half 1: correction
+                        const int blk = c0 / h2, u0 = c0 - blk * h2;
+                        if ((blk >= 1) != (half == 1)) continue;
                         float x[32];
                         tmem_ld_sum32(taddr + (uint32_t)c0, taddr + (uint32_t)(N + c0), out_scale, x);
 #pragma unroll
@@ -694,37 +701,30 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             x[j] = fmaxf(x[j] + b.x, 0.f); x[j + 1] = fmaxf(x[j + 1] + b.y, 0.f);
                             x[j + 2] = fmaxf(x[j + 2] + b.z, 0.f); x[j + 3] = fmaxf(x[j + 3] + b.w, 0.f);
                         }
-                        const int blk = c0 / h2, u0 = c0 - blk * h2;
-                        // four independent partial sums per output: a 32-long serial FMA chain per class is latency-bound
+                        // four independent partial sums per output (a 32-long serial FMA chain is latency-bound), kept as two
+                        // packed pairs: (p0, p1), (p2, p3)
+                        auto dot32 = [&](const float* wv) {
+                            uint64_t p01 = 0ull, p23 = 0ull;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wv + j);
+                                p01 = ffma2(pk2(x[j], x[j + 1]), w.x, p01);
+                                p23 = ffma2(pk2(x[j + 2], x[j + 3]), w.y, p23);
+                            }
+                            float p0, p1, p2, p3;
+                            unpk2(p01, p0, p1); unpk2(p23, p2, p3);
+                            return (p0 + p1) + (p2 + p3);
+                        };
                         if (blk == 0) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
-                                if (k < ncls) {
-                                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll
-                                    for (int j = 0; j < 32; j += 4) {
-                                        const float4 w = *reinterpret_cast<const float4*>(w2 + k * h2 + u0 + j);
-                                        p0 = fmaf(x[j], w.x, p0); p1 = fmaf(x[j + 1], w.y, p1);
-                                        p2 = fmaf(x[j + 2], w.z, p2); p3 = fmaf(x[j + 3], w.w, p3);
-                                    }
-                                    lg[k] += (p0 + p1) + (p2 + p3);
-                                }
+                                if (k < ncls) lg[k] += dot32(w2 + k * h2 + u0);
                         } else {
-                            const float* wv = w2 + (blk == 1 ? ncls : ncls + 1) * h2 + u0;
-                            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 w = *reinterpret_cast<const float4*>(wv + j);
-                                p0 = fmaf(x[j], w.x, p0); p1 = fmaf(x[j + 1], w.y, p1);
-                                p2 = fmaf(x[j + 2], w.z, p2); p3 = fmaf(x[j + 3], w.w, p3);
-                            }
-                            const float acc = (p0 + p1) + (p2 + p3);
+                            const float acc = dot32(w2 + (blk == 1 ? ncls : ncls + 1) * h2 + u0);
                             if (blk == 1) pc += acc; else pr += acc;
                         }
                     }
-                    if (row < M && half == 1) {
-                        if (P.corr && P.nblk > 2) P.corr[row] = pr + b2[ncls + 1];
-                    } else if (row < M) {
+                    if (half == 0) {
                         float best = -CUDART_INF_F;
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
@@ -739,13 +739,19 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             if (k < ncls) {
                                 pb[k] = pb[k] / sum;
                                 if (pb[k] > pmax) { pmax = pb[k]; arg = k; }      // first max wins (torch.argmax)
-                                if (P.logits) P.logits[row * ncls + k] = lg[k];
-                                if (P.probs) P.probs[row * ncls + k] = pb[k];
+                                if (row < M && P.logits) P.logits[row * ncls + k] = lg[k];
+                                if (row < M && P.probs) P.probs[row * ncls + k] = pb[k];
                             }
+                        if (row < M && P.cls) P.cls[row] = arg;
+                        s_arg[quarter * 32 + lane] = arg;
+                        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quarter) : "memory");
+                    } else {
                         const float cf = 1.f / (1.f + expf(-(pc + b2[ncls])));
-                        if (P.cls) P.cls[row] = arg;
-                        if (P.conf) P.conf[row] = cf;
-                        if (P.action) {
+                        if (row < M && P.conf) P.conf[row] = cf;
+                        if (row < M && P.corr && P.nblk > 2) P.corr[row] = pr + b2[ncls + 1];
+                        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quarter) : "memory");
+                        if (row < M && P.action) {
+                            const int arg = s_arg[quarter * 32 + lane];
                             int64_t a = (arg == 2 && cf > P.thr_auto) ? 1 : 0;          // gnn.py:439-441
                             if (cf < P.thr_review) a = 2;                                // gnn.py:444-445
                             P.action[row] = a;
