@@ -24,6 +24,7 @@
 #include "proj_umma.cuh"
 
 static bool g_use_umma = true;
+static bool g_window = getenv("BGNN_NO_WINDOW") == nullptr;       // ragged batches: windowed shared-memory CSR aggregation
 static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
 static bool g_fuse_last = false;      // aggregation of layer L-2 fused with the projection of layer L-1 (tcgen05 in the tiled kernel): correct, but measured slower (3.37 vs 1.80 + 1.03 ms) -> off by default
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
@@ -867,6 +868,206 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
     }
     dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
     kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes, SO);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ windowed CSR aggregation
+// Ragged batches (scripts/inference_native.py:249-342: thousands of small refinement grids packed end to end) have no
+// single grid to tile, but their edges are LOCAL in node-id space: nodes are numbered in raster order per grid, so every
+// source of a destination lies within (grid width + 1) ids of it.  A CTA takes 128 CONSECUTIVE destinations, finds the id
+// range [lo, hi] their in-edges (and self loops) touch, and -- because h is head-major ([H][N][C]) -- stages that range of
+// one head as ONE contiguous bulk copy in shared memory; destinations then read their source rows from shared memory
+// instead of gathering 9 x 1 KB per destination through L1 / L2 (gat_aggregate).  Thread t owns destination t for the
+// scores + softmax of all heads (computed once; weights and source ids parked in shared memory), warp w then walks 16
+// destinations per head with lane <-> channel pair, FMAs in CSR order, self loop last -- the arithmetic of the tiled grid
+// kernel, including its optional fp16 hi | lo output.  A block whose range does not fit (wide grids, foreign graphs) reads
+// its rows from global memory instead.  Requires in-degree <= 8 (the caller's stencil hint) and C = 64.
+template <int H> struct WinCfg {
+    static constexpr int D = 128, MAXD = 8, SLOTS = MAXD + 1, C = 64, NT = 256;
+    static constexpr int RCAP = 320;                                       // rows of one head kept in shared memory (80 KB)
+    static constexpr size_t SMEM = (size_t)RCAP * C * 4 + (size_t)D * SLOTS * H * 4 + (size_t)D * SLOTS * 4 + D * 4 + 64;
+};
+
+template <int H>
+__global__ void __launch_bounds__(256, 2)
+gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alpha, const int32_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ csr_src, const float* __restrict__ eattr, int ED,
+                     const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
+                     const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t N,
+                     const SplitOut SO) {
+    using G = WinCfg<H>;
+    constexpr int D = G::D, SLOTS = G::SLOTS, C = G::C, HC = H * C, RCAP = G::RCAP;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* rows = reinterpret_cast<float*>(smem_raw);                 // [RCAP][C]       source rows lo .. hi of the current head
+    float* w_sm = rows + RCAP * C;                                    // [D][SLOTS][H]   attention weights (slot order = CSR order, self last)
+    int* j_sm = reinterpret_cast<int*>(w_sm + D * SLOTS * H);         // [D][SLOTS]      source ids
+    int* cnt_sm = j_sm + D * SLOTS;                                   // [D]             in-degree + 1 (0: no such destination)
+    int* s_rng = cnt_sm + D;                                          // lo, hi
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_rng + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t d0 = (int64_t)blockIdx.x * D;
+    const float sA = SO.hi ? operand_scale(SO.amax_src, SO.mul, SO.add) : 1.f;
+    if (tid == 0) {
+        s_rng[0] = 0x7fffffff; s_rng[1] = -1;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // ---- scores + softmax of every head: thread t <-> destination d0 + t
+    if (tid < D) {
+        const int64_t i = d0 + tid;
+        int tot = 0;
+        if (i < N) {
+            const int start = __ldg(rowptr + i);
+            const int deg = __ldg(rowptr + i + 1) - start;
+            if (deg > G::MAXD) asm volatile("trap;\n");                // the caller's in-degree hint was wrong
+            tot = deg + 1;
+            int jmin = (int)i, jmax = (int)i;
+            float ea[G::MAXD][BGNN_MAX_EDGE_FEATS], lsum[BGNN_MAX_EDGE_FEATS];
+            int js[G::MAXD];
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = 0.f;
+#pragma unroll
+            for (int e = 0; e < G::MAXD; ++e) {
+                js[e] = (int)i;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[e][d] = 0.f;
+                if (e < deg) {
+                    js[e] = __ldg(csr_src + start + e);
+                    jmin = min(jmin, js[e]); jmax = max(jmax, js[e]);
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                        if (d < ED) { ea[e][d] = __ldg(eattr + (int64_t)(start + e) * ED + d); lsum[d] += ea[e][d]; }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+            atomicMin(&s_rng[0], jmin);
+            atomicMax(&s_rng[1], jmax);
+#pragma unroll
+            for (int e = 0; e < G::MAXD; ++e)
+                if (e < deg) j_sm[tid * SLOTS + e] = js[e];
+            j_sm[tid * SLOTS + deg] = (int)i;
+#pragma unroll 1
+            for (int hh = 0; hh < H; ++hh) {
+                float Mh[BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) Mh[d] = d < ED ? __ldg(Medge + d * H + hh) : 0.f;
+                const float adh = __ldg(alpha + i * (2 * H) + H + hh);
+                float sc[SLOTS], mx = -CUDART_INF_F;
+#pragma unroll
+                for (int e = 0; e < G::MAXD; ++e) {
+                    sc[e] = 0.f;
+                    if (e < deg) {
+                        float ae = 0.f;
+#pragma unroll
+                        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[e][d], Mh[d], ae);
+                        float v = (__ldg(alpha + (int64_t)js[e] * (2 * H) + hh) + adh) + ae;
+                        v = v > 0.f ? v : v * slope;
+                        sc[e] = v;
+                        mx = fmaxf(mx, v);
+                    }
+                }
+                {
+                    float ae = 0.f;
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], Mh[d], ae);
+                    float v = (__ldg(alpha + i * (2 * H) + hh) + adh) + ae;
+                    v = v > 0.f ? v : v * slope;
+                    sc[G::MAXD] = v;
+                    mx = fmaxf(mx, v);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int e = 0; e < G::MAXD; ++e)
+                    if (e < deg) { sc[e] = expf(sc[e] - mx); sum += sc[e]; }
+                sc[G::MAXD] = expf(sc[G::MAXD] - mx);
+                sum += sc[G::MAXD];
+                sum += 1e-16f;
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int e = 0; e < G::MAXD; ++e)
+                    if (e < deg) w_sm[(tid * SLOTS + e) * H + hh] = sc[e] * inv;
+                w_sm[(tid * SLOTS + deg) * H + hh] = sc[G::MAXD] * inv;
+            }
+        }
+        cnt_sm[tid] = tot;
+    }
+    __syncthreads();
+    const int lo = s_rng[0], hi = s_rng[1];
+    const bool staged = hi >= lo && hi - lo + 1 <= RCAP;
+#pragma unroll 1
+    for (int hh = 0; hh < H; ++hh) {
+        const float* hp = h + (int64_t)hh * N * C;                    // head-major plane
+        if (staged && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            const uint32_t bytes = (uint32_t)(hi - lo + 1) * C * 4;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(smem_addr(rows)), "l"(hp + (int64_t)lo * C), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+        }
+        const int ch = hh * C + lane * 2;
+        const float bs0 = __ldg(bias + ch), bs1 = __ldg(bias + ch + 1);
+        const float ba0 = __ldg(bn_a + ch) * sA, ba1 = __ldg(bn_a + ch + 1) * sA;
+        const float bb0 = __ldg(bn_b + ch) * sA, bb1 = __ldg(bn_b + ch + 1) * sA;
+        if (staged) mbar_wait_parity(bar, (uint32_t)(hh & 1));
+#pragma unroll 1
+        for (int t = 0; t < D / 8; ++t) {
+            const int dl = warp * (D / 8) + t;
+            const int tot = cnt_sm[dl];
+            if (tot == 0) continue;
+            const int64_t i = d0 + dl;
+            float a0 = 0.f, a1 = 0.f;
+            for (int q = 0; q < tot; ++q) {
+                const int j = j_sm[dl * SLOTS + q];
+                const float a = w_sm[(dl * SLOTS + q) * H + hh];
+                const float2 hv = staged ? *reinterpret_cast<const float2*>(rows + (j - lo) * C + lane * 2)
+                                         : __ldg(reinterpret_cast<const float2*>(hp + (int64_t)j * C + lane * 2));
+                a0 = fmaf(a, hv.x, a0); a1 = fmaf(a, hv.y, a1);
+            }
+            float o0 = fmaf(a0 + bs0, ba0, bb0), o1 = fmaf(a1 + bs1, ba1, bb1);
+            if (relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+            if (SO.hi) {
+                uint16_t* prow = SO.hi + i * (2 * HC) + hh * C + lane * 2;
+                const __half2 hi2 = __floats2half2_rn(o0, o1);
+                const float2 hf = __half22float2(hi2);
+                const __half2 lo2 = __floats2half2_rn((o0 - hf.x) * 2048.f, (o1 - hf.y) * 2048.f);
+                *reinterpret_cast<__half2*>(prow) = hi2;
+                *reinterpret_cast<__half2*>(prow + HC) = lo2;
+            } else {
+                *reinterpret_cast<float2*>(out + i * HC + hh * C + lane * 2) = make_float2(o0, o1);
+            }
+        }
+        __syncthreads();                     // every warp is done with `rows` before the next head's copy lands
+    }
+}
+
+// returns 1 when the windowed kernel does not apply
+int launch_agg_window(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const int32_t* src,
+                      const float* eattr, int ED, int relu, float slope, float* out, int64_t N, const SplitOut& SO,
+                      cudaStream_t s) {
+    if (L.C != 64 || !(L.H == 1 || L.H == 2 || L.H == 4) || ED > BGNN_MAX_EDGE_FEATS) return 1;
+    if (N == 0) return BGNN_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+#define WLAUNCH(H_)                                                                                                     \
+    do {                                                                                                                \
+        using G = WinCfg<H_>;                                                                                           \
+        static_assert(G::SMEM <= 115000, "two CTAs per SM");                                                            \
+        static bool configured[64] = {};                                                                                \
+        auto kern = gat_aggregate_window<H_>;                                                                           \
+        if (!configured[dev & 63]) {                                                                                    \
+            BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));           \
+            configured[dev & 63] = true;                                                                                \
+        }                                                                                                               \
+        kern<<<(unsigned)ceil_div64(N, G::D), G::NT, G::SMEM, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,   \
+                                                                   L.bn_a, L.bn_b, relu, slope, out, N, SO);            \
+    } while (0)
+    if (L.H == 4) WLAUNCH(4); else if (L.H == 2) WLAUNCH(2); else WLAUNCH(1);
+#undef WLAUNCH
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
@@ -1729,6 +1930,9 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     bool cur_split = false;                    // `cur` holds fp16 hi / lo planes [N, in] (written by the tiled aggregation)
     bool is4_ = false;
     const bool tile_ok0 = tiled && g_use_umma && g_presplit;
+    // no single grid (ragged batch): a topology with rows == 0 only carries the stencil size = an in-degree bound, which
+    // lets the CSR aggregation run as the windowed shared-memory kernel
+    const bool windowed = !tiled && g_window && topo && topo->rows == 0 && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
         if (!proj_done) { ProfScope ps(20 + l, s);
@@ -1779,10 +1983,11 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           // when the next layer's projection runs on the tensor cores, hand it the output as fp16 hi / lo planes
           SplitOut SO = {};
           bool want_split = false;
-          if (!proj_done && tile_ok0 && l + 1 < d.layers && L.C % 64 == 0) {
+          const bool win_l = windowed && L.C == 64 && (L.H == 1 || L.H == 2 || L.H == 4);
+          if (!proj_done && (tile_ok0 || (win_l && g_use_umma && g_presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
               const LayerDev& Ln = m->layers[l + 1];
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
-                           tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_);
+                           (win_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));
               if (want_split) {
                   SO.hi = reinterpret_cast<uint16_t*>(nxt);
                   SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
@@ -1791,6 +1996,10 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           cur_split = false;
           if (rc == 1 && tiled) {
               rc = launch_agg_tile(L, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, SO, s);
+              if (rc == 0 && want_split) cur_split = true;
+          }
+          if (rc == 1 && win_l) {
+              rc = launch_agg_window(L, hsrc, al, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, SO, s);
               if (rc == 0 && want_split) cur_split = true;
           }
           if (rc == 1) rc = launch_agg(L, hsrc, al, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s);

@@ -254,8 +254,13 @@ class BathymetricGNN(nn.Module):
                         topo.off_dr[k], topo.off_dc[k] = dg.cfg.off_dr[k], dg.cfg.off_dc[k]
                     ge = getattr(dg, "grid_eattr", None)
                     topo.grid_eattr = ge.data_ptr() if ge is not None else None
+                elif self.use_grid_kernel and int(dg.cfg.n_offsets) <= 8:
+                    # ragged batch: no single grid, but the stencil bounds the in-degree (windowed CSR aggregation)
+                    topo = _lib.GridTopo()
+                    topo.rows, topo.cols, topo.node_id, topo.grid_eattr = 0, 0, None, None
+                    topo.n_offsets = int(dg.cfg.n_offsets)
                 rowptr = dg.rowptr
-                if topo is not None and lib.bgnn_gat_grid_path(h, C.byref(topo), E) == 1:
+                if topo is not None and topo.rows > 0 and lib.bgnn_gat_grid_path(h, C.byref(topo), E) == 1:
                     src, ea = None, None            # every layer runs the tiled kernel: the CSR payload is never read
                 else:
                     src, ea = dg.csr_src, dg.csr_eattr

@@ -512,12 +512,29 @@ def run_ragged(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); nodes = one_pass(); ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    kernels = {}
+    if rank == 0:                # per-kernel device time of ONE chunk (events inside the library)
+        from bathymetric_gnn_b200._lib import lib
+        lib.bgnn_profile_enable(1)
+        d, off, r, c, rs = chunks[0]
+        g = builder.build_graph_packed(d, off, r, c, rs, nodata=1.0e6); out = model.predict(g)
+        torch.cuda.synchronize()
+        n = lib.bgnn_profile_collect(0, None, None)
+        slots = (C.c_int32 * n)(); tms = (C.c_float * n)()
+        lib.bgnn_profile_collect(n, slots, tms)
+        lib.bgnn_profile_enable(0)
+        for s_, m_ in zip(slots, tms):
+            k = SLOT_NAMES.get(int(s_), str(int(s_)))
+            kernels[k] = round(kernels.get(k, 0.0) + float(m_), 4)
+        kernels["chunk_nodes"] = g.num_nodes
+        del g, out
     if rank == 0:
         print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),
                           "unit": UNIT, "n_gpus": world, "ms_total": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"configs[3]: {args.grids} refinement grids, sides U{{3..50}}, 10% nodata, "
                                                  f"{len(chunks)} ragged chunks of <= {args.chunk_cells} cells per rank",
-                                     "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"}}))
+                                     "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"},
+                          "kernels_ms_one_chunk": kernels}))
 
 
 def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):

@@ -170,7 +170,10 @@ size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes);
 /* Optional grid topology of the node set (single tile, n_grids == 1): when given, and the stencil
  * has radius 1 (4-/8-connected), the aggregation runs as a shared-memory tiled kernel: one CTA per
  * 16x16 patch of cells stages every source row of its 18x18 halo ONCE (cp.async) instead of
- * gathering 9 rows per destination through L1.  The in-edge CSR is still required (edge features). */
+ * gathering 9 rows per destination through L1.  The in-edge CSR is still required (edge features).
+ * rows == 0 (node_id NULL) marks a node set WITHOUT a single grid -- a ragged batch of grids packed end to end -- and
+ * only n_offsets is read: it bounds the in-degree (<= 8), which lets the CSR aggregation stage each block's source-id
+ * window in shared memory (raster numbering keeps sources within a grid width of their destination). */
 typedef struct bgnn_grid_topo {
     int32_t        rows, cols;
     const int32_t* node_id;                      /* [dev] int32 [rows*cols] from bgnn_graph_emit */
