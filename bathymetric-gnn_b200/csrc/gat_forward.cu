@@ -885,9 +885,9 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
 // kernel, including its optional fp16 hi | lo output.  A block whose range does not fit (wide grids, foreign graphs) reads
 // its rows from global memory instead.  Requires in-degree <= 8 (the caller's stencil hint) and C = 64.
 template <int H> struct WinCfg {
-    static constexpr int D = 128, MAXD = 8, SLOTS = MAXD + 1, C = 64, NT = 256;
+    static constexpr int D = 128, MAXD = 8, SLOTS = MAXD + 1, SP = 12, C = 64, NT = 256;     // SP: padded slot stride (16 B rows)
     static constexpr int RCAP = 320;                                       // rows of one head kept in shared memory (80 KB)
-    static constexpr size_t SMEM = (size_t)RCAP * C * 4 + (size_t)D * SLOTS * H * 4 + (size_t)D * SLOTS * 4 + D * 4 + 64;
+    static constexpr size_t SMEM = (size_t)RCAP * C * 4 + (size_t)D * H * SP * 4 + (size_t)D * SP * 4 + D * 4 + 64;
 };
 
 template <int H>
@@ -898,12 +898,13 @@ gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alph
                      const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t N,
                      const SplitOut SO) {
     using G = WinCfg<H>;
-    constexpr int D = G::D, SLOTS = G::SLOTS, C = G::C, HC = H * C, RCAP = G::RCAP;
+    constexpr int D = G::D, SLOTS = G::SLOTS, SP = G::SP, C = G::C, HC = H * C, RCAP = G::RCAP;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* rows = reinterpret_cast<float*>(smem_raw);                 // [RCAP][C]       source rows lo .. hi of the current head
-    float* w_sm = rows + RCAP * C;                                    // [D][SLOTS][H]   attention weights (slot order = CSR order, self last)
-    int* j_sm = reinterpret_cast<int*>(w_sm + D * SLOTS * H);         // [D][SLOTS]      source ids
-    int* cnt_sm = j_sm + D * SLOTS;                                   // [D]             in-degree + 1 (0: no such destination)
+    float* w_sm = rows + RCAP * C;                                    // [D][H][SP]      attention weights (slot order = CSR order, self loop
+                                                                      //                 last; unused slots: weight 0 on the node itself)
+    int* j_sm = reinterpret_cast<int*>(w_sm + D * H * SP);            // [D][SP]         source ids
+    int* cnt_sm = j_sm + D * SP;                                      // [D]             in-degree + 1 (0: no such destination)
     int* s_rng = cnt_sm + D;                                          // lo, hi
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_rng + 2);
 
@@ -916,9 +917,11 @@ gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alph
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    // ---- scores + softmax of every head: thread t <-> destination d0 + t
-    if (tid < D) {
-        const int64_t i = d0 + tid;
+    // ---- scores + softmax: threads t and t + 128 <-> destination d0 + t, each taking half of the heads
+    {
+        const int dl = tid & (D - 1), hsel = tid >> 7;
+        constexpr int HPT = H >= 2 ? H / 2 : 1;                       // heads per thread
+        const int64_t i = d0 + dl;
         int tot = 0;
         if (i < N) {
             const int start = __ldg(rowptr + i);
@@ -945,14 +948,14 @@ gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alph
             }
 #pragma unroll
             for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
-            atomicMin(&s_rng[0], jmin);
-            atomicMax(&s_rng[1], jmax);
+            if (hsel == 0) {
+                atomicMin(&s_rng[0], jmin);
+                atomicMax(&s_rng[1], jmax);
 #pragma unroll
-            for (int e = 0; e < G::MAXD; ++e)
-                if (e < deg) j_sm[tid * SLOTS + e] = js[e];
-            j_sm[tid * SLOTS + deg] = (int)i;
+                for (int e = 0; e < SLOTS; ++e) j_sm[dl * SP + e] = (e < G::MAXD && e < deg) ? js[e < G::MAXD ? e : 0] : (int)i;
+            }
 #pragma unroll 1
-            for (int hh = 0; hh < H; ++hh) {
+            for (int hh = hsel * HPT; hh < (hsel + 1) * HPT && hh < H; ++hh) {
                 float Mh[BGNN_MAX_EDGE_FEATS];
 #pragma unroll
                 for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) Mh[d] = d < ED ? __ldg(Medge + d * H + hh) : 0.f;
@@ -988,13 +991,16 @@ gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alph
                 sum += sc[G::MAXD];
                 sum += 1e-16f;
                 const float inv = 1.0f / sum;
+                float* wr = w_sm + (dl * H + hh) * SP;
+#pragma unroll
+                for (int e = 0; e < SLOTS; ++e) wr[e] = 0.f;
 #pragma unroll
                 for (int e = 0; e < G::MAXD; ++e)
-                    if (e < deg) w_sm[(tid * SLOTS + e) * H + hh] = sc[e] * inv;
-                w_sm[(tid * SLOTS + deg) * H + hh] = sc[G::MAXD] * inv;
+                    if (e < deg) wr[e] = sc[e] * inv;
+                wr[deg] = sc[G::MAXD] * inv;
             }
         }
-        cnt_sm[tid] = tot;
+        if (hsel == 0) cnt_sm[dl] = tot;
     }
     __syncthreads();
     const int lo = s_rng[0], hi = s_rng[1];
@@ -1020,14 +1026,24 @@ gat_aggregate_window(const float* __restrict__ h, const float* __restrict__ alph
             const int tot = cnt_sm[dl];
             if (tot == 0) continue;
             const int64_t i = d0 + dl;
-            float a0 = 0.f, a1 = 0.f;
-            for (int q = 0; q < tot; ++q) {
-                const int j = j_sm[dl * SLOTS + q];
-                const float a = w_sm[(dl * SLOTS + q) * H + hh];
-                const float2 hv = staged ? *reinterpret_cast<const float2*>(rows + (j - lo) * C + lane * 2)
-                                         : __ldg(reinterpret_cast<const float2*>(hp + (int64_t)j * C + lane * 2));
-                a0 = fmaf(a, hv.x, a0); a1 = fmaf(a, hv.y, a1);
+            // all nine slots, unrolled: independent loads first, then the FMA chain in slot order (unused slots add w = 0
+            // times the node's own finite row: a no-op)
+            const int4 j0 = *reinterpret_cast<const int4*>(j_sm + dl * SP), j1 = *reinterpret_cast<const int4*>(j_sm + dl * SP + 4);
+            const int jj[SLOTS] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j_sm[dl * SP + 8]};
+            const float* wr = w_sm + (dl * H + hh) * SP;
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+            const float ww[SLOTS] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wr[8]};
+            float2 hv[SLOTS];
+            if (staged) {
+#pragma unroll
+                for (int q = 0; q < SLOTS; ++q) hv[q] = *reinterpret_cast<const float2*>(rows + (jj[q] - lo) * C + lane * 2);
+            } else {
+#pragma unroll
+                for (int q = 0; q < SLOTS; ++q) hv[q] = __ldg(reinterpret_cast<const float2*>(hp + (int64_t)jj[q] * C + lane * 2));
             }
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < SLOTS; ++q) { a0 = fmaf(ww[q], hv[q].x, a0); a1 = fmaf(ww[q], hv[q].y, a1); }
             float o0 = fmaf(a0 + bs0, ba0, bb0), o1 = fmaf(a1 + bs1, ba1, bb1);
             if (relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
             if (SO.hi) {
