@@ -73,7 +73,6 @@ SYMBOLS = {
     "bgnn_stitch_finalize": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_apply_corrections": (C.c_int, [P, P, I64, P, P, P, P, F32, P]),
     "bgnn_set_tensor_cores": (C.c_int, [C.c_int]),
-    "bgnn_set_fusion": (C.c_int, [C.c_int]),
     "bgnn_set_presplit": (C.c_int, [C.c_int]),
     "bgnn_test_proj_umma_presplit": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_test_proj_umma": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),

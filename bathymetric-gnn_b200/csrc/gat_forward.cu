@@ -26,9 +26,7 @@
 static bool g_use_umma = true;
 static bool g_window = getenv("BGNN_NO_WINDOW") == nullptr;       // ragged batches: windowed shared-memory CSR aggregation
 static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
-static bool g_fuse_last = false;      // aggregation of layer L-2 fused with the projection of layer L-1 (tcgen05 in the tiled kernel): correct, but measured slower (3.37 vs 1.80 + 1.03 ms) -> off by default
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
-extern "C" int bgnn_set_fusion(int on) { g_fuse_last = on != 0; return BGNN_OK; }
 extern "C" int bgnn_set_presplit(int on) { g_presplit = on != 0; return BGNN_OK; }
 #ifdef BGNN_AGG_TIMING
 extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset);
@@ -1090,478 +1088,6 @@ int launch_agg_window(const LayerDev& L, const float* h, const float* alpha, con
 
 static bool tile_supported(const TopoDev& T, int H, int C, int ED, const float* grid_eattr, bool* conn4);
 
-// ------------------------------------------------------------------------------------------ fused aggregation + next projection
-// Last-but-one layer: the aggregated row (BN + ReLU applied) of layer l is the A operand of layer l+1's projection, whose
-// output is only NOUT = 64 wide (GATConv(heads*C -> C, heads=1), models/gnn.py:125-132).  Its accumulators {main, corr}
-// need just 2*NOUT TMEM columns, so two CTAs per SM keep the latency hiding of the tiled kernel and the [N, heads*C]
-// intermediate never reaches HBM: each head's aggregated slice is split into fp16 hi/lo (same scheme and scales as
-// proj_umma.cu) straight into K-major SWIZZLE_64B tiles, one thread issues that head's tcgen05.mma against the matching 16 KB
-// slice of the pre-split weights, and after the last head warps 0..3 drain TMEM (alpha_src/alpha_dst, max|h|, rows of h_{l+1}).
-// Arithmetic and accumulation order are those of gat_aggregate_tile followed by proj_umma_kernel: results are bit-identical.
-constexpr int FKC = 32;                          // K per chunk
-constexpr int F_ATILE = 128 * FKC * 2;           // 8 KB: [128 rows x 32] fp16
-constexpr uint32_t F_SBO = 8 * FKC * 2;
-
-__device__ __forceinline__ uint64_t f_make_desc(uint32_t saddr) {      // K-major SWIZZLE_64B (see proj_umma.cu)
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((F_SBO >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-__device__ __forceinline__ uint32_t f_sw64_off(int r, int c) {
-    return (uint32_t)((r >> 3) * F_SBO + (r & 7) * 64 + ((c ^ ((r & 7) >> 1)) << 4));
-}
-__device__ __forceinline__ void f_umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void f_umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_addr(bar)) : "memory");
-}
-
-struct FuseArgs {
-    const uint16_t* Wsplit;        // layer l+1 weights, pre-split / pre-swizzled: [K/32][2][NOUT x 32]
-    float w_inv;                   // 1 / (power-of-two scale applied to W)
-    const float* amax_src;         // max|h_l| (device); |A| <= amax_mul * max|h_l| + amax_add
-    float amax_mul, amax_add;
-    const float* att_src;          // [NOUT] (layer l+1 has one head)
-    const float* att_dst;
-    float* Cout;                   // h_{l+1}  [N][NOUT]
-    float* alpha_out;              // [N][2]
-    float* cmax_out;               // atomicMax of |h_{l+1}|
-};
-
-template <int H, int C, int NOUT> struct FuseCfg {
-    static constexpr int PH = 8, PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, ND = PH * PW, NT = 256, AST = 12;
-    static constexpr int A_BYTES = (C / FKC) * 2 * F_ATILE;                // one head's K-slice: C/32 chunks x {hi, lo}
-    static constexpr int BT = NOUT * FKC * 2;                              // one W tile
-    static constexpr int W_BYTES = (C / FKC) * 2 * BT;
-    static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= ND * AST;
-    static constexpr size_t SMEM = (size_t)A_BYTES + W_BYTES +
-                                   (size_t)(NSLOT * C + NSLOT + NSLOT * H + ND * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C + 2 * NOUT) * 4 + 64;
-};
-
-template <int H, int C, bool CONN4, int NOUT>
-__global__ void __launch_bounds__(256, 2)
-gat_aggregate_tile_proj(const float* __restrict__ h, const float* __restrict__ alpha, const TopoDev T,
-                        const float* __restrict__ grid_eattr, int ED,
-                        const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
-                        const float* __restrict__ bn_b, int relu, float slope, int64_t n_nodes, const FuseArgs F) {
-    using G = FuseCfg<H, C, NOUT>;
-    using O = EdgeOrder<CONN4>;
-    constexpr int HW = G::HW, NSLOT = G::NSLOT, NT = G::NT, ND = G::ND, AST = G::AST, HR = G::HR;
-    constexpr int VEC = C / 32, HC = H * C, NCH = C / FKC;
-    static_assert(VEC == 2, "the fused kernel is written for C = 64");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* At = smem_raw;                                  // [NCH][2][128 x 32 fp16]  this head's A slice
-    unsigned char* Wb = At + G::A_BYTES;                           // [NCH][2][NOUT x 32 fp16] the matching W slice
-    float* rows = reinterpret_cast<float*>(Wb + G::W_BYTES);       // [NSLOT][C]
-    int* ids = reinterpret_cast<int*>(rows + NSLOT * C);
-    float* asrc = reinterpret_cast<float*>(ids + NSLOT);           // [H][NSLOT]
-    float* a_sm = asrc + NSLOT * H;                                // [ND][AST]
-    float* al_sm = a_sm;
-    float* M_s = a_sm + ND * AST;
-    float* s_bn = M_s + BGNN_MAX_EDGE_FEATS * H;                   // [3][HC]
-    float* s_att = s_bn + 3 * HC;                                  // [2][NOUT]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_att + 2 * NOUT); // 0 rows, 1 alpha, 2 W, 3 MMA done, 4 accumulators complete
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 5);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pr0 = blockIdx.y * G::PH, pc0 = blockIdx.x * 16;
-
-    // operand scale of the projection (same rule as proj_umma_kernel)
-    float sA = 1.f, out_scale = F.w_inv;
-    {
-        float bound = F.amax_add;
-        if (F.amax_src) bound = fmaf(F.amax_mul, __ldg(F.amax_src), F.amax_add);
-        const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);
-        const int es = 253 - e;
-        if (e > 0 && e < 255 && es >= 1 && es <= 253) {
-            sA = __uint_as_float((uint32_t)es << 23);
-            out_scale *= __uint_as_float((uint32_t)(254 - es) << 23);
-        }
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(NT));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar + 1)), "r"(HR));
-        for (int b = 2; b < 5; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar + b)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_addr(s_tmem)), "n"(2 * NOUT) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    for (int s = tid; s < NSLOT; s += NT) {
-        const int r = pr0 - 1 + s / HW, c = pc0 - 1 + s % HW;
-        int id = -1;
-        if (r >= 0 && r < T.rows && c >= 0 && c < T.cols) id = __ldg(T.node_id + (int64_t)r * T.cols + c);
-        ids[s] = id;
-    }
-    for (int i = tid; i < HC; i += NT) { s_bn[i] = __ldg(bias + i); s_bn[HC + i] = __ldg(bn_a + i); s_bn[2 * HC + i] = __ldg(bn_b + i); }
-    if (tid < BGNN_MAX_EDGE_FEATS * H) M_s[tid] = (tid / H) < ED ? __ldg(Medge + tid) : 0.f;
-    if (tid < NOUT) { s_att[tid] = __ldg(F.att_src + tid); s_att[NOUT + tid] = __ldg(F.att_dst + tid); }
-    const bool scorer = tid < ND;
-    const int cs = scorer ? (tid / 16 + 1) * HW + (tid % 16 + 1) : HW + 1;
-    float ea[8][BGNN_MAX_EDGE_FEATS];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
-    if (scorer) {
-        const int r = pr0 + tid / 16, c = pc0 + tid % 16;
-        if (ED > 0 && r < T.rows && c < T.cols) {
-            const float* ge = grid_eattr + ((int64_t)r * T.cols + c) * (T.K * ED);
-            if (T.K == 8 && ED == 3) {
-                float v[24];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ge) + q);
-                    v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) ea[k][d] = v[k * 3 + d];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-#pragma unroll
-                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
-                        if (k < T.K && d < ED) ea[k][d] = __ldg(ge + k * ED + d);
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_base = *s_tmem;
-
-    auto issue_rows = [&](int hh) {
-        if (tid < HR) {
-            const float* hp = h + (int64_t)hh * n_nodes * C;
-            const int s0 = tid * HW;
-            int run = -1;
-            for (int c = 0; c <= HW; ++c) {
-                const int id = c < HW ? ids[s0 + c] : -1;
-                if (id >= 0 && run < 0) run = c;
-                if (id < 0 && run >= 0) {
-                    bulk_g2s(rows + (s0 + run) * C, hp + (int64_t)ids[s0 + run] * C, (uint32_t)(c - run) * C * 4, bar);
-                    run = -1;
-                }
-            }
-        }
-    };
-    auto issue_w = [&](int hh) {          // the 16 KB W slice of head hh: chunks NCH*hh .. NCH*hh + NCH-1, hi and lo tiles
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar + 2)), "r"((uint32_t)G::W_BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                     ::"r"(smem_addr(Wb)), "l"(reinterpret_cast<const unsigned char*>(F.Wsplit) + (size_t)hh * G::W_BYTES),
-                       "r"((uint32_t)G::W_BYTES), "r"(smem_addr(bar + 2)) : "memory");
-    };
-    if (G::ALPHA_BULK && tid < HR) {
-        const int s0 = tid * HW;
-        int run = -1;
-        for (int c = 0; c <= HW; ++c) {
-            const int id = c < HW ? ids[s0 + c] : -1;
-            if (id >= 0 && run < 0) run = c;
-            if (id < 0 && run >= 0) {
-                bulk_g2s(al_sm + (s0 + run) * 2 * H, alpha + (int64_t)ids[s0 + run] * 2 * H, (uint32_t)(c - run) * 2 * H * 4, bar + 1);
-                run = -1;
-            }
-        }
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar + 1)) : "memory");
-    }
-    issue_rows(0);
-    if (tid == 0) issue_w(0);
-
-    const int myid = scorer ? ids[cs] : -1;
-    float lsum[BGNN_MAX_EDGE_FEATS], ad[H];
-    unsigned nbv = 0;
-#pragma unroll
-    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = 0.f;
-#pragma unroll
-    for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
-    if (myid >= 0) {
-        int deg = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < T.K && ids[cs - T.dr[k] * HW - T.dc[k]] >= 0) {
-                nbv |= 1u << k;
-                ++deg;
-#pragma unroll
-                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] += ea[k][d];
-            }
-#pragma unroll
-        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
-    }
-    for (int s = tid; s < NSLOT; s += NT)
-        if (ids[s] < 0) {
-#pragma unroll
-            for (int q = 0; q < C / 4; ++q) *reinterpret_cast<float4*>(rows + s * C + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    if (G::ALPHA_BULK) {
-        mbar_wait_parity(bar + 1, 0);
-        for (int s = tid; s < NSLOT; s += NT)
-            if (ids[s] >= 0) {
-#pragma unroll
-                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = al_sm[s * 2 * H + hh];
-            }
-        if (myid >= 0) {
-#pragma unroll
-            for (int hh = 0; hh < H; ++hh) ad[hh] = al_sm[cs * 2 * H + H + hh];
-        }
-    } else {
-        for (int s = tid; s < NSLOT; s += NT) {
-            const int id = ids[s];
-            if (id >= 0) {
-#pragma unroll
-                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + s] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
-            }
-        }
-        if (myid >= 0) {
-#pragma unroll
-            for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
-        }
-    }
-    __syncthreads();
-    int wpos[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) wpos[k] = (1 - T.dr[k]) * 3 + (1 - T.dc[k]);
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-#pragma unroll 1
-    for (int hh = 0; hh < H; ++hh) {
-        if (hh > 0) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            issue_rows(hh);
-        }
-        if (scorer) {
-            float4* az = reinterpret_cast<float4*>(a_sm + tid * AST);
-            az[0] = make_float4(0.f, 0.f, 0.f, 0.f); az[1] = make_float4(0.f, 0.f, 0.f, 0.f); az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (myid >= 0) {
-            float Mh[BGNN_MAX_EDGE_FEATS], adh = ad[0];
-#pragma unroll
-            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) Mh[d] = M_s[d * H + hh];
-#pragma unroll
-            for (int q = 1; q < H; ++q) adh = (q == hh) ? ad[q] : adh;
-            float sc[9], mx = -CUDART_INF_F;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                sc[k] = 0.f;
-                if ((nbv >> k) & 1u) {
-                    float ae = 0.f;
-#pragma unroll
-                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], Mh[d], ae);
-                    float v = (asrc[hh * NSLOT + cs - T.dr[k] * HW - T.dc[k]] + adh) + ae;
-                    v = v > 0.f ? v : v * slope;
-                    sc[k] = v;
-                    mx = fmaxf(mx, v);
-                }
-            }
-            {
-                float ae = 0.f;
-#pragma unroll
-                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], Mh[d], ae);
-                float v = (asrc[hh * NSLOT + cs] + adh) + ae;
-                v = v > 0.f ? v : v * slope;
-                sc[8] = v;
-                mx = fmaxf(mx, v);
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((nbv >> k) & 1u) { sc[k] = expf(sc[k] - mx); sum += sc[k]; }
-            sc[8] = expf(sc[8] - mx);
-            sum += sc[8];
-            sum += 1e-16f;
-            const float inv = 1.0f / sum;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] * inv;
-            a_sm[tid * AST + 4] = sc[8] * inv;
-        }
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
-        mbar_wait_parity(bar, (uint32_t)(hh & 1));
-        if (hh > 0) {                        // the previous head's MMAs have read the A slice and the W slice
-            mbar_wait_parity(bar + 3, (uint32_t)((hh - 1) & 1));
-            if (tid == 0) issue_w(hh);
-        }
-        // aggregate: warp w <-> patch row w; lane <-> 2 channels; result -> fp16 hi/lo into the K-major A tiles
-        float bs[VEC], ba[VEC], bb[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const int ch = hh * C + lane * VEC + v;
-            bs[v] = s_bn[ch]; ba[v] = s_bn[HC + ch]; bb[v] = s_bn[2 * HC + ch];
-        }
-        {
-            const int pr = warp;
-            const float* base = rows + (pr * HW) * C + lane * VEC;
-            unsigned char* atile = At + (lane >> 4) * (2 * F_ATILE) + (lane & 3) * 4;     // chunk = lane / 16
-            const int c16 = (lane & 15) >> 2;
-            float win[3][3][VEC];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const float2 t0 = *reinterpret_cast<const float2*>(base + (dy * HW + 0) * C);
-                const float2 t1 = *reinterpret_cast<const float2*>(base + (dy * HW + 1) * C);
-                win[dy][1][0] = t0.x; win[dy][1][1] = t0.y; win[dy][2][0] = t1.x; win[dy][2][1] = t1.y;
-            }
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    win[dy][0][0] = win[dy][1][0]; win[dy][0][1] = win[dy][1][1];
-                    win[dy][1][0] = win[dy][2][0]; win[dy][1][1] = win[dy][2][1];
-                    const float2 t2v = *reinterpret_cast<const float2*>(base + (dy * HW + c + 2) * C);
-                    win[dy][2][0] = t2v.x; win[dy][2][1] = t2v.y;
-                }
-                const int t2 = pr * 16 + c;
-                const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
-                const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
-                const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
-                float acc[VEC] = {0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < O::N; ++q) {
-                    const int p = O::pos(q);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(aw[p], win[p / 3][p % 3][v], acc[v]);
-                }
-                float o[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    float y = acc[v] + bs[v];
-                    y = fmaf(y, ba[v], bb[v]);
-                    o[v] = relu ? fmaxf(y, 0.f) : y;
-                }
-                if (ids[(pr + 1) * HW + c + 1] < 0) { o[0] = 0.f; o[1] = 0.f; }        // invalid destination: a finite (ignored) row
-                const float s0v = o[0] * sA, s1v = o[1] * sA;
-                const __half2 hi = __floats2half2_rn(s0v, s1v);
-                const float2 hf = __half22float2(hi);
-                const __half2 lo = __floats2half2_rn((s0v - hf.x) * 2048.f, (s1v - hf.y) * 2048.f);
-                unsigned char* dst = atile + f_sw64_off(t2, c16);
-                *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&hi);
-                *reinterpret_cast<uint32_t*>(dst + F_ATILE) = *reinterpret_cast<const uint32_t*>(&lo);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");         // A tiles (generic proxy) -> tensor core (async proxy)
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait_parity(bar + 2, (uint32_t)(hh & 1));                          // W slice landed
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t sAt = smem_addr(At), sWb = smem_addr(Wb);
-            const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)NOUT;
-            const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
-#pragma unroll
-            for (int q = 0; q < NCH; ++q)
-#pragma unroll
-                for (int p = 0; p < 3; ++p)
-#pragma unroll
-                    for (int ks = 0; ks < FKC / 16; ++ks) {
-                        const uint64_t da = f_make_desc(sAt + (q * 2 + pa[p]) * F_ATILE + ks * 32);
-                        const uint64_t db = f_make_desc(sWb + (q * 2 + pb[p]) * G::BT + ks * 32);
-                        const bool first = hh == 0 && q == 0 && ks == 0 && (p == 0 || p == 1);
-                        f_umma_f16(p == 0 ? d_main : d_corr, da, db, idesc, first ? 0u : 1u);
-                    }
-            f_umma_commit(bar + 3);
-            if (hh == H - 1) f_umma_commit(bar + 4);
-        }
-    }
-    // ---- epilogue: warp w < 4 <-> TMEM lanes 32w .., thread <-> destination t = tid
-    if (warp < 4) {
-        mbar_wait_parity(bar + 4, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int t = tid;
-        const int id = ids[(t / 16 + 1) * HW + (t % 16 + 1)];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float as_acc = 0.f, ad_acc = 0.f, cmax = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
-            uint32_t v[32], u[32];
-#define BGNN_F_LD32(arr, addr)                                                                                                 \
-            asm volatile(                                                                                                      \
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                    \
-                : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
-                  "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]),     \
-                  "=r"(arr[15]), "=r"(arr[16]), "=r"(arr[17]), "=r"(arr[18]), "=r"(arr[19]), "=r"(arr[20]), "=r"(arr[21]),   \
-                  "=r"(arr[22]), "=r"(arr[23]), "=r"(arr[24]), "=r"(arr[25]), "=r"(arr[26]), "=r"(arr[27]), "=r"(arr[28]),   \
-                  "=r"(arr[29]), "=r"(arr[30]), "=r"(arr[31])                                                                  \
-                : "r"(addr))
-            BGNN_F_LD32(v, taddr + (uint32_t)c0);
-            BGNN_F_LD32(u, taddr + (uint32_t)(NOUT + c0));
-#undef BGNN_F_LD32
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(u[j]), 1.f / 2048.f, __uint_as_float(v[j])) * out_scale;
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                m0 = fmaxf(m0, fabsf(x[j])); m1 = fmaxf(m1, fabsf(x[j + 1])); m2 = fmaxf(m2, fabsf(x[j + 2])); m3 = fmaxf(m3, fabsf(x[j + 3]));
-                const float4 s4 = *reinterpret_cast<const float4*>(s_att + c0 + j);
-                const float4 d4 = *reinterpret_cast<const float4*>(s_att + NOUT + c0 + j);
-                s0 = fmaf(x[j], s4.x, s0); s1 = fmaf(x[j + 1], s4.y, s1); s2 = fmaf(x[j + 2], s4.z, s2); s3 = fmaf(x[j + 3], s4.w, s3);
-                d0 = fmaf(x[j], d4.x, d0); d1 = fmaf(x[j + 1], d4.y, d1); d2 = fmaf(x[j + 2], d4.z, d2); d3 = fmaf(x[j + 3], d4.w, d3);
-            }
-            as_acc += (s0 + s1) + (s2 + s3);
-            ad_acc += (d0 + d1) + (d2 + d3);
-            if (id >= 0) {
-                cmax = fmaxf(cmax, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-                float* dst = F.Cout + (int64_t)id * NOUT + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-            }
-        }
-        if (id >= 0) {
-            F.alpha_out[(int64_t)id * 2] = as_acc;
-            F.alpha_out[(int64_t)id * 2 + 1] = ad_acc;
-        }
-        if (F.cmax_out) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(F.cmax_out), __float_as_uint(cmax));
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(2 * NOUT) : "memory");
-    }
-}
-
-// returns 1 when the fused kernel does not apply
-int launch_agg_tile_proj(const LayerDev& L, const LayerDev& Ln, const float* h, const float* alpha, const TopoDev& T,
-                         const float* grid_eattr, int ED, int relu, float slope, int64_t n_nodes, const FuseArgs& F, cudaStream_t s) {
-    bool is4 = false;
-    if (!(L.H == 4 && L.C == 64 && Ln.H == 1 && Ln.HC == 64 && Ln.in == L.HC && Ln.Wsplit)) return 1;
-    if (!tile_supported(T, L.H, L.C, ED, grid_eattr, &is4)) return 1;
-    using G = FuseCfg<4, 64, 64>;
-    static_assert(G::SMEM <= 115000, "two CTAs per SM");
-    static bool configured[64][2] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + G::PH - 1) / G::PH));
-#define FLAUNCH(CONN4_)                                                                                                        \
-    do {                                                                                                                       \
-        auto kern = gat_aggregate_tile_proj<4, 64, CONN4_, 64>;                                                                \
-        if (!configured[dev & 63][CONN4_ ? 1 : 0]) {                                                                           \
-            BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));                  \
-            configured[dev & 63][CONN4_ ? 1 : 0] = true;                                                                       \
-        }                                                                                                                      \
-        kern<<<grid, G::NT, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, n_nodes, F); \
-    } while (0)
-    if (is4) FLAUNCH(true); else FLAUNCH(false);
-#undef FLAUNCH
-    BGNN_LAUNCH_CHECK();
-    return BGNN_OK;
-}
-
 // the reference's own offset lists (graph_construction.py:79-87) in their order; a tiled instantiation exists for (H, C)
 static bool tile_supported(const TopoDev& T, int H, int C, int ED, const float* grid_eattr, bool* conn4) {
     static const int r8[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, c8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
@@ -1864,8 +1390,7 @@ static size_t act_bytes(const bgnn_model* m, int64_t n) { return align_up((size_
 
 extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes) {
     if (!m || n_nodes < 0) return 0;
-    return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256 /*operand maxima*/ +
-           align_up((size_t)n_nodes * 2 * sizeof(float), 256) /*alpha of the fused last projection*/ + 256;
+    return 3 * act_bytes(m, n_nodes) + align_up((size_t)n_nodes * 2 * m->d.heads * sizeof(float), 256) + 256 /*operand maxima*/ + 256;
 }
 
 static bool topo_to_dev(const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
@@ -1923,7 +1448,6 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     float* alpha = (float*)w; w += align_up((size_t)N * 2 * m->d.heads * sizeof(float), 256);
     // operand maxima for the fp16-split tensor-core GEMMs: [0] = max|x| (or max|MLP output|), [1+l] = max|h_l|
     float* amax = (float*)w; w += 256;
-    float* alpha_b = (float*)w;                // alpha of a projection fused into the previous layer's aggregation
     const bgnn_model_desc& d = m->d;
     BGNN_CHECK_ARG(d.layers + 1 <= 64, "too many layers");
     if (g_use_umma) BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
@@ -1942,7 +1466,6 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     float* nxt = bufA;
     const float* hsrc = hbuf;                  // where h_l and its alpha live
     const float* al = alpha;
-    bool proj_done = false;                    // h_l was already produced by the fused kernel of layer l-1
     bool cur_split = false;                    // `cur` holds fp16 hi / lo planes [N, in] (written by the tiled aggregation)
     bool is4_ = false;
     const bool tile_ok0 = tiled && g_use_umma && g_presplit;
@@ -1951,8 +1474,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const bool windowed = !tiled && g_window && topo && topo->rows == 0 && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
-        if (!proj_done) { ProfScope ps(20 + l, s);
-          hsrc = hbuf; al = alpha;
+        { ProfScope ps(20 + l, s);
           if (l == 0 && fused0) {
               if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
               UmmaArgs a = {};
@@ -1981,26 +1503,14 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               if (!rc && g_use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
           }
           if (rc) return rc; }
-        proj_done = false;
         const int relu = l < d.layers - 1;
         { ProfScope ps(40 + l, s);
           rc = 1;
-          if (tiled && g_use_umma && g_fuse_last && l + 1 == d.layers - 1) {
-              // aggregation of layer l fused with the projection of the last layer: h_{l+1} -> nxt, its alpha -> alpha_b
-              const LayerDev& Ln = m->layers[l + 1];
-              FuseArgs F;
-              F.Wsplit = Ln.Wsplit; F.w_inv = Ln.w_inv;
-              F.amax_src = amax + 1 + l; F.amax_mul = L.out_mul; F.amax_add = L.out_add;
-              F.att_src = Ln.att_src; F.att_dst = Ln.att_dst;
-              F.Cout = nxt; F.alpha_out = alpha_b; F.cmax_out = amax + 2 + l;
-              rc = launch_agg_tile_proj(L, Ln, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, N, F, s);
-              if (rc == 0) { hsrc = nxt; al = alpha_b; proj_done = true; }
-          }
           // when the next layer's projection runs on the tensor cores, hand it the output as fp16 hi / lo planes
           SplitOut SO = {};
           bool want_split = false;
           const bool win_l = windowed && L.C == 64 && (L.H == 1 || L.H == 2 || L.H == 4);
-          if (!proj_done && (tile_ok0 || (win_l && g_use_umma && g_presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
+          if ((tile_ok0 || (win_l && g_use_umma && g_presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
               const LayerDev& Ln = m->layers[l + 1];
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
                            (win_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));

@@ -249,9 +249,6 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
  * tcgen05 path (N in {32,64,128,256}, K % 32 == 0) runs as a bf16x3-split GEMM with fp32 accumulation
  * in TMEM (fp32-grade accuracy); otherwise, or when switched off, the fp32 FMA GEMM is used. */
 int bgnn_set_tensor_cores(int on);
-/* Fusion of the last-but-one layer's aggregation with the last layer's projection (tcgen05 inside the tiled aggregation
- * kernel; the [N, heads*C] intermediate then never reaches HBM): on by default, bit-identical results either way. */
-int bgnn_set_fusion(int on);
 /* Operand hand-over between a tiled aggregation and the next layer's tcgen05 projection as fp16 hi / lo planes (the
  * projection then has no conversion stage): on by default, bit-identical results either way. */
 int bgnn_set_presplit(int on);

@@ -70,32 +70,6 @@ def test_umma_toggle_equivalence_in_forward():
     assert torch.equal(a["predicted_class"], b["predicted_class"]) or (a["predicted_class"] != b["predicted_class"]).float().mean() < 1e-3
 
 
-def test_fused_last_projection_is_bit_identical():
-    """Aggregation of layer L-2 fused with the projection of layer L-1 (tcgen05 inside the tiled kernel) vs the two
-    separate kernels: same operands, same splits, same accumulation order -> identical bits."""
-    import bathymetric_gnn_b200 as bg
-    from bathymetric_gnn_b200._lib import lib
-    from oracle import model_oracle as mo
-    from tests import synth
-    d = synth.noisy_tile(300, 333, seed=9)
-    mask = synth.blob_mask(300, 333, seed=9, invalid_frac=0.05)
-    cfg = mo.ModelCfg(in_channels=7)
-    sd = mo.init_state_dict(cfg, seed=7, randomize_bn=True)
-    m = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
-    m.load_state_dict(sd)
-    m = m.cuda().eval()
-    g = bg.GraphBuilder().build_graph(d, mask, None, (0.5, 0.5))
-    try:
-        lib.bgnn_set_fusion(1)
-        a = m._run(g, 0.85, 0.6, True, return_hidden=True)
-        lib.bgnn_set_fusion(0)
-        b = m._run(g, 0.85, 0.6, True, return_hidden=True)
-    finally:
-        lib.bgnn_set_fusion(1)
-    for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
-        assert torch.equal(a[k], b[k]), k
-
-
 @pytest.mark.parametrize("M,K,N,heads", [(256, 256, 256, 4), (1000, 256, 256, 4), (70001, 256, 256, 4), (4099, 256, 64, 1),
                                          (513, 64, 64, 1), (50000, 64, 256, 4), (333, 128, 256, 8)])
 def test_umma_presplit_is_bit_identical(M, K, N, heads):
