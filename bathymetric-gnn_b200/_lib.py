@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("BGNN_LIB") or os.path.join(HERE, "libbgnn.so")      #
 
 MAX_OFFSETS, MAX_NODE_FEATS, MAX_EDGE_FEATS = 24, 8, 4
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3, -4
+PREC_F32, PREC_BF16 = 0, 1
 
 NF_CODES = dict(depth=0, local_mean=1, local_std=2, gradient_x=3, gradient_y=4,
                 gradient_magnitude=5, curvature=6, uncertainty=7)
@@ -64,6 +65,9 @@ SYMBOLS = {
     "bgnn_model_create": (C.c_int, [C.POINTER(ModelDesc), P, I64, C.c_int, C.POINTER(P)]),
     "bgnn_model_destroy": (None, [P]),
     "bgnn_gat_workspace_bytes": (SZ, [P, I64]),
+    "bgnn_model_set_precision": (C.c_int, [P, C.c_int]),
+    "bgnn_model_precision": (C.c_int, [P]),
+    "bgnn_test_proj_bf16": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_gat_forward": (C.c_int, [P, I64, I64, P, P, P, P, P, SZ, P, P, P, P, P, P, F32, F32, P, P, P]),
     "bgnn_gat_grid_path": (C.c_int, [P, C.POINTER(GridTopo), I64]),
     "bgnn_scatter_tile": (C.c_int, [P, I64, P, P, P, P, F32, P, P, P, P]),

@@ -26,6 +26,7 @@ SOURCES = [
     ("stitch.cu", ["-fmad=false"]),
     ("gat_forward.cu", []),
     ("proj_umma.cu", []),
+    ("proj_bf16.cu", []),
 ]
 
 

@@ -15,6 +15,7 @@
 //                    (mean of the incoming edge attributes, fill_value='mean') is reduced on the fly.
 //   heads_finish     second layer of the three heads + softmax / argmax / sigmoid / action
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -38,6 +39,8 @@ struct LayerDev {
     uint16_t* Wsplit;        // 2 x fp16 split of W for the tcgen05 path (nullptr if the shape is not compiled)
     float w_inv;             // 1 / (power-of-two scale applied to W before the split)
     float out_mul, out_add;  // |layer output| <= out_mul * max|h| + out_add   (BN(eval) after a convex combination + bias)
+    float* Wr;               // bf16 mode: W rounded to bf16 (RN), kept as fp32 values for the FMA GEMM (nullptr until requested)
+    uint16_t* Wbf;           // bf16 mode: the same values as bf16 bit patterns [HC, in] for the tensor-core GEMM
 };
 
 struct bgnn_model {
@@ -59,6 +62,8 @@ struct bgnn_model {
     uint16_t* hWsplit;       // fp16 split of the concatenated head first layers (zero padded to hNpad rows)
     float heads_inv;
     int hNpad;
+    int precision;           // BGNN_PREC_F32 | BGNN_PREC_BF16 (bgnn_model_set_precision)
+    float* blob_bf;          // bf16 mode: rounded projection weights (fp32 values, then bf16 bit patterns)
 };
 
 namespace {
@@ -66,7 +71,15 @@ namespace {
 // ------------------------------------------------------------------------------------------ GEMM
 constexpr int BM = 128, BK = 16, GEMM_THREADS = 256, PAD = 4;
 
-template <int BN, int CH, bool ALPHA>
+// bf16 mode (bgnn_model_set_precision): IO_F32 = fp32 in / fp32 out, IO_F32_BF16 = fp32 A, C stored as bf16 (RN),
+// IO_BF16 = A and C are bf16 in HBM (A / Cout are then uint16 arrays behind the float pointers).  The arithmetic is
+// always fp32 FMA on exactly converted operands; alpha comes from the fp32 accumulators.
+enum { IO_F32 = 0, IO_F32_BF16 = 1, IO_BF16 = 2, IO_BF16_F32 = 3 };
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) { return f32_to_bf16_bits(a) | (f32_to_bf16_bits(b) << 16); }
+
+template <int BN, int CH, bool ALPHA, int IO = IO_F32>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K, int64_t M, int N,
         float* __restrict__ Cout, int ldc, const float* __restrict__ bias, int relu,
@@ -93,7 +106,19 @@ gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K
             const int row = f >> 2, kq = (f & 3) * 4;
             const int64_t gm = m0 + row;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gm < M) {
+            if (gm < M && IO == IO_BF16) {
+                const uint16_t* p = reinterpret_cast<const uint16_t*>(A) + gm * lda + k0 + kq;
+                if (vec_ok && k0 + kq + 3 < K) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+                    v = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u),
+                                    __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
+                } else {
+                    if (k0 + kq + 0 < K) v.x = bf16_bits_to_f32(__ldg(p + 0));
+                    if (k0 + kq + 1 < K) v.y = bf16_bits_to_f32(__ldg(p + 1));
+                    if (k0 + kq + 2 < K) v.z = bf16_bits_to_f32(__ldg(p + 2));
+                    if (k0 + kq + 3 < K) v.w = bf16_bits_to_f32(__ldg(p + 3));
+                }
+            } else if (gm < M) {
                 const float* p = A + gm * lda + k0 + kq;
                 if (vec_ok && k0 + kq + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
                 else {
@@ -234,11 +259,20 @@ gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K
                     if (relu) v[j] = fmaxf(v[j], 0.f);
                 }
                 // projections (ALPHA) store h head-major: [Htot][M][CH], one contiguous plane per head
-                float* p = ALPHA ? Cout + ((int64_t)(gn / CH) * M + gm) * CH + (gn % CH) : Cout + gm * ldc + gn;
-                if (gn + 3 < N && (ldc % 4 == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-                else
-                    for (int j = 0; j < 4; ++j)
-                        if (gn + j < N) p[j] = v[j];
+                const int64_t off = ALPHA ? ((int64_t)(gn / CH) * M + gm) * CH + (gn % CH) : gm * ldc + gn;
+                if (IO == IO_F32_BF16 || IO == IO_BF16) {
+                    uint16_t* p = reinterpret_cast<uint16_t*>(Cout) + off;
+                    if (gn + 3 < N && (ldc % 4 == 0)) *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+                    else
+                        for (int j = 0; j < 4; ++j)
+                            if (gn + j < N) p[j] = (uint16_t)f32_to_bf16_bits(v[j]);
+                } else {
+                    float* p = Cout + off;
+                    if (gn + 3 < N && (ldc % 4 == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                    else
+                        for (int j = 0; j < 4; ++j)
+                            if (gn + j < N) p[j] = v[j];
+                }
             }
         }
     }
@@ -246,15 +280,20 @@ gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int K
 
 int launch_gemm(const float* A, int lda, const float* W, int K, int64_t M, int N, float* C, int ldc,
                 const float* bias, int relu, int CH, const float* att_src, const float* att_dst,
-                float* alpha, int Htot, cudaStream_t s) {
+                float* alpha, int Htot, cudaStream_t s, int io = IO_F32) {
     if (M == 0) return BGNN_OK;
     const bool al = alpha != nullptr;
     dim3 block(GEMM_THREADS);
+    if ((io == IO_F32_BF16 && al) || (io == IO_BF16 && !al)) { bgnn_set_error("internal: bf16 GEMM variant not compiled"); return BGNN_E_UNSUPPORTED; }
 #define GO(BN_, CH_, AL_)                                                                              \
     do {                                                                                               \
         dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)((N + BN_ - 1) / BN_));                       \
-        gemm_nt<BN_, CH_, AL_><<<grid, block, 0, s>>>(A, lda, W, K, M, N, C, ldc, bias, relu, att_src, \
-                                                      att_dst, alpha, Htot);                           \
+        if (io == IO_F32)                                                                              \
+            gemm_nt<BN_, CH_, AL_, IO_F32><<<grid, block, 0, s>>>(A, lda, W, K, M, N, C, ldc, bias, relu, att_src, \
+                                                                  att_dst, alpha, Htot);               \
+        else                                                                                           \
+            gemm_nt<BN_, CH_, AL_, (AL_ ? IO_BF16 : IO_F32_BF16)><<<grid, block, 0, s>>>(A, lda, W, K, M, N, C, ldc, bias, relu, att_src, \
+                                                                  att_dst, alpha, Htot);               \
     } while (0)
     if (N > 64) {
         if (!al) GO(128, 64, false);
@@ -298,9 +337,41 @@ template <> struct VecIO<16> {
     static __device__ __forceinline__ void st(float* p, const float* v) { VecIO<8>::st(p, v); VecIO<8>::st(p + 8, v + 8); }
 };
 
+// bf16 rows (bf16 mode): VEC consecutive bf16 values <-> fp32 registers (exact widening, RN narrowing)
+template <int VEC> struct VecBF {
+    static __device__ __forceinline__ void ld(const uint16_t* p, float* v) {
+        if constexpr (VEC == 1) v[0] = bf16_bits_to_f32(__ldg(p));
+        else if constexpr (VEC == 2) { const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p)); v[0] = __uint_as_float(t << 16); v[1] = __uint_as_float(t & 0xffff0000u); }
+        else if constexpr (VEC == 4) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+            v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u); v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u); }
+        else {
+#pragma unroll
+            for (int q = 0; q < VEC / 8; ++q) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + q);
+                v[8 * q + 0] = __uint_as_float(t.x << 16); v[8 * q + 1] = __uint_as_float(t.x & 0xffff0000u);
+                v[8 * q + 2] = __uint_as_float(t.y << 16); v[8 * q + 3] = __uint_as_float(t.y & 0xffff0000u);
+                v[8 * q + 4] = __uint_as_float(t.z << 16); v[8 * q + 5] = __uint_as_float(t.z & 0xffff0000u);
+                v[8 * q + 6] = __uint_as_float(t.w << 16); v[8 * q + 7] = __uint_as_float(t.w & 0xffff0000u);
+            }
+        }
+    }
+    static __device__ __forceinline__ void st(uint16_t* p, const float* v) {
+        if constexpr (VEC == 1) p[0] = (uint16_t)f32_to_bf16_bits(v[0]);
+        else if constexpr (VEC == 2) *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+        else if constexpr (VEC == 4) *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        else {
+#pragma unroll
+            for (int q = 0; q < VEC / 8; ++q)
+                reinterpret_cast<uint4*>(p)[q] = make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                            pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
+    }
+};
+
 // One warp per destination node i.  In-edges e = rowptr[i] .. rowptr[i+1]-1 (reference edge
 // order) plus the self loop as the LAST entry (PyG add_self_loops appends the loops).
-template <int H, int VEC>
+// IO (bf16 mode): IO_BF16 = h and the output are bf16 rows, IO_BF16_F32 = bf16 h, fp32 output (last layer -> heads).
+template <int H, int VEC, int IO = IO_F32>
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 gat_aggregate(const float* __restrict__ h, const float* __restrict__ alpha, const int32_t* __restrict__ rowptr,
               const int32_t* __restrict__ csr_src, const float* __restrict__ eattr, int ED,
@@ -422,7 +493,8 @@ gat_aggregate(const float* __restrict__ h, const float* __restrict__ alpha, cons
                 const int j = s_j[warp][q];
                 const float a = s_a[warp][q][my_head];
                 float hv[VEC];
-                VecIO<VEC>::ld(h + ((int64_t)my_head * N + j) * C + (lane * VEC) % C, hv);       // h is head-major [H][N][C]
+                if constexpr (IO == IO_F32) VecIO<VEC>::ld(h + ((int64_t)my_head * N + j) * C + (lane * VEC) % C, hv);       // h is head-major [H][N][C]
+                else VecBF<VEC>::ld(reinterpret_cast<const uint16_t*>(h) + ((int64_t)my_head * N + j) * C + (lane * VEC) % C, hv);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a, hv[v], acc[v]);
             }
@@ -436,27 +508,36 @@ gat_aggregate(const float* __restrict__ h, const float* __restrict__ alpha, cons
             y = fmaf(y, __ldg(bn_a + ch), __ldg(bn_b + ch));
             o[v] = relu ? fmaxf(y, 0.f) : y;
         }
-        VecIO<VEC>::st(out + i * HC + lane * VEC, o);
+        if constexpr (IO == IO_BF16) VecBF<VEC>::st(reinterpret_cast<uint16_t*>(out) + i * HC + lane * VEC, o);
+        else VecIO<VEC>::st(out + i * HC + lane * VEC, o);
     }
 }
 
 template <int H, int VEC>
 int launch_agg_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const int32_t* src,
-                 const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s) {
+                 const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s, int io) {
     int64_t blocks = ceil_div64(N, AGG_WARPS);
     const int64_t cap = (int64_t)sms * 8 * 4;            // persistent grid: multiple of the SM count
     if (blocks > cap) blocks = cap;
-    gat_aggregate<H, VEC><<<(unsigned)blocks, AGG_WARPS * 32, 0, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,
-                                                                     L.bn_a, L.bn_b, relu, slope, out, N);
+    if (io == IO_BF16)
+        gat_aggregate<H, VEC, IO_BF16><<<(unsigned)blocks, AGG_WARPS * 32, 0, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,
+                                                                                  L.bn_a, L.bn_b, relu, slope, out, N);
+    else if (io == IO_BF16_F32)
+        gat_aggregate<H, VEC, IO_BF16_F32><<<(unsigned)blocks, AGG_WARPS * 32, 0, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,
+                                                                                      L.bn_a, L.bn_b, relu, slope, out, N);
+    else
+        gat_aggregate<H, VEC, IO_F32><<<(unsigned)blocks, AGG_WARPS * 32, 0, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,
+                                                                                 L.bn_a, L.bn_b, relu, slope, out, N);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
 
 int launch_agg(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const int32_t* src,
-               const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s) {
+               const float* eattr, int ED, int relu, float slope, float* out, int64_t N, int sms, cudaStream_t s,
+               int io = IO_F32) {
     if (N == 0) return BGNN_OK;
     const int vec = L.HC / 32;
-#define CASE(H_, V_) if (L.H == H_ && vec == V_) return launch_agg_t<H_, V_>(L, h, alpha, rowptr, src, eattr, ED, relu, slope, out, N, sms, s)
+#define CASE(H_, V_) if (L.H == H_ && vec == V_) return launch_agg_t<H_, V_>(L, h, alpha, rowptr, src, eattr, ED, relu, slope, out, N, sms, s, io)
     CASE(1, 1); CASE(1, 2); CASE(1, 4);
     CASE(2, 2); CASE(2, 4); CASE(2, 8);
     CASE(4, 4); CASE(4, 8); CASE(4, 16);
@@ -1328,6 +1409,7 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     BGNN_CUDA(cudaSetDevice(device));
     bgnn_model* m = new bgnn_model();
     m->blob16 = nullptr;
+    m->precision = BGNN_PREC_F32; m->blob_bf = nullptr;
     m->d = *d; m->device = device; m->nheads_mlp = nblk;
     cudaError_t e = cudaMalloc(&m->blob, hb.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->blob, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -1346,6 +1428,7 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         L.Wsplit = (o16[l] != (size_t)-1 && m->blob16) ? m->blob16 + o16[l] : nullptr;
         L.w_inv = winv[l];
         L.out_mul = 0.f; L.out_add = 0.f;
+        L.Wr = nullptr; L.Wbf = nullptr;
         {   // |bn_a (agg + bias) + bn_b| <= max|bn_a| * max|h| + max(|bn_a||bias| + |bn_b|)
             const float *ba = hb.data() + lo[l].a, *bb = hb.data() + lo[l].b, *bi = hb.data() + lo[l].bias;
             for (int c = 0; c < L.out; ++c) {
@@ -1382,8 +1465,54 @@ extern "C" void bgnn_model_destroy(bgnn_model* m) {
     cudaSetDevice(m->device);
     cudaFree(m->blob);
     if (m->blob16) cudaFree(m->blob16);
+    if (m->blob_bf) cudaFree(m->blob_bf);
     cudaSetDevice(prev);
     delete m;
+}
+
+namespace {
+__global__ void round_to_bf16(const float* __restrict__ w, float* __restrict__ wr, uint16_t* __restrict__ wbf, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = f32_to_bf16_bits(w[i]);
+        wr[i] = bf16_bits_to_f32(b);
+        wbf[i] = (uint16_t)b;
+    }
+}
+}  // namespace
+
+extern "C" int bgnn_model_precision(const bgnn_model* m) { return m ? m->precision : -1; }
+
+extern "C" int bgnn_model_set_precision(bgnn_model* m, int precision) {
+    BGNN_CHECK_ARG(m, "model is null");
+    BGNN_CHECK_ARG(precision == BGNN_PREC_F32 || precision == BGNN_PREC_BF16, "unknown precision %d", precision);
+    if (precision == BGNN_PREC_BF16 && !m->blob_bf) {     // host-synchronous, once per model
+        size_t tot = 0;
+        for (const LayerDev& L : m->layers) tot += align_up((size_t)L.HC * L.in, 64);
+        int prev = 0;
+        BGNN_CUDA(cudaGetDevice(&prev));
+        BGNN_CUDA(cudaSetDevice(m->device));
+        cudaError_t e = cudaMalloc(&m->blob_bf, tot * (sizeof(float) + sizeof(uint16_t)));
+        if (e == cudaSuccess) {
+            float* wr = m->blob_bf;
+            uint16_t* wb = reinterpret_cast<uint16_t*>(m->blob_bf + tot);
+            for (LayerDev& L : m->layers) {
+                const int64_t n = (int64_t)L.HC * L.in;
+                round_to_bf16<<<(unsigned)ceil_div64(n, 256), 256>>>(L.W, wr, wb, n);
+                L.Wr = wr; L.Wbf = wb;
+                wr += align_up((size_t)n, 64); wb += align_up((size_t)n, 64);
+            }
+            e = cudaDeviceSynchronize();
+        }
+        cudaSetDevice(prev);
+        if (e != cudaSuccess) {
+            if (m->blob_bf) { cudaFree(m->blob_bf); m->blob_bf = nullptr; }
+            for (LayerDev& L : m->layers) { L.Wr = nullptr; L.Wbf = nullptr; }
+            bgnn_set_error("bf16 weight preparation failed: %s", cudaGetErrorString(e));
+            return BGNN_E_CUDA;
+        }
+    }
+    m->precision = precision;
+    return BGNN_OK;
 }
 
 static size_t act_bytes(const bgnn_model* m, int64_t n) { return align_up((size_t)n * m->hc_max * sizeof(float), 256); }
@@ -1406,10 +1535,60 @@ static bool topo_to_dev(const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
 
 extern "C" int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* topo, int64_t n_edges) {
     TopoDev T;
-    if (!m || !topo_to_dev(topo, n_edges, T)) return 0;
+    if (!m || m->precision != BGNN_PREC_F32 || !topo_to_dev(topo, n_edges, T)) return 0;
     for (const LayerDev& L : m->layers)
         if (!tile_supported(T, L.H, L.C, m->d.edge_dim, topo->grid_eattr, nullptr)) return 0;
     return 1;
+}
+
+// bf16 mode (BASELINE configs[4] "bf16 vs fp32 tolerance"; the reference itself has no reduced-precision path).  What is
+// bf16 is the STORAGE of the big per-node streams -- the feature-extractor output, the projection weights, h = x W^T and
+// every layer output but the last -- i.e. what the aggregation and projection kernels move through HBM; every sum
+// (GEMM accumulators, attention logits, softmax, weighted aggregation), BN and the heads stay in fp32.
+// oracle/model_oracle.py::forward(bf16_storage=True) restates exactly these rounding points.
+static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const int32_t* rowptr, const int32_t* csr_src,
+                        const float* csr_eattr, float* bufA, float* bufB, float* hbuf, float* alpha, float* logits,
+                        float* probs, int64_t* cls, float* conf, float* corr, int64_t* action, float thr_auto,
+                        float thr_review, float* hidden_out, int sms, cudaStream_t s) {
+    const bgnn_model_desc& d = m->d;
+    const int C = d.hidden, h2 = C / 2;
+    int rc;
+    { ProfScope ps(10, s);
+      if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
+    { ProfScope ps(11, s);
+      if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s, IO_F32_BF16))) return rc; }
+    float* cur = bufB;
+    float* nxt = bufA;
+    for (int l = 0; l < d.layers; ++l) {
+        const LayerDev& L = m->layers[l];
+        BGNN_CHECK_ARG(L.Wr, "internal: bf16 weights missing");
+        { ProfScope ps(20 + l, s);
+          rc = 1;
+          if (g_use_umma && proj_bf16_supported(L.HC, L.in, L.C)) {
+              rc = launch_proj_bf16(reinterpret_cast<const uint16_t*>(cur), L.Wbf, N, L.in, L.HC, reinterpret_cast<uint16_t*>(hbuf),
+                                    L.att_src, L.att_dst, alpha, L.H, L.C, sms, s);
+          }
+          if (rc == 1)
+              rc = launch_gemm(cur, L.in, L.Wr, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s, IO_BF16);
+          if (rc) return rc; }
+        const bool last = l == d.layers - 1;
+        { ProfScope ps(40 + l, s);
+          if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, !last, d.negative_slope, nxt, N, sms, s,
+                               last ? IO_BF16_F32 : IO_BF16))) return rc; }
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const int nblk = m->nheads_mlp;
+    { ProfScope ps(60, s);
+      if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc; }
+    int64_t blocks = ceil_div64(N, 8);
+    if (blocks > (int64_t)sms * 32) blocks = (int64_t)sms * 32;
+    ProfScope ps(61, s);
+    heads_finish<<<(unsigned)blocks, 256, 0, s>>>(hbuf, h2, nblk, d.num_classes, m->Wcls, m->bcls, m->Wconf, m->bconf,
+                                                 m->Wcorr, m->bcorr, logits, probs, cls, conf, corr, action, thr_auto,
+                                                 thr_review, N);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
 }
 
 extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const float* x, const int32_t* rowptr,
@@ -1453,6 +1632,9 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     if (g_use_umma) BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
     const int C = d.hidden, h2 = C / 2;
     int rc;
+    if (m->precision == BGNN_PREC_BF16)
+        return forward_bf16(m, N, x, rowptr, csr_src, csr_eattr, bufA, bufB, hbuf, alpha, logits, probs, cls, conf, corr, action,
+                            thr_auto, thr_review, hidden_out, sms, s);
     // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C).  On the tensor-core path both are fused into the
     // layer-0 projection (first Linear computed by its producers, second folded into its weights).
     const bool fused0 = g_use_umma && m->Wfold0;

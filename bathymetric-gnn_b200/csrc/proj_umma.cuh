@@ -40,3 +40,9 @@ float proj_umma_split_weights(const float* W, int N, int K, uint16_t* out);
 int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s);
 // general entry: N = accumulator width (for EM_HEADS the padded width)
 int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStream_t s);
+
+// ---- bf16 mode (proj_bf16.cu): C = A . W^T with bf16 operands straight from HBM (one tcgen05 product, fp32 accumulation in
+// TMEM), C stored as bf16 head-major [Htot][M][CH], alpha_src / alpha_dst from the fp32 accumulators.
+bool proj_bf16_supported(int N, int K, int CH);
+int launch_proj_bf16(const uint16_t* A, const uint16_t* W, int64_t M, int K, int N, uint16_t* Cout, const float* att_src,
+                     const float* att_dst, float* alpha, int Htot, int CH, int sms, cudaStream_t s);

@@ -151,6 +151,7 @@ class BathymetricGNN(nn.Module):
         self._handle = None
         self._handle_key = None
         self.use_grid_kernel = True      # tiled aggregation when the graph carries its grid topology
+        self.precision = "fp32"          # "fp32" | "bf16" (set_precision)
         logger.info("Created BathymetricGNN: %s with %d layers, %d hidden channels", gnn_type, num_gnn_layers, hidden_channels)
 
     # ------------------------------------------------------------------ packing
@@ -176,6 +177,16 @@ class BathymetricGNN(nn.Module):
         for h in heads:
             parts += [h.mlp[0].weight, h.mlp[0].bias, h.mlp[3].weight, h.mlp[3].bias]
         return torch.cat([p.detach().reshape(-1).to("cpu", torch.float32) for p in parts]).contiguous()
+
+    def set_precision(self, precision: str = "fp32") -> "BathymetricGNN":
+        """Compute precision of forward / predict (no counterpart in the reference, which has no reduced-precision path;
+        BASELINE configs[4] asks for "bf16 vs fp32 tolerance").  "fp32" is the parity path.  "bf16" keeps the big per-node
+        streams (projection operands and outputs, layer outputs) in HBM as bf16 while every sum, the softmax, BatchNorm and
+        the heads stay fp32 (include/bgnn.h: BGNN_PREC_BF16); parameters stay fp32 master copies.  Returns self."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"Unknown precision: {precision}")
+        self.precision = precision
+        return self
 
     def _ensure_handle(self, device: torch.device):
         key = (device.index if device.index is not None else torch.cuda.current_device(),
@@ -243,6 +254,9 @@ class BathymetricGNN(nn.Module):
                                    f"{self.in_channels}x{self.hidden_channels})")
             topo = None
             h = self._ensure_handle(device)
+            want = _lib.PREC_BF16 if getattr(self, "precision", "fp32") == "bf16" else _lib.PREC_F32
+            if lib.bgnn_model_precision(h) != want:
+                check(lib.bgnn_model_set_precision(h, want))
             if dg is not None:
                 E = dg.E
                 ed_have = int(dg.cfg.n_edge_feats)

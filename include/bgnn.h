@@ -167,6 +167,22 @@ void bgnn_model_destroy(bgnn_model* m);
 
 size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes);
 
+/* Compute precision of bgnn_gat_forward for this model (BASELINE configs[4] "bf16 vs fp32 tolerance"; the reference has no
+ * reduced-precision path: `grep -i "autocast|bfloat|half("` over its tree is empty).
+ *   BGNN_PREC_F32  (default)  fp32 parity path (tolerance: atol 2e-5 + rtol 1e-5 on logits / confidence / correction).
+ *   BGNN_PREC_BF16            the per-node streams live in HBM as bf16 -- feature-extractor output, projection weights,
+ *                             h = x W^T, every layer output but the last -- while every sum (GEMM accumulators in TMEM /
+ *                             registers, attention logits, softmax, weighted aggregation), BatchNorm and the heads stay
+ *                             fp32.  Halves the bytes the projection and aggregation kernels move.  Bounded separately:
+ *                             see tests/test_gpu_bf16.py (vs the fp32 oracle and vs the oracle restating the same
+ *                             rounding points).  Runs the CSR aggregation for every stencil (4-/8-/24-offset, ragged).
+ * set_precision is host-synchronous the first time bf16 is requested (weights are rounded once); not thread-safe with a
+ * concurrent forward on the same model. */
+#define BGNN_PREC_F32  0
+#define BGNN_PREC_BF16 1
+int bgnn_model_set_precision(bgnn_model* m, int precision);
+int bgnn_model_precision(const bgnn_model* m);
+
 /* Optional grid topology of the node set (single tile, n_grids == 1): when given, and the stencil
  * has radius 1 (4-/8-connected), the aggregation runs as a shared-memory tiled kernel: one CTA per
  * 16x16 patch of cells stages every source row of its 18x18 halo ONCE (cp.async) instead of
@@ -261,6 +277,11 @@ int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_hos
 int bgnn_test_proj_umma_presplit(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
                                  const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads,
                                  void* stream);
+/* testing aid, bf16 mode: C_dev (bf16 bit patterns, HEAD-MAJOR [heads][M][N/heads]) = A_dev[M,K] (bf16) . W_dev[N,K]^T (bf16)
+ * with fp32 accumulation on the tcgen05 path; alpha_dev [M, 2*heads] fp32 from the fp32 accumulators.  Returns
+ * BGNN_E_UNSUPPORTED for shapes the bf16 tensor-core kernel is not compiled for. */
+int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t* W_dev, int N, uint16_t* C_dev,
+                        const float* att_src_dev, const float* att_dst_dev, float* alpha_dev, int heads, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement aid (bench.py): per-kernel device timing with CUDA events recorded on the

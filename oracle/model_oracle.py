@@ -116,15 +116,28 @@ def param_count(sd) -> int:
                if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
 
 
-def gat_layer(sd, i, x, edge_index, edge_attr, H, C, concat, chunk=1 << 21):
-    """One restated GATConv (see pyg_restated.GATConv.forward) driven by `sd`."""
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even) -> fp32: the storage rounding of the bf16 mode."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def gat_layer(sd, i, x, edge_index, edge_attr, H, C, concat, chunk=1 << 21, bf16_storage=False):
+    """One restated GATConv (see pyg_restated.GATConv.forward) driven by `sd`.
+
+    `bf16_storage` restates the CUDA path's bf16 mode (include/bgnn.h, bgnn_model_set_precision): the
+    projection multiplies bf16-rounded operands with fp32 accumulation, the attention logits come from
+    the fp32 accumulators, and `h` is rounded to bf16 before the aggregation reads it."""
     p = f"gnn.convs.{i}."
     dt = x.dtype
     W = sd[p + "lin.weight"].to(dt) if p + "lin.weight" in sd else sd[p + "lin_src.weight"].to(dt)
     N = x.shape[0]
+    if bf16_storage:
+        W = bf16_round(W)
     h = (x @ W.t()).view(N, H, C)
     a_src = (h * sd[p + "att_src"].to(dt)).sum(-1)
     a_dst = (h * sd[p + "att_dst"].to(dt)).sum(-1)
+    if bf16_storage:
+        h = bf16_round(h)
     ei, ea = pyg.remove_self_loops(edge_index, edge_attr)
     ei, ea = pyg.add_self_loops_mean(ei, ea, N)
     src, dst = ei[0], ei[1]
@@ -154,20 +167,28 @@ def bn_eval(sd, i, x):
 
 
 def forward(sd, cfg: ModelCfg, x, edge_index, edge_attr, dtype=torch.float32,
-            return_hidden: bool = False) -> Dict[str, torch.Tensor]:
-    """gnn.py:381-408 in eval mode (dropout = identity)."""
+            return_hidden: bool = False, bf16_storage: bool = False) -> Dict[str, torch.Tensor]:
+    """gnn.py:381-408 in eval mode (dropout = identity).
+
+    `bf16_storage=True` (with dtype fp32) restates the rounding points of the CUDA path's bf16 mode:
+    the feature-extractor output, the projection weights, every `h = x W^T` and every layer output
+    except the last are rounded to bf16; all sums, the softmax, BN and the heads stay in fp32."""
     with torch.no_grad():
         x = torch.as_tensor(x).to(dtype)
         edge_index = torch.as_tensor(edge_index).long()
         edge_attr = None if edge_attr is None else torch.as_tensor(edge_attr).to(dtype)
         lin = lambda p, t: t @ sd[p + ".weight"].to(dtype).t() + sd[p + ".bias"].to(dtype)
         x = lin("feature_extractor.mlp.3", F.relu(lin("feature_extractor.mlp.0", x)))
+        if bf16_storage:
+            x = bf16_round(x)
         hidden = [x]
         for i, (_, H, concat) in enumerate(layer_dims(cfg)):
-            x = gat_layer(sd, i, x, edge_index, edge_attr, H, cfg.hidden, concat)
+            x = gat_layer(sd, i, x, edge_index, edge_attr, H, cfg.hidden, concat, bf16_storage=bf16_storage)
             x = bn_eval(sd, i, x)
             if i < cfg.layers - 1:
                 x = F.relu(x)
+                if bf16_storage:
+                    x = bf16_round(x)
             hidden.append(x)
         head = lambda p: lin(p + ".mlp.3", F.relu(lin(p + ".mlp.0", x)))
         logits = head("classification_head")
