@@ -26,6 +26,7 @@
 
 static bool g_use_umma = true;
 static bool g_window = getenv("BGNN_NO_WINDOW") == nullptr;       // ragged batches: windowed shared-memory CSR aggregation
+static bool g_tile5 = getenv("BGNN_NO_TILE5") == nullptr;         // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
 static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
 extern "C" int bgnn_set_presplit(int on) { g_presplit = on != 0; return BGNN_OK; }
@@ -1200,6 +1201,256 @@ int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------ radius-2 tiled aggregation
+// Grid path for stencils up to 5 x 5 (BASELINE configs[4]: k = 24) and for the bf16 mode on any grid stencil.  One CTA per
+// 8 x 16 patch of cells; the h rows of its 12 x 20 halo are staged ONCE per head in shared memory as 256-byte slabs
+// (128 bf16 or 64 fp32 channels per cell; cp.async, zero-filled for absent cells) instead of being gathered 25 times per
+// destination through L1/L2 (the warp-per-destination kernel moved 25 KB per destination: 31 ms per layer at 2048^2).
+// Two threads per destination compute the scores + softmax of the current head (edge features and the self-loop mean stay
+// in registers across the head loop) while the slab is in flight and leave the attention weights in shared memory indexed
+// by OFFSET (absent neighbours: weight 0); warp w then walks patch row w with lane <-> channels, FMAs in the reference's
+// edge order (offset k ascending, source = i - off_k, self loop last).  No per-edge tensor is materialised.
+struct Topo5Dev {
+    int rows, cols;
+    const int32_t* node_id;
+    int K;
+    int8_t dr[BGNN_MAX_OFFSETS], dc[BGNN_MAX_OFFSETS];
+    int16_t doff[BGNN_MAX_OFFSETS];        // halo slot of the source relative to the destination's: -dr * HW - dc
+};
+
+template <int C, int IO> struct Tile5Cfg {
+    static constexpr int PH = 8, PW = 16, R = 2, HR = PH + 2 * R, HW = PW + 2 * R, NSLOT = HR * HW, ND = PH * PW, NT = 256;
+    static constexpr int ESZ = IO == IO_F32 ? 4 : 2;                       // bytes per stored h element
+    static constexpr int CPS = C * ESZ <= 256 ? C : 256 / ESZ;             // channels per slab
+    static constexpr int RB = CPS * ESZ;                                   // slab row bytes (128 or 256)
+    static constexpr int NSLAB = C / CPS;
+    static constexpr int VEC = CPS / 32;                                   // channels per lane
+    static constexpr int WST = BGNN_MAX_OFFSETS + 4;                       // weights per destination (24 offsets + self, 16 B aligned rows)
+    static constexpr size_t SMEM = (size_t)NSLOT * RB + (size_t)ND * WST * 4 + (size_t)NSLOT * 4 + 16;
+};
+
+template <int H, int C, int IO>
+__global__ void __launch_bounds__(256, 2)
+gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alpha, const int32_t* __restrict__ rowptr,
+                    const float* __restrict__ eattr, int ED, const float* __restrict__ Medge, const float* __restrict__ bias,
+                    const float* __restrict__ bn_a, const float* __restrict__ bn_b, int relu, float slope,
+                    float* __restrict__ out_, int64_t N, const __grid_constant__ Topo5Dev T) {
+    using G = Tile5Cfg<C, IO>;
+    constexpr int HC = H * C, KH = (BGNN_MAX_OFFSETS + 1) / 2;            // offsets per thread of a pair (<= 12) + self
+    extern __shared__ __align__(16) uint8_t smem5[];
+    uint8_t* slab = smem5;                                                 // [NSLOT][RB]
+    float* wts = reinterpret_cast<float*>(slab + (size_t)G::NSLOT * G::RB);   // [ND][WST]
+    int32_t* hid = reinterpret_cast<int32_t*>(wts + G::ND * G::WST);      // [NSLOT] node id of the halo cell (-1 absent)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.y * G::PH, c0 = blockIdx.x * G::PW;
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(h_);
+
+    for (int p = tid; p < G::NSLOT; p += G::NT) {
+        const int r = r0 - G::R + p / G::HW, c = c0 - G::R + p % G::HW;
+        hid[p] = (r >= 0 && r < T.rows && c >= 0 && c < T.cols) ? __ldg(T.node_id + (int64_t)r * T.cols + c) : -1;
+    }
+    __syncthreads();
+
+    auto stage = [&](int head, int sl) {                                   // slab (head, sl) of every halo cell -> shared memory
+        constexpr int CPR = G::RB / 16;                                    // 16-byte pieces per row
+        for (int q = tid; q < G::NSLOT * CPR; q += G::NT) {
+            const int p = q / CPR, piece = q % CPR;
+            const int id = hid[p];
+            const uint8_t* src = id >= 0 ? hb + (((int64_t)head * N + id) * C + sl * G::CPS) * G::ESZ + piece * 16 : hb;
+            const uint32_t dst = smem_addr(slab + (size_t)p * G::RB + piece * 16);
+            const int nbytes = id >= 0 ? 16 : 0;                           // src-size 0: the 16 bytes are zero-filled
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    // ---- score set-up: thread pair (d, half); half handles offsets k = half, half + 2, ...; half 0 also the self loop
+    const int d = tid >> 1, half = tid & 1;
+    const int pr = d / G::PW, pc = d % G::PW;
+    const int my_id = hid[(pr + G::R) * G::HW + pc + G::R];
+    uint32_t vmask = 0;
+    float ea[KH][BGNN_MAX_EDGE_FEATS];
+    int jsrc[KH];
+    float mean[BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+    for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) mean[f] = 0.f;
+    if (my_id >= 0) {
+        for (int k = 0; k < T.K; ++k) {
+            const int hp = (pr + G::R - T.dr[k]) * G::HW + pc + G::R - T.dc[k];
+            if (hid[hp] >= 0) vmask |= 1u << k;
+        }
+        const int start = __ldg(rowptr + my_id);
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) {
+            const int k = 2 * kk + half;
+            jsrc[kk] = -1;
+#pragma unroll
+            for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ea[kk][f] = 0.f;
+            if (k < T.K && (vmask >> k & 1u)) {
+                jsrc[kk] = hid[(pr + G::R - T.dr[k]) * G::HW + pc + G::R - T.dc[k]];
+                const int e = start + __popc(vmask & ((1u << k) - 1u));
+#pragma unroll
+                for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f)
+                    if (f < ED) { ea[kk][f] = __ldg(eattr + (int64_t)e * ED + f); mean[f] += ea[kk][f]; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) jsrc[kk] = -1;
+    }
+    {   // self-loop attribute = mean of the incoming edge attributes (0 when the node has none)
+        const int deg = __popc(vmask);
+#pragma unroll
+        for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) {
+            mean[f] += __shfl_xor_sync(0xffffffffu, mean[f], 1);
+            mean[f] = mean[f] / (float)(deg > 0 ? deg : 1);
+        }
+    }
+
+    for (int head = 0; head < H; ++head) {
+        stage(head, 0);
+        // ---- scores + softmax of this head -> wts[d][k] (k = offset index, 24 = self)
+        {
+            float M[BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+            for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) M[f] = f < ED ? __ldg(Medge + f * H + head) : 0.f;
+            float sc[KH], sself = -CUDART_INF_F, mx = -CUDART_INF_F;
+            const float ad = my_id >= 0 ? __ldg(alpha + (int64_t)my_id * (2 * H) + H + head) : 0.f;
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk) {
+                sc[kk] = -CUDART_INF_F;
+                if (jsrc[kk] >= 0) {
+                    float ae = 0.f;
+#pragma unroll
+                    for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(ea[kk][f], M[f], ae);
+                    const float v = (__ldg(alpha + (int64_t)jsrc[kk] * (2 * H) + head) + ad) + ae;
+                    sc[kk] = v > 0.f ? v : v * slope;
+                    mx = fmaxf(mx, sc[kk]);
+                }
+            }
+            if (half == 0 && my_id >= 0) {
+                float ae = 0.f;
+#pragma unroll
+                for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(mean[f], M[f], ae);
+                const float v = (__ldg(alpha + (int64_t)my_id * (2 * H) + head) + ad) + ae;
+                sself = v > 0.f ? v : v * slope;
+                mx = fmaxf(mx, sself);
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            float sum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk) { sc[kk] = jsrc[kk] >= 0 ? expf(sc[kk] - mx) : 0.f; sum += sc[kk]; }
+            if (half == 0 && my_id >= 0) { sself = expf(sself - mx); sum += sself; } else sself = 0.f;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += 1e-16f;
+            float* w = wts + d * G::WST;
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk) {
+                const int k = 2 * kk + half;
+                if (k < BGNN_MAX_OFFSETS) w[k] = sc[kk] / sum;
+            }
+            if (half == 0) w[BGNN_MAX_OFFSETS] = sself / sum;
+        }
+        for (int sl = 0; sl < G::NSLAB; ++sl) {
+            if (sl > 0) stage(head, sl);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();                                               // slab landed, weights visible
+            // ---- aggregate: warp <-> patch row, lane <-> VEC channels of the slab
+            for (int pcw = 0; pcw < G::PW; ++pcw) {
+                const int dd = warp * G::PW + pcw;
+                const int id = hid[(warp + G::R) * G::HW + pcw + G::R];
+                if (id < 0) continue;                                      // warp-uniform
+                const float* w = wts + dd * G::WST;
+                float acc[G::VEC];
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) acc[v] = 0.f;
+                auto fma_row = [&](int hp, float a) {
+                    const uint8_t* row = slab + (size_t)hp * G::RB + lane * (G::VEC * G::ESZ);
+                    if constexpr (IO == IO_F32) {
+                        if constexpr (G::VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(row); acc[0] = fmaf(a, t.x, acc[0]); acc[1] = fmaf(a, t.y, acc[1]); }
+                        else { acc[0] = fmaf(a, *reinterpret_cast<const float*>(row), acc[0]); }
+                    } else {
+                        if constexpr (G::VEC == 4) {
+                            const uint2 t = *reinterpret_cast<const uint2*>(row);
+                            acc[0] = fmaf(a, __uint_as_float(t.x << 16), acc[0]); acc[1] = fmaf(a, __uint_as_float(t.x & 0xffff0000u), acc[1]);
+                            acc[2] = fmaf(a, __uint_as_float(t.y << 16), acc[2]); acc[3] = fmaf(a, __uint_as_float(t.y & 0xffff0000u), acc[3]);
+                        } else if constexpr (G::VEC == 2) {
+                            const uint32_t t = *reinterpret_cast<const uint32_t*>(row);
+                            acc[0] = fmaf(a, __uint_as_float(t << 16), acc[0]); acc[1] = fmaf(a, __uint_as_float(t & 0xffff0000u), acc[1]);
+                        } else {
+                            acc[0] = fmaf(a, bf16_bits_to_f32(*reinterpret_cast<const uint16_t*>(row)), acc[0]);
+                        }
+                    }
+                };
+                const int hp0 = (warp + G::R) * G::HW + pcw + G::R;
+                float wk[G::WST];                                          // this destination's weights: 7 x LDS.128 (broadcast)
+#pragma unroll
+                for (int q = 0; q < G::WST / 4; ++q) {
+                    const float4 t = reinterpret_cast<const float4*>(w)[q];
+                    wk[4 * q] = t.x; wk[4 * q + 1] = t.y; wk[4 * q + 2] = t.z; wk[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int k = 0; k < BGNN_MAX_OFFSETS; ++k)
+                    if (k < T.K) fma_row(hp0 + T.doff[k], wk[k]);
+                fma_row(hp0, wk[BGNN_MAX_OFFSETS]);
+                // epilogue: + bias, BN(eval) as x*a + b, ReLU
+                float o[G::VEC];
+                const int ch0 = head * C + sl * G::CPS + lane * G::VEC;
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) {
+                    float y = acc[v] + __ldg(bias + ch0 + v);
+                    y = fmaf(y, __ldg(bn_a + ch0 + v), __ldg(bn_b + ch0 + v));
+                    o[v] = relu ? fmaxf(y, 0.f) : y;
+                }
+                if constexpr (IO == IO_BF16) VecBF<G::VEC>::st(reinterpret_cast<uint16_t*>(out_) + (int64_t)id * HC + ch0, o);
+                else VecIO<G::VEC>::st(out_ + (int64_t)id * HC + ch0, o);
+            }
+            __syncthreads();                                               // slab and weights may be overwritten
+        }
+    }
+}
+
+static bool topo5_to_dev(const bgnn_grid_topo* topo, int64_t E, Topo5Dev& T) {
+    if (!(topo && topo->node_id && topo->rows > 0 && topo->n_offsets >= 1 && topo->n_offsets <= BGNN_MAX_OFFSETS && E > 0)) return false;
+    T.rows = topo->rows; T.cols = topo->cols; T.node_id = topo->node_id; T.K = topo->n_offsets;
+    for (int k = 0; k < BGNN_MAX_OFFSETS; ++k) {
+        const int dr = k < T.K ? topo->off_dr[k] : 0, dc = k < T.K ? topo->off_dc[k] : 0;
+        if (abs(dr) > 2 || abs(dc) > 2) return false;
+        T.dr[k] = (int8_t)dr; T.dc[k] = (int8_t)dc;
+        T.doff[k] = (int16_t)(-dr * 20 - dc);                 // Tile5Cfg::HW == 20
+    }
+    return true;
+}
+
+template <int H, int C, int IO>
+int launch_agg_tile5_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
+                       int relu, float slope, float* out, int64_t N, const Topo5Dev& T, cudaStream_t s) {
+    using G = Tile5Cfg<C, IO>;
+    static_assert(G::SMEM <= 113000, "two CTAs per SM");
+    auto kern = gat_aggregate_tile5<H, C, IO>;
+    BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    dim3 grid((unsigned)((T.cols + G::PW - 1) / G::PW), (unsigned)((T.rows + G::PH - 1) / G::PH));
+    kern<<<grid, G::NT, G::SMEM, s>>>(h, alpha, rowptr, eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, N, T);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+// returns 1 when the radius-2 tiled kernel does not apply
+int launch_agg_tile5(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
+                     int relu, float slope, float* out, int64_t N, const Topo5Dev& T, int io, cudaStream_t s) {
+    if (ED > BGNN_MAX_EDGE_FEATS || (ED > 0 && !eattr) || !rowptr) return 1;
+    if (T.rows > 65535 * 8) return 1;
+#define T5(H_, C_)                                                                                                              \
+    if (L.H == H_ && L.C == C_) {                                                                                               \
+        if (io == IO_F32) return launch_agg_tile5_t<H_, C_, IO_F32>(L, h, alpha, rowptr, eattr, ED, relu, slope, out, N, T, s); \
+        if (io == IO_BF16) return launch_agg_tile5_t<H_, C_, IO_BF16>(L, h, alpha, rowptr, eattr, ED, relu, slope, out, N, T, s); \
+        return launch_agg_tile5_t<H_, C_, IO_BF16_F32>(L, h, alpha, rowptr, eattr, ED, relu, slope, out, N, T, s);              \
+    }
+    T5(1, 64) T5(2, 64) T5(4, 64) T5(1, 128) T5(2, 128) T5(4, 128)
+#undef T5
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------ heads
 // hh: [N, nblk*h2] = ReLU(first layers).  One warp per node.
 __global__ void __launch_bounds__(256)
@@ -1547,7 +1798,8 @@ extern "C" int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* top
 // (GEMM accumulators, attention logits, softmax, weighted aggregation), BN and the heads stay in fp32.
 // oracle/model_oracle.py::forward(bf16_storage=True) restates exactly these rounding points.
 static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const int32_t* rowptr, const int32_t* csr_src,
-                        const float* csr_eattr, float* bufA, float* bufB, float* hbuf, float* alpha, float* logits,
+                        const float* csr_eattr, const Topo5Dev* T5, float* bufA, float* bufB, float* hbuf, float* alpha,
+                        float* amax, float* logits,
                         float* probs, int64_t* cls, float* conf, float* corr, int64_t* action, float thr_auto,
                         float thr_review, float* hidden_out, int sms, cudaStream_t s) {
     const bgnn_model_desc& d = m->d;
@@ -1573,12 +1825,28 @@ static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const in
           if (rc) return rc; }
         const bool last = l == d.layers - 1;
         { ProfScope ps(40 + l, s);
-          if ((rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, !last, d.negative_slope, nxt, N, sms, s,
-                               last ? IO_BF16_F32 : IO_BF16))) return rc; }
+          const int io = last ? IO_BF16_F32 : IO_BF16;
+          rc = 1;
+          if (T5) rc = launch_agg_tile5(L, hbuf, alpha, rowptr, csr_eattr, d.edge_dim, !last, d.negative_slope, nxt, N, *T5, io, s);
+          if (rc == 1) rc = launch_agg(L, hbuf, alpha, rowptr, csr_src, csr_eattr, d.edge_dim, !last, d.negative_slope, nxt, N, sms, s, io);
+          if (rc) return rc; }
         float* t = cur; cur = nxt; nxt = t;
     }
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     const int nblk = m->nheads_mlp;
+    if (g_use_umma && m->hWsplit) {         // heads stay fp32: the fused tcgen05 heads kernel of the fp32 path, fed with max|x_L|
+        ProfScope ps(60, s);
+        BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
+        if ((rc = launch_absmax(cur, N * C, amax, sms, s))) return rc;
+        UmmaArgs a = {};
+        a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit; a.w_inv_scale = m->heads_inv;
+        a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f;
+        a.hb0 = m->hb0; a.h2 = h2; a.nblk = nblk; a.ncls = d.num_classes;
+        a.Wcls = m->Wcls; a.bcls = m->bcls; a.Wconf = m->Wconf; a.bconf = m->bconf; a.Wcorr = m->Wcorr; a.bcorr = m->bcorr;
+        a.logits = logits; a.probs = probs; a.cls = cls; a.conf = conf; a.corr = corr; a.action = action;
+        a.thr_auto = thr_auto; a.thr_review = thr_review;
+        return launch_umma(a, m->hNpad, PM_PLAIN, EM_HEADS, sms, s);
+    }
     { ProfScope ps(60, s);
       if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc; }
     int64_t blocks = ceil_div64(N, 8);
@@ -1618,6 +1886,8 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     // grid path: radius-1 stencil (4-/8-connected) on a single tile
     TopoDev T;
     const bool tiled = topo_to_dev(topo, E, T);
+    Topo5Dev T5;
+    const bool tiled5 = g_tile5 && topo5_to_dev(topo, E, T5);
 
     char* w = (char*)workspace;
     w = (char*)align_up((size_t)w, 256);
@@ -1633,7 +1903,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const int C = d.hidden, h2 = C / 2;
     int rc;
     if (m->precision == BGNN_PREC_BF16)
-        return forward_bf16(m, N, x, rowptr, csr_src, csr_eattr, bufA, bufB, hbuf, alpha, logits, probs, cls, conf, corr, action,
+        return forward_bf16(m, N, x, rowptr, csr_src, csr_eattr, tiled5 ? &T5 : nullptr, bufA, bufB, hbuf, alpha, amax, logits, probs, cls, conf, corr, action,
                             thr_auto, thr_review, hidden_out, sms, s);
     // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C).  On the tensor-core path both are fused into the
     // layer-0 projection (first Linear computed by its producers, second folded into its weights).
@@ -1710,6 +1980,8 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               rc = launch_agg_window(L, hsrc, al, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, SO, s);
               if (rc == 0 && want_split) cur_split = true;
           }
+          if (rc == 1 && tiled5 && !tiled)        // 5 x 5 stencil on a single grid: radius-2 tiled kernel
+              rc = launch_agg_tile5(L, hsrc, al, rowptr, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, T5, IO_F32, s);
           if (rc == 1) rc = launch_agg(L, hsrc, al, rowptr, csr_src, csr_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, sms, s);
           if (rc) return rc; }
         float* t = cur; cur = nxt; nxt = t;

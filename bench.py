@@ -537,6 +537,79 @@ def run_ragged(args):
                           "kernels_ms_one_chunk": kernels}))
 
 
+def run_wide(args):
+    """BASELINE.json configs[4]: wide variant -- 5x5 neighbourhood (k = 24), hidden 128 x 4 heads x 4 attention layers, one
+    2048^2 tile per GPU, fp32 parity mode AND bf16 mode (bgnn_model_set_precision).  Secondary workload: one JSON line with
+    both precisions, the per-kernel device times of one step each, and the bf16-vs-fp32 output differences on this tile."""
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200._lib import lib
+    from oracle import model_oracle as mo          # weights only
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    T = args.tile
+    from tests import synth
+    depth = synth.noisy_tile(T, T, seed=1234 + rank, r0=FIELD_ORIGIN[0], c0=FIELD_ORIGIN[1])
+    mask = synth.blob_mask(T, T, seed=1234 + rank, invalid_frac=0.02)
+    depth[~mask] = 1.0e6
+    cfg_m = mo.ModelCfg(in_channels=7, hidden=128)
+    sd = mo.init_state_dict(cfg_m, seed=0, randomize_bn=True)
+    model = bg.BathymetricGNN(7, 128, 4, "GAT", 4, 3, True, 0.0, 3)
+    model.load_state_dict(sd, strict=True); model = model.to(dev).eval()
+    builder = bg.GraphBuilder("24-connected")
+    d_dev = torch.from_numpy(depth).to(dev); m_dev = torch.from_numpy(mask).to(dev)
+    res, outs = {}, {}
+    for prec in ("fp32", "bf16"):
+        model.set_precision(prec)
+
+        def step():
+            g = builder.build_graph(d_dev, m_dev, None, RES)
+            o = model.predict(g)
+            return g, o
+        for _ in range(max(args.warmup, 1)):
+            g, o = step(); del g, o
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            g, o = step(); del g, o
+        ev1.record(); torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        lib.bgnn_profile_enable(1)
+        g, o = step(); torch.cuda.synchronize()
+        n = lib.bgnn_profile_collect(0, None, None)
+        slots = (C.c_int32 * n)(); tms = (C.c_float * n)()
+        lib.bgnn_profile_collect(n, slots, tms)
+        lib.bgnn_profile_enable(0)
+        kern = {}
+        for s_, m_ in zip(slots, tms):
+            k = SLOT_NAMES.get(int(s_), str(int(s_)))
+            kern[k] = round(kern.get(k, 0.0) + float(m_), 4)
+        N, E = g.num_nodes, g.num_edges
+        outs[prec] = {k: o[k].float().cpu() for k in ("class_logits", "confidence", "correction", "predicted_class")}
+        res[prec] = {"ms_per_step": round(ms, 3), "cells_per_s": world * T * T / (ms * 1e-3), "kernels_ms": kern}
+        del g, o
+    t = torch.tensor([res["fp32"]["ms_per_step"], res["bf16"]["ms_per_step"]], device=dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.destroy_process_group()
+    diff = {k: float((outs["bf16"][k] - outs["fp32"][k]).abs().max()) for k in ("class_logits", "confidence", "correction")}
+    diff["label_disagreement_frac"] = float((outs["bf16"]["predicted_class"] != outs["fp32"]["predicted_class"]).float().mean())
+    diff["logit_scale"] = float(outs["fp32"]["class_logits"].abs().max())
+    if rank == 0:
+        print(json.dumps({"metric": METRIC + ", wide variant", "value": world * T * T / (float(t[1]) * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[1]),
+                          "higher_is_better": True, "scaling": "weak", "dtype": "bf16 storage / f32 accumulate", "data": "synthetic",
+                          "config": {"workload": f"configs[4]: one {T}x{T} tile per GPU, 24-connected (5x5), F=7, GAT hidden 128 x 4 heads "
+                                                 "x 4 layers, graph build + predict; value = bf16 mode, fp32 mode beside it",
+                                     "nodes": N, "edges": E, "l2": "activations (GBs per layer) far exceed the 126 MB L2"},
+                          "fp32": {"ms_per_step": float(t[0]), "cells_per_s": world * T * T / (float(t[0]) * 1e-3), "kernels_ms": res["fp32"]["kernels_ms"]},
+                          "bf16": {"ms_per_step": float(t[1]), "kernels_ms": res["bf16"]["kernels_ms"]},
+                          "bf16_vs_fp32_max_abs_diff": diff}))
+
+
 def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):
     """Oracle (numpy/scipy graph build + torch-CPU GAT forward) on a crop x crop corner of the tile."""
     from oracle import graph_oracle as go
@@ -590,8 +663,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (used under ncu): no e2e / per-kernel / cpu legs")
-    ap.add_argument("--workload", default="tile", choices=["tile", "survey", "ragged"],
-                    help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2], ragged = configs[3] (secondary)")
+    ap.add_argument("--workload", default="tile", choices=["tile", "survey", "ragged", "wide"],
+                    help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2], ragged = configs[3], "
+                         "wide = configs[4] fp32 + bf16 (secondary)")
     ap.add_argument("--grids", type=int, default=100000)
     ap.add_argument("--chunk-cells", type=int, default=8000000)
     ap.add_argument("--survey-size", type=int, default=16384)
@@ -609,6 +683,8 @@ def main():
             run_survey(args)
         elif args.workload == "ragged":
             run_ragged(args)
+        elif args.workload == "wide":
+            run_wide(args)
         else:
             run_ours(args)
 

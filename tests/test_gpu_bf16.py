@@ -4,7 +4,7 @@ The reference has no reduced-precision path, so the bf16 mode is bounded two way
   * against the fp32 oracle (the reference arithmetic): BF16_ATOL below -- the measured envelope of bf16 storage with fp32
     accumulation is 4e-3 on logits of scale 0.1 (a plain torch bf16 run of the same model: 1.1e-2);
   * against oracle/model_oracle.py::forward(bf16_storage=True), which restates the SAME rounding points on the CPU:
-    what is left is fp32 summation order (1e-7: TIGHT_MEDIAN bounds the median of the differences) plus the
+    what is left is fp32 summation order (1e-7) plus the
     occasional activation that lands on the other side of a bf16 rounding boundary (one bf16 ulp = 0.4 % of that
     activation; the feature-extractor output reaches |x| = 30, i.e. ulps of 0.125) and then spreads over the receptive
     field of four layers: TIGHT_ATOL bounds those nodes (measured: 99.9th percentile 6e-4, maximum 2e-3).
@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 
 BF16_ATOL = 2e-2      # vs the fp32 oracle: logits / correction (confidence: 5e-3)
 TIGHT_ATOL = 5e-3     # vs the oracle restating the bf16 rounding points: every element
-TIGHT_MEDIAN = 5e-6   # ... and the median difference
+TIGHT_MEDIAN = 1e-4   # ... and the median difference (measured: 3e-8 for 3x3 stencils, 2.6e-5 for the 5x5 / hidden 128 variant,
+                      # where every node's receptive field contains flipped roundings)
 
 
 def _labels_ok(out, ref_logits, ref_cls, atol):
@@ -162,3 +163,30 @@ def test_bf16_ragged_batch():
     assert model.precision == "bf16"
     for k, tol in (("class_logits", BF16_ATOL), ("correction", BF16_ATOL), ("confidence", 5e-3)):
         np.testing.assert_allclose(obf[k].cpu().numpy(), o32[k].cpu().numpy(), rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("hidden,heads,conn", [(128, 4, "24-connected"), (64, 4, "24-connected"), (64, 2, "8-connected")])
+def test_radius2_tiled_aggregation_vs_csr_kernel(prec, hidden, heads, conn):
+    """gat_aggregate_tile5 (5x5 stencil / bf16 mode on a single grid: halo slabs in shared memory) against the
+    warp-per-destination CSR kernel (use_grid_kernel=False): same arithmetic, FMAs in the same edge order -- only the
+    softmax denominator is summed pairwise, so fp32 agrees to a few ulps; in bf16 mode a differing last bit can flip a bf16
+    rounding, hence the bf16 bound.  Ragged grid size (not a multiple of the 8 x 16 patch), holes."""
+    import bathymetric_gnn_b200 as bg
+    if prec == "fp32" and conn == "8-connected":
+        pytest.skip("fp32 radius-1 stencils run the 3x3 tiled kernel (tests/test_gpu_gnn.py)")
+    d = synth.noisy_tile(77, 53, seed=8)
+    mask = synth.blob_mask(77, 53, seed=8, invalid_frac=0.07)
+    cfg = mo.ModelCfg(in_channels=7, hidden=hidden, heads=heads)
+    sd = mo.init_state_dict(cfg, seed=2, randomize_bn=True, head_gain=1.0)
+    model = make_model(cfg, sd).set_precision(prec)
+    g = bg.GraphBuilder(conn).build_graph(d, mask, None, (0.5, 0.5))
+    a = model._run(g, 0.85, 0.6, True, return_hidden=True)
+    model.use_grid_kernel = False
+    b = model._run(g, 0.85, 0.6, True, return_hidden=True)
+    tol = 2e-6 if prec == "fp32" else TIGHT_ATOL
+    for k in ("hidden", "class_logits", "confidence", "correction"):
+        x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+        assert np.isfinite(x).all()
+        np.testing.assert_allclose(x, y, rtol=0, atol=tol * max(1.0, float(np.abs(y).max())), err_msg=k)
+        assert np.median(np.abs(x - y)) <= 1e-6
