@@ -26,7 +26,8 @@
 
 static bool g_use_umma = true;
 static bool g_window = getenv("BGNN_NO_WINDOW") == nullptr;       // ragged batches: windowed shared-memory CSR aggregation
-static bool g_tile5 = getenv("BGNN_NO_TILE5") == nullptr;         // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
+static bool g_tile5 = getenv("BGNN_NO_TILE5") == nullptr;
+static bool g_tile5_window = getenv("BGNN_NO_TILE5_WINDOW") == nullptr;   // full 5x5 stencil: sliding register window variant         // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
 static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
 extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
 extern "C" int bgnn_set_presplit(int on) { g_presplit = on != 0; return BGNN_OK; }
@@ -1218,10 +1219,12 @@ struct Topo5Dev {
     int16_t doff[BGNN_MAX_OFFSETS];        // halo slot of the source relative to the destination's: -dr * HW - dc
 };
 
-template <int C, int IO> struct Tile5Cfg {
+template <int C, int IO, bool FULL5> struct Tile5Cfg {
     static constexpr int PH = 8, PW = 16, R = 2, HR = PH + 2 * R, HW = PW + 2 * R, NSLOT = HR * HW, ND = PH * PW, NT = 256;
     static constexpr int ESZ = IO == IO_F32 ? 4 : 2;                       // bytes per stored h element
-    static constexpr int CPS = C * ESZ <= 256 ? C : 256 / ESZ;             // channels per slab
+    // channels per slab: 256-byte rows; the sliding-window variant keeps a 5 x 5 register window per lane and therefore
+    // works on 64-channel slabs (2 channels per lane: 50 window registers, two or three CTAs per SM)
+    static constexpr int CPS = FULL5 ? 64 : (C * ESZ <= 256 ? C : 256 / ESZ);
     static constexpr int RB = CPS * ESZ;                                   // slab row bytes (128 or 256)
     static constexpr int NSLAB = C / CPS;
     static constexpr int VEC = CPS / 32;                                   // channels per lane
@@ -1229,13 +1232,13 @@ template <int C, int IO> struct Tile5Cfg {
     static constexpr size_t SMEM = (size_t)NSLOT * RB + (size_t)ND * WST * 4 + (size_t)NSLOT * 4 + 16;
 };
 
-template <int H, int C, int IO>
+template <int H, int C, int IO, bool FULL5>
 __global__ void __launch_bounds__(256, 2)
 gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alpha, const int32_t* __restrict__ rowptr,
                     const float* __restrict__ eattr, int ED, const float* __restrict__ Medge, const float* __restrict__ bias,
                     const float* __restrict__ bn_a, const float* __restrict__ bn_b, int relu, float slope,
                     float* __restrict__ out_, int64_t N, const __grid_constant__ Topo5Dev T) {
-    using G = Tile5Cfg<C, IO>;
+    using G = Tile5Cfg<C, IO, FULL5>;
     constexpr int HC = H * C, KH = (BGNN_MAX_OFFSETS + 1) / 2;            // offsets per thread of a pair (<= 12) + self
     extern __shared__ __align__(16) uint8_t smem5[];
     uint8_t* slab = smem5;                                                 // [NSLOT][RB]
@@ -1356,6 +1359,60 @@ gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alph
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();                                               // slab landed, weights visible
             // ---- aggregate: warp <-> patch row, lane <-> VEC channels of the slab
+            if constexpr (FULL5) {
+                // full 5 x 5 stencil in raster order (OFFSETS_24): the warp slides a 5 x 5 register window along its patch
+                // row -- 5 new source rows per destination instead of 25 -- and multiplies in the reference's edge order
+                // (k ascending <-> window row 4..0, window column 4..0, centre = self loop last)
+                static_assert(G::VEC == 2, "window variant works on 64-channel slabs");
+                float win[5][5][2];
+                float cb[2], ca[2], cc[2];
+                const int ch0 = head * C + sl * G::CPS + lane * 2;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) { cb[v] = __ldg(bias + ch0 + v); ca[v] = __ldg(bn_a + ch0 + v); cc[v] = __ldg(bn_b + ch0 + v); }
+                auto load_col = [&](int x, float (*dst)[2], int wy) {
+                    const uint8_t* row = slab + (size_t)((warp + wy) * G::HW + x) * G::RB + lane * (2 * G::ESZ);
+                    if constexpr (IO == IO_F32) { const float2 t = *reinterpret_cast<const float2*>(row); dst[0][0] = t.x; dst[0][1] = t.y; }
+                    else { const uint32_t t = *reinterpret_cast<const uint32_t*>(row); dst[0][0] = __uint_as_float(t << 16); dst[0][1] = __uint_as_float(t & 0xffff0000u); }
+                };
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int wy = 0; wy < 5; ++wy) load_col(x, &win[wy][x % 5], wy);
+#pragma unroll
+                for (int pcw = 0; pcw < G::PW; ++pcw) {
+#pragma unroll
+                    for (int wy = 0; wy < 5; ++wy) load_col(pcw + 4, &win[wy][(pcw + 4) % 5], wy);
+                    const int id = hid[(warp + G::R) * G::HW + pcw + G::R];
+                    if (id >= 0) {                                         // warp-uniform
+                        const float* w = wts + (warp * G::PW + pcw) * G::WST;
+                        float wk[G::WST];
+#pragma unroll
+                        for (int q = 0; q < G::WST / 4; ++q) {
+                            const float4 t = reinterpret_cast<const float4*>(w)[q];
+                            wk[4 * q] = t.x; wk[4 * q + 1] = t.y; wk[4 * q + 2] = t.z; wk[4 * q + 3] = t.w;
+                        }
+                        float a0 = 0.f, a1 = 0.f;
+                        int k = 0;
+#pragma unroll
+                        for (int wy = 4; wy >= 0; --wy)
+#pragma unroll
+                            for (int wx = 4; wx >= 0; --wx) {
+                                if (wy == 2 && wx == 2) continue;
+                                a0 = fmaf(wk[k], win[wy][(pcw + wx) % 5][0], a0);
+                                a1 = fmaf(wk[k], win[wy][(pcw + wx) % 5][1], a1);
+                                ++k;
+                            }
+                        a0 = fmaf(wk[BGNN_MAX_OFFSETS], win[2][(pcw + 2) % 5][0], a0);
+                        a1 = fmaf(wk[BGNN_MAX_OFFSETS], win[2][(pcw + 2) % 5][1], a1);
+                        float o[2];
+                        o[0] = fmaf(a0 + cb[0], ca[0], cc[0]);
+                        o[1] = fmaf(a1 + cb[1], ca[1], cc[1]);
+                        if (relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); }
+                        if constexpr (IO == IO_BF16) VecBF<2>::st(reinterpret_cast<uint16_t*>(out_) + (int64_t)id * HC + ch0, o);
+                        else VecIO<2>::st(out_ + (int64_t)id * HC + ch0, o);
+                    }
+                }
+            } else
             for (int pcw = 0; pcw < G::PW; ++pcw) {
                 const int dd = warp * G::PW + pcw;
                 const int id = hid[(warp + G::R) * G::HW + pcw + G::R];
@@ -1422,17 +1479,29 @@ static bool topo5_to_dev(const bgnn_grid_topo* topo, int64_t E, Topo5Dev& T) {
     return true;
 }
 
-template <int H, int C, int IO>
-int launch_agg_tile5_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
-                       int relu, float slope, float* out, int64_t N, const Topo5Dev& T, cudaStream_t s) {
-    using G = Tile5Cfg<C, IO>;
+template <int H, int C, int IO, bool FULL5>
+int launch_agg_tile5_tt(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
+                        int relu, float slope, float* out, int64_t N, const Topo5Dev& T, cudaStream_t s) {
+    using G = Tile5Cfg<C, IO, FULL5>;
     static_assert(G::SMEM <= 113000, "two CTAs per SM");
-    auto kern = gat_aggregate_tile5<H, C, IO>;
+    auto kern = gat_aggregate_tile5<H, C, IO, FULL5>;
     BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
     dim3 grid((unsigned)((T.cols + G::PW - 1) / G::PW), (unsigned)((T.rows + G::PH - 1) / G::PH));
     kern<<<grid, G::NT, G::SMEM, s>>>(h, alpha, rowptr, eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, N, T);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
+}
+
+template <int H, int C, int IO>
+int launch_agg_tile5_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
+                       int relu, float slope, float* out, int64_t N, const Topo5Dev& T, cudaStream_t s) {
+    bool full5 = g_tile5_window && T.K == BGNN_MAX_OFFSETS;          // exactly OFFSETS_24: raster order over the 5 x 5 window
+    for (int k = 0, q = 0; full5 && k < T.K; ++k, ++q) {
+        if (q == 12) ++q;                                             // the centre is not an offset
+        full5 = T.dr[k] == q / 5 - 2 && T.dc[k] == q % 5 - 2;
+    }
+    if (full5) return launch_agg_tile5_tt<H, C, IO, true>(L, h, alpha, rowptr, eattr, ED, relu, slope, out, N, T, s);
+    return launch_agg_tile5_tt<H, C, IO, false>(L, h, alpha, rowptr, eattr, ED, relu, slope, out, N, T, s);
 }
 
 // returns 1 when the radius-2 tiled kernel does not apply

@@ -8,14 +8,17 @@
 // kernel in proj_umma.cu, which needs a 3-product fp16 split -- ONE tcgen05.mma.kind::f16 product per K step does the job
 // and no conversion stage exists: TMA -> shared memory -> tensor core.
 //
-// Persistent CTA per SM, 192 threads, warp-specialised:
+// Persistent CTA per SM, 320 threads, warp-specialised:
+//   (320 threads since the epilogue runs as two groups of four warps, see below)
 //   warp 0 (one thread)  TMA producer.  The CTA owns ONE 128-column block of W for the whole launch: its [BN x K] slab
 //                        (<= 128 KB) is fetched once and stays resident in shared memory (re-reading W per 128-row tile
 //                        would double the L2 -> SM traffic and make the kernel L2-bound).  A streams through a 6-deep ring
 //                        of [128 x 32] SWIZZLE_64B tiles, one cp.async.bulk.tensor per K chunk (rows past M read as zero).
 //   warp 1 (one thread)  MMA issuer: 2 x tcgen05.mma (M = 128, N = BN, K = 16) per chunk; tcgen05.commit frees the A stage;
 //                        accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile t overlaps tile t+1.
-//   warps 2-5            epilogue: tcgen05.ld 32x32b.x32 (thread <-> row), alpha_src / alpha_dst dot products per head from
+//   warps 2-9            epilogue, two groups of four warps: group g takes the tiles of accumulator stage g, so two tiles are
+//                        finished at a time (one warp per scheduler runs ~2 000 dependent instructions per tile: a single
+//                        group was the critical path, ncu: tensor pipe 27 % busy, issue slots 28 %).  Per tile: tcgen05.ld 32x32b.x32 (thread <-> row), alpha_src / alpha_dst dot products per head from
 //                        the fp32 accumulators, RN conversion to bf16, rows staged in shared memory and written out
 //                        coalesced (16 B per lane, consecutive lanes <-> consecutive pieces of a row) into the head-major
 //                        layout [Htot][M][CH] the aggregation reads.
@@ -33,10 +36,10 @@ namespace {
 constexpr int KC = 32;                       // K elements per stage: 64 B of bf16 = one SWIZZLE_64B row
 constexpr int TILE_M = 128;
 constexpr int A_TILE_BYTES = TILE_M * KC * 2;        // 8 KB
-constexpr int NSTAGE = 6;
+constexpr int MAX_STAGE = 8;                 // A ring depth: as many 8 KB stages as fit beside the resident W slab (>= 3)
 constexpr uint32_t SBO_BYTES = 8 * KC * 2;           // 512 B between 8-row groups
-constexpr int EPI_WARPS = 4;
-constexpr int THREADS = (2 + EPI_WARPS) * 32;        // 192
+constexpr int EPI_WARPS = 8;                 // two groups of four: group g finishes the tiles whose accumulator stage is g
+constexpr int THREADS = (2 + EPI_WARPS) * 32;        // 320
 constexpr int MAX_K = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,17 +81,26 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 struct Bf16Args {
     int64_t M; int K; int N; int NB;          // NB = N / BN column blocks
-    uint16_t* C; const float* att_src; const float* att_dst; float* alpha; int Htot; int CH;
+    uint16_t* C; const float* att_src; const float* att_dst; float* alpha; int Htot; int CH; int ch_shift;   // CH = 1 << ch_shift
+    int nstage;
 };
 
 template <int BN> struct Smem {
     static constexpr int W_CHUNK_BYTES = BN * KC * 2;                 // one K chunk of the resident W slab
-    static constexpr int PITCH = BN * 2 + 16;                          // staging row pitch (bytes): conflict-free 16 B accesses
+    static constexpr int PITCH = BN + 16;                              // staging row pitch (bytes) for HALF the columns of a tile:
+                                                                       // conflict-free 16 B accesses; staging the full width
+                                                                       // would leave only 3 A stages at K = 512 (measured: slower)
     static constexpr int STAGE_ROWS_BYTES = 32 * PITCH;                // per epilogue warp
-    static constexpr size_t bytes(int K) {
-        return 1024 /*alignment slack*/ + (size_t)(K / KC) * W_CHUNK_BYTES + (size_t)NSTAGE * A_TILE_BYTES +
-               (size_t)EPI_WARPS * STAGE_ROWS_BYTES + 2 * BN * sizeof(float) + 64 * sizeof(uint64_t);
+    static constexpr size_t fixed(int K) {
+        return 1024 /*alignment slack*/ + (size_t)(K / KC) * W_CHUNK_BYTES + (size_t)EPI_WARPS * STAGE_ROWS_BYTES +
+               2 * BN * sizeof(float) + 64 * sizeof(uint64_t);
     }
+    static int stages(int K) {
+        const long room = 232448 - 1024 /*static + reserved*/ - (long)fixed(K);
+        const int n = (int)(room / A_TILE_BYTES);
+        return n > MAX_STAGE ? MAX_STAGE : n;
+    }
+    static size_t bytes(int K) { return fixed(K) + (size_t)stages(K) * A_TILE_BYTES; }
 };
 
 template <int BN>
@@ -101,12 +113,13 @@ proj_bf16_kernel(const __grid_constant__ Bf16Args P, const __grid_constant__ CUt
     const int nkc = P.K / KC;
     uint8_t* wres = base;                                               // [nkc][BN x 64 B] swizzled
     uint8_t* aring = wres + (size_t)nkc * S::W_CHUNK_BYTES;             // [NSTAGE][128 x 64 B] swizzled
+    const int NSTAGE = P.nstage;
     uint8_t* stg = aring + (size_t)NSTAGE * A_TILE_BYTES;               // [EPI_WARPS][32][PITCH]
     float* s_att = reinterpret_cast<float*>(stg + (size_t)EPI_WARPS * S::STAGE_ROWS_BYTES);     // att_src [BN] | att_dst [BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_att + 2 * BN);
-    uint64_t* bar_full = bars;                 // [NSTAGE]
-    uint64_t* bar_empty = bars + NSTAGE;       // [NSTAGE]
-    uint64_t* bar_w = bars + 2 * NSTAGE;       // resident W landed
+    uint64_t* bar_full = bars;                 // [MAX_STAGE]
+    uint64_t* bar_empty = bars + MAX_STAGE;    // [MAX_STAGE]
+    uint64_t* bar_w = bars + 2 * MAX_STAGE;    // resident W landed
     uint64_t* bar_tfull = bar_w + 1;           // [2]
     uint64_t* bar_tempty = bar_tfull + 2;      // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
@@ -120,7 +133,7 @@ proj_bf16_kernel(const __grid_constant__ Bf16Args P, const __grid_constant__ CUt
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(bar_w, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4 * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = tid; i < BN; i += THREADS) {
@@ -188,69 +201,78 @@ proj_bf16_kernel(const __grid_constant__ Bf16Args P, const __grid_constant__ CUt
         // ===================== epilogue: thread <-> row of the tile =====================
         const int ew = warp - 2;                         // staging slot
         const int lg = warp & 3;                         // TMEM lane group this warp may access
+        const uint32_t egrp = (uint32_t)ew >> 2;         // tiles with accumulator stage == egrp are this warp's
         uint8_t* my_stg = stg + (size_t)ew * S::STAGE_ROWS_BYTES;
-        const int CH = P.CH, Htot = P.Htot;
+        const int CH = P.CH, Htot = P.Htot, chs = P.ch_shift;
         uint32_t t = 0;
         for (int64_t mt = grp; mt < n_mt; mt += ngrp, ++t) {
             const uint32_t as = t & 1;
+            if (as != egrp) continue;
             mbar_wait(&bar_tfull[as], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int64_t row = mt * TILE_M + lg * 32 + lane;
             float ps = 0.f, pd = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN + c * 32;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                if (P.alpha) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        ps = fmaf(x, s_att[c * 32 + j], ps);
-                        pd = fmaf(x, s_att[BN + c * 32 + j], pd);
-                    }
-                    if (((c + 1) * 32) % CH == 0) {           // a head is complete (CH is a multiple of 32)
-                        if (row < P.M) {
-                            const int head = (n0 + c * 32) / CH;
-                            P.alpha[row * (2 * Htot) + head] = ps;
-                            P.alpha[row * (2 * Htot) + Htot + head] = pd;
-                        }
-                        ps = 0.f; pd = 0.f;
-                    }
-                }
-                uint4* dst = reinterpret_cast<uint4*>(my_stg + (size_t)lane * S::PITCH + c * 64);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    dst[q] = make_uint4(pack2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
-                                        pack2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-                                        pack2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-                                        pack2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(&bar_tempty[as]);                  // every accumulator column of this row has been read
-            __syncwarp();
-            // coalesced write-out: 16 B pieces, consecutive lanes <-> consecutive pieces of a row
-            constexpr int PPR = BN / 8;                    // pieces per row
+            constexpr int CPH = BN / 64;                       // 32-column chunks per half tile
+            constexpr int PPR = BN / 16;                       // 16-byte pieces per staged (half) row
             const int64_t rbase = mt * TILE_M + lg * 32;
-#pragma unroll 4
-            for (int p = lane; p < 32 * PPR; p += 32) {
-                const int r = p / PPR, pc = p % PPR;
-                const int64_t m = rbase + r;
-                if (m < P.M) {
-                    const int n = n0 + pc * 8;
-                    const uint4 val = *reinterpret_cast<const uint4*>(my_stg + (size_t)r * S::PITCH + pc * 16);
-                    *reinterpret_cast<uint4*>(P.C + ((int64_t)(n / CH) * P.M + m) * CH + (n % CH)) = val;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+                for (int cc = 0; cc < CPH; ++cc) {
+                    const int c = hf * CPH + cc;
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN + c * 32;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    if (P.alpha) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(v[j]);
+                            ps = fmaf(x, s_att[c * 32 + j], ps);
+                            pd = fmaf(x, s_att[BN + c * 32 + j], pd);
+                        }
+                        if ((((c + 1) * 32) & (CH - 1)) == 0) {   // a head is complete (CH is a power of two >= 32)
+                            if (row < P.M) {
+                                const int head = (n0 + c * 32) >> chs;
+                                P.alpha[row * (2 * Htot) + head] = ps;
+                                P.alpha[row * (2 * Htot) + Htot + head] = pd;
+                            }
+                            ps = 0.f; pd = 0.f;
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(my_stg + (size_t)lane * S::PITCH + cc * 64);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_uint4(pack2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+                                            pack2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                                            pack2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                                            pack2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
                 }
+                if (hf == 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    mbar_arrive(&bar_tempty[as]);              // every accumulator column of this row has been read
+                }
+                __syncwarp();
+                // coalesced write-out of this half: 16 B pieces, consecutive lanes <-> consecutive pieces of a row
+#pragma unroll 4
+                for (int p = lane; p < 32 * PPR; p += 32) {
+                    const int r = p / PPR, pc = p % PPR;
+                    const int64_t m = rbase + r;
+                    if (m < P.M) {
+                        const int n = n0 + hf * (BN / 2) + pc * 8;
+                        const uint4 val = *reinterpret_cast<const uint4*>(my_stg + (size_t)r * S::PITCH + pc * 16);
+                        *reinterpret_cast<uint4*>(P.C + ((((int64_t)(n >> chs) * P.M + m) << chs) + (n & (CH - 1)))) = val;
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -300,7 +322,7 @@ int launch_t(const Bf16Args& a, const uint16_t* A, const uint16_t* W, int sms, c
     if ((rc = make_tmap_bf16(A, a.M, a.K, TILE_M, &tA))) return rc;
     if ((rc = make_tmap_bf16(W, a.N, a.K, BN, &tW))) return rc;
     const size_t smem = Smem<BN>::bytes(a.K);
-    BGNN_CUDA(cudaFuncSetAttribute(proj_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<BN>::bytes(MAX_K)));
+    BGNN_CUDA(cudaFuncSetAttribute(proj_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<BN>::bytes(a.K)));
     const int64_t n_mt = (a.M + TILE_M - 1) / TILE_M;
     int64_t groups = sms / a.NB;
     if (groups < 1) groups = 1;
@@ -328,7 +350,8 @@ int launch_proj_bf16(const uint16_t* A, const uint16_t* W, int64_t M, int K, int
     const int BN = N >= 128 ? 128 : 64;
     Bf16Args a = {};
     a.M = M; a.K = K; a.N = N; a.NB = N / BN; a.C = Cout; a.att_src = att_src; a.att_dst = att_dst; a.alpha = alpha;
-    a.Htot = Htot; a.CH = CH;
+    a.Htot = Htot; a.CH = CH; a.ch_shift = CH == 32 ? 5 : CH == 64 ? 6 : 7;
+    a.nstage = BN == 128 ? Smem<128>::stages(K) : Smem<64>::stages(K);
     return BN == 128 ? launch_t<128>(a, A, W, sms, s) : launch_t<64>(a, A, W, sms, s);
 }
 
