@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <array>
 #include <vector>
 
 #include "common.cuh"
@@ -41,6 +42,11 @@ struct LayerDev {
     uint16_t* Wsplit;        // 2 x fp16 split of W for the tcgen05 path (nullptr if the shape is not compiled)
     float w_inv;             // 1 / (power-of-two scale applied to W before the split)
     float out_mul, out_add;  // |layer output| <= out_mul * max|h| + out_add   (BN(eval) after a convex combination + bias)
+    // H*C = 512 (wide variant): no single tcgen05 instantiation covers N = 512, so the projection runs as nblk column blocks of
+    // 128 (whole heads), each its own launch with its own fp16 split of the block's rows of W
+    int nblk;
+    uint16_t* Wsplit_blk[4];
+    float w_inv_blk[4];
     float* Wr;               // bf16 mode: W rounded to bf16 (RN), kept as fp32 values for the FMA GEMM (nullptr until requested)
     uint16_t* Wbf;           // bf16 mode: the same values as bf16 bit patterns [HC, in] for the tensor-core GEMM
 };
@@ -1677,10 +1683,21 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     std::vector<uint16_t> h16;
     std::vector<size_t> o16(d->layers, (size_t)-1);
     std::vector<float> winv(d->layers, 1.f);
+    std::vector<std::array<size_t, 4>> o16blk(d->layers, std::array<size_t, 4>{(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1});
+    std::vector<std::array<float, 4>> winvblk(d->layers, std::array<float, 4>{1.f, 1.f, 1.f, 1.f});
     for (int l = 0; l < d->layers; ++l) {
         int in, H, Cc, HC, outc;
         layer_shape(d, l, in, H, Cc, HC, outc);
-        if (!proj_umma_supported(HC, in, Cc, true)) continue;
+        if (!proj_umma_supported(HC, in, Cc, true)) {
+            if (HC == 512 && 128 % Cc == 0 && proj_umma_supported(128, in, Cc, true)) {      // column blocks of 128
+                for (int b = 0; b < 4; ++b) {
+                    o16blk[l][b] = h16.size();
+                    h16.resize(h16.size() + (size_t)2 * 128 * in);
+                    winvblk[l][b] = proj_umma_split_weights(hb.data() + lo[l].W + (size_t)b * 128 * in, 128, in, h16.data() + o16blk[l][b]);
+                }
+            }
+            continue;
+        }
         o16[l] = h16.size();
         h16.resize(h16.size() + (size_t)2 * HC * in);
         winv[l] = proj_umma_split_weights(hb.data() + lo[l].W, HC, in, h16.data() + o16[l]);
@@ -1747,6 +1764,12 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
         L.bias = B + lo[l].bias; L.bn_a = B + lo[l].a; L.bn_b = B + lo[l].b;
         L.Wsplit = (o16[l] != (size_t)-1 && m->blob16) ? m->blob16 + o16[l] : nullptr;
         L.w_inv = winv[l];
+        L.nblk = 0;
+        for (int b = 0; b < 4; ++b) {
+            L.Wsplit_blk[b] = (o16blk[l][b] != (size_t)-1 && m->blob16) ? m->blob16 + o16blk[l][b] : nullptr;
+            L.w_inv_blk[b] = winvblk[l][b];
+            if (L.Wsplit_blk[b]) L.nblk = b + 1;
+        }
         L.out_mul = 0.f; L.out_add = 0.f;
         L.Wr = nullptr; L.Wbf = nullptr;
         {   // |bn_a (agg + bias) + bn_b| <= max|bn_a| * max|h| + max(|bn_a||bias| + |bn_b|)
@@ -2019,6 +2042,20 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               a.Cout = hbuf; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha; a.Htot = L.H; a.CH = L.C;
               a.head_major = 1;
               rc = launch_umma(a, L.HC, cur_split ? PM_SPLIT : PM_PLAIN, EM_PROJ, sms, s);
+          } else if (g_use_umma && L.nblk == 4) {      // H*C = 512: four column blocks of 128 (whole heads), one launch each
+              if (l == 0 && (rc = launch_absmax(cur, N * L.in, amax, sms, s))) return rc;
+              const int hpb = 128 / L.C;               // heads per block
+              for (int b = 0; b < L.nblk; ++b) {
+                  UmmaArgs a = {};
+                  a.A = cur; a.M = N; a.K = L.in; a.Wsplit = L.Wsplit_blk[b]; a.w_inv_scale = L.w_inv_blk[b];
+                  if (l == 0) { a.amax_src = amax; a.amax_mul = 1.f; a.amax_add = 0.f; }
+                  else { a.amax_src = amax + l; a.amax_mul = m->layers[l - 1].out_mul; a.amax_add = m->layers[l - 1].out_add; }
+                  a.cmax_out = amax + 1 + l;
+                  a.Cout = hbuf + (size_t)b * N * 128;                     // head-major planes of this block's heads
+                  a.att_src = L.att_src + b * 128; a.att_dst = L.att_dst + b * 128;
+                  a.alpha = alpha + b * hpb; a.Htot = L.H; a.CH = L.C; a.head_major = 1;
+                  if ((rc = launch_umma(a, 128, PM_PLAIN, EM_PROJ, sms, s))) break;
+              }
           } else {
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
               if (!rc && g_use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
