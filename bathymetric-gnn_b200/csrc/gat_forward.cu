@@ -1278,6 +1278,7 @@ gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alph
     const int pr = d / G::PW, pc = d % G::PW;
     const int my_id = hid[(pr + G::R) * G::HW + pc + G::R];
     uint32_t vmask = 0;
+    int start = 0;
     float ea[KH][BGNN_MAX_EDGE_FEATS];
     int jsrc[KH];
     float mean[BGNN_MAX_EDGE_FEATS];
@@ -1288,7 +1289,7 @@ gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alph
             const int hp = (pr + G::R - T.dr[k]) * G::HW + pc + G::R - T.dc[k];
             if (hid[hp] >= 0) vmask |= 1u << k;
         }
-        const int start = __ldg(rowptr + my_id);
+        start = __ldg(rowptr + my_id);
 #pragma unroll
         for (int kk = 0; kk < KH; ++kk) {
             const int k = 2 * kk + half;
@@ -1330,8 +1331,15 @@ gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alph
                 sc[kk] = -CUDART_INF_F;
                 if (jsrc[kk] >= 0) {
                     float ae = 0.f;
+                    if constexpr (FULL5) {       // the window variant needs the registers: edge features are re-read per head (L1 hits)
+                        const int k = 2 * kk + half;
+                        const int e = start + __popc(vmask & ((1u << k) - 1u));
 #pragma unroll
-                    for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(ea[kk][f], M[f], ae);
+                        for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(f < ED ? __ldg(eattr + (int64_t)e * ED + f) : 0.f, M[f], ae);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(ea[kk][f], M[f], ae);
+                    }
                     const float v = (__ldg(alpha + (int64_t)jsrc[kk] * (2 * H) + head) + ad) + ae;
                     sc[kk] = v > 0.f ? v : v * slope;
                     mx = fmaxf(mx, sc[kk]);

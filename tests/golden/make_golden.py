@@ -304,10 +304,38 @@ def make_native_fixture():
     print("native_case.npz:", len(grids), "grids")
 
 
+def make_model_bf16_fixtures():
+    """bf16 mode (BASELINE configs[4]): the reference has no reduced-precision path, so these vectors come from the ORACLE's
+    bf16-storage restatement (oracle/model_oracle.py::forward(bf16_storage=True)) on the same graphs / weights as two of the
+    fp32 model cases; the unmodified reference module's fp32 outputs are stored beside them, so the fixture also pins how far
+    bf16 storage moves the reference's results."""
+    cases = graph_cases()
+    blob = {}
+    for gname, F, seed, hidden, heads in [("g64_holes", 7, 0, 64, 4), ("g33_k24", 7, 4, 128, 4)]:
+        g, _ = run_ref_graph(cases[gname])
+        cfg = mo.ModelCfg(in_channels=F, hidden=hidden, heads=heads)
+        sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+        cls_b, conf_b = mo.calibrate_heads(sd, cfg, g.x, g.edge_index, g.edge_attr)
+        ref32 = ref_model(cfg, sd).predict(g, 0.85, 0.6)
+        out = mo.forward(sd, cfg, g.x.numpy(), g.edge_index.numpy(), g.edge_attr.numpy(), torch.float32, bf16_storage=True)
+        key = f"{gname}_s{seed}_h{hidden}x{heads}"
+        blob[key + "/cls_bias"], blob[key + "/conf_bias"] = cls_b.numpy(), conf_b.numpy()
+        blob[key + "/meta"] = np.array([F, seed, hidden, heads], np.int64)
+        blob[key + "/graph"] = np.array(gname)
+        for k in ("class_logits", "confidence", "correction", "predicted_class"):
+            blob[f"{key}/{k}"] = out[k].numpy()
+            blob[f"{key}/ref32/{k}"] = ref32[k].numpy()
+        print(key, "max |bf16-storage - reference fp32| logits",
+              float((out["class_logits"] - ref32["class_logits"]).abs().max()), "logit scale", float(ref32["class_logits"].abs().max()),
+              "label flips", int((out["predicted_class"] != ref32["predicted_class"]).sum()), "of", len(ref32["predicted_class"]))
+    np.savez_compressed(os.path.join(HERE, "model_bf16_cases.npz"), **blob)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["graph", "c1", "model", "stitch", "pipeline", "native"]
+    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native"]
     if "graph" in which: make_graph_fixtures()
     if "model" in which: make_model_fixtures()
+    if "model_bf16" in which: make_model_bf16_fixtures()
     if "stitch" in which: make_stitch_fixtures()
     if "pipeline" in which: make_pipeline_fixture()
     if "native" in which: make_native_fixture()

@@ -190,3 +190,38 @@ def test_radius2_tiled_aggregation_vs_csr_kernel(prec, hidden, heads, conn):
         assert np.isfinite(x).all()
         np.testing.assert_allclose(x, y, rtol=0, atol=tol * max(1.0, float(np.abs(y).max())), err_msg=k)
         assert np.median(np.abs(x - y)) <= 1e-6
+
+
+BZ = None
+
+
+def _bz():
+    global BZ
+    if BZ is None:
+        from tests import golden_io as gio
+        BZ = gio.load("model_bf16_cases.npz")
+    return BZ
+
+
+@pytest.mark.parametrize("key", ["g64_holes_s0_h64x4", "g33_k24_s4_h128x4"])
+def test_forward_bf16_vs_committed_golden(key):
+    """bf16 mode against the committed vectors of tests/golden/model_bf16_cases.npz (bf16-storage oracle + the UNMODIFIED
+    reference module's fp32 outputs on the same graph and weights; classification head gain 8, so logit bounds scale by 8)."""
+    import bathymetric_gnn_b200 as bg
+    from tests import golden_io as gio
+    z = _bz()
+    F, seed, hidden, heads = (int(v) for v in z[key + "/meta"])
+    c, _ = gio.graph_case(gio.load("graph_cases.npz"), str(z[key + "/graph"]))
+    cfg = mo.ModelCfg(in_channels=F, hidden=hidden, heads=heads)
+    sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+    sd["classification_head.mlp.3.bias"] = torch.from_numpy(z[key + "/cls_bias"])
+    sd["confidence_head.mlp.3.bias"] = torch.from_numpy(z[key + "/conf_bias"])
+    model = make_model(cfg, sd).set_precision("bf16")
+    g = bg.GraphBuilder(c["conn"]).build_graph(c["depth"], c["mask"], c["unc"], c["res"])
+    out = model.predict(g, 0.85, 0.6)
+    for k, gain in (("class_logits", 8.0), ("confidence", 1.0), ("correction", 1.0)):
+        v = out[k].cpu().numpy()
+        np.testing.assert_allclose(v, z[f"{key}/{k}"], rtol=0, atol=TIGHT_ATOL * gain, err_msg=k + " vs bf16-storage golden")
+        np.testing.assert_allclose(v, z[f"{key}/ref32/{k}"], rtol=0, atol=(5e-3 if k == "confidence" else BF16_ATOL * gain),
+                                   err_msg=k + " vs reference fp32 golden")
+    _labels_ok(out, z[key + "/class_logits"], z[key + "/predicted_class"], TIGHT_ATOL * 8.0)

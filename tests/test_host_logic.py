@@ -161,3 +161,15 @@ def test_dropin_packages_resolve_reference_imports():
             "assert BathymetricGNN.CLASS_NOISE == 2\nprint('ok')\n") % os.path.join(ROOT, "bathymetric-gnn_b200", "dropin")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_set_precision_validates_and_needs_no_gpu():
+    """BathymetricGNN.set_precision (additive; BASELINE configs[4] bf16 mode): host-side state only, bad names raise
+    ValueError like the reference's other string options (`Unknown connectivity`, graph_construction.py:88-89)."""
+    import bathymetric_gnn_b200 as bg
+    m = bg.BathymetricGNN(7)
+    assert m.precision == "fp32"
+    assert m.set_precision("bf16") is m and m.precision == "bf16"
+    with pytest.raises(ValueError):
+        m.set_precision("fp8")
+    assert m.set_precision("fp32").precision == "fp32"

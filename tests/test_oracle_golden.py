@@ -173,3 +173,26 @@ def test_pipeline_oracle_vs_reference():
     np.testing.assert_allclose(res["correction"], z["ref/correction"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(res["cleaned_depth"], z["ref/cleaned_depth"], rtol=1e-6, atol=1e-5)
     assert (res["cleaned_depth"] != depth).sum() > 100
+
+
+@pytest.mark.parametrize("key", ["g64_holes_s0_h64x4", "g33_k24_s4_h128x4"])
+def test_model_oracle_bf16_storage_vs_golden(key):
+    """The bf16-storage restatement (the checker of the CUDA bf16 mode) reproduces its committed vectors, and stays within
+    the stated bf16 bound of the UNMODIFIED reference module's fp32 outputs stored beside them (logit bounds x 8: these
+    fixtures use classification head gain 8).  Across machines torch's CPU matmul may sum in a different order, which can
+    move an activation over a bf16 rounding boundary: hence 5e-3, not 0."""
+    z = gio.load("model_bf16_cases.npz")
+    F, seed, hidden, heads = (int(v) for v in z[key + "/meta"])
+    c, _ = gio.graph_case(GZ, str(z[key + "/graph"]))
+    cfg = mo.ModelCfg(in_channels=F, hidden=hidden, heads=heads)
+    sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+    sd["classification_head.mlp.3.bias"] = torch.from_numpy(z[key + "/cls_bias"])
+    sd["confidence_head.mlp.3.bias"] = torch.from_numpy(z[key + "/conf_bias"])
+    g = go.build_graph(c["depth"], c["mask"], c["unc"], c["res"], connectivity=c["conn"])
+    out = mo.forward(sd, cfg, g["x"], g["edge_index"], g["edge_attr"], torch.float32, bf16_storage=True)
+    for k, gain in (("class_logits", 8.0), ("confidence", 1.0), ("correction", 1.0)):
+        np.testing.assert_allclose(out[k].numpy(), z[f"{key}/{k}"], rtol=0, atol=5e-3 * gain)
+        np.testing.assert_allclose(out[k].numpy(), z[f"{key}/ref32/{k}"], rtol=0, atol=(5e-3 if k == "confidence" else 2e-2 * gain))
+    # fp32 evaluation of the same oracle == the reference module's fp32 vectors (the restatement itself is unchanged)
+    o32 = mo.forward(sd, cfg, g["x"], g["edge_index"], g["edge_attr"], torch.float32)
+    np.testing.assert_allclose(o32["class_logits"].numpy(), z[key + "/ref32/class_logits"], rtol=1e-5, atol=2e-5)
