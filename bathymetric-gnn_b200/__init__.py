@@ -12,6 +12,6 @@ from .config import (Config, TileConfig, GraphConfig, ModelConfig, TrainingConfi
                      InferenceConfig, CORRECTION_NORM_FLOOR, CORRECTION_NORM_CAP)
 from .tiling import BathymetricGrid, Tile, TileSpec, TileManager, TileMerger  # noqa: F401
 from .pipeline import BathymetricPipeline, NpzLoader, NpzWriter  # noqa: F401
-from .native_vr import NativeVRProcessor, apply_results  # noqa: F401
+from .native_vr import NativeVRProcessor, SidecarBuilder, apply_results, apply_results_packed  # noqa: F401
 
 __version__ = "0.1.0"

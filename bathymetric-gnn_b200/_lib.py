@@ -51,6 +51,13 @@ class Survey(C.Structure):
                 ("n_cont", C.c_int32), ("discrete", C.c_void_p), ("tracker", C.c_void_p)]
 
 
+class Sidecar(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("classification", C.c_void_p), ("confidence", C.c_void_p),
+                ("correction", C.c_void_p), ("valid_mask", C.c_void_p), ("owner", C.c_void_p)]
+
+
+SIDECAR_DESC = 6
+
 # every symbol include/bgnn.h declares: name -> (restype, argtypes)
 P, I32, I64, F32, SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -76,6 +83,9 @@ SYMBOLS = {
     "bgnn_stitch_add_tile": (C.c_int, [C.POINTER(Survey), I64, I64, I32, I32, P, P, C.POINTER(P), P, P, P]),
     "bgnn_stitch_finalize": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_apply_corrections": (C.c_int, [P, P, I64, P, P, P, P, F32, P]),
+    "bgnn_vr_apply_results": (C.c_int, [P, P, I64, F32, P, P, P, F32, P, P, P, P, P]),
+    "bgnn_sidecar_init": (C.c_int, [C.POINTER(Sidecar), P]),
+    "bgnn_sidecar_add": (C.c_int, [C.POINTER(Sidecar), I32, P, P, I64, P, P, P, P, F32, P]),
     "bgnn_set_tensor_cores": (C.c_int, [C.c_int]),
     "bgnn_set_presplit": (C.c_int, [C.c_int]),
     "bgnn_test_proj_umma_presplit": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),

@@ -24,6 +24,7 @@ SOURCES = [
     ("error.cu", []),
     ("graph_build.cu", ["-fmad=false"]),
     ("stitch.cu", ["-fmad=false"]),
+    ("vr_post.cu", ["-fmad=false"]),
     ("gat_forward.cu", []),
     ("proj_umma.cu", []),
     ("proj_bf16.cu", []),

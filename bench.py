@@ -42,7 +42,7 @@ METRIC = "depth cells/sec (graph build+GNN fwd)"
 UNIT = "cells/s"
 
 SLOT_NAMES = {0: "gb_count", 1: "gb_scan", 2: "gb_ids", 3: "gb_emit", 4: "gb_coo", 10: "mlp0", 11: "mlp1",
-              60: "heads_gemm", 61: "heads_finish", 70: "scatter_tile"}
+              60: "heads_gemm", 61: "heads_finish", 70: "scatter_tile", 75: "vr_apply_results", 76: "sidecar_add"}
 for _l in range(16):
     SLOT_NAMES[20 + _l] = f"proj_l{_l}"
     SLOT_NAMES[40 + _l] = f"agg_l{_l}"
@@ -512,7 +512,7 @@ def run_ragged(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); nodes = one_pass(); ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    kernels = {}
+    kernels, post = {}, {}
     if rank == 0:                # per-kernel device time of ONE chunk (events inside the library)
         from bathymetric_gnn_b200._lib import lib
         lib.bgnn_profile_enable(1)
@@ -527,6 +527,7 @@ def run_ragged(args):
             k = SLOT_NAMES.get(int(s_), str(int(s_)))
             kernels[k] = round(kernels.get(k, 0.0) + float(m_), 4)
         kernels["chunk_nodes"] = g.num_nodes
+        post = vr_post_row(g, out, chunks[0], dev)
         del g, out
     if rank == 0:
         print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),

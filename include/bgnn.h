@@ -261,6 +261,45 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
                            float* classification, float* confidence, float* correction,
                            float* cleaned, float auto_correct_threshold, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Native VR-BAG post-processing on the packed ragged cell space (the step right behind the ragged
+ * path).  All arrays are DEVICE pointers over the packed cells of a batch of refinement grids (grid g occupies
+ * [cell_off[g], cell_off[g+1]) in row-major order, as built by bgnn_graph_count/emit with n_grids > 1).
+ * ------------------------------------------------------------------------------------------ */
+/* Replaces the `apply_results` closure of scripts/inference_native.py:480-503 for a whole batch:
+ *   valid = depth != nodata && isfinite(depth); noise = classification == 2 && valid; apply = noise && confidence >= thr (>=);
+ *   out_depth = apply ? depth - correction : depth;  out_uncertainty = apply ? uncertainty * (2 - confidence) : uncertainty.
+ * counts3 (optional, uint64 [3], ACCUMULATED: zero it first): cells corrected, cells classified noise, valid cells;
+ * confidence_sum (optional, f64, accumulated): sum of confidence over valid cells (stats of :499-502).
+ * uncertainty / out_uncertainty may both be NULL. */
+int bgnn_vr_apply_results(const float* depth, const float* uncertainty, int64_t n_cells, float nodata,
+                          const float* classification, const float* confidence, const float* correction,
+                          float auto_correct_threshold, float* out_depth, float* out_uncertainty,
+                          uint64_t* counts3, double* confidence_sum, void* stream);
+
+/* Sidecar raster of SidecarBuilder (data/vr_bag.py:608-632): three result planes (NaN-initialised), the valid mask and an
+ * owner plane (int32, sequence number of the grid that wrote the pixel last) that makes "later grids overwrite earlier
+ * ones" deterministic on the device. */
+typedef struct bgnn_sidecar {
+    int64_t  rows, cols;
+    float*   classification;    /* [dev] f32 [rows*cols] */
+    float*   confidence;
+    float*   correction;
+    float*   valid_mask;        /* 0 / 1 */
+    int32_t* owner;             /* [dev] int32 [rows*cols] */
+} bgnn_sidecar;
+int bgnn_sidecar_init(const bgnn_sidecar* sc, void* stream);
+/* Replaces SidecarBuilder.add_refinement_results (data/vr_bag.py:695-778) for a batch of grids: every refinement cell (r, c)
+ * of grid g is painted as a scale x scale block at raster row out_row_start + (rows-1-r)*scale (refinement rows run south to
+ * north), column out_col_start + c*scale, clipped to the raster; valid_mask is set where the cell is valid.
+ * desc: [dev] int32 [n_grids][BGNN_SIDECAR_DESC] = {rows, cols, out_row_start, out_col_start, scale, sequence number};
+ * the placement integers are computed by the host exactly as the reference does (float64, int(round(.)), :716-748);
+ * sequence numbers must increase in the reference's processing order across ALL calls on one raster. */
+#define BGNN_SIDECAR_DESC 6
+int bgnn_sidecar_add(const bgnn_sidecar* sc, int32_t n_grids, const int64_t* cell_off, const int32_t* desc, int64_t n_cells,
+                     const float* classification, const float* confidence, const float* correction,
+                     const float* depth, float nodata, void* stream);
+
 /* Tensor-core projections: on by default.  When on, every `x W^T` whose shape is compiled for the
  * tcgen05 path (N in {32,64,128,256}, K % 32 == 0) runs as a bf16x3-split GEMM with fp32 accumulation
  * in TMEM (fp32-grade accuracy); otherwise, or when switched off, the fp32 FMA GEMM is used. */
@@ -288,7 +327,8 @@ int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t*
  * launching stream around every kernel the library launches.  Not thread-safe; off by default.
  * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
  * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
- * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid.
+ * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid,
+ * 75 vr_apply_results, 76 sidecar_add.
  * ------------------------------------------------------------------------------------------ */
 int bgnn_profile_enable(int on);                               /* also clears recorded events */
 /* waits for the recorded events; fills up to `cap` (slot, milliseconds) pairs in launch order;

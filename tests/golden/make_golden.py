@@ -331,11 +331,38 @@ def make_model_bf16_fixtures():
     np.savez_compressed(os.path.join(HERE, "model_bf16_cases.npz"), **blob)
 
 
+def make_sidecar_fixture():
+    """Reference SidecarBuilder.add_refinement_results (data/vr_bag.py:695-778), UNMODIFIED, on a synthetic layout.  The object
+    is created without __init__ (its GDAL georeferencing step is file I/O); the state __init__ would set is set here."""
+    import importlib
+    vb = importlib.import_module("data.vr_bag")
+    geo, grids, results = synth.sidecar_scene()
+    sb = object.__new__(vb.SidecarBuilder)
+
+    class H:
+        base_shape = geo["base_shape"]
+    sb.handler = H()
+    sb.shape, sb.geotransform, sb.bounds = geo["shape"], geo["geotransform"], geo["bounds"]
+    sb.resolution = abs(sb.geotransform[1])
+    sb.classification = np.full(sb.shape, np.nan, dtype=np.float32)
+    sb.confidence = np.full(sb.shape, np.nan, dtype=np.float32)
+    sb.correction = np.full(sb.shape, np.nan, dtype=np.float32)
+    sb.valid_mask = np.zeros(sb.shape, dtype=np.float32)
+    for g, (cls, conf, corr) in zip(grids, results):
+        sb.add_refinement_results(vb.RefinementGrid(**g), cls, conf, corr)
+    blob = dict(classification=sb.classification, confidence=sb.confidence, correction=sb.correction, valid_mask=sb.valid_mask,
+                seed=np.int64(5), n=np.int64(len(grids)))
+    np.savez_compressed(os.path.join(HERE, "sidecar_case.npz"), **blob)
+    print("sidecar_case.npz: painted pixels", int(np.isfinite(sb.classification).sum()), "of", sb.classification.size,
+          "valid", int(sb.valid_mask.sum()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native"]
+    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar"]
     if "graph" in which: make_graph_fixtures()
     if "model" in which: make_model_fixtures()
     if "model_bf16" in which: make_model_bf16_fixtures()
+    if "sidecar" in which: make_sidecar_fixture()
     if "stitch" in which: make_stitch_fixtures()
     if "pipeline" in which: make_pipeline_fixture()
     if "native" in which: make_native_fixture()

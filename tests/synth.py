@@ -74,3 +74,37 @@ def ragged_grids(n: int, seed: int = 7, lo: int = 3, hi: int = 50, nodata: float
         u = (0.1 + 0.05 * rng.random((r, c))).astype(np.float32)
         out.append((d, u, (res, res)))
     return out
+
+
+def sidecar_scene(seed=5, n=60):
+    """A synthetic VR-BAG layout: 6 x 8 base cells of 16 m, raster at 0.5 m (192 x 256), refinement grids at 0.5 / 1 / 2 / 4 m
+    sitting at sw_corner offsets inside their base cell; a few grids deliberately spill over their base cell (overlap with the
+    neighbour: later grids overwrite) and over the raster edge (clipping)."""
+    rng = np.random.default_rng(seed)
+    base_shape, cell = (6, 8), 16.0
+    bounds = (1000.0, 5000.0, 1000.0 + base_shape[1] * cell, 5000.0 + base_shape[0] * cell)
+    res = 0.5
+    shape = (int(round((bounds[3] - bounds[1]) / res)), int(round((bounds[2] - bounds[0]) / res)))
+    gt = (bounds[0], res, 0.0, bounds[3], 0.0, -res)
+    grids = []
+    for i in range(n):
+        r = float(rng.choice([0.5, 1.0, 2.0, 4.0]))
+        rows, cols = int(rng.integers(2, int(cell / r) + (4 if i % 7 == 0 else 1))), int(rng.integers(2, int(cell / r) + (4 if i % 5 == 0 else 1)))
+        br, bc = int(rng.integers(0, base_shape[0])), int(rng.integers(0, base_shape[1]))
+        sw = (float(rng.integers(0, 4)) * r, float(rng.integers(0, 4)) * r)
+        d = (20.0 + rng.normal(0, 0.3, size=(rows, cols))).astype(np.float32)
+        d[rng.random((rows, cols)) < 0.15] = 1.0e6
+        if i % 11 == 0:
+            d[0, 0] = np.nan
+        u = (0.1 + 0.05 * rng.random((rows, cols))).astype(np.float32)
+        grids.append(dict(base_row=br, base_col=bc, depth=d, uncertainty=u, resolution=(r, r), dimensions=(rows, cols),
+                          sw_corner=sw, start_index=i))
+    results = []
+    for g in grids:
+        rows, cols = g["dimensions"]
+        cls = rng.integers(0, 3, size=(rows, cols)).astype(np.float32)
+        conf = rng.random((rows, cols)).astype(np.float32)
+        conf[rng.random((rows, cols)) < 0.1] = np.float32(0.85)          # exactly on the >= threshold
+        corr = rng.normal(0, 0.5, size=(rows, cols)).astype(np.float32)
+        results.append((cls, conf, corr))
+    return dict(shape=shape, geotransform=gt, bounds=bounds, base_shape=base_shape), grids, results

@@ -196,3 +196,46 @@ def test_model_oracle_bf16_storage_vs_golden(key):
     # fp32 evaluation of the same oracle == the reference module's fp32 vectors (the restatement itself is unchanged)
     o32 = mo.forward(sd, cfg, g["x"], g["edge_index"], g["edge_attr"], torch.float32)
     np.testing.assert_allclose(o32["class_logits"].numpy(), z[key + "/ref32/class_logits"], rtol=1e-5, atol=2e-5)
+
+
+class _Grid:
+    """Attribute bag with the RefinementGrid surface (data/vr_bag.py:66-97) the sidecar code reads."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def valid_mask(self):
+        return (self.depth != 1.0e6) & np.isfinite(self.depth)
+
+
+def test_sidecar_oracle_bit_exact_vs_reference():
+    """oracle/vr_post_oracle.py::SidecarOracle == the UNMODIFIED reference SidecarBuilder.add_refinement_results on the
+    committed scene (overlapping grids, raster-edge clipping, NaN / nodata cells): all four planes bit for bit."""
+    from oracle import vr_post_oracle as vo
+    z = gio.load("sidecar_case.npz")
+    geo, grids, results = synth.sidecar_scene()
+    sc = vo.SidecarOracle(**geo)
+    for g, (cls, conf, corr) in zip(grids, results):
+        sc.add_refinement_results(_Grid(**g), cls, conf, corr)
+    for k in ("classification", "confidence", "correction", "valid_mask"):
+        assert np.array_equal(getattr(sc, k), z[k], equal_nan=True), k
+    assert np.isnan(z["classification"]).any() and (z["valid_mask"] == 1).any()
+
+
+def test_vr_apply_results_oracle_properties():
+    """apply_results restatement (inference_native.py:480-503): untouched outside the apply mask, `>=` threshold, fp32 ops."""
+    from oracle import vr_post_oracle as vo
+    _, grids, results = synth.sidecar_scene()
+    n_apply = 0
+    for g, (cls, conf, corr) in zip(grids, results):
+        cd, cu, st = vo.apply_results(g["depth"], g["uncertainty"], cls, conf, corr, 0.85)
+        v = vo.valid_mask(g["depth"])
+        m = (cls == 2) & v & (conf >= np.float32(0.85))
+        assert st["cells_corrected"] == int(m.sum()) and st["cells_processed"] == int(v.sum())
+        assert np.array_equal(cd[~m], g["depth"][~m], equal_nan=True) and np.array_equal(cu[~m], g["uncertainty"][~m])
+        assert np.array_equal(cd[m], g["depth"][m] - corr[m]) and np.array_equal(cu[m], g["uncertainty"][m] * (np.float32(2.0) - conf[m]))
+        assert cd.dtype == np.float32 and cu.dtype == np.float32
+        n_apply += int(m.sum())
+        assert ((conf == np.float32(0.85)) & (cls == 2) & v).sum() == ((conf == np.float32(0.85)) & m).sum()
+    assert n_apply > 50
