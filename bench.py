@@ -535,7 +535,60 @@ def run_ragged(args):
                           "config": {"workload": f"configs[3]: {args.grids} refinement grids, sides U{{3..50}}, 10% nodata, "
                                                  f"{len(chunks)} ragged chunks of <= {args.chunk_cells} cells per rank",
                                      "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"},
-                          "kernels_ms_one_chunk": kernels}))
+                          "kernels_ms_one_chunk": kernels, "vr_post_one_chunk": post}))
+
+
+def vr_post_row(g, out, chunk, dev):
+    """SURVEY.md 8(f) rank 2 on one ragged chunk: results scattered into the packed cell space, then `apply_results`
+    (scripts/inference_native.py:480-503) and the sidecar rasterisation (data/vr_bag.py:695-778) as device kernels, timed by
+    the library's events; beside it the CPU oracle port of the same two steps on the first 300 grids (the reference's own
+    sidecar loop is a 4-deep Python loop, far slower than this vectorised port)."""
+    import types
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200._lib import lib, check, ptr, stream_ptr
+    from bathymetric_gnn_b200.config import CORRECTION_NORM_FLOOR
+    d, off, rows, cols, res2 = chunk
+    dg = g._dev
+    n = int(off[-1]); G = len(rows)
+    planes = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    check(lib.bgnn_scatter_tile(ptr(dg.node_id), n, ptr(out["predicted_class"]), ptr(out["confidence"]), ptr(out["correction"]),
+                                ptr(dg.local_std), float(CORRECTION_NORM_FLOOR), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]),
+                                stream_ptr()))
+    unc = torch.full((n,), 0.1, dtype=torch.float32, device=dev)
+    side = int(np.ceil(np.sqrt(G)))                       # one base cell of 50 x 50 raster pixels per grid, raster at 0.5 m
+    geo = dict(shape=(side * 50, side * 50), geotransform=(0.0, 0.5, 0.0, side * 25.0, 0.0, -0.5), bounds=(0.0, 0.0, side * 25.0, side * 25.0),
+               base_shape=(side, side))
+    grids = [types.SimpleNamespace(base_row=i // side, base_col=i % side, sw_corner=(0.0, 0.0), dimensions=(int(rows[i]), int(cols[i])),
+                                   resolution=(0.5, 0.5)) for i in range(G)]
+    sb = bg.SidecarBuilder(**geo, device=dev)
+    torch.cuda.synchronize()
+    lib.bgnn_profile_enable(1)
+    od, ou, st = bg.apply_results_packed(d, unc, planes[0], planes[1], planes[2], 0.85)
+    sb.add_batch(grids, off, d, planes[0], planes[1], planes[2])
+    torch.cuda.synchronize()
+    k = lib.bgnn_profile_collect(0, None, None)
+    slots = (C.c_int32 * k)(); tms = (C.c_float * k)()
+    lib.bgnn_profile_collect(k, slots, tms)
+    lib.bgnn_profile_enable(0)
+    ms = {SLOT_NAMES.get(int(s_), str(int(s_))): round(float(m_), 4) for s_, m_ in zip(slots, tms)}
+    # CPU port on a bounded sample
+    from oracle import vr_post_oracle as vo
+    ns = min(300, G)
+    hp = planes[:, :int(off[ns])].cpu().numpy(); hd = d[:int(off[ns])].cpu().numpy(); hu = unc[:int(off[ns])].cpu().numpy()
+    so = vo.SidecarOracle(**geo)
+    t0 = time.perf_counter()
+    for i in range(ns):
+        sl = slice(int(off[i]), int(off[i + 1])); shp = (int(rows[i]), int(cols[i]))
+        gd = hd[sl].reshape(shp)
+        vo.apply_results(gd, hu[sl].reshape(shp), hp[0, sl].reshape(shp), hp[1, sl].reshape(shp), hp[2, sl].reshape(shp), 0.85)
+        grids[i].depth = gd
+        grids[i].valid_mask = vo.valid_mask(gd)
+        so.add_refinement_results(grids[i], hp[0, sl].reshape(shp), hp[1, sl].reshape(shp), hp[2, sl].reshape(shp))
+    cpu_s = time.perf_counter() - t0
+    gpu_ms = sum(ms.values())
+    return {"cells": n, "grids": G, "device_ms": ms, "cells_per_s_device": n / (gpu_ms * 1e-3) if gpu_ms > 0 else None,
+            "alg_bytes": n * 28 + n * 48, "cells_corrected": st["cells_corrected"],
+            "cpu_port": {"grids": ns, "cells": int(off[ns]), "seconds": round(cpu_s, 4), "cells_per_s": int(off[ns]) / cpu_s, "cores": 1}}
 
 
 def run_wide(args):

@@ -113,8 +113,8 @@ def test_forward_bf16_wide_variant_k24_hidden128():
 
 @pytest.mark.parametrize("conn,hidden,heads", [("8-connected", 64, 4), ("4-connected", 64, 2), ("8-connected", 32, 4)])
 def test_forward_bf16_default_shapes(conn, hidden, heads):
-    """bf16 mode on the default model (hidden 64 x 4 heads) and on shapes without a bf16 tensor-core kernel
-    (hidden 32: FMA GEMM on bf16 operands), holes in the grid."""
+    """bf16 mode on the default model (hidden 64 x 4 heads), with 2 heads on a 4-connected grid, and at hidden 32 (32-channel
+    heads: four heads per 128-column block of the bf16 tensor-core projection), holes in the grid."""
     import bathymetric_gnn_b200 as bg
     d = synth.noisy_tile(90, 70, seed=3)
     mask = synth.blob_mask(90, 70, seed=3, invalid_frac=0.06)
