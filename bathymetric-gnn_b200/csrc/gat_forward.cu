@@ -1331,15 +1331,8 @@ gat_aggregate_tile5(const float* __restrict__ h_, const float* __restrict__ alph
                 sc[kk] = -CUDART_INF_F;
                 if (jsrc[kk] >= 0) {
                     float ae = 0.f;
-                    if constexpr (FULL5) {       // the window variant needs the registers: edge features are re-read per head (L1 hits)
-                        const int k = 2 * kk + half;
-                        const int e = start + __popc(vmask & ((1u << k) - 1u));
 #pragma unroll
-                        for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(f < ED ? __ldg(eattr + (int64_t)e * ED + f) : 0.f, M[f], ae);
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(ea[kk][f], M[f], ae);
-                    }
+                    for (int f = 0; f < BGNN_MAX_EDGE_FEATS; ++f) ae = fmaf(ea[kk][f], M[f], ae);
                     const float v = (__ldg(alpha + (int64_t)jsrc[kk] * (2 * H) + head) + ad) + ae;
                     sc[kk] = v > 0.f ? v : v * slope;
                     mx = fmaxf(mx, sc[kk]);

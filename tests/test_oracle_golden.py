@@ -239,3 +239,54 @@ def test_vr_apply_results_oracle_properties():
         n_apply += int(m.sum())
         assert ((conf == np.float32(0.85)) & (cls == 2) & v).sum() == ((conf == np.float32(0.85)) & m).sum()
     assert n_apply > 50
+
+
+def test_gat_layer_vs_independent_dense_formulation():
+    """Second opinion on the restated GATConv (PyG is absent, so the attention arithmetic cannot be pinned to it): the same
+    layer written INDEPENDENTLY as dense [N, N] attention in fp64 -- Velickovic et al. 2018, eq. (1)-(4), plus PyG's
+    documented edge term a_e^T (W_e e_ij) and `add_self_loops(fill_value='mean')` -- shares no code with
+    oracle/pyg_restated.py (no scatter / index_add / segment softmax).  Agreement to fp64 round-off on a graph with holes,
+    an isolated node and asymmetric edge attributes."""
+    torch.manual_seed(3)
+    N, Fin, H, C, ED = 37, 10, 3, 8, 3
+    x = torch.randn(N, Fin, dtype=torch.float64)
+    dense = (torch.rand(N, N) < 0.15)
+    dense.fill_diagonal_(False)
+    dense[:, 5] = False                                          # node 5 has no out-edges ...
+    dense[5, :] = False                                          # ... and no in-edges: only its self loop, loop attribute 0
+    src, dst = dense.nonzero(as_tuple=True)                      # edge j -> i stored as dense[j, i]
+    ei = torch.stack([src, dst])
+    ea = torch.randn(ei.shape[1], ED, dtype=torch.float64)
+    sd = {}
+    p = "gnn.convs.0."
+    sd[p + "lin.weight"] = torch.randn(H * C, Fin, dtype=torch.float64) * 0.3
+    sd[p + "att_src"] = torch.randn(1, H, C, dtype=torch.float64)
+    sd[p + "att_dst"] = torch.randn(1, H, C, dtype=torch.float64)
+    sd[p + "lin_edge.weight"] = torch.randn(H * C, ED, dtype=torch.float64) * 0.3
+    sd[p + "att_edge"] = torch.randn(1, H, C, dtype=torch.float64)
+    sd[p + "bias"] = torch.randn(H * C, dtype=torch.float64)
+    got = mo.gat_layer(sd, 0, x, ei, ea, H, C, True)
+    # ---- dense formulation
+    h = (x @ sd[p + "lin.weight"].T).view(N, H, C)
+    a_s = torch.einsum("nhc,hc->nh", h, sd[p + "att_src"][0])
+    a_d = torch.einsum("nhc,hc->nh", h, sd[p + "att_dst"][0])
+    E = torch.zeros(N, N, ED, dtype=torch.float64)
+    E[src, dst] = ea
+    deg = dense.sum(0)                                           # in-degree of i
+    loop_attr = torch.where(deg[:, None] > 0, E.sum(0) / deg.clamp(min=1)[:, None], torch.zeros(N, ED, dtype=torch.float64))
+    A = dense.clone()
+    idx = torch.arange(N)
+    A[idx, idx] = True
+    E[idx, idx] = loop_attr
+    We = sd[p + "lin_edge.weight"].view(H, C, ED)
+    m_e = torch.einsum("hcd,hc->hd", We, sd[p + "att_edge"][0])               # a_e^T W_e as one [H, ED] map
+    a_e = torch.einsum("jid,hd->jih", E, m_e)
+    score = torch.nn.functional.leaky_relu(a_s[:, None, :] + a_d[None, :, :] + a_e, 0.2)      # [j, i, h]
+    score = score.masked_fill(~A[:, :, None], float("-inf"))
+    att = torch.softmax(score, dim=0)                                          # over sources j of target i
+    want = torch.einsum("jih,jhc->ihc", att, h).reshape(N, H * C) + sd[p + "bias"]
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-12, atol=1e-12)
+    # mean over heads (the last layer's concat=False)
+    got_m = mo.gat_layer({**sd, p + "bias": sd[p + "bias"][:C]}, 0, x, ei, ea, H, C, False)
+    want_m = torch.einsum("jih,jhc->ihc", att, h).mean(1) + sd[p + "bias"][:C]
+    np.testing.assert_allclose(got_m.numpy(), want_m.numpy(), rtol=1e-12, atol=1e-12)
