@@ -80,11 +80,14 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start streaming BEFORE the warm-up: nvidia-smi needs 0.1-1 s to print its first row, longer than a short timed
+        region; rows are time-stamped on arrival and only those inside [begin(), end()] are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -93,19 +96,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.end()
+        time.sleep(0.1)                       # rows sampled inside the window may still be in the pipe
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for (t, r) in self.rows if t0 <= t <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside:                        # region shorter than the sampling period: fall back to the rows under load around it
+            inside = [r for (t, r) in self.rows if t0 - 0.25 <= t <= self.t1 + 0.1]
+            window = "timed region +- 0.25 s (GPU under the same load: warm-up steps)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -114,7 +131,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "rows_total": len(self.rows)}
 
 
 def ncu_traffic(slot_name):
@@ -212,22 +229,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         g, out = step_resident()
     N, E = g.num_nodes, g.num_edges
     del g, out
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if rank == 0 and sampler.proc is not None:      # keep the GPU under the same load until nvidia-smi streams (<= 3 s, untimed)
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            g, out = step_resident()
+            del g, out
+            torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     ev0.record()
     for _ in range(args.steps):
         g, out = step_resident()
         del g, out
     ev1.record()
     barrier()
+    sampler.end()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
