@@ -225,3 +225,33 @@ def test_forward_bf16_vs_committed_golden(key):
         np.testing.assert_allclose(v, z[f"{key}/ref32/{k}"], rtol=0, atol=(5e-3 if k == "confidence" else BF16_ATOL * gain),
                                    err_msg=k + " vs reference fp32 golden")
     _labels_ok(out, z[key + "/class_logits"], z[key + "/predicted_class"], TIGHT_ATOL * 8.0)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 2), (1, 6), (6, 1), (3, 7), (9, 17), (16, 33)])
+def test_wide_variant_tiny_and_ragged_edge_grids(prec, shape):
+    """5x5 stencil on grids smaller than the stencil / the 8 x 16 patch, single-row and single-column grids and sizes one past
+    a patch boundary: radius-2 tiled kernel vs the oracle (fp32 tolerance; bf16: vs the bf16-storage oracle)."""
+    import bathymetric_gnn_b200 as bg
+    r, c = shape
+    d = synth.noisy_tile(max(r, 2), max(c, 2), seed=r * 31 + c)[:r, :c].copy()
+    mask = np.ones((r, c), bool)
+    if r * c > 8:
+        mask[r // 2, c // 2] = False
+    cfg = mo.ModelCfg(in_channels=7, hidden=128)
+    sd = mo.init_state_dict(cfg, seed=6, randomize_bn=True, head_gain=1.0)
+    try:
+        og = go.build_graph(d, mask, None, (0.5, 0.5), connectivity="24-connected")
+    except ValueError:
+        # np.gradient needs >= 2 samples per axis: the reference raises for 1 x n grids (graph_construction.py:284); so do we
+        with pytest.raises(ValueError):
+            bg.GraphBuilder("24-connected").build_graph(d, mask, None, (0.5, 0.5))
+        return
+    model = make_model(cfg, sd).set_precision(prec)
+    g = bg.GraphBuilder("24-connected").build_graph(d, mask, None, (0.5, 0.5))
+    assert np.array_equal(g.edge_index.cpu().numpy(), og["edge_index"])
+    out = model.predict(g)
+    ref = mo.forward(sd, cfg, g.x.cpu().numpy(), og["edge_index"], og["edge_attr"], torch.float32, bf16_storage=(prec == "bf16"))
+    tol = dict(rtol=1e-5, atol=2e-5) if prec == "fp32" else dict(rtol=0, atol=TIGHT_ATOL)
+    for k in ("class_logits", "confidence", "correction"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), err_msg=k, **tol)
