@@ -186,3 +186,22 @@ def coo_to_in_csr(edge_index: np.ndarray, edge_attr: np.ndarray, num_nodes: int)
     rowptr = np.zeros(num_nodes + 1, np.int64)
     np.add.at(rowptr, edge_index[1] + 1, 1)
     return np.cumsum(rowptr), edge_index[0][order], edge_attr[order], order
+
+
+def build_multiscale_graph(depth, valid_mask=None, uncertainty=None, resolution=(1.0, 1.0), scales=(1, 2, 4), **kw):
+    """MultiScaleGraphBuilder.build_multiscale_graph, graph_construction.py:508-607: {scale: build_graph dict}.  The block
+    reductions are the reference's own NumPy calls (np.nanmean / np.mean over the [h/s, s, w/s, s] view)."""
+    if valid_mask is None:
+        valid_mask = np.isfinite(depth)
+    out = {}
+    for s in sorted(scales):
+        if s == 1:
+            d, m, u, res = depth, valid_mask, uncertainty, resolution
+        else:
+            blk = lambda a: a[:a.shape[0] // s * s, :a.shape[1] // s * s].reshape(a.shape[0] // s, s, a.shape[1] // s, s)
+            d = np.nanmean(blk(depth), axis=(1, 3))                                   # :582-594
+            m = np.mean(blk(valid_mask), axis=(1, 3)) >= 0.5                          # :596-606
+            u = np.nanmean(blk(uncertainty), axis=(1, 3)) if uncertainty is not None else None
+            res = (resolution[0] * s, resolution[1] * s)
+        out[s] = build_graph(d, m, u, res, **kw)
+    return out

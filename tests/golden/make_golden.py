@@ -331,6 +331,22 @@ def make_model_bf16_fixtures():
     np.savez_compressed(os.path.join(HERE, "model_bf16_cases.npz"), **blob)
 
 
+def make_multiscale_fixture():
+    """Reference MultiScaleGraphBuilder (data/graph_construction.py:508-607), UNMODIFIED: scales 1 / 2 / 4 of a 37 x 50 grid
+    with holes (NaN-marked in the depth, so nanmean has work to do) and an uncertainty plane."""
+    d, m, u = synth.multiscale_case()
+    b = ref_gc.MultiScaleGraphBuilder(scales=[4, 1, 2], connectivity="8-connected")
+    graphs = b.build_multiscale_graph(d, m, u, (0.5, 1.0))
+    blob = {}
+    for s, g in graphs.items():
+        for k in ("x", "edge_index", "edge_attr", "pos", "valid_rows", "valid_cols", "local_std"):
+            blob[f"s{s}/{k}"] = getattr(g, k).numpy()
+        blob[f"s{s}/grid_shape"] = np.array(g.grid_shape, np.int64)
+        blob[f"s{s}/num_valid_cells"] = np.int64(g.num_valid_cells)
+        print("scale", s, "nodes", g.num_nodes, "edges", g.edge_index.shape[1], "grid", g.grid_shape)
+    np.savez_compressed(os.path.join(HERE, "multiscale_case.npz"), **blob)
+
+
 def make_sidecar_fixture():
     """Reference SidecarBuilder.add_refinement_results (data/vr_bag.py:695-778), UNMODIFIED, on a synthetic layout.  The object
     is created without __init__ (its GDAL georeferencing step is file I/O); the state __init__ would set is set here."""
@@ -358,11 +374,12 @@ def make_sidecar_fixture():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar"]
+    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar", "multiscale"]
     if "graph" in which: make_graph_fixtures()
     if "model" in which: make_model_fixtures()
     if "model_bf16" in which: make_model_bf16_fixtures()
     if "sidecar" in which: make_sidecar_fixture()
+    if "multiscale" in which: make_multiscale_fixture()
     if "stitch" in which: make_stitch_fixtures()
     if "pipeline" in which: make_pipeline_fixture()
     if "native" in which: make_native_fixture()

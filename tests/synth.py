@@ -108,3 +108,16 @@ def sidecar_scene(seed=5, n=60):
         corr = rng.normal(0, 0.5, size=(rows, cols)).astype(np.float32)
         results.append((cls, conf, corr))
     return dict(shape=shape, geotransform=gt, bounds=bounds, base_shape=base_shape), grids, results
+
+
+def multiscale_case(seed=21):
+    """37 x 50 grid (not a multiple of 2 or 4: the crop of the block reduction is exercised), ~12 % holes marked NaN in the
+    depth AND False in the mask, uncertainty plane."""
+    rng = np.random.default_rng(seed)
+    d = noisy_tile(37, 50, seed=seed)
+    m = rng.random((37, 50)) > 0.12
+    m[10:14, 20:27] = False
+    d = d.copy()
+    d[~m] = np.nan
+    u = (0.1 + 0.05 * rng.random((37, 50))).astype(np.float32)
+    return d, m, u

@@ -221,3 +221,22 @@ def test_packed_ragged_entry_equals_batch():
     assert ga.num_nodes == gb.num_nodes and ga.num_edges == gb.num_edges
     for k in ("x", "edge_index", "edge_attr", "local_std", "valid_rows", "valid_cols"):
         assert torch.equal(getattr(ga, k), getattr(gb, k)), k
+
+
+def test_multiscale_graph_builder_vs_reference_golden():
+    """MultiScaleGraphBuilder drop-in (graph_construction.py:508-607): host block reduction with the reference's NumPy calls,
+    device graph build per scale -- against the golden Data fields of the unmodified reference (same tolerances as a tile)."""
+    import warnings
+    import bathymetric_gnn_b200 as bg
+    z = gio.load("multiscale_case.npz")
+    d, m, u = synth.multiscale_case()
+    b = bg.MultiScaleGraphBuilder(scales=[4, 1, 2], connectivity="8-connected")
+    assert b.scales == [1, 2, 4]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        graphs = b.build_multiscale_graph(d, m, u, (0.5, 1.0))
+    assert sorted(graphs) == [1, 2, 4]
+    for s, g in graphs.items():
+        ref = {k: z[f"s{s}/{k}"] for k in ("x", "edge_index", "edge_attr", "pos", "valid_rows", "valid_cols", "local_std")}
+        ref["grid_shape"], ref["num_valid_cells"] = tuple(z[f"s{s}/grid_shape"]), z[f"s{s}/num_valid_cells"]
+        check_graph(g, ref, None, has_holes=True)

@@ -290,3 +290,19 @@ def test_gat_layer_vs_independent_dense_formulation():
     got_m = mo.gat_layer({**sd, p + "bias": sd[p + "bias"][:C]}, 0, x, ei, ea, H, C, False)
     want_m = torch.einsum("jih,jhc->ihc", att, h).mean(1) + sd[p + "bias"][:C]
     np.testing.assert_allclose(got_m.numpy(), want_m.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_multiscale_oracle_bit_exact_vs_reference():
+    """graph_oracle.build_multiscale_graph == the UNMODIFIED reference MultiScaleGraphBuilder (scales 1 / 2 / 4, cropped
+    block means with NaN holes, majority mask, scaled resolution): every Data field bit for bit."""
+    import warnings
+    z = gio.load("multiscale_case.npz")
+    d, m, u = synth.multiscale_case()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)          # nanmean of an all-NaN block, as in the reference
+        graphs = go.build_multiscale_graph(d, m, u, (0.5, 1.0), scales=(4, 1, 2))
+    assert sorted(graphs) == [1, 2, 4]
+    for s, g in graphs.items():
+        for k in ("x", "edge_index", "edge_attr", "pos", "valid_rows", "valid_cols", "local_std"):
+            assert np.array_equal(g[k], z[f"s{s}/{k}"], equal_nan=True), (s, k)
+        assert tuple(g["grid_shape"]) == tuple(z[f"s{s}/grid_shape"]) and int(g["num_valid_cells"]) == int(z[f"s{s}/num_valid_cells"])
