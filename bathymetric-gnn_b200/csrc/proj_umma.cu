@@ -121,6 +121,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// arrive on the barrier at the same shared-memory offset in every CTA of `mask` when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -271,6 +279,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     const int64_t st_first = NH > 1 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
     const int64_t st_step = NH > 1 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
     const int cg0 = nh * N;                                    // first global output column of this CTA
+    // 2-CTA cluster with multicast A (PM_SPLIT pairs): a stage is free when BOTH CTAs' MMAs have retired (empty count 2)
+    const bool mc = (PMODE == PM_SPLIT && NH == 2) && P.mc != 0;
 
     // power-of-two operand scale from the upper bound of max|A|: |a * sA| < 1 (exact; undone in the epilogue)
     float sA = 1.f, out_scale = P.w_inv_scale;
@@ -286,7 +296,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     }
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PMODE == PM_SPLIT ? 1 : PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars[BAR_FULL + s], PMODE == PM_SPLIT ? 1 : PROD_GROUP_THREADS); mbar_init(&bars[BAR_EMPTY + s], mc ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bars[BAR_TFULL + a], 1); mbar_init(&bars[BAR_TEMPTY + a], 4 * 32 * S::EPI_SPLIT); }
         for (int r = 0; r < MAX_RAW; ++r) { mbar_init(&bars[BAR_RFULL + r], 1); mbar_init(&bars[BAR_REMPTY + r], PROD_GROUP_THREADS); }
         for (int w = 0; w < NW; ++w) { mbar_init(&bars[BAR_WFULL + w], 1); mbar_init(&bars[BAR_WEMPTY + w], 1); }
@@ -329,6 +339,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
+    if (mc) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast to them
 
     if (warp >= PROD_WARP0) {
         if constexpr (PMODE != PM_SPLIT) {          // (PM_SPLIT: the operand arrives already split, the TMA fills the stages)
@@ -446,6 +457,18 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     const uint32_t bar = smem_u32(&bars[BAR_FULL + sidx]);
                     const uint32_t dst = smem_u32(base + (size_t)sidx * S::STAGE_BYTES);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)S::STAGE_BYTES) : "memory");
+                    if (mc) {
+                        // this CTA fetches ONE plane (rank 0: hi, rank 1: lo) and multicasts it to the same stage of both CTAs;
+                        // each CTA's full barrier collects the bytes of both planes
+                        const uint16_t both = 3;
+                        if (nh == 0)
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n"
+                                         ::"r"(dst), "l"(&tmapA), "r"(kc * KC), "r"(row0), "r"(bar), "h"(both) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n"
+                                         ::"r"(dst + (uint32_t)(MT * A_TILE_BYTES)), "l"(&tmapA2), "r"(kc * KC), "r"(row0), "r"(bar), "h"(both) : "memory");
+                        continue;
+                    }
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
                                  ::"r"(dst), "l"(&tmapA), "r"(kc * KC), "r"(row0), "r"(bar) : "memory");
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
@@ -545,7 +568,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                             }
                         }
                     }
-                    umma_commit(&bars[BAR_EMPTY + s]);                 // A stage and W slot free when these MMAs retire
+                    if (mc) umma_commit_mc(&bars[BAR_EMPTY + s], 3);   // ... in BOTH CTAs of the pair (either may refill the stage)
+                    else umma_commit(&bars[BAR_EMPTY + s]);            // A stage and W slot free when these MMAs retire
                     if (NH == 1) umma_commit(&bars[BAR_WEMPTY + w]);
                     UT_TICK(2);
                 }
@@ -779,6 +803,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
     }
+    if (mc) cluster_sync_all();          // no CTA leaves while its peer may still arrive on its barriers
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -888,6 +913,20 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
     if (NH > 1) {                                   // pairs of CTAs (one per column block) share the M tiles
         const int64_t pairs = n_super < sms / 2 ? n_super : sms / 2;
         grid = (unsigned)(2 * (pairs > 0 ? pairs : 1));
+    }
+    static const bool mc_env = getenv("BGNN_NO_MULTICAST") == nullptr;        // on by default (A/B: tools/ab_mc.sh)
+    if (PMODE == PM_SPLIT && NH == 2 && mc_env) {
+        UmmaArgs am = a;
+        am.mc = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = S::BYTES; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t el = cudaLaunchKernelEx(&cfg, kern, am, tmap, tmap2, tmapC);
+        if (el != cudaSuccess) { bgnn_set_error("cluster launch of proj_umma_kernel failed: %s", cudaGetErrorString(el)); return BGNN_E_CUDA; }
+        return BGNN_OK;
     }
     kern<<<grid, UM_THREADS, S::BYTES, s>>>(a, tmap, tmap2, tmapC);
     const cudaError_t e = cudaGetLastError();

@@ -22,6 +22,8 @@ struct UmmaArgs {
     // EM_PROJ: Cout [M,N] (+ bias [N], optional); alpha (optional) [M, 2*Htot] from att_src / att_dst [N]
     float* Cout; const float* bias; const float* att_src; const float* att_dst; float* alpha; int Htot; int CH;
     int head_major;           // EM_PROJ: store C as [Htot][M][CH] (one contiguous plane per head) instead of [M][N]
+    int mc;                   // set by launch_umma: the CTA pair of an N = 256 PM_SPLIT launch runs as a 2-CTA cluster and each CTA
+                              // multicasts one fp16 plane of every A chunk to both (A crosses HBM / L2 once per pair)
     // EM_HEADS: W = concatenated first layers [nblk*h2 (zero padded to N), K]; hb0 their biases; second layers below
     const float* hb0; int h2, nblk, ncls;
     const float *Wcls, *bcls, *Wconf, *bconf, *Wcorr, *bcorr;
