@@ -85,7 +85,10 @@ constexpr int BM = 128, BK = 16, GEMM_THREADS = 256, PAD = 4;
 enum { IO_F32 = 0, IO_F32_BF16 = 1, IO_BF16 = 2, IO_BF16_F32 = 3 };
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t b) { return __uint_as_float(b << 16); }
 __device__ __forceinline__ uint32_t f32_to_bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) { return f32_to_bf16_bits(a) | (f32_to_bf16_bits(b) << 16); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // one packed convert, a in the low half
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 template <int BN, int CH, bool ALPHA, int IO = IO_F32>
 __global__ void __launch_bounds__(GEMM_THREADS)

@@ -12,9 +12,9 @@
 //   (320 threads since the epilogue runs as two groups of four warps, see below)
 //   warp 0 (one thread)  TMA producer.  The CTA owns ONE 128-column block of W for the whole launch: its [BN x K] slab
 //                        (<= 128 KB) is fetched once and stays resident in shared memory (re-reading W per 128-row tile
-//                        would double the L2 -> SM traffic and make the kernel L2-bound).  A streams through a 6-deep ring
-//                        of [128 x 32] SWIZZLE_64B tiles, one cp.async.bulk.tensor per K chunk (rows past M read as zero).
-//   warp 1 (one thread)  MMA issuer: 2 x tcgen05.mma (M = 128, N = BN, K = 16) per chunk; tcgen05.commit frees the A stage;
+//                        would double the L2 -> SM traffic and make the kernel L2-bound).  A streams through a 3-6 deep ring
+//                        of [128 x 64] SWIZZLE_128B tiles, one cp.async.bulk.tensor per K chunk (rows past M read as zero).
+//   warp 1 (one thread)  MMA issuer: 4 x tcgen05.mma (M = 128, N = BN, K = 16) per chunk; tcgen05.commit frees the A stage;
 //                        accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile t overlaps tile t+1.
 //   warps 2-9            epilogue, two groups of four warps: group g takes the tiles of accumulator stage g, so two tiles are
 //                        finished at a time (one warp per scheduler runs ~2 000 dependent instructions per tile: a single
@@ -33,11 +33,11 @@
 
 namespace {
 
-constexpr int KC = 32;                       // K elements per stage: 64 B of bf16 = one SWIZZLE_64B row
+constexpr int KC = 64;                       // K elements per stage: 128 B of bf16 = one SWIZZLE_128B row
 constexpr int TILE_M = 128;
-constexpr int A_TILE_BYTES = TILE_M * KC * 2;        // 8 KB
-constexpr int MAX_STAGE = 8;                 // A ring depth: as many 8 KB stages as fit beside the resident W slab (>= 3)
-constexpr uint32_t SBO_BYTES = 8 * KC * 2;           // 512 B between 8-row groups
+constexpr int A_TILE_BYTES = TILE_M * KC * 2;        // 16 KB
+constexpr int MAX_STAGE = 6;                 // A ring depth: as many 16 KB stages as fit beside the resident W slab (>= 3)
+constexpr uint32_t SBO_BYTES = 8 * KC * 2;           // 1024 B between 8-row groups
 constexpr int EPI_WARPS = 8;                 // two groups of four: group g finishes the tiles whose accumulator stage is g
 constexpr int THREADS = (2 + EPI_WARPS) * 32;        // 320
 constexpr int MAX_K = 512;
@@ -57,14 +57,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// K-major SWIZZLE_64B shared-memory matrix descriptor (same encoding as proj_umma.cu::make_desc)
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout; layout type 2 = SWIZZLE_128B).
+// The fp32-parity kernel uses SWIZZLE_64B tiles (KC = 32); 128-byte rows halve the number of TMA copies / barrier round trips
+// per tile and read shared memory without the 2-way conflicts of 64-byte rows.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)((SBO_BYTES >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -75,8 +77,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+__device__ __forceinline__ uint32_t pack2(float a, float b) {      // one packed convert (F2FP.BF16.F32.PACK_AB), a in the low half
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
 }
 
 struct Bf16Args {
@@ -232,12 +235,19 @@ proj_bf16_kernel(const __grid_constant__ Bf16Args P, const __grid_constant__ CUt
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                     if (P.alpha) {
+                        // four partial sums per dot product: the 32-long dependent FMA chains were a third of the chunk's latency
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = __uint_as_float(v[j]);
-                            ps = fmaf(x, s_att[c * 32 + j], ps);
-                            pd = fmaf(x, s_att[BN + c * 32 + j], pd);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(s_att + c * 32 + j);
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_att + BN + c * 32 + j);
+                            const float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                            const float x2 = __uint_as_float(v[j + 2]), x3 = __uint_as_float(v[j + 3]);
+                            s0 = fmaf(x0, a4.x, s0); s1 = fmaf(x1, a4.y, s1); s2 = fmaf(x2, a4.z, s2); s3 = fmaf(x3, a4.w, s3);
+                            d0 = fmaf(x0, b4.x, d0); d1 = fmaf(x1, b4.y, d1); d2 = fmaf(x2, b4.z, d2); d3 = fmaf(x3, b4.w, d3);
                         }
+                        ps += (s0 + s1) + (s2 + s3);
+                        pd += (d0 + d1) + (d2 + d3);
                         if ((((c + 1) * 32) & (CH - 1)) == 0) {   // a head is complete (CH is a power of two >= 32)
                             if (row < P.M) {
                                 const int head = (n0 + c * 32) >> chs;
@@ -300,7 +310,7 @@ int encode_fn(EncodeTiledFn* out) {
     return BGNN_OK;
 }
 
-// 2-D tensor map over a row-major bf16 matrix [rows, K] with a [box_rows x 32] SWIZZLE_64B box; rows past the end read as zero
+// 2-D tensor map over a row-major bf16 matrix [rows, K] with a [box_rows x 64] SWIZZLE_128B box; rows past the end read as zero
 int make_tmap_bf16(const uint16_t* base, int64_t rows, int K, int box_rows, CUtensorMap* out) {
     EncodeTiledFn fn = nullptr;
     { int rc = encode_fn(&fn); if (rc) return rc; }
@@ -309,7 +319,7 @@ int make_tmap_bf16(const uint16_t* base, int64_t rows, int K, int box_rows, CUte
     const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for bf16 matrix %p rows=%lld K=%d", (int)r, (const void*)base, (long long)rows, K); return BGNN_E_CUDA; }
     return BGNN_OK;
