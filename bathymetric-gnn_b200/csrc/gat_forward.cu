@@ -67,6 +67,8 @@ struct bgnn_model {
     float* bias_fold0;       // [HC_0] = W_lin0 . b_fe1
     float fold0_inv;
     float mlp0_mul, mlp0_add;   // |relu(x W0^T + b0)| <= mlp0_mul * max|x| + mlp0_add
+    uint16_t* fe1split;      // fp16 split of feature_extractor.mlp.3.weight: the unfused MLP's second Linear on the tensor cores
+    float fe1_inv;
     uint16_t* hWsplit;       // fp16 split of the concatenated head first layers (zero padded to hNpad rows)
     float heads_inv;
     int hNpad;
@@ -1734,6 +1736,14 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
             fold0_inv = proj_umma_split_weights(Wf.data(), HC, C, h16.data() + oFold16);
         }
     }
+    // unfused feature extractor (shapes without the PM_MLP0 fusion, e.g. hidden 128): second Linear as a plain split GEMM
+    size_t oFe1 = (size_t)-1;
+    float fe1_inv = 1.f;
+    if (oFold16 == (size_t)-1 && proj_umma_supported(C, C, C, false)) {
+        oFe1 = h16.size();
+        h16.resize(h16.size() + (size_t)2 * C * C);
+        fe1_inv = proj_umma_split_weights(hb.data() + oW1, C, C, h16.data() + oFe1);
+    }
     // heads: concatenated first layers, zero padded to the accumulator width
     size_t oHeads16 = (size_t)-1;
     int hNpad = 0;
@@ -1792,6 +1802,8 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     m->Wfold0 = (oFold16 != (size_t)-1 && m->blob16) ? m->blob16 + oFold16 : nullptr;
     m->bias_fold0 = B + oFoldBias;
     m->hWsplit = (oHeads16 != (size_t)-1 && m->blob16) ? m->blob16 + oHeads16 : nullptr;
+    m->fe1split = (oFe1 != (size_t)-1 && m->blob16) ? m->blob16 + oFe1 : nullptr;
+    m->fe1_inv = fe1_inv;
     m->hNpad = hNpad;
     m->fold0_inv = fold0_inv; m->heads_inv = heads_inv;
     m->mlp0_mul = 0.f; m->mlp0_add = 0.f;
@@ -2008,7 +2020,15 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
         { ProfScope ps(10, s);
           if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
         { ProfScope ps(11, s);
-          if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc; }
+          if (g_use_umma && m->fe1split) {      // |relu(x W0^T + b0)| <= mlp0_mul * max|x| + mlp0_add bounds the operand
+              if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
+              UmmaArgs a = {};
+              a.A = bufA; a.M = N; a.K = C; a.Wsplit = m->fe1split; a.w_inv_scale = m->fe1_inv;
+              a.amax_src = amax; a.amax_mul = m->mlp0_mul; a.amax_add = m->mlp0_add;
+              a.Cout = bufB; a.bias = m->feb1; a.Htot = 1; a.CH = C; a.head_major = 0;
+              if ((rc = launch_umma(a, C, PM_PLAIN, EM_PROJ, sms, s))) return rc;
+              BGNN_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), s));     // slot 0 is re-measured on the MLP output below
+          } else if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s))) return rc; }
     }
     float* cur = bufB;
     float* nxt = bufA;
