@@ -1900,6 +1900,16 @@ extern "C" int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* top
     return 1;
 }
 
+namespace {
+// n8 groups of 8 consecutive fp32 values -> 8 bf16 (RN)
+__global__ void __launch_bounds__(256) f32_to_bf16_rows(const float* __restrict__ in, uint16_t* __restrict__ out, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+}
+}  // namespace
+
 // bf16 mode (BASELINE configs[4] "bf16 vs fp32 tolerance"; the reference itself has no reduced-precision path).  What is
 // bf16 is the STORAGE of the big per-node streams -- the feature-extractor output, the projection weights, h = x W^T and
 // every layer output but the last -- i.e. what the aggregation and projection kernels move through HBM; every sum
@@ -1916,7 +1926,21 @@ static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const in
     { ProfScope ps(10, s);
       if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
     { ProfScope ps(11, s);
-      if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s, IO_F32_BF16))) return rc; }
+      if (g_use_umma && m->fe1split && ((int64_t)N * C) % 8 == 0) {
+          // second Linear on the tensor cores (fp32-grade split GEMM into hbuf), then one RN pass to the bf16 rows the layer-0
+          // projection reads: the same rounding point as the FMA GEMM's bf16 store
+          if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
+          UmmaArgs a = {};
+          a.A = bufA; a.M = N; a.K = C; a.Wsplit = m->fe1split; a.w_inv_scale = m->fe1_inv;
+          a.amax_src = amax; a.amax_mul = m->mlp0_mul; a.amax_add = m->mlp0_add;
+          a.Cout = hbuf; a.bias = m->feb1; a.Htot = 1; a.CH = C; a.head_major = 0;
+          if ((rc = launch_umma(a, C, PM_PLAIN, EM_PROJ, sms, s))) return rc;
+          const int64_t n8 = (int64_t)N * C / 8;
+          int64_t blocks = ceil_div64(n8, 256);
+          if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+          f32_to_bf16_rows<<<(unsigned)blocks, 256, 0, s>>>(hbuf, reinterpret_cast<uint16_t*>(bufB), n8);
+          BGNN_LAUNCH_CHECK();
+      } else if ((rc = launch_gemm(bufA, C, m->feW1, C, N, C, bufB, C, m->feb1, 0, C, 0, 0, 0, 0, s, IO_F32_BF16))) return rc; }
     float* cur = bufB;
     float* nxt = bufA;
     for (int l = 0; l < d.layers; ++l) {

@@ -184,7 +184,9 @@ def test_radius2_tiled_aggregation_vs_csr_kernel(prec, hidden, heads, conn):
     a = model._run(g, 0.85, 0.6, True, return_hidden=True)
     model.use_grid_kernel = False
     b = model._run(g, 0.85, 0.6, True, return_hidden=True)
-    tol = 2e-6 if prec == "fp32" else TIGHT_ATOL
+    # bf16: a differing last bit can put an activation on the other side of a bf16 rounding boundary: one bf16 ulp = 2^-7 = 0.8 %
+    # of the value, so the bound is 1 % of the largest magnitude (measured: 1 of 485 248 hidden values off by 0.58 %)
+    tol = 2e-6 if prec == "fp32" else 1e-2
     for k in ("hidden", "class_logits", "confidence", "correction"):
         x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
         assert np.isfinite(x).all()
