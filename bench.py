@@ -667,7 +667,22 @@ def run_wide(args):
             kern[k] = round(kern.get(k, 0.0) + float(m_), 4)
         N, E = g.num_nodes, g.num_edges
         outs[prec] = {k: o[k].float().cpu() for k in ("class_logits", "confidence", "correction", "predicted_class")}
-        res[prec] = {"ms_per_step": round(ms, 3), "cells_per_s": world * T * T / (ms * 1e-3), "kernels_ms": kern}
+        # algorithmic bytes per launch: projections N*(in + out + 8H), aggregations N*(h + out + 8H) + E*12 + 4*cells + 4N,
+        # element size 2 (bf16 storage) or 4; the last layer's output stays fp32
+        peak, _ = peaks()
+        esz = 2 if prec == "bf16" else 4
+        roof = {}
+        for l in range(4):
+            last = l == 3
+            H_l, HC = (1 if last else 4), (128 if last else 512)
+            in_l = 128 if l == 0 else 512
+            b_proj = N * (esz * in_l + esz * HC + 8 * H_l)
+            b_agg = N * (esz * HC + (4 if last else esz) * HC + 8 * H_l + 4) + E * 12 + 4 * T * T
+            for name, b in ((f"proj_l{l}", b_proj), (f"agg_l{l}", b_agg)):
+                if name in kern and kern[name] > 0:
+                    gbs = b / (kern[name] * 1e-3) / 1e9
+                    roof[name] = {"alg_bytes": int(b), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        res[prec] = {"ms_per_step": round(ms, 3), "cells_per_s": world * T * T / (ms * 1e-3), "kernels_ms": kern, "roofline": roof}
         del g, o
     t = torch.tensor([res["fp32"]["ms_per_step"], res["bf16"]["ms_per_step"]], device=dev)
     if world > 1:
@@ -684,8 +699,9 @@ def run_wide(args):
                           "config": {"workload": f"configs[4]: one {T}x{T} tile per GPU, 24-connected (5x5), F=7, GAT hidden 128 x 4 heads "
                                                  "x 4 layers, graph build + predict; value = bf16 mode, fp32 mode beside it",
                                      "nodes": N, "edges": E, "l2": "activations (GBs per layer) far exceed the 126 MB L2"},
-                          "fp32": {"ms_per_step": float(t[0]), "cells_per_s": world * T * T / (float(t[0]) * 1e-3), "kernels_ms": res["fp32"]["kernels_ms"]},
-                          "bf16": {"ms_per_step": float(t[1]), "kernels_ms": res["bf16"]["kernels_ms"]},
+                          "fp32": {"ms_per_step": float(t[0]), "cells_per_s": world * T * T / (float(t[0]) * 1e-3), "kernels_ms": res["fp32"]["kernels_ms"],
+                                   "roofline": res["fp32"]["roofline"]},
+                          "bf16": {"ms_per_step": float(t[1]), "kernels_ms": res["bf16"]["kernels_ms"], "roofline": res["bf16"]["roofline"]},
                           "bf16_vs_fp32_max_abs_diff": diff}))
 
 
