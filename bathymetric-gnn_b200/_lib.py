@@ -48,7 +48,7 @@ class GridTopo(C.Structure):
 
 class Survey(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("cont", C.c_void_p * 4), ("wsum", C.c_void_p * 4),
-                ("n_cont", C.c_int32), ("discrete", C.c_void_p), ("tracker", C.c_void_p)]
+                ("n_cont", C.c_int32), ("discrete", C.c_void_p), ("tracker", C.c_void_p), ("f64_mask", C.c_int32)]
 
 
 class Sidecar(C.Structure):
@@ -81,6 +81,8 @@ SYMBOLS = {
     "bgnn_graph_to_grid": (C.c_int, [P, I64, P, F32, P, P]),
     "bgnn_stitch_init": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_stitch_add_tile": (C.c_int, [C.POINTER(Survey), I64, I64, I32, I32, P, P, C.POINTER(P), P, P, P]),
+    "bgnn_stitch_add_tile_nodes": (C.c_int, [C.POINTER(Survey), I64, I64, I32, I32, P, P, P, P, P, P, P, F32, P]),
+    "bgnn_stitch_blend_tile": (C.c_int, [P, I64, I64, I64, I64, I32, I32, P, P, P, P]),
     "bgnn_stitch_finalize": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_apply_corrections": (C.c_int, [P, P, I64, P, P, P, P, F32, P]),
     "bgnn_vr_apply_results": (C.c_int, [P, P, I64, F32, P, P, P, F32, P, P, P, P, P]),

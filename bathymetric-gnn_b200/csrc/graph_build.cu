@@ -106,8 +106,13 @@ __global__ void __launch_bounds__(GB_THREADS) gb_count(const GraphParams P, int3
 }
 
 // one CTA per column: exclusive scan of column blockIdx.x of table[ncol][nblocks+1]; totals land at [nblocks]
-__global__ void __launch_bounds__(1024) gb_scan(int32_t* __restrict__ table, int64_t nblocks, int ncol) {
+// The node / edge totals (columns 0 and 1) are ALSO summed in 64 bits into totals64[col]: the int32 table wraps once a
+// cell space holds 2^31 edges (268 M valid cells at K = 8, 89 M at K = 24) and bgnn_graph_count must refuse such a space
+// instead of handing a wrapped E to the caller (silent out-of-bounds CSR writes).
+__global__ void __launch_bounds__(1024) gb_scan(int32_t* __restrict__ table, int64_t nblocks, int ncol,
+                                                long long* __restrict__ totals64) {
     __shared__ int s_part[1024];
+    __shared__ long long s_wide[32];
     const int tid = threadIdx.x;
     const int64_t per = (nblocks + 1023) / 1024;
     const int64_t b0 = min((int64_t)tid * per, nblocks), b1 = min(b0 + per, nblocks);
@@ -116,7 +121,17 @@ __global__ void __launch_bounds__(1024) gb_scan(int32_t* __restrict__ table, int
         int sum = 0;
         for (int64_t b = b0; b < b1; ++b) sum += colp[b];
         s_part[tid] = sum;
+        if (col < 2) {                              // 64-bit total (per-thread partials stay far below 2^31)
+            long long w = sum;
+            for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if ((tid & 31) == 0) s_wide[tid >> 5] = w;
+        }
         __syncthreads();
+        if (col < 2 && tid < 32) {
+            long long w = s_wide[tid];
+            for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if (tid == 0) totals64[col] = w;
+        }
         for (int o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan
             int v = tid >= o ? s_part[tid - o] : 0;
             __syncthreads();
@@ -594,7 +609,11 @@ int make_params(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, GraphParams&
 
 extern "C" size_t bgnn_graph_scratch_bytes(int64_t n_cells, int32_t n_offsets) {
     const int64_t nblocks = ceil_div64(n_cells < 0 ? 0 : n_cells, GB_THREADS);
-    return align_up((size_t)(n_offsets + 2) * (size_t)(nblocks + 1) * sizeof(int32_t), 256);
+    return align_up((size_t)(n_offsets + 2) * (size_t)(nblocks + 1) * sizeof(int32_t), 256) + 256;   // + 64-bit totals
+}
+
+static long long* totals64_of(void* scratch, const GraphParams& P) {
+    return (long long*)((char*)scratch + align_up((size_t)P.ncol * (size_t)(P.nblocks + 1) * sizeof(int32_t), 256));
 }
 
 extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch,
@@ -609,15 +628,18 @@ extern "C" int bgnn_graph_count(const bgnn_cells* cells, const bgnn_graph_cfg* c
     int32_t* table = (int32_t*)scratch;
     { ProfScope ps(0, stream); gb_count<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table); }
     BGNN_LAUNCH_CHECK();
-    { ProfScope ps(1, stream); gb_scan<<<P.ncol, 1024, 0, stream>>>(table, P.nblocks, P.ncol); }
+    long long* tot64 = totals64_of(scratch, P);
+    { ProfScope ps(1, stream); gb_scan<<<P.ncol, 1024, 0, stream>>>(table, P.nblocks, P.ncol, tot64); }
     BGNN_LAUNCH_CHECK();
-    int32_t tot[2];
-    BGNN_CUDA(cudaMemcpyAsync(&tot[0], table + P.nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    BGNN_CUDA(cudaMemcpyAsync(&tot[1], table + (P.nblocks + 1) + P.nblocks, sizeof(int32_t),
-                              cudaMemcpyDeviceToHost, stream));
+    long long tot[2];
+    BGNN_CUDA(cudaMemcpyAsync(tot, tot64, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
     BGNN_CUDA(cudaStreamSynchronize(stream));
     totals_host[0] = tot[0];
     totals_host[1] = tot[1];
+    // node ids, rowptr and the scan table are int32: refuse a space whose edge list does not fit (the totals above
+    // are exact, so the caller can still report the size)
+    BGNN_CHECK_ARG(tot[0] < (long long)INT32_MAX && tot[1] < (long long)INT32_MAX,
+                   "graph too large: node / edge count does not fit int32 CSR offsets (split the cell space)");
     return BGNN_OK;
 }
 

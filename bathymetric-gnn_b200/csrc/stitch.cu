@@ -47,8 +47,31 @@ k_to_grid(const int32_t* __restrict__ node_id, int64_t n, const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) k_fill(float* __restrict__ p, int64_t n, float v) {
+template <typename T>
+__global__ void __launch_bounds__(ST_THREADS) k_fill(T* __restrict__ p, int64_t n, T v) {
     for (int64_t t = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * ST_THREADS) p[t] = v;
+}
+
+// accumulator planes are float32 (reference default) or float64 (TileMerger.initialize(dtypes=...), tiling.py:370-373):
+// bit k of bgnn_survey::f64_mask says cont[k] is a double plane, bit 4 the discrete plane.  NumPy semantics: the fp32
+// product / tile value is widened on the add / store, the weight sums stay fp32.
+__device__ __forceinline__ void acc_add(const bgnn_survey& s, int k, int64_t g, float contrib) {
+    if ((s.f64_mask >> k) & 1) {
+        double* p = (double*)s.cont[k];
+        double a = p[g];
+        if (isnan(a)) a = 0.0;
+        p[g] = a + (double)contrib;
+    } else {
+        float a = s.cont[k][g];
+        if (isnan(a)) a = 0.0f;                                              // first write (:251-252)
+        s.cont[k][g] = a + contrib;                                          // :258 (separate mul, add)
+    }
+}
+__device__ __forceinline__ bool disc_isnan(const bgnn_survey& s, int64_t g) {
+    return (s.f64_mask >> 4) & 1 ? isnan(((const double*)s.discrete)[g]) : isnan(s.discrete[g]);
+}
+__device__ __forceinline__ void disc_store(const bgnn_survey& s, int64_t g, float v) {
+    if ((s.f64_mask >> 4) & 1) ((double*)s.discrete)[g] = (double)v; else s.discrete[g] = v;
 }
 
 struct AddArgs {
@@ -74,19 +97,78 @@ __global__ void __launch_bounds__(ST_THREADS) k_add_tile(const AddArgs a) {
             if (k >= a.s.n_cont || !a.cont[k]) continue;
             const float v = __ldg(a.cont[k] + t);
             if (!isfinite(v)) continue;                                      // tiling.py:247
-            float acc = a.s.cont[k][g];
-            if (isnan(acc)) acc = 0.0f;                                      // first write (:251-252)
             if (a.wsum_first[k]) a.s.wsum[k][g] += wt;                       // :255
-            a.s.cont[k][g] = acc + v * wt;                                   // :258 (separate mul, add)
+            acc_add(a.s, k, g, v * wt);
         }
         if (a.disc && a.conf && a.s.discrete && a.s.tracker) {              // tiling.py:408-420
             const float dv = __ldg(a.disc + t), cf = __ldg(a.conf + t);
-            const float cur = a.s.discrete[g];
-            if (isfinite(dv) && (cf > a.s.tracker[g] || isnan(cur))) {
-                a.s.discrete[g] = dv;
+            if (isfinite(dv) && (cf > a.s.tracker[g] || disc_isnan(a.s, g))) {
+                disc_store(a.s, g, dv);
                 a.s.tracker[g] = cf;
             }
         }
+    }
+}
+
+// Scatter fused into the accumulate: the per-node outputs of one tile go straight into the survey accumulators through
+// the tile's node-id grid, without materialising the [3, h, w] tile grids (graph_to_grid x4 of pipeline.py:278-304 +
+// merger.add_tile).  Channel order: cont[0] = confidence, cont[1] = correction (denormalised by max(local_std, floor),
+// pipeline.py:306-307), discrete = class.  Cells that are invalid in the tile carry 0.0 like the reference's
+// fill_value=0.0 grids (finite, so they take part in the blend).
+struct NodeArgs {
+    bgnn_survey s;
+    int64_t r0, c0;
+    int h, w;
+    const float* row_w;
+    const float* col_w;
+    const int32_t* node_id;
+    const int64_t* cls;
+    const float* conf;
+    const float* corr;
+    const float* lstd;
+    float floor_;
+    int shared_wsum;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) k_add_tile_nodes(const NodeArgs a) {
+    const int64_t n = (int64_t)a.h * a.w;
+    for (int64_t t = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * ST_THREADS) {
+        const int i = (int)(t / a.w), j = (int)(t - (int64_t)i * a.w);
+        const int64_t g = (a.r0 + i) * a.s.cols + (a.c0 + j);
+        const float wt = __ldg(a.row_w + i) * __ldg(a.col_w + j);
+        const int id = __ldg(a.node_id + t);
+        const bool v = id >= 0;
+        const float cf = v ? __ldg(a.conf + id) : 0.0f;
+        const float cl = v ? (float)__ldg(a.cls + id) : 0.0f;
+        float cr = 0.0f;
+        if (a.corr) cr = (v ? __ldg(a.corr + id) : 0.0f) * fmaxf(v ? __ldg(a.lstd + id) : 0.0f, a.floor_);
+        a.s.wsum[0][g] += wt;
+        acc_add(a.s, 0, g, cf * wt);
+        if (a.s.n_cont > 1) {
+            if (!a.shared_wsum) a.s.wsum[1][g] += wt;
+            acc_add(a.s, 1, g, cr * wt);
+        }
+        if (a.s.discrete && a.s.tracker && (cf > a.s.tracker[g] || disc_isnan(a.s, g))) {
+            disc_store(a.s, g, cl);
+            a.s.tracker[g] = cf;
+        }
+    }
+}
+
+// TileManager.merge_tile WITHOUT a weight grid (tiling.py:259-272): where both are finite
+// out = out * (1 - w) + tile * w (fp32, separate ops), where only the tile is finite out = tile.
+__global__ void __launch_bounds__(ST_THREADS)
+k_blend_tile(float* __restrict__ out, int64_t cols, int64_t r0, int64_t c0, int h, int w, const float* __restrict__ row_w,
+             const float* __restrict__ col_w, const float* __restrict__ tile) {
+    const int64_t n = (int64_t)h * w;
+    for (int64_t t = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * ST_THREADS) {
+        const int i = (int)(t / w), j = (int)(t - (int64_t)i * w);
+        const int64_t g = (r0 + i) * cols + (c0 + j);
+        const float v = __ldg(tile + t);
+        if (!isfinite(v)) continue;
+        const float wt = __ldg(row_w + i) * __ldg(col_w + j);
+        const float cur = out[g];
+        out[g] = isfinite(cur) ? cur * (1.0f - wt) + v * wt : v;
     }
 }
 
@@ -97,7 +179,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_finalize(const bgnn_survey s) {
         for (int k = 0; k < 4; ++k) {
             if (k >= s.n_cont) continue;
             const float w = s.wsum[k][t];
-            if (w > 0.0f) s.cont[k][t] = s.cont[k][t] / w;                   // tiling.py:289-292
+            if (!(w > 0.0f)) continue;                                       // tiling.py:289-292
+            if ((s.f64_mask >> k) & 1) ((double*)s.cont[k])[t] = ((double*)s.cont[k])[t] / (double)w;
+            else s.cont[k][t] = s.cont[k][t] / w;
         }
     }
 }
@@ -148,11 +232,15 @@ extern "C" int bgnn_stitch_init(const bgnn_survey* s, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     for (int k = 0; k < s->n_cont; ++k) {
         BGNN_CHECK_ARG(s->cont[k] && s->wsum[k], "null accumulator plane %d", k);
-        k_fill<<<grid_for(n), ST_THREADS, 0, st>>>(s->cont[k], n, nanf(""));
-        k_fill<<<grid_for(n), ST_THREADS, 0, st>>>(s->wsum[k], n, 0.0f);
+        if ((s->f64_mask >> k) & 1) k_fill<double><<<grid_for(n), ST_THREADS, 0, st>>>((double*)s->cont[k], n, nan(""));
+        else k_fill<float><<<grid_for(n), ST_THREADS, 0, st>>>(s->cont[k], n, nanf(""));
+        k_fill<float><<<grid_for(n), ST_THREADS, 0, st>>>(s->wsum[k], n, 0.0f);
     }
-    if (s->discrete) k_fill<<<grid_for(n), ST_THREADS, 0, st>>>(s->discrete, n, nanf(""));
-    if (s->tracker) k_fill<<<grid_for(n), ST_THREADS, 0, st>>>(s->tracker, n, -1.0f);
+    if (s->discrete) {
+        if ((s->f64_mask >> 4) & 1) k_fill<double><<<grid_for(n), ST_THREADS, 0, st>>>((double*)s->discrete, n, nan(""));
+        else k_fill<float><<<grid_for(n), ST_THREADS, 0, st>>>(s->discrete, n, nanf(""));
+    }
+    if (s->tracker) k_fill<float><<<grid_for(n), ST_THREADS, 0, st>>>(s->tracker, n, -1.0f);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
@@ -176,6 +264,38 @@ extern "C" int bgnn_stitch_add_tile(const bgnn_survey* s, int64_t r0, int64_t c0
     a.disc = discrete_tile; a.conf = conf_tile;
     ProfScope ps(71, (cudaStream_t)stream);
     k_add_tile<<<grid_for((int64_t)h * w), ST_THREADS, 0, (cudaStream_t)stream>>>(a);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_stitch_add_tile_nodes(const bgnn_survey* s, int64_t r0, int64_t c0, int32_t h, int32_t w,
+                                          const float* row_w, const float* col_w, const int32_t* node_id,
+                                          const int64_t* cls, const float* conf, const float* corr,
+                                          const float* local_std, float norm_floor, void* stream) {
+    BGNN_CHECK_ARG(s && row_w && col_w && node_id && cls && conf, "null argument");
+    BGNN_CHECK_ARG(s->n_cont >= 1 && s->n_cont <= 2 && s->cont[0] && s->wsum[0], "survey must carry confidence [+ correction] planes");
+    BGNN_CHECK_ARG(s->n_cont == 1 || (s->cont[1] && s->wsum[1]), "null correction plane");
+    BGNN_CHECK_ARG(!corr || local_std, "correction needs local_std");
+    BGNN_CHECK_ARG(h >= 0 && w >= 0 && r0 >= 0 && c0 >= 0 && r0 + h <= s->rows && c0 + w <= s->cols,
+                   "tile [%lld:%lld, %lld:%lld] outside survey %lldx%lld", (long long)r0, (long long)(r0 + h),
+                   (long long)c0, (long long)(c0 + w), (long long)s->rows, (long long)s->cols);
+    if ((int64_t)h * w == 0) return BGNN_OK;
+    NodeArgs a;
+    a.s = *s; a.r0 = r0; a.c0 = c0; a.h = h; a.w = w; a.row_w = row_w; a.col_w = col_w;
+    a.node_id = node_id; a.cls = cls; a.conf = conf; a.corr = corr; a.lstd = local_std; a.floor_ = norm_floor;
+    a.shared_wsum = s->n_cont > 1 && s->wsum[0] == s->wsum[1];
+    ProfScope ps(75, (cudaStream_t)stream);
+    k_add_tile_nodes<<<grid_for((int64_t)h * w), ST_THREADS, 0, (cudaStream_t)stream>>>(a);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_stitch_blend_tile(float* out, int64_t rows, int64_t cols, int64_t r0, int64_t c0, int32_t h, int32_t w,
+                                      const float* row_w, const float* col_w, const float* tile, void* stream) {
+    BGNN_CHECK_ARG(out && row_w && col_w && tile, "null argument");
+    BGNN_CHECK_ARG(h >= 0 && w >= 0 && r0 >= 0 && c0 >= 0 && r0 + h <= rows && c0 + w <= cols, "tile outside the grid");
+    if ((int64_t)h * w == 0) return BGNN_OK;
+    k_blend_tile<<<grid_for((int64_t)h * w), ST_THREADS, 0, (cudaStream_t)stream>>>(out, cols, r0, c0, h, w, row_w, col_w, tile);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }

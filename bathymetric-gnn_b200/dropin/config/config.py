@@ -1,3 +1,3 @@
 """Drop-in for config/config.py."""
-from . import (Config, TileConfig, GraphConfig, ModelConfig, TrainingConfig, SyntheticNoiseConfig,  # noqa: F401
-               InferenceConfig)
+from bathymetric_gnn_b200.config import (Config, TileConfig, GraphConfig, ModelConfig, TrainingConfig,  # noqa: F401
+                                         SyntheticNoiseConfig, InferenceConfig)

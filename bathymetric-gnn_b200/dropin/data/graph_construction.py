@@ -1,2 +1,2 @@
 """Drop-in for data/graph_construction.py."""
-from . import GraphBuilder, Data  # noqa: F401
+from bathymetric_gnn_b200.graph import GraphBuilder, MultiScaleGraphBuilder, Data, Batch  # noqa: F401

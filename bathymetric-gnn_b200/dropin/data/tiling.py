@@ -1,2 +1,2 @@
 """Drop-in for data/tiling.py."""
-from . import Tile, TileSpec, TileManager, TileMerger  # noqa: F401
+from bathymetric_gnn_b200.tiling import Tile, TileSpec, TileManager, TileMerger  # noqa: F401

@@ -1,3 +1,3 @@
 """Drop-in for models/gnn.py."""
-from . import (BathymetricGNN, LocalFeatureExtractor, GNNBackbone, ClassificationHead, ConfidenceHead,  # noqa: F401
-               CorrectionHead)
+from bathymetric_gnn_b200.gnn import (BathymetricGNN, LocalFeatureExtractor, GNNBackbone, ClassificationHead,  # noqa: F401
+                                      ConfidenceHead, CorrectionHead)

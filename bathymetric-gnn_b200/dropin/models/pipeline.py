@@ -1,2 +1,2 @@
 """Drop-in for models/pipeline.py."""
-from . import BathymetricPipeline  # noqa: F401
+from bathymetric_gnn_b200.pipeline import BathymetricPipeline  # noqa: F401

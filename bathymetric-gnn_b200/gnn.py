@@ -71,6 +71,53 @@ class GATConvParams(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
+class _LinB(nn.Module):
+    """Parameter holder for a PyG `Linear` with bias (torch.nn.Linear's default init)."""
+
+    def __init__(self, fin: int, fout: int):
+        super().__init__()
+        ref = nn.Linear(fin, fout)
+        self.weight, self.bias = ref.weight, ref.bias
+
+
+class GCNConvParams(nn.Module):
+    """PyG `GCNConv(in, out)` (models/gnn.py:120-121): `lin` without bias (glorot) + `bias` (zeros); defaults
+    add_self_loops=True, normalize=True:  out_i = sum_{j in N(i) + i} h_j / sqrt(d_i d_j) + b,  d = in-degree + 1."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+
+class SAGEConvParams(nn.Module):
+    """PyG `SAGEConv(in, out)` (models/gnn.py:134-135): aggr='mean', root_weight=True:
+    out_i = lin_l(mean_{j in N(i)} x_j) + lin_r(x_i); `lin_l` carries the bias, `lin_r` has none."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = _LinB(in_channels, out_channels)
+        self.lin_r = _LinB(in_channels, out_channels)
+        self.lin_r.bias = None
+
+
+class GINConvParams(nn.Module):
+    """PyG `GINConv(nn)` (models/gnn.py:137-143), eps = 0 (not trained; kept as the buffer PyG registers):
+    out_i = nn((1 + eps) x_i + sum_{j in N(i)} x_j)."""
+
+    def __init__(self, mlp: nn.Module, eps: float = 0.0):
+        super().__init__()
+        self.nn = mlp
+        self.register_buffer("eps", torch.tensor([float(eps)]))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        if prefix + "eps" not in state_dict:           # PyG versions that keep eps as a plain attribute
+            state_dict[prefix + "eps"] = self.eps.detach().clone()
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
 class BatchNormParams(nn.Module):
     """`torch_geometric.nn.BatchNorm` wrapper layout: `.module` is a BatchNorm1d."""
 
@@ -244,6 +291,8 @@ class BathymetricGNN(nn.Module):
         if self.training and self.dropout > 0:
             raise RuntimeError("BathymetricGNN (B200 build) is inference-only: call .eval() first")
         dg = data.__dict__.get("_dev")
+        if dg is not None and hasattr(data, "topology_overridden") and data.topology_overridden():
+            dg = None               # caller-assigned edge_index / edge_attr: honour them (COO path)
         x = data.x
         device = dg.device if dg is not None else (x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device()))
         with torch.cuda.device(device):

@@ -115,7 +115,7 @@ class GridGraph(Data):
 
     @property
     def num_edges(self) -> int:
-        return int(self._dev.E)
+        return int(self._dev.E) + (int(self._dev.N) if self.__dict__.get("_self_loops") else 0)
 
     def _materialise(self, name):
         dg = self._dev
@@ -127,8 +127,15 @@ class GridGraph(Data):
                 ea = torch.empty((dg.E, ED), dtype=torch.float32, device=dg.device)
                 check(lib.bgnn_graph_coo(C.byref(dg.cells), C.byref(dg.cfg), ptr(dg.scratch), dg.scratch.numel(),
                                          ptr(dg.node_id), dg.E, ptr(ei), ptr(ea), stream_ptr()))
+                if self.__dict__.get("_self_loops"):
+                    # include_self_loops=True (graph_construction.py:226-229): N (i, i) edges appended AFTER the stencil
+                    # edges; their features are distance 0, depth_difference 0, slope 0 (:344-364)
+                    loops = torch.arange(dg.N, dtype=torch.int64, device=dg.device)
+                    ei = torch.cat([ei, torch.stack([loops, loops])], dim=1)
+                    ea = torch.cat([ea, torch.zeros((dg.N, ED), dtype=torch.float32, device=dg.device)])
                 self.__dict__["edge_index"] = ei.to(tgt)
                 self.__dict__["edge_attr"] = ea.to(tgt)
+                self.__dict__["_emitted"] = dict(edge_index=self.__dict__["edge_index"], edge_attr=self.__dict__["edge_attr"])
             else:
                 cell = dg.node_cell.to(torch.int64)
                 if dg.grid_meta is None:
@@ -148,15 +155,96 @@ class GridGraph(Data):
         out = super()._apply(fn)
         probe = fn(torch.empty(0, device=self._dev.device))
         out.__dict__["_target_device"] = probe.device
+        em = self.__dict__.get("_emitted")
+        if em is not None:          # moved copies of kernel-emitted tensors still count as kernel-emitted
+            out.__dict__["_emitted"] = {k: out.__dict__[k] for k, v in em.items() if self.__dict__.get(k) is v}
         return out
+
+    def topology_overridden(self) -> bool:
+        """True when `edge_index` / `edge_attr` were assigned by the caller after the build: the cached device
+        topology no longer describes this object and the model falls back to the COO path."""
+        em = self.__dict__.get("_emitted", {})
+        return any(k in self.__dict__ and self.__dict__[k] is not em.get(k) for k in ("edge_index", "edge_attr"))
 
 
 class Batch(Data):
     """`torch_geometric.data.Batch.from_data_list` replacement
     (scripts/inference_native.py:312): block-diagonal concatenation."""
 
+    _LAZY = GridGraph._LAZY
+
+    def __getattr__(self, name):
+        parts = self.__dict__.get("_parts")
+        if parts is not None and name in Batch._LAZY:
+            tgt = self.__dict__.get("_target_device", self.__dict__["_dev"].device)
+            vs, offs = [], 0
+            for d in parts:
+                v = getattr(d, name).to(tgt)
+                vs.append(v + offs if name == "edge_index" else v)
+                offs += d.num_nodes
+            self.__dict__[name] = torch.cat(vs, dim=1 if name == "edge_index" else 0)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _apply(self, fn):
+        out = super()._apply(fn)
+        if "_dev" in self.__dict__:
+            out.__dict__["_target_device"] = fn(torch.empty(0, device=self._dev.device)).device
+        return out
+
+    @property
+    def num_edges(self) -> int:
+        dg = self.__dict__.get("_dev")
+        return int(dg.E) if dg is not None else super().num_edges
+
+    @classmethod
+    def _from_grid_graphs(cls, graphs: List["GridGraph"]) -> "Batch":
+        """All members come from the device GraphBuilder: concatenate their device arrays (node features, in-edge CSR
+        with node / edge offsets) into one block-diagonal device graph, so that `model.predict(batch)` runs the CSR /
+        windowed aggregation kernels directly; the int64 COO is still available lazily."""
+        dgs = [g._dev for g in graphs]
+        dev = dgs[0].device
+        with torch.cuda.device(dev):
+            n = torch.tensor([d.N for d in dgs], dtype=torch.int64)
+            e = torch.tensor([d.E for d in dgs], dtype=torch.int64)
+            noff = torch.zeros(len(dgs) + 1, dtype=torch.int64); noff[1:] = torch.cumsum(n, 0)
+            eoff = torch.zeros(len(dgs) + 1, dtype=torch.int64); eoff[1:] = torch.cumsum(e, 0)
+            N, E = int(noff[-1]), int(eoff[-1])
+            if N >= 2 ** 31 or E >= 2 ** 31:
+                raise ValueError("batch exceeds the int32 node / edge id range")
+            dg = _DeviceGraph()
+            dg.cells, dg.cfg, dg.scratch, dg.device = _lib.Cells(), dgs[0].cfg, None, dev
+            dg.cells.n_grids, dg.cells.n_cells = len(dgs), sum(d.n_cells for d in dgs)
+            dg.keep = [graphs]                       # the members own the inputs
+            dg.grid_meta = dict(batched=True)
+            dg.N, dg.E, dg.n_cells = N, E, int(dg.cells.n_cells)
+            dg.x = torch.cat([d.x for d in dgs])
+            dg.local_std = torch.cat([d.local_std for d in dgs])
+            rp = [d.rowptr[:-1] + int(eoff[i]) for i, d in enumerate(dgs)]
+            dg.rowptr = torch.cat(rp + [torch.tensor([E], dtype=torch.int32, device=dev)]).to(torch.int32)
+            dg._csr_src = torch.cat([d.csr_src[:d.E] + int(noff[i]) for i, d in enumerate(dgs)]
+                                    + [torch.zeros(1 if E == 0 else 0, dtype=torch.int32, device=dev)]).to(torch.int32)
+            ED = max(int(dg.cfg.n_edge_feats), 1)
+            dg._csr_eattr = torch.cat([d.csr_eattr[:d.E] for d in dgs]
+                                      + [torch.zeros((1 if E == 0 else 0, ED), dtype=torch.float32, device=dev)])
+            dg.node_id = dg.node_cell = dg.grid_eattr = None
+            out = cls()
+            out.__dict__["_dev"], out.__dict__["_parts"] = dg, list(graphs)
+            out.x, out.local_std = dg.x, dg.local_std
+            out.batch = torch.repeat_interleave(torch.arange(len(dgs), device=dev), n.to(dev))
+            out.num_graphs = len(graphs)
+            out.num_valid_cells = [g.num_valid_cells for g in graphs]
+            out.grid_shape = [getattr(g, "grid_shape", None) for g in graphs]
+        return out
+
     @classmethod
     def from_data_list(cls, data_list: List[Data]) -> "Batch":
+        if data_list and all(isinstance(d, GridGraph) and "_dev" in d.__dict__ and not d.topology_overridden()
+                             and d.x is d._dev.x for d in data_list):
+            d0 = data_list[0]._dev
+            same = lambda d: (d.device == d0.device and bytes(d.cfg) == bytes(d0.cfg))
+            if all(same(d._dev) for d in data_list):
+                return cls._from_grid_graphs(list(data_list))
         out = cls()
         offs, cat, batch_vec = 0, {}, []
         for g, d in enumerate(data_list):
@@ -239,9 +327,6 @@ class GraphBuilder:
             self.neighbor_offsets = list(OFFSETS_24)
         else:
             raise ValueError(f"Unknown connectivity: {connectivity}")
-        if include_self_loops:
-            raise NotImplementedError("include_self_loops=True is never used by the reference pipelines "
-                                      "(GATConv adds its own self loops); not built")
         self.device = device
 
     # ------------------------------------------------------------------ build
@@ -432,6 +517,10 @@ class GraphBuilder:
         g.x = dg.x
         g.local_std = dg.local_std
         g.num_valid_cells = N
+        if self.include_self_loops:
+            # GATConv removes existing self loops before adding its own (PyG `remove_self_loops`), so the forward on the
+            # cached device topology is unchanged; only the API-visible COO carries the extra N edges
+            g.__dict__["_self_loops"] = True
         if grid_shape is not None:
             g.grid_shape = tuple(grid_shape)
         if shapes is not None:

@@ -200,9 +200,11 @@ class SidecarBuilder:
         self.handler = handler
         self.shape, self.geotransform, self.bounds = g("shape", shape), g("geotransform", geotransform), g("bounds", bounds)
         self.base_shape, self.crs = g("base_shape", base_shape), g("crs", crs)
+        if handler is not None and (self.shape is None or self.geotransform is None):
+            self._georef_from_handler(handler)
         if self.shape is None or self.geotransform is None or self.bounds is None or self.base_shape is None:
             raise RuntimeError("SidecarBuilder (B200 build) needs shape, geotransform, bounds and base_shape "
-                               "(the GDAL resampled-view lookup of the reference is file I/O and not built)")
+                               "(pass them, or a handler that carries them)")
         self.shape = (int(self.shape[0]), int(self.shape[1]))
         self.resolution = abs(self.geotransform[1])                                     # :681
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -216,6 +218,28 @@ class SidecarBuilder:
             check(lib.bgnn_sidecar_init(self._sc, stream_ptr()))
         self._seq = 0
         logger.info("SidecarBuilder initialized: %s at %sm", self.shape, self.resolution)
+
+    def _georef_from_handler(self, handler):
+        """`SidecarBuilder(handler)` as the entry script calls it (scripts/inference_native.py:461).  With GDAL installed
+        the raster geometry comes from GDAL's resampled view of the container like in the reference (data/vr_bag.py:638-693:
+        file I/O); without it, from the handler's own extent at its finest refinement resolution (the reference has no
+        GDAL-free mode and raises ImportError there)."""
+        try:
+            from osgeo import gdal
+            ds = gdal.OpenEx(str(handler.path), gdal.OF_RASTER | gdal.OF_READONLY, open_options=["MODE=RESAMPLED_GRID"]) \
+                or gdal.Open(str(handler.path))
+        except ImportError:
+            ds = None
+        if ds is not None:
+            self.shape, self.geotransform, self.crs = (ds.RasterYSize, ds.RasterXSize), ds.GetGeoTransform(), ds.GetProjection()
+            gt = self.geotransform
+            self.bounds = (gt[0], gt[3] + self.shape[0] * gt[5], gt[0] + self.shape[1] * gt[1], gt[3])
+            return
+        b = tuple(float(v) for v in handler.bounds)
+        res = float(getattr(handler, "finest_resolution", None) or getattr(handler, "_resolution", 1.0))
+        shape = getattr(handler, "resampled_shape", None) or handler.base_shape
+        self.shape, self.bounds = (int(shape[0]), int(shape[1])), b
+        self.geotransform = (b[0], res, 0.0, b[3], 0.0, -res)
 
     # placement integers exactly as the reference computes them (float64, int(round(.))): vr_bag.py:716-748
     def _placement(self, base_row, base_col, sw_corner, dimensions, resolution):
@@ -270,8 +294,32 @@ class SidecarBuilder:
     valid_mask = property(lambda self: self._planes[3].cpu().numpy())
 
     def save(self, path):
-        raise NotImplementedError("GeoTIFF export (GDAL) is file I/O outside the accelerated path: read .classification / "
-                                  ".confidence / .correction / .valid_mask and hand them to a writer")
+        """data/vr_bag.py:780-834: four float32 bands (classification, confidence, correction, valid_mask).  GeoTIFF through
+        GDAL when it is installed; `.npz` paths (and any path when GDAL is missing, where the reference only logs an error)
+        get the same four planes + the geotransform as an .npz next to the requested name."""
+        from pathlib import Path
+        path = Path(path)
+        bands = [("classification", self.classification), ("confidence", self.confidence),
+                 ("correction", self.correction), ("valid_mask", self.valid_mask)]
+        gdal = None
+        if path.suffix.lower() != ".npz":
+            try:
+                from osgeo import gdal
+            except ImportError:
+                logger.error("GDAL required for GeoTIFF export; writing %s instead", path.with_suffix(".npz"))
+        if gdal is None:
+            np.savez_compressed(path.with_suffix(".npz"), geotransform=np.array(self.geotransform, np.float64), **dict(bands))
+            return
+        ds = gdal.GetDriverByName("GTiff").Create(str(path), self.shape[1], self.shape[0], len(bands), gdal.GDT_Float32,
+                                                  options=["COMPRESS=LZW", "TILED=YES"])
+        ds.SetGeoTransform(self.geotransform)
+        if self.crs:
+            ds.SetProjection(self.crs)
+        for i, (name, plane) in enumerate(bands, 1):
+            band = ds.GetRasterBand(i)
+            band.WriteArray(plane)
+            band.SetDescription(name)
+        ds.FlushCache()
 
 
 def apply_results(depth, uncertainty, valid_mask, classification, confidence, correction, auto_correct_threshold=0.85):

@@ -56,11 +56,42 @@ class NpzWriter:
         np.savez_compressed(Path(path), **out)
 
 
+def _reference_io(name: str):
+    """The reference's own GDAL `BathymetricLoader` / `BathymetricWriter` (data/loaders.py:93-822), loaded unmodified from
+    a reference checkout (file formats are outside the accelerated path and are not re-implemented)."""
+    from .dropin import _passthrough
+    ns = {"__name__": "data._reference_loaders", "__package__": "data"}
+    _passthrough.exec_reference("data/loaders.py", ns)
+    if not ns.get("GDAL_AVAILABLE", False):
+        raise ImportError("GDAL is required for loading bathymetric data. Install with: conda install -c conda-forge gdal")
+    return ns[name]
+
+
+class FormatDispatchLoader:
+    """`BathymetricLoader(vr_bag_mode)` of the drop-in (data/loaders.py:98-118 signature): .npz is read here, every other
+    format (BAG / GeoTIFF / ASC) goes to the reference's GDAL loader."""
+
+    def __init__(self, vr_bag_mode: str = "resampled"):
+        self.vr_bag_mode = vr_bag_mode
+
+    def load(self, path) -> BathymetricGrid:
+        if Path(path).suffix.lower() == ".npz":
+            return NpzLoader(self.vr_bag_mode).load(path)
+        return _reference_io("BathymetricLoader")(vr_bag_mode=self.vr_bag_mode).load(path)
+
+
+class FormatDispatchWriter:
+    def save(self, grid: BathymetricGrid, path, additional_bands: Optional[Dict[str, np.ndarray]] = None):
+        if Path(path).suffix.lower() == ".npz":
+            return NpzWriter().save(grid, path, additional_bands)
+        return _reference_io("BathymetricWriter")().save(grid, path, additional_bands=additional_bands)
+
+
 class BathymetricPipeline:
     def __init__(self, config: Config, vr_bag_mode: str = "resampled", loader=None, writer=None):
         self.config = config
-        self.loader = loader if loader is not None else NpzLoader(vr_bag_mode)
-        self.writer = writer if writer is not None else NpzWriter()
+        self.loader = loader if loader is not None else FormatDispatchLoader(vr_bag_mode)
+        self.writer = writer if writer is not None else FormatDispatchWriter()
         self.tile_manager = TileManager(config.tile.tile_size, config.tile.overlap, config.tile.min_valid_ratio)
         self.graph_builder = GraphBuilder(connectivity=config.graph.connectivity, edge_features=config.graph.edge_features)
         self.model: Optional[BathymetricGNN] = None
@@ -88,8 +119,9 @@ class BathymetricPipeline:
         logger.info("Model loaded from %s", model_path)
 
     # ------------------------------------------------------------------ per tile
-    def _tile_on_device(self, depth_view, unc_view, mask, resolution, nodata, min_valid_ratio=None):
-        """graph build -> predict -> scatter; returns (device tile grids [class, conf, corr] or None, N)."""
+    def _tile_on_device(self, depth_view, unc_view, mask, resolution, nodata, min_valid_ratio=None, into=None):
+        """graph build -> predict -> scatter; returns (device tile grids [class, conf, corr] or None, N).
+        `into=(merger, spec)`: the scatter is fused into the stitch accumulate instead (returns (True, N))."""
         graph = self.graph_builder.build_graph(depth_view, mask, unc_view, resolution, nodata=nodata)
         shape = tuple(depth_view.shape)
         if graph.num_nodes == 0:
@@ -99,6 +131,11 @@ class BathymetricPipeline:
         out = self.model.predict(graph, auto_correct_threshold=self.config.inference.auto_correct_threshold,
                                  review_threshold=self.config.inference.review_threshold)
         dg = graph._dev
+        if into is not None:
+            merger, spec = into
+            merger.add_tile_nodes(spec, dg.node_id, out["predicted_class"], out["confidence"], out.get("correction"),
+                                  dg.local_std, float(CORRECTION_NORM_FLOOR))
+            return True, graph.num_nodes
         dev = dg.device
         n = shape[0] * shape[1]
         grids = torch.empty((3, shape[0], shape[1]), dtype=torch.float32, device=dev)
@@ -157,13 +194,14 @@ class BathymetricPipeline:
                 dv = depth[sl]
                 # valid = isfinite & != nodata is derived in-kernel (== grid.valid_mask, loaders.py:58-69)
                 grids, n = self._tile_on_device(dv, None if unc is None else unc[sl], None, grid.resolution,
-                                                float(nodata) if use_nodata else None, tm.min_valid_ratio)
+                                                float(nodata) if use_nodata else None, tm.min_valid_ratio,
+                                                into=(merger, spec))
                 size = dv.shape[0] * dv.shape[1]
                 if n / size < tm.min_valid_ratio:            # tiling.py:200 (skip_empty)
                     continue
                 if grids is None:                            # pipeline.py:257-264 (only when min_valid_ratio <= 0)
                     grids = torch.zeros((3,) + tuple(dv.shape), dtype=torch.float32, device=dev)
-                merger.add_tile(spec, {"classification": grids[0], "confidence": grids[1], "correction": grids[2]})
+                    merger.add_tile(spec, {"classification": grids[0], "confidence": grids[1], "correction": grids[2]})
                 num_tiles += 1
             logger.info("Processed %d tiles (%d skipped below min_valid_ratio)", num_tiles, len(specs) - num_tiles)
             if keep_on_device == "partial":                  # sharded runs gather unfinalised band planes (parallel.py)

@@ -158,10 +158,19 @@ class TileManager:
     #      round-tripped through the device kernels, CUDA tensors are updated in place
     def merge_tile(self, output, tile_data, spec: TileSpec, weight_grid=None):
         _lib.require_cuda()
-        if weight_grid is None:
-            raise NotImplementedError("merge_tile without a weight grid (overwrite-blend branch, tiling.py:259-272) "
-                                      "is not used by any reference pipeline and is not built")
         dev = output.device if isinstance(output, torch.Tensor) and output.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if weight_grid is None:                      # overwrite-with-blend branch (tiling.py:259-272)
+            out_d, t = _dev(output, dev), _dev(tile_data, dev)
+            h, w = spec.row_end - spec.row_start, spec.col_end - spec.col_start
+            with torch.cuda.device(dev):
+                check(lib.bgnn_stitch_blend_tile(ptr(out_d), int(out_d.shape[0]), int(out_d.shape[1]), spec.row_start,
+                                                 spec.col_start, h, w, ptr(self.blend_table_device(h, dev)),
+                                                 ptr(self.blend_table_device(w, dev)), ptr(t), stream_ptr()))
+            if isinstance(output, np.ndarray):
+                output[...] = out_d.cpu().numpy()
+            elif out_d.data_ptr() != output.data_ptr():
+                output.copy_(out_d)
+            return
         out_d, w_d = _dev(output, dev), _dev(weight_grid, dev)
         s = _lib.Survey()
         s.rows, s.cols, s.n_cont = int(out_d.shape[0]), int(out_d.shape[1]), 1
@@ -217,19 +226,22 @@ class TileMerger:
     def initialize(self, grid_shape: Tuple[int, int], channels: List[str], dtypes: Optional[dict] = None):
         dev = self._dev()
         self._shape = (int(grid_shape[0]), int(grid_shape[1]))
-        if dtypes and any(np.dtype(v) != np.float32 for v in dtypes.values()):
-            raise NotImplementedError("device TileMerger accumulates in float32 (the reference default)")
+        dtypes = dtypes or {}
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+        for c, v in dtypes.items():                  # tiling.py:370-373: NaN-initialised planes => floating dtypes only
+            if np.dtype(v) not in tdt:
+                raise ValueError(f"channel {c!r}: accumulator dtype must be float32 or float64 (NaN-initialised), got {np.dtype(v)}")
         cont = [c for c in channels if c not in self.DISCRETE_CHANNELS]
-        if len(cont) > 4:
-            raise ValueError("at most 4 continuous channels are supported")
         for c in channels:
-            self.outputs[c] = torch.empty(self._shape, dtype=torch.float32, device=dev)
+            self.outputs[c] = torch.empty(self._shape, dtype=tdt[np.dtype(dtypes.get(c, np.float32))], device=dev)
             self.weights[c] = torch.empty(self._shape, dtype=torch.float32, device=dev)
         disc = [c for c in channels if c in self.DISCRETE_CHANNELS]
         if disc:
             self._confidence_tracker = torch.empty(self._shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.bgnn_stitch_init(C.byref(self._survey(cont, disc[0] if disc else None)), stream_ptr()))
+            for i in range(0, max(len(cont), 1), 4):
+                d = disc[0] if (disc and i == 0) else None
+                check(lib.bgnn_stitch_init(C.byref(self._survey(cont[i:i + 4], d)), stream_ptr()))
             for c in disc:                      # weight plane of a discrete channel is unused (stays 0)
                 self.weights[c].zero_()
         logger.info("Initialized %d output channels for %s", len(channels), grid_shape)
@@ -239,9 +251,33 @@ class TileMerger:
         s.rows, s.cols, s.n_cont = self._shape[0], self._shape[1], len(cont)
         for k, c in enumerate(cont):
             s.cont[k], s.wsum[k] = self.outputs[c].data_ptr(), self.weights[c].data_ptr()
+            if self.outputs[c].dtype == torch.float64:
+                s.f64_mask |= 1 << k
         if disc is not None and self._confidence_tracker is not None:
             s.discrete, s.tracker = self.outputs[disc].data_ptr(), self._confidence_tracker.data_ptr()
+            if self.outputs[disc].dtype == torch.float64:
+                s.f64_mask |= 1 << 4
         return s
+
+    def add_tile_nodes(self, spec: TileSpec, node_id: torch.Tensor, predicted_class: torch.Tensor, confidence: torch.Tensor,
+                       correction: Optional[torch.Tensor], local_std: Optional[torch.Tensor], norm_floor: float):
+        """`add_tile` with the per-tile scatter fused in (bgnn_stitch_add_tile_nodes): the model's per-node outputs go
+        straight into the accumulators through the tile's node-id grid.  Needs exactly the pipeline's channel set
+        (classification, confidence[, correction]); same results, bit for bit, as graph_to_grid + add_tile."""
+        chans = set(self.outputs)
+        if not ({"classification", "confidence"} <= chans <= {"classification", "confidence", "correction"}):
+            raise ValueError(f"add_tile_nodes needs the channels classification, confidence[, correction]; have {sorted(chans)}")
+        dev = self._dev()
+        h, w = spec.row_end - spec.row_start, spec.col_end - spec.col_start
+        tm = self.tile_manager
+        cont = ["confidence"] + (["correction"] if "correction" in chans else [])
+        with torch.cuda.device(dev):
+            check(lib.bgnn_stitch_add_tile_nodes(C.byref(self._survey(cont, "classification")), spec.row_start, spec.col_start,
+                                                 h, w, ptr(tm.blend_table_device(h, dev)), ptr(tm.blend_table_device(w, dev)),
+                                                 ptr(node_id), ptr(predicted_class), ptr(confidence),
+                                                 ptr(correction) if "correction" in chans else None,
+                                                 ptr(local_std) if correction is not None else None, float(norm_floor),
+                                                 stream_ptr()))
 
     def add_tile(self, spec: TileSpec, channel_data: dict):
         """Tile arrays may be NumPy (uploaded) or CUDA tensors (consumed in place).

@@ -239,6 +239,8 @@ typedef struct bgnn_survey {
     int32_t n_cont;
     float* discrete;     /* classification (float, NaN = never written) */
     float* tracker;      /* confidence tracker, init -1 (tiling.py:382) */
+    int32_t f64_mask;    /* bit k: cont[k] is a DOUBLE plane, bit 4: discrete is (TileMerger.initialize(dtypes=...),
+                          * tiling.py:356-373); the weight sums and the tracker are always float32 like the reference's */
 } bgnn_survey;
 
 int bgnn_stitch_init(const bgnn_survey* s, void* stream);
@@ -251,6 +253,19 @@ int bgnn_stitch_add_tile(const bgnn_survey* s, int64_t r0, int64_t c0, int32_t h
                          const float* row_w, const float* col_w,
                          const float* const* cont_tiles, const float* discrete_tile,
                          const float* conf_tile, void* stream);
+/* The same accumulate with the per-tile scatter fused in (replaces the 4x graph_to_grid of models/pipeline.py:278-304 +
+ * TileMerger.add_tile, data/tiling.py:384-428): the tile's per-node outputs are read through its node-id grid
+ * (node_id [h*w], -1 = invalid -> 0.0 like fill_value=0.0) and accumulated into cont[0] = confidence,
+ * cont[1] = correction * max(local_std, norm_floor) (n_cont == 1: confidence only; corr may be NULL -> 0),
+ * discrete = class by arg-max confidence.  Bit-identical to bgnn_scatter_tile + bgnn_stitch_add_tile. */
+int bgnn_stitch_add_tile_nodes(const bgnn_survey* s, int64_t r0, int64_t c0, int32_t h, int32_t w,
+                               const float* row_w, const float* col_w, const int32_t* node_id,
+                               const int64_t* cls, const float* conf, const float* corr,
+                               const float* local_std, float norm_floor, void* stream);
+/* TileManager.merge_tile WITHOUT a weight grid (tiling.py:259-272): out [rows, cols] f32 is blended in place,
+ * out = out * (1 - w) + tile * w where both are finite, out = tile where only the tile is. */
+int bgnn_stitch_blend_tile(float* out, int64_t rows, int64_t cols, int64_t r0, int64_t c0, int32_t h, int32_t w,
+                           const float* row_w, const float* col_w, const float* tile, void* stream);
 /* out = acc / wsum where wsum > 0 (tiling.py:289-292) */
 int bgnn_stitch_finalize(const bgnn_survey* s, void* stream);
 

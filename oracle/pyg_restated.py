@@ -274,6 +274,7 @@ def install():
         gdal = types.ModuleType("osgeo.gdal")
         gdal.UseExceptions = lambda: None
         gdal.SetConfigOption = lambda *a, **k: None
+        gdal.Open = lambda *a, **k: None               # "could not open": VRBagHandler falls back to no georeferencing (vr_bag.py:140-153)
         osgeo.gdal = gdal
         osgeo.osr = types.ModuleType("osgeo.osr")
         osgeo.ogr = types.ModuleType("osgeo.ogr")

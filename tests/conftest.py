@@ -24,3 +24,6 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+# tests/fixtures/ref_layout/scripts/test_pipeline.py mirrors a reference SCRIPT of that name: not a test module
+collect_ignore_glob = ["fixtures/*"]

@@ -373,8 +373,117 @@ def make_sidecar_fixture():
           "valid", int(sb.valid_mask.sum()))
 
 
+def make_vr_bag_fixture():
+    """Reference VRBagHandler.iterate_refinements (data/vr_bag.py:243-298), VRBagWriter.update_refinement_batch (:550-588),
+    detect_bag_type (:29-63) and the SR handler / writer (:315-475), UNMODIFIED, on synthetic containers served by the
+    h5py stand-in of tests/fake_h5py.py (h5py itself is absent from this image)."""
+    import importlib
+    import tempfile
+    from tests import fake_h5py
+    fake_h5py.install()
+    vb = importlib.import_module("data.vr_bag")
+    vb = importlib.reload(vb)                      # picks the stand-in up (H5PY_AVAILABLE is latched at import)
+    assert vb.H5PY_AVAILABLE
+    blob = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for case, kw in dict(shuffled=dict(seed=3, shuffle_storage=True), ordered=dict(seed=5, shuffle_storage=False, base_shape=(4, 6))).items():
+            src, dst = os.path.join(tmp, case + ".bag"), os.path.join(tmp, case + "_out.bag")
+            meta, ref = fake_h5py.write_vr_bag(src, **kw)
+            blob[f"{case}/kw"] = np.array(repr(kw))
+            blob[f"{case}/meta"], blob[f"{case}/ref"] = meta, ref
+            blob[f"{case}/type"] = np.array(vb.detect_bag_type(src))
+            h = vb.VRBagHandler(src)
+            info = h.get_refinement_info()
+            blob[f"{case}/info"] = np.array([info["num_refined_cells"], info["total_refinement_nodes"]], np.int64)
+            blob[f"{case}/unique_resolutions"] = np.array(info["unique_resolutions"], np.float64)
+            for mvr in (0.0, 0.5):
+                grids = list(h.iterate_refinements(mvr))
+                tag = f"{case}/mvr{mvr}"
+                blob[tag + "/desc"] = np.array([[g.base_row, g.base_col, g.dimensions[0], g.dimensions[1], g.start_index] for g in grids], np.int64)
+                blob[tag + "/res"] = np.array([g.resolution for g in grids], np.float64)
+                blob[tag + "/sw"] = np.array([g.sw_corner for g in grids], np.float64)
+                blob[tag + "/depth"] = np.concatenate([g.depth.ravel() for g in grids])
+                blob[tag + "/unc"] = np.concatenate([g.uncertainty.ravel() for g in grids])
+                blob[tag + "/num_valid"] = np.array([g.num_valid for g in grids], np.int64)
+            # write-back of seeded "corrections" through the reference writer, grid by grid
+            w = h.copy_and_open_for_writing(dst)
+            rng = np.random.default_rng(17)
+            for g in h.iterate_refinements(0.0):
+                cd = g.depth.copy()
+                cu = g.uncertainty.copy()
+                m = g.valid_mask & (rng.random(g.shape) < 0.3)
+                cd[m] -= rng.normal(0, 0.5, int(m.sum())).astype(np.float32)
+                cu[m] *= np.float32(1.25)
+                w.update_refinement_batch(g, cd, cu)
+            blob[f"{case}/corrections_applied"] = np.int64(w._corrections_applied)
+            w.close()
+            with fake_h5py.File(dst, "r") as f:
+                blob[f"{case}/ref_after"] = f["BAG_root"]["varres_refinements"][:]
+        # SR container
+        src, dst = os.path.join(tmp, "sr.bag"), os.path.join(tmp, "sr_out.bag")
+        d = fake_h5py.write_sr_bag(src)
+        blob["sr/type"] = np.array(vb.detect_bag_type(src))
+        h = vb.SRBagHandler(src)
+        g = next(iter(h.iterate_refinements(0.0)))
+        blob["sr/depth"], blob["sr/unc"], blob["sr/res"] = g.depth, g.uncertainty, np.array(g.resolution)
+        blob["sr/info"] = np.array([h.get_refinement_info()["total_refinement_nodes"]], np.int64)
+        blob["sr/n_grids_mvr0.95"] = np.int64(len(list(h.iterate_refinements(0.95))))
+        w = h.copy_and_open_for_writing(dst)
+        w.update_refinement_batch(g, g.depth + np.float32(1.0), g.uncertainty * np.float32(2.0))
+        w.close()
+        with fake_h5py.File(dst, "r") as f:
+            blob["sr/elev_after"], blob["sr/unc_after"] = f["BAG_root"]["elevation"][:], f["BAG_root"]["uncertainty"][:]
+    np.savez_compressed(os.path.join(HERE, "vr_bag_case.npz"), **blob)
+    print("vr_bag_case.npz:", {k: blob[k].tolist() for k in blob if k.endswith("/info")})
+
+
+def make_native_script_fixture():
+    """The UNMODIFIED scripts/inference_native.py run as __main__ (runpy) on the reference's own packages, CPU: VR container
+    served by the h5py stand-in, checkpoint with the pickled reference Config, `--no-export-sidecar` (its georeferencing
+    needs GDAL).  A module-level `logger` is pre-seeded: the shipped script uses one it never defines (:148 vs :348).
+    The output container's refinement records are the fixture."""
+    import importlib
+    import runpy
+    import tempfile
+    from tests import fake_h5py
+    fake_h5py.install()
+    importlib.reload(importlib.import_module("data.vr_bag"))
+    import data as ref_data
+    importlib.reload(ref_data)                   # re-exports the reloaded handler classes
+    kw = dict(base_shape=(6, 8), seed=23, lo=3, hi=20, nodata_frac=0.08)
+    mcfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(mcfg, seed=4, randomize_bn=True, head_gain=8.0)
+    with tempfile.TemporaryDirectory() as tmp:
+        src, dst, ckpt = os.path.join(tmp, "in.bag"), os.path.join(tmp, "out", "out.bag"), os.path.join(tmp, "model.pt")
+        meta, ref = fake_h5py.write_vr_bag(src, **kw)
+        # calibrate the heads on the biggest grid so that noise / confident cells exist
+        big = max(importlib.import_module("data.vr_bag").VRBagHandler(src).iterate_refinements(0.0), key=lambda g: g.num_valid)
+        gbig = ref_gc.GraphBuilder("8-connected").build_graph(big.depth, big.valid_mask, None, big.resolution)
+        cls_b, conf_b = mo.calibrate_heads(sd, mcfg, gbig.x, gbig.edge_index, gbig.edge_attr, conf_target=0.8)
+        torch.save({"model_state_dict": sd, "config": ref_config.Config(), "in_channels": 7, "edge_dim": 3}, ckpt)
+        argv = ["--input", src, "--model", ckpt, "--output", dst, "--device", "cpu", "--no-export-sidecar",
+                "--min-valid-ratio", "0.05", "--auto-correct-threshold", "0.7", "--log-level", "ERROR"]
+        old = sys.argv
+        sys.argv = [os.path.join(REF, "scripts", "inference_native.py")] + argv
+        try:
+            g = runpy.run_path(sys.argv[0], init_globals={"logger": logging.getLogger("ref_native_script")}, run_name="__main__")
+        finally:
+            sys.argv = old
+        g["NativeVRProcessor"].BATCH_NODE_BUDGET = 50000
+        with fake_h5py.File(dst, "r") as f:
+            after = f["BAG_root"]["varres_refinements"][:]
+    blob = dict(kw=np.array(repr(kw)), model_seed=np.int64(4), cls_bias=cls_b.numpy(), conf_bias=conf_b.numpy(),
+                argv=np.array(argv[6:]), ref_before=ref, ref_after=after)
+    np.savez_compressed(os.path.join(HERE, "native_script_case.npz"), **blob)
+    changed = int((after["depth"] != ref["depth"]).sum())
+    print("native_script_case.npz: records", ref.shape[1], "depth changed", changed,
+          "uncertainty changed", int((after["depth_uncrt"] != ref["depth_uncrt"]).sum()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar", "multiscale"]
+    which = sys.argv[1:] or ["native_script", "graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar", "multiscale", "vr_bag"]
+    if "vr_bag" in which: make_vr_bag_fixture()
+    if "native_script" in which: make_native_script_fixture()
     if "graph" in which: make_graph_fixtures()
     if "model" in which: make_model_fixtures()
     if "model_bf16" in which: make_model_bf16_fixtures()
