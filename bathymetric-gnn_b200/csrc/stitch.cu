@@ -201,7 +201,50 @@ k_apply(const float* __restrict__ depth, const uint8_t* __restrict__ valid, int6
     }
 }
 
+// finalize + unprocessed-cell fill + _apply_corrections of a row range in ONE pass (the survey path emits rows as soon as
+// every tile touching them has been accumulated): tiling.py:289-292, pipeline.py:196-211, 316-349.  Same fp32 operations
+// as k_finalize followed by k_apply (bit-identical); valid = isfinite(depth) && depth != nodata (loaders.py:58-69) is
+// derived here instead of being read from a mask plane; the class plane leaves as uint8 (255 = NaN / never written).
+__global__ void __launch_bounds__(ST_THREADS)
+k_survey_emit(const bgnn_survey s, const float* __restrict__ depth, int use_nodata, float nodata, float thr,
+              float* __restrict__ cleaned, uint8_t* __restrict__ cls_u8) {
+    const int64_t n = s.rows * s.cols;
+    for (int64_t t = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * ST_THREADS) {
+        float cf = s.cont[0][t];
+        float cr = s.n_cont > 1 ? s.cont[1][t] : 0.0f;
+        const float w0 = s.wsum[0][t];
+        if (w0 > 0.0f) cf = cf / w0;
+        if (s.n_cont > 1) {
+            const float w1 = s.wsum[1][t];
+            if (w1 > 0.0f) cr = cr / w1;
+        }
+        float c = s.discrete[t];
+        const float d = depth[t];
+        const bool v = isfinite(d) && !(use_nodata && d == nodata);
+        if (v && isnan(c)) { c = 0.0f; cf = 0.0f; cr = 0.0f; }
+        s.cont[0][t] = cf;
+        if (s.n_cont > 1) s.cont[1][t] = cr;
+        s.discrete[t] = c;
+        if (cls_u8) cls_u8[t] = isnan(c) ? (uint8_t)255 : (uint8_t)c;
+        if (cleaned) cleaned[t] = (c == 2.0f && cf > thr && v) ? d - cr : d;
+    }
+}
+
 }  // namespace
+
+extern "C" int bgnn_survey_emit(const bgnn_survey* s, const float* depth, int32_t use_nodata, float nodata,
+                                float auto_correct_threshold, float* cleaned, uint8_t* class_u8, void* stream) {
+    BGNN_CHECK_ARG(s && depth, "null argument");
+    BGNN_CHECK_ARG(s->n_cont >= 1 && s->n_cont <= 2 && s->cont[0] && s->wsum[0] && s->discrete && s->f64_mask == 0,
+                   "survey must carry float32 confidence [+ correction] and class planes");
+    BGNN_CHECK_ARG(s->n_cont == 1 || (s->cont[1] && s->wsum[1]), "null correction plane");
+    if (s->rows * s->cols <= 0) return BGNN_OK;
+    ProfScope ps(77, (cudaStream_t)stream);
+    k_survey_emit<<<grid_for(s->rows * s->cols), ST_THREADS, 0, (cudaStream_t)stream>>>(*s, depth, use_nodata, nodata,
+                                                                                     auto_correct_threshold, cleaned, class_u8);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
 
 extern "C" int bgnn_scatter_tile(const int32_t* node_id, int64_t n_cells, const int64_t* cls, const float* conf,
                                  const float* corr, const float* local_std, float norm_floor, float* class_grid,

@@ -119,9 +119,10 @@ class BathymetricPipeline:
         logger.info("Model loaded from %s", model_path)
 
     # ------------------------------------------------------------------ per tile
-    def _tile_on_device(self, depth_view, unc_view, mask, resolution, nodata, min_valid_ratio=None, into=None):
+    def _tile_on_device(self, depth_view, unc_view, mask, resolution, nodata, min_valid_ratio=None, into=None, sink=None):
         """graph build -> predict -> scatter; returns (device tile grids [class, conf, corr] or None, N).
-        `into=(merger, spec)`: the scatter is fused into the stitch accumulate instead (returns (True, N))."""
+        `into=(merger, spec)`: the scatter is fused into the stitch accumulate instead (returns (True, N));
+        `sink(device_graph, outputs)`: the caller consumes the per-node outputs itself (survey.py; returns (True, N))."""
         graph = self.graph_builder.build_graph(depth_view, mask, unc_view, resolution, nodata=nodata)
         shape = tuple(depth_view.shape)
         if graph.num_nodes == 0:
@@ -131,6 +132,9 @@ class BathymetricPipeline:
         out = self.model.predict(graph, auto_correct_threshold=self.config.inference.auto_correct_threshold,
                                  review_threshold=self.config.inference.review_threshold)
         dg = graph._dev
+        if sink is not None:
+            sink(dg, out)
+            return True, graph.num_nodes
         if into is not None:
             merger, spec = into
             merger.add_tile_nodes(spec, dg.node_id, out["predicted_class"], out["confidence"], out.get("correction"),
@@ -171,6 +175,8 @@ class BathymetricPipeline:
         dev = self.device
         H, W = grid.shape
         tm = self.tile_manager
+        if specs is None and not keep_on_device and not isinstance(grid.depth, torch.Tensor):
+            return self._process_grid_streamed(grid)
         with torch.cuda.device(dev):
             def to_dev(a):          # host arrays are uploaded once; a survey already resident in HBM is used in place
                 if isinstance(a, torch.Tensor):
@@ -216,6 +222,20 @@ class BathymetricPipeline:
             if keep_on_device:
                 return res
             return {k: v.cpu().numpy() for k, v in res.items()}
+
+    def _process_grid_streamed(self, grid: BathymetricGrid) -> Dict[str, np.ndarray]:
+        """Host grid in, host planes out through the streaming survey driver (survey.py): rows go up tile-row by
+        tile-row, finalised rows come back while later tiles are still computing.  Same results, bit for bit, as the
+        resident path above (tests/test_gpu_survey.py)."""
+        from . import survey as sv
+        H, W = grid.shape
+        pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        plan, res = sv.process_survey(self, pin(grid.depth), pin(grid.uncertainty), grid.nodata_value, grid.resolution)
+        logger.info("Processed %d tiles (%d skipped below min_valid_ratio)", res["stats"]["tiles"], res["stats"]["skipped"])
+        out = {"classification": sv.classification_as_float(res["classification"]), "confidence": res["confidence"].numpy(),
+               "correction": res["correction"].numpy(), "cleaned_depth": res["cleaned_depth"].numpy()}
+        out["valid_mask"] = grid.valid_mask.astype(np.float32)
+        return out
 
     def process(self, input_path, output_path, export_extras: bool = True) -> Dict[str, np.ndarray]:
         """models/pipeline.py:134-241."""

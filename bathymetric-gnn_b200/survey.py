@@ -1,0 +1,356 @@
+"""Whole-survey driver (BASELINE configs[2]): host grid in -> host result planes out, tiles streamed through ONE GPU
+per rank, tile-row BANDS per rank, bit-identical to the single-process reference order for any number of ranks.
+
+What the reference does (models/pipeline.py:154-241, data/tiling.py:384-454): iterate the overlapping tiles in
+row-major order, blend every tile's result grids into whole-survey host accumulators, finalize, fill unprocessed cells,
+apply corrections.  Here, per rank:
+
+  * the rank's band of survey rows goes host -> device ONCE, tile-row by tile-row on a copy stream (events gate the
+    tile-rows that need them), so the first tiles start while the rest of the band is still in flight;
+  * per tile: graph build -> predict -> scatter fused into the stitch accumulate (five band-resident planes:
+    confidence sum, correction sum, ONE shared weight sum -- every tile cell is finite, so the reference's per-channel
+    weight planes are identical --, class, confidence tracker);
+  * as soon as every tile touching a range of rows is done, those rows are finalised + corrected in one pass
+    (`bgnn_survey_emit`) and copied device -> host on a second copy stream, overlapped with the next tile-rows: the full
+    result planes never exist on the device, "only the final grid is gathered" (SURVEY.md 8(e));
+  * SEAMS between bands: the rows of a band that the previous band's tiles also touch are NOT accumulated at first --
+    the tile strips covering them are parked as small tile grids; when the previous rank hands over its partial planes
+    for those rows (one point-to-point message of 5 x seam_rows x W floats over NVLink), they are copied in and the
+    parked strips are replayed on top in tile order.  Every cell therefore sees `((A + B) + C) + D` in exactly the
+    reference's tile order: the sharded result is bit-identical to the one-GPU result, seams included.  There is no
+    collective; ranks without a neighbour skip the hand-over.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+from .config import CORRECTION_NORM_FLOOR
+from .tiling import TileSpec
+
+CLASS_NAN_U8 = 255          # `classification` leaves the device as uint8; 255 = NaN (never written and not valid)
+
+
+# ------------------------------------------------------------------------------------------------ planning (host integers)
+@dataclass
+class BandPlan:
+    """Rows and tiles of one rank.  Rows are survey rows; [r0, r1) = rows the rank's tiles touch."""
+    rank: int
+    world: int
+    shape: Tuple[int, int]
+    tile_rows: List[List[TileSpec]] = field(default_factory=list)   # reference order, grouped by tile_row
+    r0: int = 0
+    r1: int = 0
+    top_end: int = 0        # rows [r0, top_end) are also touched by earlier bands: parked until their planes arrive
+    bottom0: int = 0        # rows [bottom0, r1) are handed to the next band (== r1 when there is none)
+    prev_rank: Optional[int] = None
+    next_rank: Optional[int] = None
+
+    @property
+    def specs(self) -> List[TileSpec]:
+        return [s for row in self.tile_rows for s in row]
+
+    @property
+    def own_rows(self) -> Tuple[int, int]:
+        """Rows this rank emits: its band minus the seam it hands down."""
+        return (self.r0, self.bottom0)
+
+    @property
+    def empty(self) -> bool:
+        return not self.tile_rows
+
+
+def plan_bands(specs: Sequence[TileSpec], num_tile_rows: int, world: int, shape: Tuple[int, int]) -> List[BandPlan]:
+    """Contiguous, balanced bands of tile-rows (one per rank), their seams and the rows each rank owns.  The owned row
+    ranges partition [0, H)."""
+    from .parallel import band_partition
+    H, W = int(shape[0]), int(shape[1])
+    plans = []
+    for rank, (lo, hi) in enumerate(band_partition(num_tile_rows, world)):
+        p = BandPlan(rank=rank, world=world, shape=(H, W))
+        for tr in range(lo, hi):
+            row = [s for s in specs if s.tile_row == tr]
+            if row:
+                p.tile_rows.append(row)
+        if p.tile_rows:
+            p.r0 = min(s.row_start for s in p.specs)
+            p.r1 = max(s.row_end for s in p.specs)
+        plans.append(p)
+    live = [p for p in plans if not p.empty]
+    for i, p in enumerate(live):
+        prev, nxt = (live[i - 1] if i > 0 else None), (live[i + 1] if i + 1 < len(live) else None)
+        p.prev_rank = prev.rank if prev else None
+        p.next_rank = nxt.rank if nxt else None
+        p.top_end = min(max(prev.r1, p.r0), p.r1) if prev else p.r0
+        p.bottom0 = max(min(nxt.r0, p.r1), p.r0) if nxt else p.r1
+        if prev is not None:
+            assert prev.r0 <= p.r0 and prev.r1 <= p.r1, "bands must be monotone in their row ranges"
+    if live:
+        assert live[0].r0 == 0 and live[-1].r1 == H, "tiles must cover the survey rows"
+    return plans
+
+
+# ------------------------------------------------------------------------------------------------ seam hand-over
+class DistLink:
+    """Point-to-point seam hand-over between neighbouring ranks over torch.distributed (NCCL: NVLink P2P; gloo on CPU)."""
+
+    def __init__(self, dist, group=None):
+        self.dist, self.group = dist, group
+
+    def exchange(self, send: Optional[Tuple[int, List[torch.Tensor]]], recv: Optional[Tuple[int, List[torch.Tensor]]]):
+        ops = []
+        if send is not None:
+            ops += [self.dist.P2POp(self.dist.isend, t, send[0], self.group) for t in send[1]]
+        if recv is not None:
+            ops += [self.dist.P2POp(self.dist.irecv, t, recv[0], self.group) for t in recv[1]]
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class LocalLink:
+    """In-process mailbox: several bands executed one after the other on one device (tests, single-GPU debugging)."""
+
+    def __init__(self):
+        self.box: Dict[Tuple[int, int], List[torch.Tensor]] = {}
+        self.rank = 0
+
+    def exchange(self, send, recv):
+        if recv is not None:
+            parts = self.box.pop((recv[0], self.rank))
+            for dst, src in zip(recv[1], parts):
+                dst.copy_(src)
+        if send is not None:
+            self.box[(self.rank, send[0])] = [t.clone() for t in send[1]]
+
+
+# ------------------------------------------------------------------------------------------------ band accumulators
+class BandStitcher:
+    """The five band-resident planes and the kernels that touch them.  Row indices are BAND-local."""
+    PLANES = ("confidence", "correction", "wsum", "classification", "tracker")
+
+    def __init__(self, tile_manager, rows: int, cols: int, device, predict_correction: bool = True):
+        self.tm, self.rows, self.cols, self.device = tile_manager, int(rows), int(cols), device
+        self.planes = torch.empty((5, self.rows, self.cols), dtype=torch.float32, device=device)
+        self.conf, self.corr, self.wsum, self.cls, self.trk = self.planes.unbind(0)
+        self.n_cont = 2
+        check(lib.bgnn_stitch_init(C.byref(self._survey(0, self.rows)), stream_ptr()))
+        self.parked: List[Tuple[TileSpec, int, torch.Tensor]] = []
+
+    def _survey(self, a: int, b: int) -> _lib.Survey:
+        s = _lib.Survey()
+        s.rows, s.cols, s.n_cont = b - a, self.cols, self.n_cont
+        off = a * self.cols * 4
+        s.cont[0], s.cont[1] = self.conf.data_ptr() + off, self.corr.data_ptr() + off
+        s.wsum[0] = s.wsum[1] = self.wsum.data_ptr() + off
+        s.discrete, s.tracker = self.cls.data_ptr() + off, self.trk.data_ptr() + off
+        return s
+
+    def add_tile_nodes(self, spec: TileSpec, dg, out: Dict[str, torch.Tensor], park_rows: int = 0):
+        """Accumulate one tile (spec in band-local rows) straight from its per-node outputs.  The first `park_rows` rows
+        of the tile lie in the seam owned by the previous band: they are scattered into a small strip grid and parked."""
+        h, w = spec.row_end - spec.row_start, spec.col_end - spec.col_start
+        dev = self.device
+        row_w, col_w = self.tm.blend_table_device(h, dev), self.tm.blend_table_device(w, dev)
+        corr = out.get("correction")
+        floor_ = float(CORRECTION_NORM_FLOOR)
+        k = min(max(int(park_rows), 0), h)
+        if k > 0:
+            strip = torch.empty((3, k, w), dtype=torch.float32, device=dev)
+            check(lib.bgnn_scatter_tile(ptr(dg.node_id), k * w, ptr(out["predicted_class"]), ptr(out["confidence"]), ptr(corr),
+                                        ptr(dg.local_std), floor_, ptr(strip[0]), ptr(strip[1]),
+                                        ptr(strip[2]) if corr is not None else None, stream_ptr()))
+            if corr is None:
+                strip[2].zero_()
+            self.parked.append((spec, k, strip))
+        if k < h:
+            nid = dg.node_id.view(-1)[k * w:]
+            check(lib.bgnn_stitch_add_tile_nodes(C.byref(self._survey(0, self.rows)), spec.row_start + k, spec.col_start, h - k, w,
+                                                 ptr(row_w[k:]), ptr(col_w), ptr(nid), ptr(out["predicted_class"]),
+                                                 ptr(out["confidence"]), ptr(corr), ptr(dg.local_std) if corr is not None else None,
+                                                 floor_, stream_ptr()))
+
+    def add_zero_tile(self, spec: TileSpec, park_rows: int = 0):
+        """pipeline.py:257-264: a tile without valid cells that is not skipped contributes zeros."""
+        h, w = spec.row_end - spec.row_start, spec.col_end - spec.col_start
+        z = torch.zeros((3, h, w), dtype=torch.float32, device=self.device)
+        k = min(max(int(park_rows), 0), h)
+        if k > 0:
+            self.parked.append((spec, k, z[:, :k].contiguous()))
+        if k < h:
+            self._add_grid(spec.row_start + k, spec.col_start, h - k, w, self.tm.blend_table_device(h, self.device)[k:],
+                           self.tm.blend_table_device(w, self.device), z[:, k:].contiguous())
+
+    def _add_grid(self, r0, c0, h, w, row_w, col_w, grids):
+        arr = (C.c_void_p * 4)(grids[1].data_ptr(), grids[2].data_ptr(), None, None)
+        check(lib.bgnn_stitch_add_tile(C.byref(self._survey(0, self.rows)), r0, c0, h, w, ptr(row_w), ptr(col_w), arr,
+                                       ptr(grids[0]), ptr(grids[1]), stream_ptr()))
+
+    def replay_parked(self):
+        """Accumulate the parked strips in tile order (after the previous band's partial planes have been copied in)."""
+        for spec, k, strip in self.parked:
+            h, w = spec.row_end - spec.row_start, spec.col_end - spec.col_start
+            self._add_grid(spec.row_start, spec.col_start, k, w, self.tm.blend_table_device(h, self.device),
+                           self.tm.blend_table_device(w, self.device), strip)
+        self.parked = []
+
+    def seam_views(self, a: int, b: int) -> List[torch.Tensor]:
+        """Contiguous row slices [a, b) of the five planes (what one band hands to the next)."""
+        return [p[a:b] for p in (self.conf, self.corr, self.wsum, self.cls, self.trk)]
+
+    def emit(self, a: int, b: int, depth: torch.Tensor, use_nodata: bool, nodata: float, thr: float, cls_u8: torch.Tensor):
+        """Rows [a, b): finalize + fill + corrections in place; `depth[a:b]` becomes the cleaned depth."""
+        if b <= a:
+            return
+        check(lib.bgnn_survey_emit(C.byref(self._survey(a, b)), ptr(depth[a:b]), 1 if use_nodata else 0, float(nodata), float(thr),
+                                   ptr(depth[a:b]), ptr(cls_u8[a:b]), stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------ the band loop
+def pinned_outputs(rows: int, cols: int) -> Dict[str, torch.Tensor]:
+    mk = lambda dt: torch.empty((rows, cols), dtype=dt, pin_memory=bool(rows * cols))
+    return dict(cleaned_depth=mk(torch.float32), classification=mk(torch.uint8), confidence=mk(torch.float32),
+                correction=mk(torch.float32))
+
+
+def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata: Optional[float] = None,
+                 resolution: Tuple[float, float] = (1.0, 1.0), out: Optional[Dict[str, torch.Tensor]] = None,
+                 link=None) -> Dict[str, torch.Tensor]:
+    """Run one rank's band.  `depth_host` / `uncertainty_host`: the band's rows [plan.r0, plan.r1) as host tensors / arrays
+    (pinned for asynchronous copies) or CUDA tensors; `out`: host tensors for the OWNED rows [plan.r0, plan.bottom0)
+    (allocated pinned when None).  Returns `out` (+ counters) once its copies have completed."""
+    if pipe.model is None:
+        raise RuntimeError("Model not loaded. Call load_model() first.")
+    dev = pipe.device
+    H, W = plan.shape
+    own_rows = plan.bottom0 - plan.r0
+    if out is None:
+        out = pinned_outputs(own_rows if not plan.empty else 0, W)
+    stats = dict(tiles=0, skipped=0, nodes=0)
+    if plan.empty:
+        out["stats"] = stats
+        return out
+    bh = plan.r1 - plan.r0
+    as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    src_d = as_t(depth_host)
+    src_u = None if uncertainty_host is None else as_t(uncertainty_host)
+    assert tuple(src_d.shape) == (bh, W), f"band depth must be rows [{plan.r0}, {plan.r1}) x {W}"
+    use_nodata = nodata is not None and not np.isnan(nodata)
+    thr = float(pipe.config.inference.auto_correct_threshold)
+    tm = pipe.tile_manager
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        depth = torch.empty((bh, W), dtype=torch.float32, device=dev)
+        unc = None if src_u is None else torch.empty((bh, W), dtype=torch.float32, device=dev)
+        cls_u8 = torch.empty((max(own_rows, 1), W), dtype=torch.uint8, device=dev)
+        st = BandStitcher(tm, bh, W, dev)
+        # ---- host -> device, tile-row by tile-row, all queued now on the copy stream
+        ready, up_to = [], 0
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            for row in plan.tile_rows:
+                need = max(s.row_end for s in row) - plan.r0
+                if need > up_to:
+                    depth[up_to:need].copy_(src_d[up_to:need], non_blocking=True)
+                    if unc is not None:
+                        unc[up_to:need].copy_(src_u[up_to:need], non_blocking=True)
+                    up_to = need
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ready.append(ev)
+        done_events = []
+
+        def emit_rows(a: int, b: int):
+            """band-local rows [a, b) are final: finalise on the main stream, copy out on the output stream"""
+            if b <= a:
+                return
+            st.emit(a, b, depth, use_nodata, nodata if use_nodata else 0.0, thr, cls_u8)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev)
+                out["cleaned_depth"][a:b].copy_(depth[a:b], non_blocking=True)
+                out["classification"][a:b].copy_(cls_u8[a:b], non_blocking=True)
+                out["confidence"][a:b].copy_(st.conf[a:b], non_blocking=True)
+                out["correction"][a:b].copy_(st.corr[a:b], non_blocking=True)
+
+        top = plan.top_end - plan.r0                      # band-local end of the parked seam
+        bottom = plan.bottom0 - plan.r0
+        emitted = top
+        for ti, row in enumerate(plan.tile_rows):
+            main.wait_event(ready[ti])
+            for spec in row:
+                loc = TileSpec(spec.row_start - plan.r0, spec.col_start, spec.row_end - plan.r0, spec.col_end, spec.tile_row, spec.tile_col)
+                sl = (slice(loc.row_start, loc.row_end), slice(loc.col_start, loc.col_end))
+                park = max(0, min(top, loc.row_end) - loc.row_start)
+
+                def sink(dg, o, _loc=loc, _park=park):
+                    st.add_tile_nodes(_loc, dg, o, _park)
+                got, n = pipe._tile_on_device(depth[sl], None if unc is None else unc[sl], None, resolution,
+                                              float(nodata) if use_nodata else None, tm.min_valid_ratio, sink=sink)
+                size = (loc.row_end - loc.row_start) * (loc.col_end - loc.col_start)
+                if n / size < tm.min_valid_ratio:          # tiling.py:200 (skip_empty)
+                    stats["skipped"] += 1
+                    continue
+                if got is None:                            # pipeline.py:257-264 (only when min_valid_ratio <= 0)
+                    st.add_zero_tile(loc, park)
+                stats["tiles"] += 1
+                stats["nodes"] += n
+            nxt = plan.tile_rows[ti + 1] if ti + 1 < len(plan.tile_rows) else None
+            final_to = min(min(s.row_start for s in nxt) - plan.r0, bottom) if nxt else bottom
+            if final_to > emitted:
+                emit_rows(emitted, final_to)
+                emitted = final_to
+        # ---- seams: hand [bottom0, r1) down, take [r0, top_end) from above, replay the parked strips
+        send = (plan.next_rank, st.seam_views(bottom, bh)) if plan.next_rank is not None and bh > bottom else None
+        recv = (plan.prev_rank, st.seam_views(0, top)) if plan.prev_rank is not None and top > 0 else None
+        if link is None and (send or recv):
+            raise RuntimeError("a band with neighbours needs a seam link")
+        if link is not None:
+            if isinstance(link, LocalLink):
+                link.rank = plan.rank
+            if send and recv and top > bottom:             # thin band: its two seams overlap -> strictly in order
+                link.exchange(None, recv)
+                st.replay_parked()
+                link.exchange(send, None)
+            else:
+                link.exchange(send, recv)
+                if recv:
+                    st.replay_parked()
+        if top > 0:
+            emit_rows(0, min(top, bottom))
+        s_out.synchronize()
+        main.synchronize()
+    out["stats"] = stats
+    return out
+
+
+def process_survey(pipe, depth, uncertainty=None, nodata: Optional[float] = None, resolution=(1.0, 1.0), dist=None,
+                   out: Optional[Dict[str, torch.Tensor]] = None):
+    """Whole survey on `world` ranks (dist = torch.distributed module with an initialised group, or None for one rank).
+    `depth`: the FULL host grid (each rank reads only its band's rows) -- a rank that holds just its band calls
+    `process_band` directly.  Returns (plan, out) with `out` covering plan.own_rows."""
+    H, W = int(depth.shape[0]), int(depth.shape[1])
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    ntr, _, specs = pipe.tile_manager.compute_tile_grid((H, W))
+    plan = plan_bands(specs, ntr, world, (H, W))[rank]
+    sl = slice(plan.r0, plan.r1)
+    res = process_band(pipe, plan, depth[sl], None if uncertainty is None else uncertainty[sl], nodata, resolution, out,
+                       DistLink(dist) if world > 1 else None)
+    return plan, res
+
+
+def classification_as_float(cls_u8) -> np.ndarray:
+    """uint8 class plane -> the reference's float32 plane (NaN where never written and not valid)."""
+    a = cls_u8.numpy() if isinstance(cls_u8, torch.Tensor) else np.asarray(cls_u8)
+    f = a.astype(np.float32)
+    f[a == CLASS_NAN_U8] = np.nan
+    return f

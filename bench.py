@@ -187,22 +187,7 @@ def run_ours(args):
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        # NCCL may print its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+    dist = _init_dist(dev) if world > 1 else None
 
     depth_np, mask_np = make_tile(rank)
     cfg, sd = make_weights(0)
@@ -276,7 +261,8 @@ def run_ours(args):
     # Two sets of pinned result buffers and device input buffers: step t's H2D and step t-1's D2H run on a copy stream
     # while step t-1 / t computes (the way a caller streams tiles through the public API); every step's input upload and
     # result read-back is inside the timed region, and each step's result is consumed on the host (float(conf[0])).
-    host_out = [(torch.empty(N, dtype=torch.int64).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
+    # class labels cross PCIe as uint8 (3 classes; the int64 tensor of the reference API stays on the device)
+    host_out = [(torch.empty(N, dtype=torch.uint8).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
                  torch.empty(N, dtype=torch.float32).pin_memory()) for _ in range(2)]
     dev_in = [(torch.empty_like(depth_dev), torch.empty_like(mask_dev)) for _ in range(2)]
     main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
@@ -304,11 +290,12 @@ def run_ours(args):
             flush.fill_(1)
             g = builder.build_graph(dev_in[b][0], dev_in[b][1], None, RES)
             out = model.predict(g)
+            cls_u8 = out["predicted_class"].to(torch.uint8)
             ev_cmp[b].record(main_s)
-            keep[b] = (g, out)                                  # alive until their read-back has finished
+            keep[b] = (g, out, cls_u8)                          # alive until their read-back has finished
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(ev_cmp[b])
-                host_out[b][0].copy_(out["predicted_class"], non_blocking=True)
+                host_out[b][0].copy_(cls_u8, non_blocking=True)
                 host_out[b][1].copy_(out["confidence"], non_blocking=True)
                 host_out[b][2].copy_(out["correction"], non_blocking=True)
                 ev_out[b].record(copy_s)
@@ -334,7 +321,7 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = world * cells / (e2e_ms / args.steps * 1e-3)
     h2d = depth_np.nbytes + mask_np.nbytes
-    d2h = N * (8 + 4 + 4)
+    d2h = N * (1 + 4 + 4)
 
     # ---- per-kernel timing for the roofline (separate pass, same step, events inside the library)
     roof, kernels, launches_per_step = None, {}, 0
@@ -382,6 +369,16 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=args.cpu_crop)
 
+    # ---- BASELINE configs[2]: the 60 000^2 survey, strong scaling over the ranks (north_star's scaling claim)
+    survey = None
+    if not args.no_survey:
+        del depth_dev, mask_dev, flush, dev_in, host_out
+        torch.cuda.empty_cache()
+        try:
+            survey = survey_leg(args, dev, rank, world, dist, model)
+        except (RuntimeError, MemoryError) as e:        # e.g. not enough pinned host memory on this box: say so, keep the line
+            survey = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -394,67 +391,42 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks}
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "survey": survey}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
-def make_survey_band(r0, r1, W, dev, seed=1234, nodata=1.0e6):
-    """Synthetic survey rows [r0, r1) generated on the device from (seed, row, col): analytic surface + gaussian noise
-    (sigma 0.2 m) + spikes (p = 0.005, +-U(1,5) m) + ~5 % invalid area (a smooth 'coast' field) marked with nodata."""
-    depth = torch.empty((r1 - r0, W), dtype=torch.float32, device=dev)
-    cols = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
-    g = torch.Generator(device=dev)
-    for rs in range(r0, r1, 1024):
-        re_ = min(rs + 1024, r1)
-        g.manual_seed(seed * 1000003 + rs)
-        rows = torch.arange(rs, re_, device=dev, dtype=torch.float32)[:, None]
-        d = 30.0 + 5.0 * torch.sin(cols / 60.0) + 3.0 * torch.cos(rows / 45.0) + 0.01 * cols
-        d += 0.2 * torch.randn(d.shape, device=dev, generator=g)
-        u = torch.rand(d.shape, device=dev, generator=g)
-        amp = 1.0 + 4.0 * torch.rand(d.shape, device=dev, generator=g)
-        d += torch.where(u < 0.0025, amp, torch.zeros_like(d)) - torch.where(u > 0.9975, amp, torch.zeros_like(d))
-        coast = torch.sin(rows / 2900.0) + torch.cos(cols / 2300.0) + 0.3 * torch.sin((rows + cols) / 700.0)
-        d[coast > 1.72] = nodata
-        depth[rs - r0:re_ - r0] = d
-    return depth
+def _init_dist(dev):
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return dist
+    # NCCL may print its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+    sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    return dist
 
 
-def run_survey(args):
-    """BASELINE.json configs[2]: an S x S survey, overlapping tiles (2048 / 128) sharded as tile-row bands across the
-    ranks, each band stitched on its own GPU (no data-path collective).  Secondary workload: one JSON line per run,
-    `value` = survey cells / slowest rank's device time for tiles + stitch + finalize of its band."""
+def survey_leg(args, dev, rank, world, dist, model, S=None):
+    """BASELINE.json configs[2]: the S x S synthetic survey (tests/synth.py: a counter-based function of (seed, row, col),
+    ~5 % invalid 'coast'), tile 2048 / overlap 128, tile-row bands per rank (strong scaling), through
+    `bathymetric_gnn_b200.survey.process_band`.  TIMED REGION (device events on the main stream, barrier on both sides,
+    max over ranks): host->device copy of the rank's band from PINNED HOST memory + every tile (graph build, predict,
+    scatter+stitch) + seam hand-over to the neighbour rank (point-to-point, NCCL over NVLink) + replay of the parked seam
+    strips + finalize + unprocessed-cell fill + apply_corrections + device->host copy of the four final planes
+    (cleaned depth f32, class u8, confidence f32, correction f32) into pinned host buffers."""
     import bathymetric_gnn_b200 as bg
-    from bathymetric_gnn_b200 import parallel as par
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
-    S = args.survey_size
-    cfg_m, sd = make_weights(0)
-    model = bg.BathymetricGNN(cfg_m.in_channels, cfg_m.hidden, cfg_m.layers, "GAT", cfg_m.heads, cfg_m.num_classes,
-                              cfg_m.predict_correction, 0.0, cfg_m.edge_dim)
-    model.load_state_dict(sd, strict=True)
+    from bathymetric_gnn_b200 import survey as sv
+    from tests import synth
+    S = S or args.survey_size
     cfg = bg.Config()
     cfg.tile.tile_size, cfg.tile.overlap, cfg.tile.min_valid_ratio = args.tile, args.overlap, 0.1
     pipe = bg.BathymetricPipeline(cfg)
-    pipe.model = model.to(dev).eval()
-    ntr, ntc, specs = pipe.tile_manager.compute_tile_grid((S, S))
-    mine = par.band_specs(specs, par.band_partition(ntr, world)[rank])
-    r0, r1 = par.band_rows(mine)
-    depth = make_survey_band(r0, r1, S, dev)
-    grid = bg.BathymetricGrid(depth=depth, uncertainty=None, nodata_value=1.0e6, resolution=RES)
-    local = par.shift_specs(mine, r0)
+    pipe.model = model
+    link = sv.DistLink(dist) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -462,28 +434,91 @@ def run_survey(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up on the first tiles of the band (module load, allocator), then the timed pass over the whole band
-    pipe.process_grid(grid, specs=local[:min(3, len(local))], keep_on_device="partial")
+    def make_band(size_rows, size_cols, plan, tabs_dev):
+        """the band's rows generated on the device chunk by chunk, parked in pinned host memory (untimed set-up)"""
+        host = torch.empty((plan.r1 - plan.r0, size_cols), dtype=torch.float32, pin_memory=True)
+        for a in range(plan.r0, plan.r1, 2048):
+            b_ = min(a + 2048, plan.r1)
+            blk = synth.survey_block_torch(size_rows, a, b_, 0, size_cols, dev, tables=tabs_dev)
+            host[a - plan.r0:b_ - plan.r0].copy_(blk)
+        torch.cuda.synchronize()
+        return host
+
+    # ---- warm-up: one 2048^2 tile per rank with a seam between every pair of neighbours (module load, allocator, NCCL p2p)
+    Hw, Ww = (args.tile - args.overlap) * world + args.overlap, args.tile
+    tabs_w = {k: torch.from_numpy(v).to(dev) for k, v in synth.survey_tables(max(Hw, Ww)).items()}
+    ntr_w, _, specs_w = pipe.tile_manager.compute_tile_grid((Hw, Ww))
+    plan_w = sv.plan_bands(specs_w, ntr_w, world, (Hw, Ww))[rank]
+    band_w = make_band(max(Hw, Ww), Ww, plan_w, tabs_w)
+    for _ in range(2):
+        sv.process_band(pipe, plan_w, band_w, None, synth.SURVEY_NODATA, RES, None, link)
+        barrier()
+    del band_w, tabs_w
+    # ---- the survey
+    ntr, ntc, specs = pipe.tile_manager.compute_tile_grid((S, S))
+    plans = sv.plan_bands(specs, ntr, world, (S, S))
+    plan = plans[rank]
+    tabs = {k: torch.from_numpy(v).to(dev) for k, v in synth.survey_tables(S).items()}
+    t_setup = time.perf_counter()
+    band = make_band(S, S, plan, tabs)
+    out = sv.pinned_outputs(plan.bottom0 - plan.r0, S)
+    del tabs
+    torch.cuda.empty_cache()
+    t_setup = time.perf_counter() - t_setup
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    state = pipe.process_grid(grid, specs=local, keep_on_device="partial" if world > 1 else True)
+    res = sv.process_band(pipe, plan, band, None, synth.SURVEY_NODATA, RES, out, link)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    per_rank = [ms]
     if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = ms
+        dist.all_reduce(t)
+        per_rank = [float(v) for v in t.tolist()]
+        ms = max(per_rank)
+        cnt = torch.tensor([res["stats"]["tiles"], res["stats"]["skipped"], res["stats"]["nodes"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt)
+        tiles, skipped, nodes = (int(v) for v in cnt.tolist())
+    else:
+        tiles, skipped, nodes = res["stats"]["tiles"], res["stats"]["skipped"], res["stats"]["nodes"]
+    # spot check on the host result (not timed): classes are 0/1/2/255 and corrected cells differ from the input
+    cls = res["classification"]
+    sample = cls[:: max(1, cls.shape[0] // 64), :: max(1, cls.shape[1] // 64)]
+    assert bool(((sample <= 2) | (sample == 255)).all())
+    seam_rows = sum(p.r1 - p.bottom0 for p in plans if not p.empty)
+    return {"metric": "depth cells/sec (graph build+GNN fwd+stitch), whole survey, host in -> host out", "value": S * S / (ms * 1e-3),
+            "unit": UNIT, "scaling": "strong", "n_gpus": world, "seconds": ms * 1e-3,
+            "workload": f"configs[2]: {S}x{S} synthetic survey @0.5 m, tile {args.tile} / overlap {args.overlap}, {len(specs)} tiles "
+                        f"({ntr} tile-rows as contiguous bands over {world} rank(s)), min_valid_ratio 0.1",
+            "tiles_processed": tiles, "tiles_skipped": skipped, "valid_tile_cells": nodes,
+            "tile_cells_per_s": tiles * args.tile * args.tile / (ms * 1e-3),
+            "timed_region": "H2D of the band (pinned host) + tiles + stitch + seam hand-over (p2p) + finalize + fill + "
+                            "apply_corrections + D2H of cleaned/class(u8)/confidence/correction to pinned host",
+            "h2d_bytes": S * S * 4 + seam_rows * S * 4, "d2h_bytes": S * S * 13, "seam_p2p_bytes": seam_rows * S * 20,
+            "per_rank_seconds": [round(v * 1e-3, 4) for v in per_rank], "setup_seconds_rank0_untimed": round(t_setup, 2),
+            "bit_identical_to_one_rank": "by construction (parked seam strips replayed in reference tile order; "
+                                         "tests/test_gpu_survey.py, tests/test_host_logic.py::test_exact_seam_protocol_gloo)"}
+
+
+def run_survey(args):
+    """`--workload survey`: the configs[2] leg alone (same object the default line carries under "survey")."""
+    import bathymetric_gnn_b200 as bg
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = _init_dist(dev) if world > 1 else None
+    cfg_m, sd = make_weights(0)
+    model = bg.BathymetricGNN(cfg_m.in_channels, cfg_m.hidden, cfg_m.layers, "GAT", cfg_m.heads, cfg_m.num_classes,
+                              cfg_m.predict_correction, 0.0, cfg_m.edge_dim)
+    model.load_state_dict(sd, strict=True)
+    line = survey_leg(args, dev, rank, world, dist, model.to(dev).eval())
     if rank == 0:
-        print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd+stitch)", "value": S * S / (ms * 1e-3), "unit": UNIT,
-                          "n_gpus": world, "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "f32",
-                          "data": "synthetic",
-                          "config": {"workload": f"configs[2]: {S}x{S} survey, tile {args.tile} / overlap {args.overlap}, "
-                                                 f"{len(specs)} tiles in {ntr} tile-rows, bands of tile-rows per GPU, device stitch",
-                                     "tiles_rank0": len(local), "band_rows_rank0": [r0, r1],
-                                     "note": "survey band resident in HBM; per-band planes stay on the device (the final gather "
-                                             "of band planes and the seam merge are outside the timed region)"}}))
+        line.update({"higher_is_better": True, "dtype": "f32", "data": "synthetic"})
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -763,7 +798,8 @@ def main():
                          "wide = configs[4] fp32 + bf16 (secondary)")
     ap.add_argument("--grids", type=int, default=100000)
     ap.add_argument("--chunk-cells", type=int, default=8000000)
-    ap.add_argument("--survey-size", type=int, default=16384)
+    ap.add_argument("--survey-size", type=int, default=60000, help="side of the configs[2] survey (the `survey` object of the default line)")
+    ap.add_argument("--no-survey", action="store_true", help="default line without the configs[2] survey leg")
     ap.add_argument("--tile", type=int, default=2048)
     ap.add_argument("--overlap", type=int, default=128)
     ap.add_argument("--cpu-crop", type=int, default=1024, help="cpu_baseline sample: crop x crop corner (about 10-15 s of CPU work)")

@@ -276,6 +276,16 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
                            float* classification, float* confidence, float* correction,
                            float* cleaned, float auto_correct_threshold, void* stream);
 
+/* Survey path: finalize (tiling.py:289-292) + the fill of unprocessed valid cells (pipeline.py:196-207) +
+ * _apply_corrections (pipeline.py:316-349) over the rows of `s` in ONE pass, in place: cont[0] = confidence and
+ * cont[1] = correction leave finalised, `cleaned` ([rows, cols], may alias `depth`) receives the corrected depth and
+ * `class_u8` (may be NULL) the class plane as uint8 (255 = NaN: never written and not valid).  valid = isfinite(depth)
+ * && depth != nodata (data/loaders.py:58-69).  Bit-identical to bgnn_stitch_finalize + bgnn_apply_corrections.  `s`
+ * describes a ROW RANGE of the survey (plane pointers offset to its first row), so rows can be emitted as soon as every
+ * tile that touches them has been accumulated. */
+int bgnn_survey_emit(const bgnn_survey* s, const float* depth, int32_t use_nodata, float nodata,
+                     float auto_correct_threshold, float* cleaned, uint8_t* class_u8, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Native VR-BAG post-processing on the packed ragged cell space (the step right behind the ragged
  * path).  All arrays are DEVICE pointers over the packed cells of a batch of refinement grids (grid g occupies
@@ -342,7 +352,7 @@ int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t*
  * launching stream around every kernel the library launches.  Not thread-safe; off by default.
  * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
  * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
- * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid,
+ * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit,
  * 75 vr_apply_results, 76 sidecar_add.
  * ------------------------------------------------------------------------------------------ */
 int bgnn_profile_enable(int on);                               /* also clears recorded events */

@@ -18,6 +18,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -215,3 +216,34 @@ def predict(sd, cfg, x, edge_index, edge_attr, auto_correct_threshold=0.85,
     out["needs_review"] = action == 2
     out["auto_correct"] = action == 1
     return out
+
+
+def forward_row_bands(sd, cfg: ModelCfg, x, edge_index, edge_attr, node_rows, radius: int = 1, band_rows: int = 128,
+                      keys=("class_logits", "confidence", "correction", "predicted_class"), **kw):
+    """`forward` evaluated band by band over DESTINATION rows, for tiles whose `[E+N, H*C]` per-edge tensors do not fit
+    in host memory (gnn.py:381-408 on 4.2 M nodes materialises 2 x 38.6 GB per layer).
+
+    Nodes are in raster order, `node_rows[i]` = grid row of node i, `radius` = the stencil radius in rows (1 for the
+    4-/8-connected lists, 2 for 5x5).  A band of rows [a, b) is evaluated on the sub-graph induced by the rows
+    [a - L*radius, b + L*radius) (L = number of GAT layers): every node of the band then sees its complete L-hop
+    receptive field, so the band's outputs are those of the whole-graph forward (same per-destination edge order =>
+    same fp32 sums); halo rows are discarded."""
+    x = np.asarray(x)
+    ei = np.asarray(edge_index)
+    ea = None if edge_attr is None else np.asarray(edge_attr)
+    node_rows = np.asarray(node_rows)
+    assert np.all(np.diff(node_rows) >= 0), "nodes must be in raster order"
+    n_rows = int(node_rows.max()) + 1 if node_rows.size else 0
+    halo = cfg.layers * radius
+    out = {k: [] for k in keys}
+    src, dst = ei[0], ei[1]
+    for a in range(0, n_rows, band_rows):
+        b = min(a + band_rows, n_rows)
+        lo, hi = np.searchsorted(node_rows, [a - halo, b + halo], side="left")
+        own_lo, own_hi = np.searchsorted(node_rows, [a, b], side="left")
+        sel = (src >= lo) & (src < hi) & (dst >= lo) & (dst < hi)
+        o = forward(sd, cfg, x[lo:hi], ei[:, sel] - lo, None if ea is None else ea[sel], **kw)
+        for k in keys:
+            if k in o:
+                out[k].append(o[k][own_lo - lo:own_hi - lo])
+    return {k: torch.cat(v) for k, v in out.items() if v}

@@ -121,3 +121,80 @@ def multiscale_case(seed=21):
     d[~m] = np.nan
     u = (0.1 + 0.05 * rng.random((37, 50))).astype(np.float32)
     return d, m, u
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: the synthetic survey as a COUNTER-BASED function of (seed, row, col), so that any block of it can
+# be regenerated on the CPU for spot parity.  Everything that is not exactly reproducible across
+# CPU / GPU math libraries (sin, cos) lives in 1-D HOST tables; the per-cell part is integer hashing + a handful of
+# IEEE fp32 adds / multiplies carried out in the same order by `survey_block` (NumPy) and `survey_block_torch`.
+_M32 = 0xFFFFFFFF
+SURVEY_NODATA = 1.0e6
+
+
+def survey_tables(S: int):
+    """1-D fp32 tables over rows / cols / (row + col) of an S x S survey: the analytic surface of SURVEY.md 8(d)
+    (30 + 5 sin(x/60) + 3 cos(y/45) + 0.01 x, separable) and the smooth 'coast' field that marks ~5 % of the area invalid."""
+    i = np.arange(S, dtype=np.float64)
+    k = np.arange(2 * S, dtype=np.float64)
+    return dict(col_surface=(30.0 + 5.0 * np.sin(i / 60.0) + 0.01 * i).astype(np.float32), row_surface=(3.0 * np.cos(i / 45.0)).astype(np.float32),
+                coast_row=np.sin(i / 2900.0).astype(np.float32), coast_col=np.cos(i / 2300.0).astype(np.float32),
+                coast_diag=(0.3 * np.sin(k / 700.0)).astype(np.float32))
+
+
+def _mix32(h, xp):
+    h = h ^ (h >> 16)
+    h = (h * 0x85EBCA6B) & _M32
+    h = h ^ (h >> 13)
+    h = (h * 0xC2B2AE35) & _M32
+    return h ^ (h >> 16)
+
+
+def _survey_cells(xp, f32, rows, cols, seed, tabs_rc, sigma, spike_p, where):
+    """shared recipe; `rows` [h,1] / `cols` [1,w] int64, tabs_rc = the five tables already gathered to [h,1] / [1,w] / [h,w]"""
+    col_s, row_s, c_row, c_col, c_diag = tabs_rc
+    key = (rows * 0x85EBCA77 + cols * 0xC2B2AE3D + (int(seed) * 0x9E3779B1 & _M32)) & _M32
+    h1, h2 = _mix32(key ^ 0x3C6EF372, xp), _mix32(key ^ 0x1B873593, xp)
+    h3, h4 = _mix32(key ^ 0x27D4EB2F, xp), _mix32(key ^ 0x165667B1, xp)
+    g = (h1 & 0xFFFF) + (h1 >> 16) + (h2 & 0xFFFF) + (h2 >> 16) - 131070          # Irwin-Hall(4): std 37837.2 counts
+    d = (col_s + row_s) + f32(g) * np.float32(sigma / 37837.2)
+    amp = np.float32(1.0) + f32(h4 & 0xFFFF) * np.float32(4.0 / 65536.0)
+    amp = where(((h4 >> 16) & 1) == 1, -amp, amp)
+    d = where(h3 < int(spike_p * 4294967296.0), d + amp, d)
+    coast = (c_row + c_col) + c_diag
+    return where(coast > np.float32(1.72), np.float32(SURVEY_NODATA), d)
+
+
+def survey_block(S: int, r0: int, r1: int, c0: int, c1: int, seed: int = 1234, sigma: float = 0.2, spike_p: float = 0.005,
+                 tables=None) -> np.ndarray:
+    """Rows [r0, r1) x cols [c0, c1) of the S x S synthetic survey (fp32, nodata = 1e6), NumPy."""
+    t = tables or survey_tables(S)
+    rows = np.arange(r0, r1, dtype=np.int64)[:, None]
+    cols = np.arange(c0, c1, dtype=np.int64)[None, :]
+    tabs = (t["col_surface"][c0:c1][None, :], t["row_surface"][r0:r1][:, None], t["coast_row"][r0:r1][:, None],
+            t["coast_col"][c0:c1][None, :], t["coast_diag"][(rows + cols)])
+    with np.errstate(over="ignore"):
+        out = _survey_cells(np, lambda a: a.astype(np.float32), rows, cols, seed, tabs, sigma, spike_p, np.where)
+    return np.ascontiguousarray(out, dtype=np.float32)
+
+
+def survey_block_torch(S: int, r0: int, r1: int, c0: int, c1: int, device, seed: int = 1234, sigma: float = 0.2,
+                       spike_p: float = 0.005, tables=None, out=None, chunk_rows: int = 512):
+    """The same block generated on `device` (bit-identical to `survey_block`); `tables` = survey_tables(S) moved to the
+    device once by the caller (dict of tensors) or None."""
+    import torch
+    if tables is None or not isinstance(tables["col_surface"], torch.Tensor):
+        tables = {k: torch.from_numpy(v).to(device) for k, v in (tables or survey_tables(S)).items()}
+    if out is None:
+        out = torch.empty((r1 - r0, c1 - c0), dtype=torch.float32, device=device)
+    cols = torch.arange(c0, c1, dtype=torch.int64, device=device)[None, :]
+    t = tables
+    where = lambda c, a, b: torch.where(c, torch.as_tensor(a, device=device) if not isinstance(a, torch.Tensor) else a,
+                                        torch.as_tensor(b, device=device) if not isinstance(b, torch.Tensor) else b)
+    for a in range(r0, r1, chunk_rows):
+        b = min(a + chunk_rows, r1)
+        rows = torch.arange(a, b, dtype=torch.int64, device=device)[:, None]
+        tabs = (t["col_surface"][c0:c1][None, :], t["row_surface"][a:b][:, None], t["coast_row"][a:b][:, None],
+                t["coast_col"][c0:c1][None, :], t["coast_diag"][(rows + cols)])
+        out[a - r0:b - r0] = _survey_cells(torch, lambda v: v.to(torch.float32), rows, cols, seed, tabs, sigma, spike_p, where)
+    return out

@@ -149,6 +149,128 @@ def test_sharded_stitch_two_ranks_gloo():
         assert (diff == 0).mean() > 0.9
 
 
+def test_plan_bands_partitions_the_rows():
+    """survey.plan_bands: owned row ranges partition [0, H); seams are exactly the rows two neighbouring bands touch;
+    thin bands (one tile-row each, shifted last tile-row) may have overlapping seams."""
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200 import survey as sv
+    for (H, W, ts, ov) in ((60000, 60000, 2048, 128), (5000, 3000, 2048, 128), (180, 200, 96, 16), (300, 90, 96, 16)):
+        ntr, ntc, specs = bg.TileManager(ts, ov, 0.1).compute_tile_grid((H, W))
+        for world in (1, 2, 3, 8, 40):
+            plans = sv.plan_bands(specs, ntr, world, (H, W))
+            live = [p for p in plans if not p.empty]
+            assert len(plans) == world and sum(len(p.specs) for p in plans) == len(specs)
+            assert [s for p in plans for s in p.specs] == list(specs)          # reference order kept
+            cover = 0
+            for i, p in enumerate(live):
+                assert p.own_rows[0] == cover and p.own_rows[1] >= p.own_rows[0]
+                cover = p.own_rows[1]
+                if i + 1 < len(live):
+                    assert p.next_rank == live[i + 1].rank and p.bottom0 == live[i + 1].r0 and live[i + 1].top_end == p.r1
+                else:
+                    assert p.next_rank is None and p.bottom0 == p.r1 == H
+            assert cover == H
+    ntr, _, specs = bg.TileManager(96, 16, 0.1).compute_tile_grid((180, 200))
+    mid = sv.plan_bands(specs, ntr, 3, (180, 200))[1]
+    assert mid.top_end > mid.bottom0                                           # the thin-band case exists
+
+
+def _seam_worker(rank, world, port, q):
+    """One rank of the EXACT seam protocol of survey.py on the CPU: the band loop of `process_band` with the oracle
+    merger standing in for the device planes -- park the strips that lie in the previous band's seam, hand the bottom seam
+    down through `DistLink` (gloo), copy the received planes in, replay the parked strips in tile order, emit the owned rows."""
+    import torch.distributed as dist
+    import bathymetric_gnn_b200 as bg
+    from bathymetric_gnn_b200 import survey as sv
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    z = gio.load("stitch_cases.npz")
+    H, W, ts, ov = (int(v) for v in z["merge/cfg"])
+    ntr, ntc, specs = bg.TileManager(ts, ov, 0.1).compute_tile_grid((H, W))
+    ids = set(int(i) for i in z["merge/tile_ids"])
+    plan = sv.plan_bands(specs, ntr, world, (H, W))[rank]
+    chans = ["classification", "confidence", "correction"]
+    own = {}
+    if not plan.empty:
+        bh = plan.r1 - plan.r0
+        m = so.Merger((bh, W), chans, ov)
+
+        def add_rows(spec, data, i0, i1):            # Merger.add_tile restricted to tile rows [i0, i1)
+            if i1 <= i0:
+                return
+            r0, c0, r1, c1 = spec.row_start - plan.r0, spec.col_start, spec.row_end - plan.r0, spec.col_end
+            wts = so.blend_2d((r1 - r0, c1 - c0), ov)[i0:i1]
+            conf = data["confidence"][i0:i1]
+            for ch in chans:
+                d = data[ch][i0:i1]
+                region = m.out[ch][r0 + i0:r0 + i1, c0:c1]
+                if ch == "classification":
+                    creg = m.tracker[r0 + i0:r0 + i1, c0:c1]
+                    upd = np.isfinite(d) & ((conf > creg) | np.isnan(region))
+                    region[upd] = d[upd]
+                    creg[upd] = conf[upd]
+                else:
+                    wreg = m.w[ch][r0 + i0:r0 + i1, c0:c1]
+                    valid = np.isfinite(d)
+                    region[np.isnan(region) & valid] = 0.0
+                    wreg[valid] += wts[valid]
+                    region[valid] += (d * wts)[valid]
+        top, bottom = plan.top_end - plan.r0, plan.bottom0 - plan.r0
+        parked = []
+        for s in plan.specs:
+            i = specs.index(s)
+            if i not in ids:
+                continue
+            data = {k: z[f"merge/tile{i}/{k}"] for k in chans}
+            k = max(0, min(top, s.row_end - plan.r0) - (s.row_start - plan.r0))
+            if k:
+                parked.append((s, data, k))
+            add_rows(s, data, k, s.row_end - s.row_start)
+        views = lambda a, b: [torch.from_numpy(p[a:b]) for p in (m.out["confidence"], m.out["correction"], m.w["confidence"],
+                                                                 m.w["correction"], m.out["classification"], m.tracker)]
+        send = (plan.next_rank, views(bottom, bh)) if plan.next_rank is not None and bh > bottom else None
+        recv = (plan.prev_rank, views(0, top)) if plan.prev_rank is not None and top > 0 else None
+        link = sv.DistLink(dist)
+
+        def replay():
+            for s, data, k in parked:
+                add_rows(s, data, 0, k)
+        if send and recv and top > bottom:
+            link.exchange(None, recv); replay(); link.exchange(send, None)
+        else:
+            link.exchange(send, recv)
+            if recv:
+                replay()
+        res = m.finalize()
+        own = {k: v[:bottom].copy() for k, v in res.items()}
+    gathered = [None] * world
+    dist.gather_object((plan.own_rows, own), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        full = {k: np.concatenate([g[1][k] for g in gathered if g[1]], axis=0) for k in chans}
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exact_seam_protocol_gloo(world):
+    """world_size 2 and 3 over gloo: bands + parked seam strips + point-to-point hand-over reproduce the UNMODIFIED
+    reference TileMerger result bit for bit (stitch_cases.npz merge/ref/*), seams included -- no tolerance."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_seam_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    z = gio.load("stitch_cases.npz")
+    for c in ("classification", "confidence", "correction"):
+        assert np.array_equal(res[c], z[f"merge/ref/{c}"], equal_nan=True), c
+
+
 def test_dropin_packages_resolve_reference_imports():
     """The import lines of scripts/inference.py:24-25, models/pipeline.py:21-31 and
     scripts/inference_native.py:32-36 resolve against the drop-in directory."""
