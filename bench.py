@@ -488,6 +488,15 @@ def survey_leg(args, dev, rank, world, dist, model, S=None):
     cls = res["classification"]
     sample = cls[:: max(1, cls.shape[0] // 64), :: max(1, cls.shape[1] // 64)]
     assert bool(((sample <= 2) | (sample == 255)).all())
+    # order-independent bit-pattern checksums of the host planes (untimed): equal across rank counts <=> bit-identical results
+    sums = []
+    for k in ("cleaned_depth", "classification", "confidence", "correction"):
+        t_ = res[k]
+        sums.append(int((t_.view(torch.int32) if t_.dtype == torch.float32 else t_).sum(dtype=torch.int64)) if t_.numel() else 0)
+    if dist is not None:
+        cs = torch.tensor(sums, device=dev, dtype=torch.int64)
+        dist.all_reduce(cs)
+        sums = [int(v) for v in cs.tolist()]
     seam_rows = sum(p.r1 - p.bottom0 for p in plans if not p.empty)
     return {"metric": "depth cells/sec (graph build+GNN fwd+stitch), whole survey, host in -> host out", "value": S * S / (ms * 1e-3),
             "unit": UNIT, "scaling": "strong", "n_gpus": world, "seconds": ms * 1e-3,
@@ -498,6 +507,7 @@ def survey_leg(args, dev, rank, world, dist, model, S=None):
             "timed_region": "H2D of the band (pinned host) + tiles + stitch + seam hand-over (p2p) + finalize + fill + "
                             "apply_corrections + D2H of cleaned/class(u8)/confidence/correction to pinned host",
             "h2d_bytes": S * S * 4 + seam_rows * S * 4, "d2h_bytes": S * S * 13, "seam_p2p_bytes": seam_rows * S * 20,
+            "checksum": dict(zip(("cleaned_depth", "classification", "confidence", "correction"), sums)),
             "per_rank_seconds": [round(v * 1e-3, 4) for v in per_rank], "setup_seconds_rank0_untimed": round(t_setup, 2),
             "bit_identical_to_one_rank": "by construction (parked seam strips replayed in reference tile order; "
                                          "tests/test_gpu_survey.py, tests/test_host_logic.py::test_exact_seam_protocol_gloo)"}
