@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BGNN_LIB") or os.path.join(HERE, "libbgnn.so")      #
 MAX_OFFSETS, MAX_NODE_FEATS, MAX_EDGE_FEATS = 24, 8, 4
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3, -4
 PREC_F32, PREC_BF16 = 0, 1
+OPTIONS = dict(tensor_cores=0, presplit=1, window=2, tile5=3, tile5_window=4)
 
 NF_CODES = dict(depth=0, local_mean=1, local_std=2, gradient_x=3, gradient_y=4,
                 gradient_magnitude=5, curvature=6, uncertainty=7)
@@ -89,8 +90,7 @@ SYMBOLS = {
     "bgnn_vr_apply_results": (C.c_int, [P, P, I64, F32, P, P, P, F32, P, P, P, P, P]),
     "bgnn_sidecar_init": (C.c_int, [C.POINTER(Sidecar), P]),
     "bgnn_sidecar_add": (C.c_int, [C.POINTER(Sidecar), I32, P, P, I64, P, P, P, P, F32, P]),
-    "bgnn_set_tensor_cores": (C.c_int, [C.c_int]),
-    "bgnn_set_presplit": (C.c_int, [C.c_int]),
+    "bgnn_model_set_option": (C.c_int, [P, C.c_int, C.c_int]),
     "bgnn_test_proj_umma_presplit": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_test_proj_umma": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_profile_enable": (C.c_int, [C.c_int]),

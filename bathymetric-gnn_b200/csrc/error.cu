@@ -1,6 +1,7 @@
 // Error channel, version and device query of libbgnn.so (see include/bgnn.h).
 #include <stdarg.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -28,28 +29,36 @@ extern "C" int bgnn_device_info(int device, int* out3) {
 }
 
 // ---------------------------------------------------------------- per-kernel timing (bench aid)
-struct ProfRec { int slot; cudaEvent_t a, b; };
+struct ProfRec { int slot; cudaEvent_t a, b; cudaStream_t s; bool open; };
+// The one piece of process-wide state in the library: a measurement aid, off by default, guarded by a mutex (launches from
+// several host threads may record concurrently; a start/stop pair is matched per stream).
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_recs;
+static std::mutex g_prof_mu;
 
 void bgnn_prof_start(int slot, cudaStream_t s) {
     if (!g_prof_on) return;
-    ProfRec r; r.slot = slot;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r; r.slot = slot; r.s = s; r.open = true;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, s);
     g_recs.push_back(r);
 }
 void bgnn_prof_stop(cudaStream_t s) {
-    if (!g_prof_on || g_recs.empty()) return;
-    cudaEventRecord(g_recs.back().b, s);
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto it = g_recs.rbegin(); it != g_recs.rend(); ++it)
+        if (it->open && it->s == s) { cudaEventRecord(it->b, s); it->open = false; return; }
 }
 extern "C" int bgnn_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_recs.clear();
     g_prof_on = on != 0;
     return BGNN_OK;
 }
 extern "C" int bgnn_profile_collect(int cap, int32_t* slots, float* ms) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     int n = 0;
     for (auto& r : g_recs) {
         BGNN_CUDA(cudaEventSynchronize(r.b));

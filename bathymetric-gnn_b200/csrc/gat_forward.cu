@@ -25,13 +25,24 @@
 #include "common.cuh"
 #include "proj_umma.cuh"
 
-static bool g_use_umma = true;
-static bool g_window = getenv("BGNN_NO_WINDOW") == nullptr;       // ragged batches: windowed shared-memory CSR aggregation
-static bool g_tile5 = getenv("BGNN_NO_TILE5") == nullptr;
-static bool g_tile5_window = getenv("BGNN_NO_TILE5_WINDOW") == nullptr;   // full 5x5 stencil: sliding register window variant         // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
-static bool g_presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;   // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
-extern "C" int bgnn_set_tensor_cores(int on) { g_use_umma = on != 0; return BGNN_OK; }
-extern "C" int bgnn_set_presplit(int on) { g_presplit = on != 0; return BGNN_OK; }
+// Kernel-selection switches live in the MODEL HANDLE (bgnn_model::opt, bgnn_model_set_option): the library keeps no mutable
+// process-wide state, so handles on different devices / host threads never see each other's settings.  The BGNN_NO_*
+// environment variables only seed the defaults of a handle at creation (A/B runs of the bench without code changes).
+struct ModelOpts {
+    bool use_umma = true;           // tensor-core (tcgen05) projections
+    bool presplit = true;           // tiled aggregation writes fp16 hi / lo planes for the next tcgen05 projection
+    bool window = true;             // ragged batches: windowed shared-memory CSR aggregation
+    bool tile5 = true;              // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
+    bool tile5_window = true;       // full 5x5 stencil: sliding register window variant
+};
+static ModelOpts default_opts() {
+    ModelOpts o;
+    o.presplit = getenv("BGNN_NO_PRESPLIT") == nullptr;
+    o.window = getenv("BGNN_NO_WINDOW") == nullptr;
+    o.tile5 = getenv("BGNN_NO_TILE5") == nullptr;
+    o.tile5_window = getenv("BGNN_NO_TILE5_WINDOW") == nullptr;
+    return o;
+}
 #ifdef BGNN_AGG_TIMING
 extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset);
 #endif
@@ -73,6 +84,7 @@ struct bgnn_model {
     float heads_inv;
     int hNpad;
     int precision;           // BGNN_PREC_F32 | BGNN_PREC_BF16 (bgnn_model_set_precision)
+    ModelOpts opt;           // kernel-selection switches (bgnn_model_set_option)
     float* blob_bf;          // bf16 mode: rounded projection weights (fp32 values, then bf16 bit patterns)
 };
 
@@ -589,12 +601,21 @@ struct TopoDev {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int H, int C, int PH> struct TileCfg {
-    static constexpr int PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, NT = PH * PW, AST = 12;
+    static constexpr int PW = 16, HR = PH + 2, HW = PW + 2, NSLOT = HR * HW, NT = PH * PW;
+    // C == 64: a HALF-WARP per destination (lane <-> 4 channels), the two halves of a warp walk two patch rows at once and
+    // multiply with packed fp32 pairs (fma.rn.f32x2): the attention weights are stored DUPLICATED (w, w) so that a pair is one
+    // 64-bit operand; 20 floats per destination, patch rows 8 floats apart modulo the 128-byte bank period (the two halves of a
+    // warp read two different destinations with one LDS.128: no bank conflict)
+#ifndef BGNN_AGG_PAIR_MINH
+#define BGNN_AGG_PAIR_MINH 2          /* smallest H that uses the half-warp / packed-pair aggregate phase (H = 1, 8 x 16 patches: 0.62 vs 0.69 ms without) */
+#endif
+    static constexpr bool PAIR = C == 64 && H >= BGNN_AGG_PAIR_MINH;
+    static constexpr int AST = PAIR ? 20 : 12, AROW = PW * AST + (PAIR ? 8 : 0), ASZ = PH * AROW;
     // alpha_src / alpha_dst of the halo arrive by bulk copy (one per run) when a node's 2H floats are a 16 B multiple and
     // the landing area fits the (not yet used) attention-weight buffer; otherwise they are loaded cell by cell
-    static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= NT * AST;
+    static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= ASZ;
     static constexpr int RT = 2 * (HW / 2) + 2;      // run table per halo row: count, then (start << 16 | length, node id) pairs
-    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C + HR * RT) * 4 + 32;
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + ASZ + BGNN_MAX_EDGE_FEATS * H + 3 * H * C + HR * RT) * 4 + 32;
 };
 
 // window position p = dy*3 + dx (dy, dx in 0..2 <-> source at row r-1+dy, column c-1+dx) visited in reference edge order
@@ -617,6 +638,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// packed fp32 pairs (sm_100: two IEEE fp32 operations per issue slot)
+__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
 
 // Optional output format: instead of fp32 rows, the layer output is written as fp16 rows [N][2][H*C] = hi | lo of
@@ -653,9 +684,9 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
     float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
     int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
     float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [H][NSLOT]   alpha_src per halo cell
-    float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    3x3 attention weights of the current head
+    float* a_sm = asrc + NSLOT * H;                            // [PH][AROW]   3x3 attention weights of the current head (TileCfg)
     float* al_sm = a_sm;                                       // [NSLOT][2H]  landing area of the alpha bulk copies (setup only)
-    float* M_s = a_sm + NT * AST;                              // [ED_MAX][H]  folded edge projection
+    float* M_s = a_sm + G::ASZ;                                // [ED_MAX][H]  folded edge projection
     float* s_bn = M_s + BGNN_MAX_EDGE_FEATS * H;               // [3][HC]      bias | bn scale | bn shift
     int* run_tab = reinterpret_cast<int*>(s_bn + 3 * HC);      // [HR][RT]     runs of valid cells per halo row
     uint64_t* bar = reinterpret_cast<uint64_t*>(run_tab + HR * G::RT);   // [0] source rows, [1] alpha
@@ -818,9 +849,11 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             issue_rows(hh);
         }
         // 2. scores + softmax of this head while the copies are in flight -> a_sm[t][window position]
+        float* aw_t = a_sm + (tid / 16) * G::AROW + (tid % 16) * AST;           // this destination's weights
         {
-            float4* az = reinterpret_cast<float4*>(a_sm + tid * AST);
-            az[0] = make_float4(0.f, 0.f, 0.f, 0.f); az[1] = make_float4(0.f, 0.f, 0.f, 0.f); az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* az = reinterpret_cast<float4*>(aw_t);
+#pragma unroll
+            for (int q = 0; q < AST / 4; ++q) az[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (myid >= 0) {
             float Mh[BGNN_MAX_EDGE_FEATS], adh = ad[0];
@@ -861,14 +894,80 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
             const float inv = 1.0f / sum;            // one IEEE division, nine multiplies (<= 1 ulp from exp / sum)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] * inv;
-            a_sm[tid * AST + 4] = sc[8] * inv;
+                if ((nbv >> k) & 1u) {
+                    const float w = sc[k] * inv;
+                    if (G::PAIR) *reinterpret_cast<float2*>(aw_t + 2 * wpos[k]) = make_float2(w, w);
+                    else aw_t[wpos[k]] = w;
+                }
+            {
+                const float w = sc[8] * inv;
+                if (G::PAIR) *reinterpret_cast<float2*>(aw_t + 8) = make_float2(w, w);
+                else aw_t[4] = w;
+            }
         }
         AGG_TICK(2);
         // 3. all threads arrive (release: a_sm, zero rows), then wait for the arrivals and the copied bytes
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
         mbar_wait_parity(bar, (uint32_t)(hh & 1));
         AGG_TICK(3);
+        if constexpr (G::PAIR) {
+        // 4. aggregate, C == 64: half-warp <-> destination (lane <-> 4 channels); the two halves of warp w walk patch rows 2w
+        //    and 2w + 1 together; 3x3 sliding window of float4 in registers (3 new LDS.128 per step); FMAs on packed fp32 pairs
+        //    (two IEEE fmas per issue slot) in the reference's edge order; epilogue on pairs as well
+        const int l16 = lane & 15, pr = warp * 2 + (lane >> 4);
+        const int ch0 = hh * C + l16 * 4;
+        const uint64_t bs01 = pk2(s_bn[ch0], s_bn[ch0 + 1]), bs23 = pk2(s_bn[ch0 + 2], s_bn[ch0 + 3]);
+        // split output: the power-of-two operand scale rides on the BN constants (exact: relu(y) * sA == relu(y * sA))
+        const uint64_t ba01 = pk2(s_bn[HC + ch0] * sA, s_bn[HC + ch0 + 1] * sA), ba23 = pk2(s_bn[HC + ch0 + 2] * sA, s_bn[HC + ch0 + 3] * sA);
+        const uint64_t bb01 = pk2(s_bn[2 * HC + ch0] * sA, s_bn[2 * HC + ch0 + 1] * sA), bb23 = pk2(s_bn[2 * HC + ch0 + 2] * sA, s_bn[2 * HC + ch0 + 3] * sA);
+        const float* base = rows + (pr * HW) * C + l16 * 4;
+        const float* abase = a_sm + pr * G::AROW;
+        ulonglong2 win[3][3];                                   // .x = channels (0, 1), .y = channels (2, 3)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            win[dy][1] = *reinterpret_cast<const ulonglong2*>(base + (dy * HW + 0) * C);
+            win[dy][2] = *reinterpret_cast<const ulonglong2*>(base + (dy * HW + 1) * C);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                win[dy][0] = win[dy][1]; win[dy][1] = win[dy][2];
+                win[dy][2] = *reinterpret_cast<const ulonglong2*>(base + (dy * HW + c + 2) * C);
+            }
+            const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(abase + c * AST);          // (w0,w0) (w1,w1)
+            const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(abase + c * AST + 4);
+            const ulonglong2 w45 = *reinterpret_cast<const ulonglong2*>(abase + c * AST + 8);
+            const ulonglong2 w67 = *reinterpret_cast<const ulonglong2*>(abase + c * AST + 12);
+            const unsigned long long w8 = *reinterpret_cast<const unsigned long long*>(abase + c * AST + 16);
+            const unsigned long long aw[9] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w8};
+            unsigned long long acc01 = 0ull, acc23 = 0ull;
+#pragma unroll
+            for (int q = 0; q < O::N; ++q) {
+                const int pz = O::pos(q);
+                acc01 = ffma2(aw[pz], win[pz / 3][pz % 3].x, acc01);
+                acc23 = ffma2(aw[pz], win[pz / 3][pz % 3].y, acc23);
+            }
+            const int id2 = ids[(pr + 1) * HW + c + 1];
+            float y0, y1, y2, y3;
+            upk2(ffma2(fadd2(acc01, bs01), ba01, bb01), y0, y1);
+            upk2(ffma2(fadd2(acc23, bs23), ba23, bb23), y2, y3);
+            if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+            if (SO.hi) {
+                const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);     // already scaled by sA
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn((y0 - f01.x) * 2048.f, (y1 - f01.y) * 2048.f);
+                const __half2 l23 = __floats2half2_rn((y2 - f23.x) * 2048.f, (y3 - f23.y) * 2048.f);
+                if (id2 >= 0) {
+                    uint16_t* prow = SO.hi + (int64_t)id2 * (2 * HC) + ch0;
+                    *reinterpret_cast<uint2*>(prow) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                    *reinterpret_cast<uint2*>(prow + HC) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                }
+            } else if (id2 >= 0) {
+                *reinterpret_cast<float4*>(out + (int64_t)id2 * HC + ch0) = make_float4(y0, y1, y2, y3);
+            }
+        }
+        } else {
         // 4. aggregate: warp w walks patch rows 2w, 2w+1; lane <-> VEC channels; 3x3 sliding window in registers
         float bs[VEC], ba[VEC], bb[VEC];
 #pragma unroll
@@ -900,10 +999,9 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                     for (int v = 0; v < VEC; ++v) { win[dy][0][v] = win[dy][1][v]; win[dy][1][v] = win[dy][2][v]; }
                     ldrow(base + (dy * HW + c + 2) * C, win[dy][2]);
                 }
-                const int t2 = pr * 16 + c;
-                const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
-                const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
-                const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
+                const float4 a0 = *reinterpret_cast<const float4*>(a_sm + pr * G::AROW + c * AST);
+                const float4 a1 = *reinterpret_cast<const float4*>(a_sm + pr * G::AROW + c * AST + 4);
+                const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[pr * G::AROW + c * AST + 8]};
                 float acc[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -924,6 +1022,7 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                     }
                     if (VEC % 2 == 0 && SO.hi) {
                         uint16_t* prow = SO.hi + (int64_t)id2 * (2 * HC) + hh * C + lane * VEC;
+                        const int lo_off = HC;
 #pragma unroll
                         for (int v = 0; v + 1 < VEC; v += 2) {
                             const float s0v = o[v], s1v = o[v + 1];             // already scaled by sA
@@ -931,13 +1030,14 @@ gat_aggregate_tile(const float* __restrict__ h, const float* __restrict__ alpha,
                             const float2 hf = __half22float2(hi2);
                             const __half2 lo2 = __floats2half2_rn((s0v - hf.x) * 2048.f, (s1v - hf.y) * 2048.f);
                             *reinterpret_cast<__half2*>(prow + v) = hi2;
-                            *reinterpret_cast<__half2*>(prow + HC + v) = lo2;
+                            *reinterpret_cast<__half2*>(prow + lo_off + v) = lo2;
                         }
                     } else {
                         VecIO<VEC>::st(out + (int64_t)id2 * HC + hh * C + lane * VEC, o);
                     }
                 }
             }
+        }
         }
         AGG_TICK(4);
         __syncthreads();                     // every warp is done with rows / a_sm before the next head overwrites them
@@ -950,14 +1050,8 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
                       int ED, int relu, float slope, float* out, int64_t n_nodes, const SplitOut& SO, cudaStream_t s) {
     using G = TileCfg<H, C, PH>;
     static_assert(G::SMEM <= 232448, "shared memory budget exceeded");
-    static bool configured[64] = {};                    // the attribute is per device
     auto kern = gat_aggregate_tile<H, C, PH, CONN4>;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        configured[dev & 63] = true;
-    }
+    BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per device, idempotent, thread-safe
     dim3 grid((unsigned)((T.cols + 15) / 16), (unsigned)((T.rows + PH - 1) / PH));
     kern<<<grid, PH * 16, G::SMEM, s>>>(h, alpha, T, grid_eattr, ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes, SO);
     BGNN_LAUNCH_CHECK();
@@ -1159,18 +1253,12 @@ int launch_agg_window(const LayerDev& L, const float* h, const float* alpha, con
                       cudaStream_t s) {
     if (L.C != 64 || !(L.H == 1 || L.H == 2 || L.H == 4) || ED > BGNN_MAX_EDGE_FEATS) return 1;
     if (N == 0) return BGNN_OK;
-    int dev = 0;
-    cudaGetDevice(&dev);
 #define WLAUNCH(H_)                                                                                                     \
     do {                                                                                                                \
         using G = WinCfg<H_>;                                                                                           \
         static_assert(G::SMEM <= 115000, "two CTAs per SM");                                                            \
-        static bool configured[64] = {};                                                                                \
         auto kern = gat_aggregate_window<H_>;                                                                           \
-        if (!configured[dev & 63]) {                                                                                    \
-            BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));           \
-            configured[dev & 63] = true;                                                                                \
-        }                                                                                                               \
+        BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));               \
         kern<<<(unsigned)ceil_div64(N, G::D), G::NT, G::SMEM, s>>>(h, alpha, rowptr, src, eattr, ED, L.Medge, L.bias,   \
                                                                    L.bn_a, L.bn_b, relu, slope, out, N, SO);            \
     } while (0)
@@ -1228,6 +1316,7 @@ struct Topo5Dev {
     int K;
     int8_t dr[BGNN_MAX_OFFSETS], dc[BGNN_MAX_OFFSETS];
     int16_t doff[BGNN_MAX_OFFSETS];        // halo slot of the source relative to the destination's: -dr * HW - dc
+    bool window;                           // full 5x5 stencil: sliding register window variant allowed (ModelOpts::tile5_window)
 };
 
 template <int C, int IO, bool FULL5> struct Tile5Cfg {
@@ -1507,7 +1596,7 @@ int launch_agg_tile5_tt(const LayerDev& L, const float* h, const float* alpha, c
 template <int H, int C, int IO>
 int launch_agg_tile5_t(const LayerDev& L, const float* h, const float* alpha, const int32_t* rowptr, const float* eattr, int ED,
                        int relu, float slope, float* out, int64_t N, const Topo5Dev& T, cudaStream_t s) {
-    bool full5 = g_tile5_window && T.K == BGNN_MAX_OFFSETS;          // exactly OFFSETS_24: raster order over the 5 x 5 window
+    bool full5 = T.window && T.K == BGNN_MAX_OFFSETS;          // exactly OFFSETS_24: raster order over the 5 x 5 window
     for (int k = 0, q = 0; full5 && k < T.K; ++k, ++q) {
         if (q == 12) ++q;                                             // the centre is not an offset
         full5 = T.dr[k] == q / 5 - 2 && T.dc[k] == q % 5 - 2;
@@ -1761,6 +1850,7 @@ extern "C" int bgnn_model_create(const bgnn_model_desc* d, const float* p, int64
     bgnn_model* m = new bgnn_model();
     m->blob16 = nullptr;
     m->precision = BGNN_PREC_F32; m->blob_bf = nullptr;
+    m->opt = default_opts();
     m->d = *d; m->device = device; m->nheads_mlp = nblk;
     cudaError_t e = cudaMalloc(&m->blob, hb.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->blob, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -1840,6 +1930,20 @@ __global__ void round_to_bf16(const float* __restrict__ w, float* __restrict__ w
 }  // namespace
 
 extern "C" int bgnn_model_precision(const bgnn_model* m) { return m ? m->precision : -1; }
+
+extern "C" int bgnn_model_set_option(bgnn_model* m, int option, int value) {
+    BGNN_CHECK_ARG(m, "null model");
+    const bool on = value != 0;
+    switch (option) {
+        case BGNN_OPT_TENSOR_CORES: m->opt.use_umma = on; break;
+        case BGNN_OPT_PRESPLIT: m->opt.presplit = on; break;
+        case BGNN_OPT_WINDOW: m->opt.window = on; break;
+        case BGNN_OPT_TILE5: m->opt.tile5 = on; break;
+        case BGNN_OPT_TILE5_WINDOW: m->opt.tile5_window = on; break;
+        default: BGNN_CHECK_ARG(false, "unknown option %d", option);
+    }
+    return BGNN_OK;
+}
 
 extern "C" int bgnn_model_set_precision(bgnn_model* m, int precision) {
     BGNN_CHECK_ARG(m, "model is null");
@@ -1926,7 +2030,7 @@ static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const in
     { ProfScope ps(10, s);
       if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
     { ProfScope ps(11, s);
-      if (g_use_umma && m->fe1split && ((int64_t)N * C) % 8 == 0) {
+      if (m->opt.use_umma && m->fe1split && ((int64_t)N * C) % 8 == 0) {
           // second Linear on the tensor cores (fp32-grade split GEMM into hbuf), then one RN pass to the bf16 rows the layer-0
           // projection reads: the same rounding point as the FMA GEMM's bf16 store
           if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
@@ -1948,7 +2052,7 @@ static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const in
         BGNN_CHECK_ARG(L.Wr, "internal: bf16 weights missing");
         { ProfScope ps(20 + l, s);
           rc = 1;
-          if (g_use_umma && proj_bf16_supported(L.HC, L.in, L.C)) {
+          if (m->opt.use_umma && proj_bf16_supported(L.HC, L.in, L.C)) {
               rc = launch_proj_bf16(reinterpret_cast<const uint16_t*>(cur), L.Wbf, N, L.in, L.HC, reinterpret_cast<uint16_t*>(hbuf),
                                     L.att_src, L.att_dst, alpha, L.H, L.C, sms, s);
           }
@@ -1966,7 +2070,7 @@ static int forward_bf16(const bgnn_model* m, int64_t N, const float* x, const in
     }
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     const int nblk = m->nheads_mlp;
-    if (g_use_umma && m->hWsplit) {         // heads stay fp32: the fused tcgen05 heads kernel of the fp32 path, fed with max|x_L|
+    if (m->opt.use_umma && m->hWsplit) {         // heads stay fp32: the fused tcgen05 heads kernel of the fp32 path, fed with max|x_L|
         ProfScope ps(60, s);
         BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
         if ((rc = launch_absmax(cur, N * C, amax, sms, s))) return rc;
@@ -2019,7 +2123,8 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     TopoDev T;
     const bool tiled = topo_to_dev(topo, E, T);
     Topo5Dev T5;
-    const bool tiled5 = g_tile5 && topo5_to_dev(topo, E, T5);
+    const bool tiled5 = m->opt.tile5 && topo5_to_dev(topo, E, T5);
+    T5.window = m->opt.tile5_window;
 
     char* w = (char*)workspace;
     w = (char*)align_up((size_t)w, 256);
@@ -2031,7 +2136,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     float* amax = (float*)w; w += 256;
     const bgnn_model_desc& d = m->d;
     BGNN_CHECK_ARG(d.layers + 1 <= 64, "too many layers");
-    if (g_use_umma) BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
+    if (m->opt.use_umma) BGNN_CUDA(cudaMemsetAsync(amax, 0, 256, s));
     const int C = d.hidden, h2 = C / 2;
     int rc;
     if (m->precision == BGNN_PREC_BF16)
@@ -2039,12 +2144,12 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
                             thr_auto, thr_review, hidden_out, sms, s);
     // LocalFeatureExtractor: Linear(F,C) + ReLU, Linear(C,C).  On the tensor-core path both are fused into the
     // layer-0 projection (first Linear computed by its producers, second folded into its weights).
-    const bool fused0 = g_use_umma && m->Wfold0;
+    const bool fused0 = m->opt.use_umma && m->Wfold0;
     if (!fused0) {
         { ProfScope ps(10, s);
           if ((rc = launch_gemm(x, d.in_channels, m->feW0, d.in_channels, N, C, bufA, C, m->feb0, 1, C, 0, 0, 0, 0, s))) return rc; }
         { ProfScope ps(11, s);
-          if (g_use_umma && m->fe1split) {      // |relu(x W0^T + b0)| <= mlp0_mul * max|x| + mlp0_add bounds the operand
+          if (m->opt.use_umma && m->fe1split) {      // |relu(x W0^T + b0)| <= mlp0_mul * max|x| + mlp0_add bounds the operand
               if ((rc = launch_absmax(x, N * d.in_channels, amax, sms, s))) return rc;
               UmmaArgs a = {};
               a.A = bufA; a.M = N; a.K = C; a.Wsplit = m->fe1split; a.w_inv_scale = m->fe1_inv;
@@ -2060,10 +2165,10 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     const float* al = alpha;
     bool cur_split = false;                    // `cur` holds fp16 hi / lo planes [N, in] (written by the tiled aggregation)
     bool is4_ = false;
-    const bool tile_ok0 = tiled && g_use_umma && g_presplit;
+    const bool tile_ok0 = tiled && m->opt.use_umma && m->opt.presplit;
     // no single grid (ragged batch): a topology with rows == 0 only carries the stencil size = an in-degree bound, which
     // lets the CSR aggregation run as the windowed shared-memory kernel
-    const bool windowed = !tiled && g_window && topo && topo->rows == 0 && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0;
+    const bool windowed = !tiled && m->opt.window && topo && topo->rows == 0 && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0;
     for (int l = 0; l < d.layers; ++l) {
         const LayerDev& L = m->layers[l];
         { ProfScope ps(20 + l, s);
@@ -2076,7 +2181,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               a.Cout = hbuf; a.bias = m->bias_fold0; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha;
               a.Htot = L.H; a.CH = L.C; a.head_major = 1;
               rc = launch_umma(a, L.HC, PM_MLP0, EM_PROJ, sms, s);
-          } else if (g_use_umma && L.Wsplit) {
+          } else if (m->opt.use_umma && L.Wsplit) {
               UmmaArgs a = {};
               a.A = cur; a.M = N; a.K = L.in; a.Wsplit = L.Wsplit; a.w_inv_scale = L.w_inv;
               if (cur_split) { a.A_hi = reinterpret_cast<const uint16_t*>(cur); a.A_lo = a.A_hi + L.in; a.a_ld = 2 * L.in; }
@@ -2090,7 +2195,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               a.Cout = hbuf; a.att_src = L.att_src; a.att_dst = L.att_dst; a.alpha = alpha; a.Htot = L.H; a.CH = L.C;
               a.head_major = 1;
               rc = launch_umma(a, L.HC, cur_split ? PM_SPLIT : PM_PLAIN, EM_PROJ, sms, s);
-          } else if (g_use_umma && L.nblk == 4) {      // H*C = 512: four column blocks of 128 (whole heads), one launch each
+          } else if (m->opt.use_umma && L.nblk == 4) {      // H*C = 512: four column blocks of 128 (whole heads), one launch each
               if (l == 0 && (rc = launch_absmax(cur, N * L.in, amax, sms, s))) return rc;
               const int hpb = 128 / L.C;               // heads per block
               for (int b = 0; b < L.nblk; ++b) {
@@ -2106,7 +2211,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               }
           } else {
               rc = launch_gemm(cur, L.in, L.W, L.in, N, L.HC, hbuf, L.HC, nullptr, 0, L.C, L.att_src, L.att_dst, alpha, L.H, s);
-              if (!rc && g_use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
+              if (!rc && m->opt.use_umma) rc = launch_absmax(hbuf, N * L.HC, amax + 1 + l, sms, s);   // a later tensor-core GEMM needs max|h_l|
           }
           if (rc) return rc; }
         const int relu = l < d.layers - 1;
@@ -2116,7 +2221,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           SplitOut SO = {};
           bool want_split = false;
           const bool win_l = windowed && L.C == 64 && (L.H == 1 || L.H == 2 || L.H == 4);
-          if ((tile_ok0 || (win_l && g_use_umma && g_presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
+          if ((tile_ok0 || (win_l && m->opt.use_umma && m->opt.presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
               const LayerDev& Ln = m->layers[l + 1];
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
                            (win_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));
@@ -2143,7 +2248,7 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     if (hidden_out) BGNN_CUDA(cudaMemcpyAsync(hidden_out, cur, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // heads
     const int nblk = m->nheads_mlp;
-    if (g_use_umma && m->hWsplit) {         // one kernel: first layers on the tensor cores, the rest in its epilogue
+    if (m->opt.use_umma && m->hWsplit) {         // one kernel: first layers on the tensor cores, the rest in its epilogue
         ProfScope ps(60, s);
         UmmaArgs a = {};
         a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit; a.w_inv_scale = m->heads_inv;

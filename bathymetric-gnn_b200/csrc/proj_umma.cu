@@ -876,14 +876,8 @@ template <int N, int PMODE, int EMODE, int NH = 1>
 int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
     using S = UmmaSmem<N, PMODE, EMODE, NH>;
     static_assert(S::BYTES <= 232448, "shared memory budget exceeded");
-    static bool configured[64] = {};                    // the attribute is per device
     auto kern = proj_umma_kernel<N, PMODE, EMODE, NH>;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
-        configured[dev & 63] = true;
-    }
+    BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));   // per device, idempotent, thread-safe
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (PMODE == PM_PLAIN) {
@@ -1045,9 +1039,9 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
     return BGNN_OK;
 }
 
-static bool g_mlp0_whole = getenv("BGNN_MLP0_WHOLE") != nullptr;       // dev switch: one 128 x 256 tile per CTA (1.30 vs 1.25 ms paired)
-static bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
-static bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
+static const bool g_mlp0_whole = getenv("BGNN_MLP0_WHOLE") != nullptr;       // dev switch: one 128 x 256 tile per CTA (1.30 vs 1.25 ms paired)
+static const bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
+static const bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
                                                                          // 2-deep operand ring cannot hide the split latency)
 
 int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStream_t s) {

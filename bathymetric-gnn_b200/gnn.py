@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import logging
 import math
+import threading
 from typing import Dict, Optional
 
 import torch
@@ -197,6 +198,8 @@ class BathymetricGNN(nn.Module):
         self.correction_head = CorrectionHead(hidden_channels, hidden_channels // 2, dropout) if predict_correction else None
         self._handle = None
         self._handle_key = None
+        self._handle_lock = threading.RLock()      # handle (re)creation / destruction vs a concurrent forward
+        self._options: Dict[str, int] = {}         # kernel-selection switches of THIS model's handle (set_option)
         self.use_grid_kernel = True      # tiled aggregation when the graph carries its grid topology
         self.precision = "fp32"          # "fp32" | "bf16" (set_precision)
         logger.info("Created BathymetricGNN: %s with %d layers, %d hidden channels", gnn_type, num_gnn_layers, hidden_channels)
@@ -235,19 +238,58 @@ class BathymetricGNN(nn.Module):
         self.precision = precision
         return self
 
+    def set_option(self, name: str, value) -> "BathymetricGNN":
+        """Kernel-selection switch of this model's device handle (include/bgnn.h: bgnn_model_set_option): tensor_cores,
+        presplit, window, tile5, tile5_window.  Per model, not per process; used by the tests to cross-check variants."""
+        if name not in _lib.OPTIONS:
+            raise ValueError(f"Unknown option: {name}")
+        with self._handle_lock:
+            self._options[name] = int(bool(value))
+            if self._handle is not None:
+                check(lib.bgnn_model_set_option(self._handle, _lib.OPTIONS[name], self._options[name]))
+        return self
+
+    def invalidate(self) -> "BathymetricGNN":
+        """Drop the folded device weights; the next forward re-packs them from the module's parameters.  Called by
+        load_state_dict / _apply (.to, .cuda, .float) / train; call it yourself after editing parameters through `.data`
+        or an external view (those edits do not bump the tensors' version counters that the cache key watches)."""
+        with self._handle_lock:
+            self._release()
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.invalidate()
+        return r
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse) if recurse is True else super()._apply(fn, recurse=recurse)
+        if "_handle_lock" in self.__dict__:
+            self.invalidate()
+        return r
+
+    def train(self, mode: bool = True):
+        r = super().train(mode)
+        if "_handle_lock" in self.__dict__ and mode:
+            self.invalidate()
+        return r
+
     def _ensure_handle(self, device: torch.device):
         key = (device.index if device.index is not None else torch.cuda.current_device(),
                tuple(t._version for t in list(self.parameters()) + list(self.buffers())),
                tuple(t.data_ptr() for t in self.parameters()))
-        if self._handle is not None and self._handle_key == key:
-            return self._handle
-        self._release()
-        flat = self._flat_params()
-        d = self._desc()
-        h = C.c_void_p()
-        check(lib.bgnn_model_create(C.byref(d), C.c_void_p(flat.data_ptr()), flat.numel(), key[0], C.byref(h)))
-        self._handle, self._handle_key = h, key
-        return h
+        with self._handle_lock:
+            if self._handle is not None and self._handle_key == key:
+                return self._handle
+            self._release()
+            flat = self._flat_params()
+            d = self._desc()
+            h = C.c_void_p()
+            check(lib.bgnn_model_create(C.byref(d), C.c_void_p(flat.data_ptr()), flat.numel(), key[0], C.byref(h)))
+            for name, v in self._options.items():
+                check(lib.bgnn_model_set_option(h, _lib.OPTIONS[name], v))
+            self._handle, self._handle_key = h, key
+            return h
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:
@@ -263,7 +305,12 @@ class BathymetricGNN(nn.Module):
     def __getstate__(self):            # the device handle is never copied / pickled
         s = self.__dict__.copy()
         s["_handle"], s["_handle_key"] = None, None
+        s.pop("_handle_lock", None)
         return s
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._handle_lock = threading.RLock()
 
     # ------------------------------------------------------------------ forward
     @staticmethod

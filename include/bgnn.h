@@ -325,13 +325,17 @@ int bgnn_sidecar_add(const bgnn_sidecar* sc, int32_t n_grids, const int64_t* cel
                      const float* classification, const float* confidence, const float* correction,
                      const float* depth, float nodata, void* stream);
 
-/* Tensor-core projections: on by default.  When on, every `x W^T` whose shape is compiled for the
- * tcgen05 path (N in {32,64,128,256}, K % 32 == 0) runs as a bf16x3-split GEMM with fp32 accumulation
- * in TMEM (fp32-grade accuracy); otherwise, or when switched off, the fp32 FMA GEMM is used. */
-int bgnn_set_tensor_cores(int on);
-/* Operand hand-over between a tiled aggregation and the next layer's tcgen05 projection as fp16 hi / lo planes (the
- * projection then has no conversion stage): on by default, bit-identical results either way. */
-int bgnn_set_presplit(int on);
+/* Kernel-selection switches of ONE model handle (the library keeps no mutable process-wide state: handles on different
+ * devices / host threads are independent).  All on by default; results stay within the stated tolerances either way
+ * (presplit: bit-identical).  Used by the tests to cross-check the kernel variants against each other.
+ *   BGNN_OPT_TENSOR_CORES  every `x W^T` whose shape is compiled for the tcgen05 path runs as an fp16 hi/lo-split GEMM with
+ *                          fp32 accumulation in TMEM (fp32-grade accuracy); off -> the fp32 FMA GEMM
+ *   BGNN_OPT_PRESPLIT      a tiled aggregation hands its output to the next tcgen05 projection as fp16 hi / lo planes
+ *   BGNN_OPT_WINDOW        ragged batches: windowed shared-memory aggregation (off -> warp-per-destination CSR kernel)
+ *   BGNN_OPT_TILE5         5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation (off -> CSR kernel)
+ *   BGNN_OPT_TILE5_WINDOW  full 5x5 stencil: sliding register window variant of the radius-2 kernel */
+enum { BGNN_OPT_TENSOR_CORES = 0, BGNN_OPT_PRESPLIT = 1, BGNN_OPT_WINDOW = 2, BGNN_OPT_TILE5 = 3, BGNN_OPT_TILE5_WINDOW = 4 };
+int bgnn_model_set_option(bgnn_model* m, int option, int value);
 /* testing aid: C_dev[M,N] = A_dev[M,K] . W_host[N,K]^T through the tcgen05 path (host-synchronous);
  * alpha_dev (optional) [M, 2*heads] receives the per-head dot products with att_src / att_dst [N]. */
 int bgnn_test_proj_umma(const float* A_dev, int64_t M, int K, const float* W_host, int N, float* C_dev,
@@ -349,7 +353,7 @@ int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t*
 
 /* ------------------------------------------------------------------------------------------
  * Measurement aid (bench.py): per-kernel device timing with CUDA events recorded on the
- * launching stream around every kernel the library launches.  Not thread-safe; off by default.
+ * launching stream around every kernel the library launches.  Off by default; the record list is mutex-guarded.
  * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
  * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
  * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit,

@@ -141,11 +141,7 @@ def test_bf16_tensor_cores_vs_fma_projection():
     model = make_model(cfg, sd).set_precision("bf16")
     g = bg.GraphBuilder("24-connected").build_graph(d, mask, unc, (0.5, 0.5))
     a = model.predict(g)
-    lib.bgnn_set_tensor_cores(0)
-    try:
-        b = model.predict(g)
-    finally:
-        lib.bgnn_set_tensor_cores(1)
+    b = model.set_option("tensor_cores", 0).predict(g)
     for k in ("class_logits", "confidence", "correction"):
         np.testing.assert_allclose(a[k].cpu().numpy(), b[k].cpu().numpy(), rtol=0, atol=TIGHT_ATOL)
 

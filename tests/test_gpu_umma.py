@@ -59,13 +59,12 @@ def test_umma_toggle_equivalence_in_forward():
     m.load_state_dict(sd)
     m = m.cuda().eval()
     g = bg.GraphBuilder().build_graph(d, None, None, (0.5, 0.5))
-    try:
-        lib.bgnn_set_tensor_cores(1)
-        a = m(g)
-        lib.bgnn_set_tensor_cores(0)
-        b = m(g)
-    finally:
-        lib.bgnn_set_tensor_cores(1)
+    a = m.set_option("tensor_cores", 1)(g)
+    b = m.set_option("tensor_cores", 0)(g)           # a switch of THIS model's handle, not of the process
+    m2 = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    m2.load_state_dict(sd)
+    c = m2.cuda().eval()(g)                           # another handle is unaffected: tensor cores on
+    assert torch.equal(a["class_logits"], c["class_logits"])
     np.testing.assert_allclose(a["class_logits"].cpu().numpy(), b["class_logits"].cpu().numpy(), rtol=1e-5, atol=1e-5)
     assert torch.equal(a["predicted_class"], b["predicted_class"]) or (a["predicted_class"] != b["predicted_class"]).float().mean() < 1e-3
 
@@ -98,12 +97,7 @@ def test_presplit_handover_is_bit_identical_in_forward():
     m.load_state_dict(sd)
     m = m.cuda().eval()
     g = bg.GraphBuilder().build_graph(d, mask, None, (0.5, 0.5))
-    try:
-        lib.bgnn_set_presplit(1)
-        a = m._run(g, 0.85, 0.6, True, return_hidden=True)
-        lib.bgnn_set_presplit(0)
-        b = m._run(g, 0.85, 0.6, True, return_hidden=True)
-    finally:
-        lib.bgnn_set_presplit(1)
+    a = m.set_option("presplit", 1)._run(g, 0.85, 0.6, True, return_hidden=True)
+    b = m.set_option("presplit", 0)._run(g, 0.85, 0.6, True, return_hidden=True)
     for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
         assert torch.equal(a[k], b[k]), k

@@ -1,6 +1,17 @@
 #!/bin/bash
-# A/B one environment switch of libbgnn.so inside ONE gpurun call (same GPU): tools/ab_env.sh VAR [reps]
-for rep in $(seq 1 ${2:-2}); do for v in "" 1; do
-  env ${v:+$1=1} timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
-import json,sys; j=json.loads(sys.stdin.read()); k=j['kernels']; print('$1=$v', round(j['ms_per_step'],3), {n:round(v['ms'],3) for n,v in k.items() if not n.startswith('gb_')})"
-done; done
+# bench --quick-ish runs under different environment settings: tools/ab_env.sh tag "VAR=val VAR2=val" "VAR=val" ...
+TAG=$1; shift
+mkdir -p gpurun_out
+i=0
+for setting in "$@"; do
+  i=$((i+1))
+  env $setting python bench.py --no-survey --no-cpu --steps 20 --warmup 5 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
+  python - <<PY
+import json
+try:
+    j=json.load(open("gpurun_out/${TAG}_$i.json")); k=j["kernels"]
+    print("[$setting] ms_per_step %.3f | " % j["ms_per_step"] + " ".join("%s=%.3f" % (n, k[n]["ms"]) for n in sorted(k) if n.startswith(("agg","proj","heads","graph_build_total"))))
+except Exception as e:
+    print("[$setting] failed", e)
+PY
+done
