@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BGNN_LIB") or os.path.join(HERE, "libbgnn.so")      #
 MAX_OFFSETS, MAX_NODE_FEATS, MAX_EDGE_FEATS = 24, 8, 4
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3, -4
 PREC_F32, PREC_BF16 = 0, 1
+AGG_GCN, AGG_MEAN, AGG_GIN = 0, 1, 2
 OPTIONS = dict(tensor_cores=0, presplit=1, window=2, tile5=3, tile5_window=4)
 
 NF_CODES = dict(depth=0, local_mean=1, local_std=2, gradient_x=3, gradient_y=4,
@@ -78,6 +79,9 @@ SYMBOLS = {
     "bgnn_test_proj_bf16": (C.c_int, [P, I64, C.c_int, P, C.c_int, P, P, P, P, C.c_int, P]),
     "bgnn_gat_forward": (C.c_int, [P, I64, I64, P, P, P, P, P, SZ, P, P, P, P, P, P, F32, F32, P, P, P]),
     "bgnn_gat_grid_path": (C.c_int, [P, C.POINTER(GridTopo), I64]),
+    "bgnn_csr_aggregate": (C.c_int, [C.c_int, I64, C.c_int, P, I64, P, P, P, C.c_int, F32, P, P, P, C.c_int, P, I64, C.c_int, P]),
+    "bgnn_linear": (C.c_int, [P, I64, I64, C.c_int, P, P, C.c_int, C.c_int, P, I64, P]),
+    "bgnn_heads_finish": (C.c_int, [P, I64, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, P, P, P, P, P, F32, F32, P]),
     "bgnn_scatter_tile": (C.c_int, [P, I64, P, P, P, P, F32, P, P, P, P]),
     "bgnn_graph_to_grid": (C.c_int, [P, I64, P, F32, P, P]),
     "bgnn_stitch_init": (C.c_int, [C.POINTER(Survey), P]),

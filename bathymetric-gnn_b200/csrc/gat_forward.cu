@@ -2272,6 +2272,101 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     return BGNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------ GCN / GraphSAGE / GIN backbones
+// models/gnn.py:120-143 (`gnn_type != "GAT"`): layers without attention on the same in-edge CSR.  The host layer
+// (bathymetric-gnn_b200/gnn.py::_run_plain) composes a layer from these entry points; PyG semantics as restated in
+// oracle/pyg_restated.py (GCNConv / SAGEConv / GINConv).  Hidden width only (64 by default): 256 B per node and layer, a small
+// fraction of the GAT path's traffic, so one warp-per-destination gather kernel + the fp32 FMA GEMM serve all three.
+namespace {
+// one warp per destination; lane <-> channels (strided); sources in CSR order = the reference's edge order, self term last
+template <int MODE>
+__global__ void __launch_bounds__(256)
+csr_reduce(int64_t N, int C, const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
+           const int32_t* __restrict__ src, const float* __restrict__ dis_tab, int dis_n, float eps,
+           const float* __restrict__ pre_add, const float* __restrict__ mul, const float* __restrict__ add, int relu,
+           float* __restrict__ out, int64_t ldo, int copy_self) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = wid; i < N; i += nw) {
+        const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+        const int deg = e1 - e0;
+        float di = 0.f;
+        if (MODE == BGNN_AGG_GCN) di = __ldg(dis_tab + min(deg + 1, dis_n - 1));          // deg^-1/2 of (in-degree + self loop)
+        for (int c = lane; c < C; c += 32) {
+            float acc = 0.f;
+            for (int e = e0; e < e1; ++e) {
+                const int j = __ldg(src + e);
+                const float v = __ldg(x + (int64_t)j * ldx + c);
+                if (MODE == BGNN_AGG_GCN) {
+                    const int dj = __ldg(rowptr + j + 1) - __ldg(rowptr + j);
+                    const float nrm = __ldg(dis_tab + min(dj + 1, dis_n - 1)) * di;       // (dis[src] * 1) * dis[dst]   (gcn_norm)
+                    acc += nrm * v;
+                } else {
+                    acc += v;
+                }
+            }
+            const float xi = __ldg(x + i * ldx + c);
+            float y;
+            if (MODE == BGNN_AGG_GCN) y = acc + (di * di) * xi;                           // self loop appended behind the edges
+            else if (MODE == BGNN_AGG_MEAN) y = acc / (float)(deg > 0 ? deg : 1);         // scatter-mean: sum / clamp(count, 1)
+            else y = acc + (1.0f + eps) * xi;                                             // GIN: out + (1 + eps) * x
+            if (pre_add) y += __ldg(pre_add + c);
+            if (mul) y = y * __ldg(mul + c) + (add ? __ldg(add + c) : 0.f);
+            if (relu) y = fmaxf(y, 0.f);
+            out[i * ldo + c] = y;
+            if (copy_self) out[i * ldo + C + c] = xi;                                     // SAGE: [mean | x] rows for ONE GEMM
+        }
+    }
+}
+}  // namespace
+
+extern "C" int bgnn_csr_aggregate(int mode, int64_t n_nodes, int channels, const float* x, int64_t ldx, const int32_t* rowptr,
+                                  const int32_t* csr_src, const float* deg_inv_sqrt, int deg_table_len, float eps,
+                                  const float* pre_add, const float* mul, const float* add, int relu, float* out, int64_t ldo,
+                                  int copy_self, void* stream) {
+    BGNN_CHECK_ARG(n_nodes >= 0 && channels > 0, "bad shape");
+    if (n_nodes == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(x && rowptr && out && ldx >= channels && ldo >= channels * (copy_self ? 2 : 1), "null / short argument");
+    BGNN_CHECK_ARG(mode != BGNN_AGG_GCN || (deg_inv_sqrt && deg_table_len >= 2), "GCN needs the deg^-1/2 table");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(80, s);
+    const unsigned blocks = (unsigned)(ceil_div64(n_nodes, 8) > 148 * 32 ? 148 * 32 : ceil_div64(n_nodes, 8));
+#define RED(M_) csr_reduce<M_><<<blocks, 256, 0, s>>>(n_nodes, channels, x, ldx, rowptr, csr_src, deg_inv_sqrt, deg_table_len, eps, pre_add, mul, add, relu, out, ldo, copy_self)
+    if (mode == BGNN_AGG_GCN) RED(BGNN_AGG_GCN);
+    else if (mode == BGNN_AGG_MEAN) RED(BGNN_AGG_MEAN);
+    else if (mode == BGNN_AGG_GIN) RED(BGNN_AGG_GIN);
+    else BGNN_CHECK_ARG(false, "unknown aggregation mode %d", mode);
+#undef RED
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_linear(const float* x, int64_t ldx, int64_t n_rows, int in_features, const float* weight, const float* bias,
+                           int relu, int out_features, float* out, int64_t ldo, void* stream) {
+    BGNN_CHECK_ARG(n_rows >= 0 && in_features > 0 && out_features > 0, "bad shape");
+    if (n_rows == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(x && weight && out && ldx >= in_features && ldo >= out_features && ldx < (1ll << 31) && ldo < (1ll << 31), "null / short argument");
+    ProfScope ps(81, (cudaStream_t)stream);
+    return launch_gemm(x, (int)ldx, weight, in_features, n_rows, out_features, out, (int)ldo, bias, relu, 64, nullptr, nullptr,
+                       nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int bgnn_heads_finish(const float* hidden, int64_t n_nodes, int h2, int nblk, int num_classes, const float* Wcls,
+                                 const float* bcls, const float* Wconf, const float* bconf, const float* Wcorr, const float* bcorr,
+                                 float* logits, float* probs, int64_t* cls, float* conf, float* corr, int64_t* action,
+                                 float thr_auto, float thr_review, void* stream) {
+    BGNN_CHECK_ARG(n_nodes >= 0 && h2 > 0 && (nblk == 2 || nblk == 3) && num_classes >= 1 && num_classes <= 8, "bad shape");
+    if (n_nodes == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(hidden && Wcls && bcls && Wconf && bconf && (nblk == 2 || (Wcorr && bcorr)), "null argument");
+    ProfScope ps(61, (cudaStream_t)stream);
+    const int64_t blocks = ceil_div64(n_nodes, 8) > 148 * 16 ? 148 * 16 : ceil_div64(n_nodes, 8);
+    heads_finish<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hidden, h2, nblk, num_classes, Wcls, bcls, Wconf, bconf, Wcorr, bcorr,
+                                                                     logits, probs, cls, conf, corr, action, thr_auto, thr_review, n_nodes);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
 #ifdef BGNN_AGG_TIMING
 extern "C" int bgnn_debug_agg_timing(unsigned long long* out8, int reset) {
     if (out8) cudaMemcpyFromSymbol(out8, g_agg_t, sizeof(unsigned long long) * 8);

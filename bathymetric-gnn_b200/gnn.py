@@ -4,8 +4,10 @@
 The sub-module names are the reference's, so a reference checkpoint's
 `model_state_dict` loads with `strict=True` (SURVEY.md 8(b) "State-dict
 compatibility"); GATConv parameters use the PyG >= 2.4 names and the PyG <= 2.3
-spelling (`lin_src` / `lin_dst`) is accepted on load.  Only the GAT backbone is
-built (GCN / GraphSAGE / GIN are outside the hot path).
+spelling (`lin_src` / `lin_dst`) is accepted on load.  The GAT backbone is the hot
+path (fused tensor-core / tiled kernels behind one model handle); GCN / GraphSAGE / GIN
+(models/gnn.py:120-143) run on the same in-edge CSR through `bgnn_csr_aggregate` +
+`bgnn_linear` + `bgnn_heads_finish` (`_run_plain`).
 Inference only: there is no autograd through the kernels and no CPU fallback.
 """
 from __future__ import annotations
@@ -145,20 +147,31 @@ class LocalFeatureExtractor(nn.Module):
 
 
 class GNNBackbone(nn.Module):
-    """models/gnn.py:74-188, GAT branch."""
+    """models/gnn.py:74-188: the module tree (parameter holders) of every `gnn_type` the reference accepts."""
 
     def __init__(self, in_channels, hidden_channels, num_layers, gnn_type="GAT", heads=4, dropout=0.1, edge_dim=None):
         super().__init__()
-        if gnn_type != "GAT":
-            raise NotImplementedError(f"gnn_type={gnn_type!r}: only the GAT backbone is on the accelerated hot path")
+        if gnn_type not in ("GAT", "GCN", "GraphSAGE", "GIN"):
+            raise ValueError(f"Unknown GNN type: {gnn_type}")                   # models/gnn.py:145-146
         self.gnn_type, self.num_layers, self.dropout = gnn_type, num_layers, dropout
         self.convs, self.norms = nn.ModuleList(), nn.ModuleList()
         for i in range(num_layers):
             last = i == num_layers - 1
-            layer_in = in_channels if i == 0 else hidden_channels * heads
-            self.convs.append(GATConvParams(layer_in, hidden_channels, heads=1 if last else heads,
-                                            concat=not last, edge_dim=edge_dim))
-            self.norms.append(BatchNormParams(hidden_channels if last else hidden_channels * heads))
+            if gnn_type == "GAT":
+                layer_in = in_channels if i == 0 else hidden_channels * heads
+                self.convs.append(GATConvParams(layer_in, hidden_channels, heads=1 if last else heads,
+                                                concat=not last, edge_dim=edge_dim))
+                self.norms.append(BatchNormParams(hidden_channels if last else hidden_channels * heads))
+                continue
+            layer_in = in_channels if i == 0 else hidden_channels                # models/gnn.py:109-114
+            if gnn_type == "GCN":
+                self.convs.append(GCNConvParams(layer_in, hidden_channels))
+            elif gnn_type == "GraphSAGE":
+                self.convs.append(SAGEConvParams(layer_in, hidden_channels))
+            else:
+                self.convs.append(GINConvParams(nn.Sequential(nn.Linear(layer_in, hidden_channels), nn.ReLU(),
+                                                              nn.Linear(hidden_channels, hidden_channels))))
+            self.norms.append(BatchNormParams(hidden_channels))
 
 
 class ClassificationHead(nn.Module):
@@ -249,12 +262,16 @@ class BathymetricGNN(nn.Module):
                 check(lib.bgnn_model_set_option(self._handle, _lib.OPTIONS[name], self._options[name]))
         return self
 
+    def _invalidate_plain(self):
+        self.__dict__.pop("_plain_cache", None)
+
     def invalidate(self) -> "BathymetricGNN":
         """Drop the folded device weights; the next forward re-packs them from the module's parameters.  Called by
         load_state_dict / _apply (.to, .cuda, .float) / train; call it yourself after editing parameters through `.data`
         or an external view (those edits do not bump the tensors' version counters that the cache key watches)."""
         with self._handle_lock:
             self._release()
+            self._invalidate_plain()
         return self
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -348,6 +365,8 @@ class BathymetricGNN(nn.Module):
             if x.dim() != 2 or x.shape[1] != self.in_channels:
                 raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({N}x{x.shape[-1]} and "
                                    f"{self.in_channels}x{self.hidden_channels})")
+            if self.gnn.gnn_type != "GAT":
+                return self._run_plain(data, dg, x, device, auto_thr, review_thr, want_action, return_hidden)
             topo = None
             h = self._ensure_handle(device)
             want = _lib.PREC_BF16 if getattr(self, "precision", "fp32") == "bf16" else _lib.PREC_F32
@@ -401,6 +420,107 @@ class BathymetricGNN(nn.Module):
                 out["action"] = action
             if return_hidden:
                 out["hidden"] = hidden
+        return out
+
+    # ------------------------------------------------------------------ GCN / GraphSAGE / GIN (models/gnn.py:120-143)
+    def _plain_weights(self, device):
+        """Device copies of the folded weights of the attention-free backbones: BatchNorm(eval) becomes a per-channel
+        scale / shift folded into the layer's last Linear (or applied by the aggregation epilogue for GCN); cached on the
+        parameters' version counters like the GAT handle."""
+        key = (str(device), tuple(t._version for t in list(self.parameters()) + list(self.buffers())),
+               tuple(t.data_ptr() for t in self.parameters()))
+        cache = self.__dict__.get("_plain_cache")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        fe = self.feature_extractor.mlp
+        w = dict(fe=[(f(fe[0].weight), f(fe[0].bias)), (f(fe[3].weight), f(fe[3].bias))], layers=[])
+        for conv, norm in zip(self.gnn.convs, self.gnn.norms):
+            bn = norm.module
+            s_ = (bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps))
+            t_ = bn.bias.detach().double() - bn.running_mean.detach().double() * s_
+            if isinstance(conv, GCNConvParams):
+                w["layers"].append(dict(W=f(conv.lin.weight), pre=f(conv.bias), mul=f(s_.float()), add=f(t_.float())))
+            elif isinstance(conv, SAGEConvParams):          # BN(lin_l(mean) + lin_r(x)) = [mean | x] . (s * [Wl | Wr])^T + (s * bl + t)
+                Wc = torch.cat([conv.lin_l.weight.detach().double(), conv.lin_r.weight.detach().double()], dim=1) * s_[:, None]
+                w["layers"].append(dict(W=f(Wc.float()), b=f((conv.lin_l.bias.detach().double() * s_ + t_).float())))
+            else:
+                l1, l2 = conv.nn[0], conv.nn[2]
+                w["layers"].append(dict(W1=f(l1.weight), b1=f(l1.bias), W2=f((l2.weight.detach().double() * s_[:, None]).float()),
+                                        b2=f((l2.bias.detach().double() * s_ + t_).float()), eps=float(conv.eps)))
+        heads = [self.classification_head, self.confidence_head] + ([self.correction_head] if self.predict_correction else [])
+        w["hW0"] = f(torch.cat([h.mlp[0].weight.detach() for h in heads], dim=0))
+        w["hb0"] = f(torch.cat([h.mlp[0].bias.detach() for h in heads], dim=0))
+        w["h1"] = [(f(h.mlp[3].weight), f(h.mlp[3].bias)) for h in heads]
+        # deg^-1/2 exactly as PyG's gcn_norm computes it (torch float32 pow), indexed by in-degree + 1
+        w["dis"] = f(torch.cat([torch.zeros(1), torch.arange(1, 64, dtype=torch.float32).pow(-0.5)]))
+        self.__dict__["_plain_cache"] = (key, w)
+        return w
+
+    def _run_plain(self, data, dg, x, device, auto_thr, review_thr, want_action, return_hidden):
+        """forward / predict for gnn_type in {GCN, GraphSAGE, GIN}: conv(x, edge_index) -> BatchNorm(eval) -> ReLU (all but the
+        last layer), models/gnn.py:173-186; edge attributes are not used by these layers (gnn.py:177-178)."""
+        if getattr(self, "precision", "fp32") != "fp32":
+            raise NotImplementedError("the bf16 mode covers the GAT backbone only")
+        N, Cc, L = int(x.shape[0]), self.hidden_channels, self.num_gnn_layers
+        if dg is not None:
+            rowptr, src = dg.rowptr, (dg.csr_src if dg.E > 0 else None)
+            max_deg = int(dg.cfg.n_offsets)
+        else:
+            rowptr, src, _, E = self._csr_from_coo(data, device)
+            max_deg = int((rowptr[1:] - rowptr[:-1]).max()) if N else 0
+        w = self._plain_weights(device)
+        if max_deg + 1 >= w["dis"].numel():
+            raise NotImplementedError(f"in-degree {max_deg} exceeds the GCN normalisation table")
+        new = lambda c: torch.empty((N, c), dtype=torch.float32, device=device)
+        st = stream_ptr()
+        lin = lambda a, K, W, b, relu, o, Nout: check(lib.bgnn_linear(ptr(a), a.stride(0), N, K, ptr(W), ptr(b), int(relu), Nout, ptr(o), o.stride(0), st))
+        agg = lambda mode, a, o, Cin, eps=0.0, pre=None, mul=None, add=None, relu=0, copy_self=0: check(lib.bgnn_csr_aggregate(
+            mode, N, Cin, ptr(a), a.stride(0), ptr(rowptr), ptr(src), ptr(w["dis"]), int(w["dis"].numel()), float(eps), ptr(pre), ptr(mul),
+            ptr(add), int(relu), ptr(o), o.stride(0), int(copy_self), st))
+        out = dict(class_logits=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
+                   class_probs=torch.empty((N, self.num_classes), dtype=torch.float32, device=device),
+                   predicted_class=torch.empty(N, dtype=torch.int64, device=device),
+                   confidence=torch.empty(N, dtype=torch.float32, device=device))
+        if self.predict_correction:
+            out["correction"] = torch.empty(N, dtype=torch.float32, device=device)
+        action = torch.empty(N, dtype=torch.int64, device=device) if want_action else None
+        if N > 0:
+            t0, cur = new(Cc), new(Cc)
+            lin(x, self.in_channels, *w["fe"][0], True, t0, Cc)                     # LocalFeatureExtractor (gnn.py:34-71)
+            lin(t0, Cc, *w["fe"][1], False, cur, Cc)
+            kind = self.gnn.gnn_type
+            for l, lw in enumerate(w["layers"]):
+                relu = l < L - 1
+                nxt = new(Cc)
+                if kind == "GCN":                                                   # BN(A_norm (x W^T) + b)
+                    lin(cur, Cc, lw["W"], None, False, t0, Cc)
+                    agg(_lib.AGG_GCN, t0, nxt, Cc, pre=lw["pre"], mul=lw["mul"], add=lw["add"], relu=relu)
+                elif kind == "GraphSAGE":
+                    cat = new(2 * Cc)
+                    agg(_lib.AGG_MEAN, cur, cat, Cc, copy_self=1)
+                    lin(cat, 2 * Cc, lw["W"], lw["b"], relu, nxt, Cc)
+                else:                                                               # GIN: BN(nn((1 + eps) x + sum x_j))
+                    agg(_lib.AGG_GIN, cur, t0, Cc, eps=lw["eps"])
+                    t1 = new(Cc)
+                    lin(t0, Cc, lw["W1"], lw["b1"], True, t1, Cc)
+                    lin(t1, Cc, lw["W2"], lw["b2"], relu, nxt, Cc)
+                cur = nxt
+            h2, nblk = Cc // 2, (3 if self.predict_correction else 2)
+            hh = new(nblk * h2)
+            lin(cur, Cc, w["hW0"], w["hb0"], True, hh, nblk * h2)
+            hc = w["h1"]
+            check(lib.bgnn_heads_finish(ptr(hh), N, h2, nblk, self.num_classes, ptr(hc[0][0]), ptr(hc[0][1]), ptr(hc[1][0]), ptr(hc[1][1]),
+                                        ptr(hc[2][0]) if nblk > 2 else None, ptr(hc[2][1]) if nblk > 2 else None,
+                                        ptr(out["class_logits"]), ptr(out["class_probs"]), ptr(out["predicted_class"]),
+                                        ptr(out["confidence"]), ptr(out.get("correction")), ptr(action), float(auto_thr),
+                                        float(review_thr), st))
+            if return_hidden:
+                out["hidden"] = cur
+        elif return_hidden:
+            out["hidden"] = new(Cc)
+        if want_action:
+            out["action"] = action
         return out
 
     def forward(self, data: Data) -> Dict[str, torch.Tensor]:

@@ -214,6 +214,33 @@ int bgnn_gat_forward(const bgnn_model* m, int64_t n_nodes, int64_t n_edges,
                      float* hidden_out, const bgnn_grid_topo* topo /* may be NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GCN / GraphSAGE / GIN backbones (models/gnn.py:120-143, `gnn_type != "GAT"`).  Layers without
+ * attention on the same in-edge CSR; the host layer composes a layer from these three entry points (PyG semantics:
+ * oracle/pyg_restated.py).  All pointers are DEVICE pointers; rows may be strided (ld* in floats).
+ * ------------------------------------------------------------------------------------------ */
+enum { BGNN_AGG_GCN = 0, BGNN_AGG_MEAN = 1, BGNN_AGG_GIN = 2 };
+/* out[i, 0:C] = epilogue(reduce over the in-edges of i, sources in CSR order = the reference's edge order, self term last):
+ *   BGNN_AGG_GCN   sum_j x_j * (t[d_j + 1] * t[d_i + 1]) + x_i * t[d_i + 1]^2,  t = deg_inv_sqrt table (t[k] = k^-1/2 as float32,
+ *                  computed by the caller exactly as the reference does), d = in-degree (PyG gcn_norm with self loops of weight 1)
+ *   BGNN_AGG_MEAN  sum_j x_j / max(d_i, 1)                                       (SAGEConv, aggr = 'mean')
+ *   BGNN_AGG_GIN   sum_j x_j + (1 + eps) * x_i                                   (GINConv)
+ * epilogue: (+ pre_add[c]) (* mul[c] + add[c]) (ReLU), each optional (NULL / 0).  copy_self = 1 additionally writes x_i to
+ * out[i, C:2C] (SAGEConv's `lin_l(mean) + lin_r(x)` as one GEMM over [mean | x]). */
+int bgnn_csr_aggregate(int mode, int64_t n_nodes, int channels, const float* x, int64_t ldx, const int32_t* rowptr,
+                       const int32_t* csr_src, const float* deg_inv_sqrt, int deg_table_len, float eps,
+                       const float* pre_add, const float* mul, const float* add, int relu, float* out, int64_t ldo,
+                       int copy_self, void* stream);
+/* out[n, 0:out_features] = (ReLU)(x[n, 0:in_features] . weight[out_features, in_features]^T + bias)   (torch.nn.Linear layout) */
+int bgnn_linear(const float* x, int64_t ldx, int64_t n_rows, int in_features, const float* weight, const float* bias,
+                int relu, int out_features, float* out, int64_t ldo, void* stream);
+/* second layers of the heads + softmax / argmax (first max) / sigmoid / action rule (models/gnn.py:191-260, 381-451) from
+ * hidden = ReLU(first layers) [N, nblk * h2] (blocks: classification | confidence | correction).  Outputs may be NULL. */
+int bgnn_heads_finish(const float* hidden, int64_t n_nodes, int h2, int nblk, int num_classes, const float* Wcls,
+                      const float* bcls, const float* Wconf, const float* bconf, const float* Wcorr, const float* bcorr,
+                      float* logits, float* probs, int64_t* cls, float* conf, float* corr, int64_t* action,
+                      float auto_correct_threshold, float review_threshold, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Scatter + stitch.  Replaces GraphBuilder.graph_to_grid (graph_construction.py:471-505) as
  * used by BathymetricPipeline._process_tile (models/pipeline.py:277-314), TileManager.merge_tile
  * weighted branch (data/tiling.py:242-258), TileMerger.add_tile discrete branch (:408-420) and
@@ -356,7 +383,7 @@ int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t*
  * launching stream around every kernel the library launches.  Off by default; the record list is mutex-guarded.
  * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
  * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
- * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit,
+ * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit, 80 csr_aggregate, 81 linear,
  * 75 vr_apply_results, 76 sidecar_add.
  * ------------------------------------------------------------------------------------------ */
 int bgnn_profile_enable(int on);                               /* also clears recorded events */

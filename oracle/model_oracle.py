@@ -35,6 +35,7 @@ class ModelCfg:
     num_classes: int = 3
     predict_correction: bool = True
     edge_dim: Optional[int] = 3
+    gnn_type: str = "GAT"              # "GAT" | "GCN" | "GraphSAGE" | "GIN" (models/gnn.py:120-146)
 
 
 def layer_dims(cfg: ModelCfg):
@@ -66,12 +67,23 @@ def init_state_dict(cfg: ModelCfg, seed: int = 0, randomize_bn: bool = True,
     linear("feature_extractor.mlp.0", cfg.in_channels, cfg.hidden)          # gnn.py:55
     linear("feature_extractor.mlp.3", cfg.hidden, cfg.hidden)               # gnn.py:66
     for i, (fin, H, concat) in enumerate(layer_dims(cfg)):
-        conv = pyg.GATConv(fin, cfg.hidden, heads=H, concat=concat, edge_dim=cfg.edge_dim)
+        if cfg.gnn_type == "GAT":
+            conv = pyg.GATConv(fin, cfg.hidden, heads=H, concat=concat, edge_dim=cfg.edge_dim)
+        elif cfg.gnn_type == "GCN":                                          # gnn.py:120-121 (layer_in = hidden for every layer)
+            conv, H, concat = pyg.GCNConv(cfg.hidden, cfg.hidden), 1, False
+        elif cfg.gnn_type == "GraphSAGE":                                    # gnn.py:134-135
+            conv, H, concat = pyg.SAGEConv(cfg.hidden, cfg.hidden), 1, False
+        elif cfg.gnn_type == "GIN":                                          # gnn.py:137-143
+            conv = pyg.GINConv(nn.Sequential(nn.Linear(cfg.hidden, cfg.hidden), nn.ReLU(), nn.Linear(cfg.hidden, cfg.hidden)))
+            H, concat = 1, False
+        else:
+            raise ValueError(f"Unknown GNN type: {cfg.gnn_type}")
         for k, v in conv.state_dict().items():
             sd[f"gnn.convs.{i}.{k}"] = v.detach().clone()
         C = cfg.hidden * H if concat else cfg.hidden
         if randomize_bn:
-            sd[f"gnn.convs.{i}.bias"] = 0.1 * torch.randn(C, generator=g)
+            if f"gnn.convs.{i}.bias" in sd:
+                sd[f"gnn.convs.{i}.bias"] = 0.1 * torch.randn(C, generator=g)
             sd[f"gnn.norms.{i}.module.weight"] = 1.0 + 0.2 * torch.randn(C, generator=g)
             sd[f"gnn.norms.{i}.module.bias"] = 0.1 * torch.randn(C, generator=g)
             sd[f"gnn.norms.{i}.module.running_mean"] = 0.1 * torch.randn(C, generator=g)
@@ -160,6 +172,25 @@ def gat_layer(sd, i, x, edge_index, edge_attr, H, C, concat, chunk=1 << 21, bf16
     return out + sd[p + "bias"].to(dt)
 
 
+def plain_layer(sd, i, x, edge_index, gnn_type: str):
+    """GCNConv / SAGEConv / GINConv of layer i driven by `sd` (pyg_restated classes; gnn.py:177-178 calls them without
+    edge attributes)."""
+    p = f"gnn.convs.{i}."
+    dt = x.dtype
+    C = x.shape[1]
+    if gnn_type == "GCN":
+        conv = pyg.GCNConv(C, sd[p + "lin.weight"].shape[0])
+    elif gnn_type == "GraphSAGE":
+        conv = pyg.SAGEConv(C, sd[p + "lin_l.weight"].shape[0])
+    elif gnn_type == "GIN":
+        out = sd[p + "nn.0.weight"].shape[0]
+        conv = pyg.GINConv(nn.Sequential(nn.Linear(C, out), nn.ReLU(), nn.Linear(out, out)))
+    else:
+        raise ValueError(f"Unknown GNN type: {gnn_type}")
+    conv.load_state_dict({k[len(p):]: v for k, v in sd.items() if k.startswith(p)}, strict=True)
+    return conv.to(dt)(x, edge_index)
+
+
 def bn_eval(sd, i, x):
     p = f"gnn.norms.{i}.module."
     dt = x.dtype
@@ -184,7 +215,10 @@ def forward(sd, cfg: ModelCfg, x, edge_index, edge_attr, dtype=torch.float32,
             x = bf16_round(x)
         hidden = [x]
         for i, (_, H, concat) in enumerate(layer_dims(cfg)):
-            x = gat_layer(sd, i, x, edge_index, edge_attr, H, cfg.hidden, concat, bf16_storage=bf16_storage)
+            if cfg.gnn_type == "GAT":
+                x = gat_layer(sd, i, x, edge_index, edge_attr, H, cfg.hidden, concat, bf16_storage=bf16_storage)
+            else:
+                x = plain_layer(sd, i, x, edge_index, cfg.gnn_type)
             x = bn_eval(sd, i, x)
             if i < cfg.layers - 1:
                 x = F.relu(x)

@@ -238,12 +238,84 @@ class BatchNorm(nn.Module):
         return self.module(x)
 
 
-class _Unsupported(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("only the GAT path of the reference is restated (SURVEY.md section 2 row 2)")
+class _LinBias(nn.Module):
+    """PyG `Linear(in, out, bias=True)`: kaiming-uniform weight / uniform bias like torch.nn.Linear."""
+
+    def __init__(self, fin, fout, bias=True):
+        super().__init__()
+        ref = nn.Linear(fin, fout, bias=bias)
+        self.weight = ref.weight
+        if bias:
+            self.bias = ref.bias
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        y = x @ self.weight.t()
+        return y if self.bias is None else y + self.bias
 
 
-GCNConv = SAGEConv = GINConv = _Unsupported
+class GCNConv(nn.Module):
+    """Public PyG `GCNConv(in, out)` with its defaults (improved=False, add_self_loops=True, normalize=True, bias=True), as
+    constructed by models/gnn.py:120-121 and called as `conv(x, edge_index)` (gnn.py:177-178):
+      lin = Linear(in, out, bias=False) (glorot); `gcn_norm`: self loops of weight 1 appended behind the edges
+      (add_remaining_self_loops), deg[i] = sum of the weights of the edges INTO i (incl. the loop), norm_e =
+      deg^-1/2[src] * w_e * deg^-1/2[dst] (inf -> 0); out = scatter_add_over_targets(norm_e * lin(x)[src]) + bias.
+    Source: Kipf & Welling 2017, eq. 2, and the PyG 2.3-2.6 `gcn_norm` / `GCNConv.forward`."""
+
+    def __init__(self, in_channels, out_channels, **kw):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index, edge_weight=None):
+        N = x.shape[0]
+        ei, _ = remove_self_loops(edge_index)                     # add_remaining_self_loops: existing loops would keep their
+        loops = torch.arange(N, dtype=ei.dtype)                   # weight; the grid graphs have none
+        src = torch.cat([ei[0], loops])
+        dst = torch.cat([ei[1], loops])
+        w = torch.ones(src.numel(), dtype=x.dtype)
+        deg = torch.zeros(N, dtype=x.dtype).index_add_(0, dst, w)
+        dis = deg.pow(-0.5)
+        dis[torch.isinf(dis)] = 0
+        norm = dis[src] * w * dis[dst]
+        h = self.lin(x)
+        out = torch.zeros(N, self.out_channels, dtype=x.dtype).index_add_(0, dst, norm.unsqueeze(-1) * h[src])
+        return out + self.bias
+
+
+class SAGEConv(nn.Module):
+    """Public PyG `SAGEConv(in, out)` with its defaults (aggr='mean', normalize=False, root_weight=True, project=False,
+    bias=True; models/gnn.py:134-135): out = lin_l(mean_{j in N(i)} x_j) + lin_r(x_i); lin_l has the bias, lin_r none; a node
+    without in-edges aggregates to 0 (sum / max(count, 1)).  Hamilton et al. 2017 (GraphSAGE-mean)."""
+
+    def __init__(self, in_channels, out_channels, **kw):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = _LinBias(in_channels, out_channels, bias=True)
+        self.lin_r = _LinBias(in_channels, out_channels, bias=False)
+
+    def forward(self, x, edge_index):
+        return self.lin_l(scatter_mean(x[edge_index[0]], edge_index[1], x.shape[0])) + self.lin_r(x)
+
+
+class GINConv(nn.Module):
+    """Public PyG `GINConv(nn, eps=0.0, train_eps=False)` (models/gnn.py:137-143): out = nn((1 + eps) * x_i + sum_{j in N(i)} x_j);
+    `eps` is a buffer when it is not trained.  Xu et al. 2019, eq. 4.1."""
+
+    def __init__(self, nn_module, eps: float = 0.0, train_eps: bool = False, **kw):
+        super().__init__()
+        self.nn = nn_module
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = nn.Parameter(torch.tensor([float(eps)]))
+        else:
+            self.register_buffer("eps", torch.tensor([float(eps)]))
+
+    def forward(self, x, edge_index):
+        out = torch.zeros_like(x).index_add_(0, edge_index[1], x[edge_index[0]])
+        return self.nn(out + (1 + self.eps) * x)
 
 
 def global_mean_pool(x, batch):

@@ -138,7 +138,7 @@ def make_c1_fixture():
 
 def ref_model(cfg: mo.ModelCfg, sd):
     m = ref_gnn.BathymetricGNN(in_channels=cfg.in_channels, hidden_channels=cfg.hidden,
-                               num_gnn_layers=cfg.layers, gnn_type="GAT", heads=cfg.heads,
+                               num_gnn_layers=cfg.layers, gnn_type=cfg.gnn_type, heads=cfg.heads,
                                num_classes=cfg.num_classes, predict_correction=cfg.predict_correction,
                                dropout=0.0, edge_dim=cfg.edge_dim)
     missing = m.load_state_dict(sd, strict=True)
@@ -176,6 +176,31 @@ def make_model_fixtures():
     blob["state_keys"] = np.array(sorted(ref_gnn.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.1, 3).state_dict().keys()))
     np.savez_compressed(os.path.join(HERE, "model_cases.npz"), **blob)
     print("model_cases.npz: params F7/F8 =", blob["param_count_F7"], blob["param_count_F8"])
+
+
+def make_model_types_fixtures():
+    """GCN / GraphSAGE / GIN backbones (models/gnn.py:120-143): the UNMODIFIED reference module on the restated PyG layers."""
+    cases = graph_cases()
+    blob = {}
+    for t, gname, F, seed in (("GCN", "g64_holes", 7, 11), ("GraphSAGE", "g64_holes_unc", 8, 12), ("GIN", "g32_sparse", 7, 13),
+                              ("GCN", "g48_4conn", 7, 14), ("GraphSAGE", "g33_k24", 7, 15), ("GIN", "g64_holes", 7, 16)):
+        g, _ = run_ref_graph(cases[gname])
+        cfg = mo.ModelCfg(in_channels=F, gnn_type=t)
+        sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+        cls_b, conf_b = mo.calibrate_heads(sd, cfg, g.x, g.edge_index, g.edge_attr)
+        m = ref_model(cfg, sd)
+        assert set(m.state_dict().keys()) == set(sd.keys()), set(m.state_dict().keys()) ^ set(sd.keys())
+        out = m.predict(g, 0.85, 0.6)
+        key = f"{t}_{gname}_s{seed}"
+        blob[key + "/cls_bias"], blob[key + "/conf_bias"] = cls_b.numpy(), conf_b.numpy()
+        blob[key + "/meta"] = np.array([F, seed], np.int64)
+        blob[key + "/graph"], blob[key + "/type"] = np.array(gname), np.array(t)
+        blob[key + "/param_count"] = np.int64(sum(p.numel() for p in m.parameters()))
+        blob[key + "/state_keys"] = np.array(sorted(m.state_dict().keys()))
+        for k, v in out.items():
+            blob[f"{key}/{k}"] = v.numpy()
+        print(key, "class hist", np.bincount(out["predicted_class"].numpy(), minlength=3), "params", int(blob[key + "/param_count"]))
+    np.savez_compressed(os.path.join(HERE, "model_types_cases.npz"), **blob)
 
 
 def make_stitch_fixtures():
@@ -481,12 +506,13 @@ def make_native_script_fixture():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["native_script", "graph", "c1", "model", "model_bf16", "stitch", "pipeline", "native", "sidecar", "multiscale", "vr_bag"]
+    which = sys.argv[1:] or ["native_script", "graph", "c1", "model", "model_bf16", "model_types", "stitch", "pipeline", "native", "sidecar", "multiscale", "vr_bag"]
     if "vr_bag" in which: make_vr_bag_fixture()
     if "native_script" in which: make_native_script_fixture()
     if "graph" in which: make_graph_fixtures()
     if "model" in which: make_model_fixtures()
     if "model_bf16" in which: make_model_bf16_fixtures()
+    if "model_types" in which: make_model_types_fixtures()
     if "sidecar" in which: make_sidecar_fixture()
     if "multiscale" in which: make_multiscale_fixture()
     if "stitch" in which: make_stitch_fixtures()

@@ -247,3 +247,80 @@ def test_ragged_batch_forward_equals_per_grid_forward():
     ref = mo.forward(sd, cfg, np.concatenate(xs), np.concatenate(eis, 1), np.concatenate(eas), torch.float32)
     np.testing.assert_allclose(ob["class_logits"].cpu().numpy(), ref["class_logits"].numpy(), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(ob["confidence"].cpu().numpy(), ref["confidence"].numpy(), rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------------------------------------ GCN / GraphSAGE / GIN
+TZ = gio.load("model_types_cases.npz")
+TYPE_KEYS = sorted({k.split("/")[0] for k in TZ.files})
+
+
+def _typed_model(gnn_type, F, sd):
+    import bathymetric_gnn_b200 as bg
+    m = bg.BathymetricGNN(F, 64, 4, gnn_type, 4, 3, True, 0.0, 3)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("key", TYPE_KEYS)
+def test_plain_backbones_vs_reference_module_golden(key):
+    """gnn_type in {GCN, GraphSAGE, GIN} (models/gnn.py:120-143): CUDA forward vs the UNMODIFIED reference module's outputs
+    (tests/golden/model_types_cases.npz), holes / uncertainty column / 4-, 8- and 24-offset stencils."""
+    import bathymetric_gnn_b200 as bg
+    F, seed = (int(v) for v in TZ[key + "/meta"])
+    t = str(TZ[key + "/type"])
+    c, _ = gio.graph_case(GZ, str(TZ[key + "/graph"]))
+    cfg = mo.ModelCfg(in_channels=F, gnn_type=t)
+    sd = mo.init_state_dict(cfg, seed=seed, randomize_bn=True, head_gain=8.0)
+    sd["classification_head.mlp.3.bias"] = torch.from_numpy(TZ[key + "/cls_bias"])
+    sd["confidence_head.mlp.3.bias"] = torch.from_numpy(TZ[key + "/conf_bias"])
+    model = _typed_model(t, F, sd)
+    assert sorted(model.state_dict().keys()) == TZ[key + "/state_keys"].tolist()
+    assert sum(p.numel() for p in model.parameters()) == int(TZ[key + "/param_count"])
+    g = bg.GraphBuilder(c["conn"]).build_graph(c["depth"], c["mask"], c["unc"], c["res"])
+    out = model.predict(g, 0.85, 0.6)
+    # Tolerance: these layers have no attention normalisation (GIN sums its neighbours: activations grow ~9x per layer), so
+    # the absolute term scales with the input's own fp32 envelope: atol_k = max(2e-5, 2 * max|reference_fp32 - oracle_fp64|),
+    # and the CUDA path is held to it against the fp64 evaluation (same rule as tests/test_gpu_fullsize.py::_compare_forward)
+    ref64 = mo.forward(sd, cfg, g.x.cpu().numpy(), g.edge_index.cpu().numpy(), g.edge_attr.cpu().numpy(), dtype=torch.float64)
+    atol_lg = ATOL
+    for k in ("class_logits", "confidence", "correction"):
+        r64 = ref64[k].numpy()
+        env = float(np.abs(TZ[f"{key}/{k}"].astype(np.float64) - r64).max())
+        atol_k = max(ATOL, 2.0 * env)
+        err = np.abs(out[k].cpu().numpy().astype(np.float64) - r64)
+        assert np.all(err <= atol_k + RTOL * np.abs(r64)), (k, float(err.max()), env)
+        if k == "class_logits":
+            atol_lg = atol_k
+    srt = np.sort(TZ[key + "/class_logits"], axis=1)
+    strict = (srt[:, -1] - srt[:, -2]) > 2 * (atol_lg + RTOL * np.abs(srt[:, -1]))
+    conf, cls = out["confidence"].cpu().numpy(), out["predicted_class"].cpu().numpy()
+    assert np.array_equal(cls[strict], TZ[key + "/predicted_class"][strict]) and strict.mean() > 0.98
+    act = np.zeros_like(cls)
+    act[(cls == 2) & (conf > 0.85)] = 1
+    act[conf < 0.6] = 2
+    assert np.array_equal(out["action"].cpu().numpy(), act)
+    out2 = model.predict(g, 0.85, 0.6)
+    assert torch.equal(out2["class_logits"], out["class_logits"])                  # deterministic
+
+
+@pytest.mark.parametrize("gnn_type", ["GCN", "GraphSAGE", "GIN"])
+def test_plain_backbones_ragged_batch_and_foreign_coo(gnn_type):
+    """The same layers on a ragged block-diagonal batch (2x2 ... 14x14 grids, 35 % nodata => isolated nodes) and on a foreign `Data` whose CSR
+    is derived from its COO: both against the oracle."""
+    import bathymetric_gnn_b200 as bg
+    grids = synth.ragged_grids(40, seed=21, lo=2, hi=14, nodata_frac=0.35)
+    b = bg.GraphBuilder("8-connected")
+    g = b.build_graph_batch(grids, nodata=1.0e6, use_uncertainty=False)
+    cfg = mo.ModelCfg(in_channels=7, gnn_type=gnn_type)
+    sd = mo.init_state_dict(cfg, seed=5, randomize_bn=True)
+    model = _typed_model(gnn_type, 7, sd)
+    out = model(g)
+    args = (sd, cfg, g.x.cpu().numpy(), g.edge_index.cpu().numpy(), g.edge_attr.cpu().numpy())
+    ref, ref64 = mo.forward(*args), mo.forward(*args, dtype=torch.float64)
+    for k in ("class_logits", "confidence", "correction"):
+        env = float((ref[k].double() - ref64[k]).abs().max())
+        err = np.abs(out[k].cpu().numpy().astype(np.float64) - ref64[k].numpy())
+        assert np.all(err <= max(ATOL, 2.0 * env) + RTOL * np.abs(ref64[k].numpy())), (k, float(err.max()), env)
+    foreign = bg.Data(x=g.x.clone(), edge_index=g.edge_index.clone(), edge_attr=g.edge_attr.clone())
+    out_f = model(foreign)
+    np.testing.assert_allclose(out_f["class_logits"].cpu().numpy(), out["class_logits"].cpu().numpy(), rtol=1e-6, atol=1e-6)

@@ -285,6 +285,23 @@ def test_dropin_packages_resolve_reference_imports():
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
 
 
+def test_every_reference_gnn_type_constructs_with_the_reference_state_dict_keys():
+    """models/gnn.py:120-146: GAT / GCN / GraphSAGE / GIN module trees load the oracle's (= the reference module's) state
+    dicts with strict=True; an unknown type raises the reference's ValueError."""
+    import bathymetric_gnn_b200 as bg
+    from oracle import model_oracle as mo
+    z = gio.load("model_types_cases.npz")
+    for t in ("GCN", "GraphSAGE", "GIN"):
+        cfg = mo.ModelCfg(in_channels=7, gnn_type=t)
+        sd = mo.init_state_dict(cfg, seed=1)
+        m = bg.BathymetricGNN(7, 64, 4, t, 4, 3, True, 0.1, 3)
+        m.load_state_dict(sd, strict=True)
+        key = [k for k in z.files if k.startswith(t + "_") and k.endswith("/state_keys")][0]
+        assert sorted(m.state_dict().keys()) == z[key].tolist()
+    with pytest.raises(ValueError, match="Unknown GNN type"):
+        bg.BathymetricGNN(7, 64, 4, "Transformer")
+
+
 def test_set_precision_validates_and_needs_no_gpu():
     """BathymetricGNN.set_precision (additive; BASELINE configs[4] bf16 mode): host-side state only, bad names raise
     ValueError like the reference's other string options (`Unknown connectivity`, graph_construction.py:88-89)."""
