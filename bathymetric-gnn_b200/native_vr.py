@@ -28,7 +28,12 @@ logger = logging.getLogger(__name__)
 
 class NativeVRProcessor:
     CLASS_NOISE = 2
-    BATCH_NODE_BUDGET = 50000          # scripts/inference_native.py:128 (raise it on B200: see DESIGN.md)
+    REFERENCE_BATCH_NODE_BUDGET = 50000    # scripts/inference_native.py:128
+    # Nodes per flush.  The reference's 50 000 keeps a CPU / small-GPU forward in cache; on a B200 a flush of that size is
+    # ~0.3 ms of kernels behind ~1 ms of per-flush host work, so the default here is 40x larger (eval-mode BatchNorm makes
+    # the per-grid results independent of how grids are batched; 2 M nodes = ~16 MB of pending host arrays).  It stays a
+    # plain class attribute like the reference's: scripts that set it keep working.
+    BATCH_NODE_BUDGET = 2_000_000
 
     def __init__(self, model: BathymetricGNN, graph_builder: GraphBuilder, device=None, auto_correct_threshold: float = 0.85):
         self.model, self.graph_builder = model, graph_builder

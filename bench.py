@@ -599,13 +599,53 @@ def run_ragged(args):
         kernels["chunk_nodes"] = g.num_nodes
         post = vr_post_row(g, out, chunks[0], dev)
         del g, out
+    api = {}
+    if rank == 0 and not args.no_api:
+        api = native_api_leg(args, model, builder, dev)
     if rank == 0:
         print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),
                           "unit": UNIT, "n_gpus": world, "ms_total": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"configs[3]: {args.grids} refinement grids, sides U{{3..50}}, 10% nodata, "
                                                  f"{len(chunks)} ragged chunks of <= {args.chunk_cells} cells per rank",
                                      "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"},
-                          "kernels_ms_one_chunk": kernels, "vr_post_one_chunk": post}))
+                          "kernels_ms_one_chunk": kernels, "vr_post_one_chunk": post, "reference_api": api}))
+
+
+def native_api_leg(args, model, builder, dev):
+    """The REFERENCE's own batching API on the same kind of input (scripts/inference_native.py:249-342 as driven by its main
+    loop, :505-560): host NumPy grids -> `NativeVRProcessor.add_to_batch` / `batch_ready` / `flush_batch` -> per-grid host
+    result arrays, wall clock with a device synchronise on both sides.  Two budgets: the reference's stock
+    BATCH_NODE_BUDGET = 50 000 nodes per flush and this build's default."""
+    import bathymetric_gnn_b200 as bg
+    from tests import synth
+    G = args.api_grids
+    grids = synth.ragged_grids(G, seed=7)
+    valid = sum(int(((d != 1.0e6) & np.isfinite(d)).sum()) for d, _, _ in grids)
+    out = {"grids": G, "valid_cells": valid, "note": "host arrays in, per-grid host arrays out; uncertainty dropped for the 7-feature model "
+                                                   "(inference_native.py:165-167)"}
+    for label, budget in (("stock_budget_50000", 50000), ("default_budget", None)):
+        proc = bg.NativeVRProcessor(model, builder, dev)
+        if budget is not None:
+            proc.BATCH_NODE_BUDGET = budget
+        for rep in range(2):                       # first pass = warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            flushes, acc = 0, 0.0
+            for d, u, res in grids:
+                r = proc.add_to_batch(d, u, res, 1.0e6)
+                if proc.batch_ready:
+                    for cls, conf, corr in proc.flush_batch():
+                        acc += float(conf.flat[0])
+                    flushes += 1
+            if proc.batch_pending:
+                for cls, conf, corr in proc.flush_batch():
+                    acc += float(conf.flat[0])
+                flushes += 1
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[label] = {"budget_nodes": int(proc.BATCH_NODE_BUDGET), "seconds": round(dt, 4), "flushes": flushes,
+                      "cells_per_s": valid / dt, "ms_per_flush": round(dt / max(flushes, 1) * 1e3, 3)}
+    return out
 
 
 def vr_post_row(g, out, chunk, dev):
@@ -807,6 +847,8 @@ def main():
                     help="tile = BASELINE configs[1] (default, the headline line); survey = configs[2], ragged = configs[3], "
                          "wide = configs[4] fp32 + bf16 (secondary)")
     ap.add_argument("--grids", type=int, default=100000)
+    ap.add_argument("--api-grids", type=int, default=20000, help="ragged workload: grids pushed through the reference's add_to_batch / flush_batch API")
+    ap.add_argument("--no-api", action="store_true", help="ragged workload without the reference-API leg")
     ap.add_argument("--chunk-cells", type=int, default=8000000)
     ap.add_argument("--survey-size", type=int, default=60000, help="side of the configs[2] survey (the `survey` object of the default line)")
     ap.add_argument("--no-survey", action="store_true", help="default line without the configs[2] survey leg")
