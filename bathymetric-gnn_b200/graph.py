@@ -74,11 +74,21 @@ class _DeviceGraph:
     `csr_eattr`) is emitted on first access: the tiled aggregation of a single tile reads
     the dense per-cell `grid_eattr` instead and never needs it."""
     __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "_csr_src",
-                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta")
+                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta", "keep_versions")
+
+    def check_sources_unchanged(self):
+        """`build_graph` consumes CUDA planes IN PLACE (no tile copy) and the lazily emitted arrays (`edge_index`, `edge_attr`,
+        the CSR payload) re-read them: an in-place edit of the caller's depth / mask / uncertainty tensor between the build and
+        the first access would yield edge features inconsistent with `x` / `rowptr`.  The tensors' version counters catch it."""
+        vs = getattr(self, "keep_versions", None)
+        if vs is not None and any(t._version != v for t, v in zip(self.keep, vs)):
+            raise RuntimeError("the depth / mask / uncertainty tensor this graph was built from has been modified in place; "
+                               "access edge_index / edge_attr before editing the survey, or build the graph from a copy")
 
     def ensure_csr(self):
         if getattr(self, "_csr_src", None) is not None:
             return
+        self.check_sources_unchanged()
         ED = int(self.cfg.n_edge_feats)
         with torch.cuda.device(self.device):
             src = torch.empty(max(self.E, 1), dtype=torch.int32, device=self.device)
@@ -122,6 +132,7 @@ class GridGraph(Data):
         tgt = self.__dict__.get("_target_device", dg.device)
         with torch.cuda.device(dg.device):
             if name in ("edge_index", "edge_attr"):
+                dg.check_sources_unchanged()
                 ED = dg.cfg.n_edge_feats
                 ei = torch.empty((2, dg.E), dtype=torch.int64, device=dg.device)
                 ea = torch.empty((dg.E, ED), dtype=torch.float32, device=dg.device)
@@ -525,6 +536,7 @@ class GraphBuilder:
         ED = cfg.n_edge_feats
         dg = _DeviceGraph()
         dg.cells, dg.cfg, dg.scratch, dg.keep, dg.device, dg.grid_meta = cells, cfg, scratch, keep, dev, meta
+        dg.keep_versions = [t._version for t in keep]
         dg.N, dg.E, dg.n_cells = N, E, n_cells
         dg.node_id = torch.empty(n_cells, dtype=torch.int32, device=dev)
         dg.node_cell = torch.empty(N, dtype=torch.int32, device=dev)

@@ -240,3 +240,20 @@ def test_multiscale_graph_builder_vs_reference_golden():
         ref = {k: z[f"s{s}/{k}"] for k in ("x", "edge_index", "edge_attr", "pos", "valid_rows", "valid_cols", "local_std")}
         ref["grid_shape"], ref["num_valid_cells"] = tuple(z[f"s{s}/grid_shape"]), z[f"s{s}/num_valid_cells"]
         check_graph(g, ref, None, has_holes=True)
+
+
+def test_lazy_arrays_refuse_a_survey_edited_after_the_build():
+    """build_graph consumes a CUDA depth plane in place and emits edge_index / edge_attr / the CSR payload lazily from it: an
+    in-place edit in between must be refused instead of returning features inconsistent with x / rowptr."""
+    import bathymetric_gnn_b200 as bg
+    d = torch.from_numpy(synth.noisy_tile(40, 50, seed=2)).cuda()
+    g = bg.GraphBuilder().build_graph(d, None, None, (1.0, 1.0))
+    ea0 = bg.GraphBuilder().build_graph(d.clone(), None, None, (1.0, 1.0)).edge_attr.clone()
+    d[3, 4] += 100.0
+    with pytest.raises(RuntimeError, match="modified in place"):
+        g.edge_attr
+    with pytest.raises(RuntimeError, match="modified in place"):
+        g._dev.csr_src
+    g2 = bg.GraphBuilder().build_graph(d, None, None, (1.0, 1.0))
+    assert torch.equal(g2.edge_index, bg.GraphBuilder().build_graph(d.clone(), None, None, (1.0, 1.0)).edge_index)
+    assert not torch.equal(g2.edge_attr, ea0)

@@ -101,3 +101,40 @@ def test_presplit_handover_is_bit_identical_in_forward():
     b = m.set_option("presplit", 0)._run(g, 0.85, 0.6, True, return_hidden=True)
     for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_adversarial_checkpoint_operand_scaling():
+    """the fp16 hi / lo operand split scales A by an ANALYTIC bound (bn_mul * max|h| + bn_add), not by the measured
+    maximum.  Adversarial checkpoint: one BatchNorm channel per layer with running_var ~ 0 (1 / sqrt(var + eps) = 316), one
+    projection-weight outlier (x 50) and input spikes of 1000 x the typical depth range, so that ordinary activations sit
+    ~2^-15 below the bound.  The forward must still hold the fp32 tolerance against the fp64 oracle, scaled by the oracle's own
+    fp32 envelope on this input (no silent degradation)."""
+    import bathymetric_gnn_b200 as bg
+    from oracle import graph_oracle as go
+    from oracle import model_oracle as mo
+    from tests import synth
+    d = synth.noisy_tile(120, 150, seed=4)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, d.size, 12)
+    d.ravel()[idx] += rng.choice([-1.0, 1.0], 12).astype(np.float32) * 3000.0        # spikes
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=9, randomize_bn=True)
+    for l in range(cfg.layers):
+        sd[f"gnn.norms.{l}.module.running_var"][3 + l] = 1e-12
+        sd[f"gnn.convs.{l}.lin.weight"][5, 7] *= 50.0
+    m = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = bg.GraphBuilder().build_graph(d, None, None, (0.5, 0.5))
+    ref_g = go.build_graph(d, None, None, (0.5, 0.5))
+    x = g.x.cpu().numpy()
+    r32 = mo.forward(sd, cfg, x, ref_g["edge_index"], ref_g["edge_attr"])
+    r64 = mo.forward(sd, cfg, x, ref_g["edge_index"], ref_g["edge_attr"], dtype=torch.float64)
+    out_tc = m.set_option("tensor_cores", 1)(g)
+    out_fma = m.set_option("tensor_cores", 0)(g)
+    for k in ("class_logits", "confidence", "correction"):
+        ref = r64[k].numpy()
+        env = float(np.abs(r32[k].numpy().astype(np.float64) - ref).max())
+        for name, o in (("tensor cores", out_tc), ("fma", out_fma)):
+            err = np.abs(o[k].cpu().numpy().astype(np.float64) - ref)
+            assert np.all(err <= max(2e-5, 3.0 * env) + 1e-5 * np.abs(ref)), (k, name, float(err.max()), env)
