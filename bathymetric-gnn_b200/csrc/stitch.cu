@@ -327,7 +327,7 @@ extern "C" int bgnn_stitch_add_tile_nodes(const bgnn_survey* s, int64_t r0, int6
     a.s = *s; a.r0 = r0; a.c0 = c0; a.h = h; a.w = w; a.row_w = row_w; a.col_w = col_w;
     a.node_id = node_id; a.cls = cls; a.conf = conf; a.corr = corr; a.lstd = local_std; a.floor_ = norm_floor;
     a.shared_wsum = s->n_cont > 1 && s->wsum[0] == s->wsum[1];
-    ProfScope ps(75, (cudaStream_t)stream);
+    ProfScope ps(78, (cudaStream_t)stream);
     k_add_tile_nodes<<<grid_for((int64_t)h * w), ST_THREADS, 0, (cudaStream_t)stream>>>(a);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;

@@ -74,12 +74,15 @@ class _DeviceGraph:
     `csr_eattr`) is emitted on first access: the tiled aggregation of a single tile reads
     the dense per-cell `grid_eattr` instead and never needs it."""
     __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "_csr_src",
-                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta", "keep_versions")
+                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta", "keep_versions", "scratch_borrowed")
 
     def check_sources_unchanged(self):
         """`build_graph` consumes CUDA planes IN PLACE (no tile copy) and the lazily emitted arrays (`edge_index`, `edge_attr`,
         the CSR payload) re-read them: an in-place edit of the caller's depth / mask / uncertainty tensor between the build and
         the first access would yield edge features inconsistent with `x` / `rowptr`.  The tensors' version counters catch it."""
+        if getattr(self, "scratch_borrowed", False):
+            raise RuntimeError("this graph was built on a caller-owned scratch buffer (pipelined survey tiles): edge_index / edge_attr "
+                               "/ the CSR payload are not available; use GraphBuilder.build_graph for a self-contained graph")
         vs = getattr(self, "keep_versions", None)
         if vs is not None and any(t._version != v for t, v in zip(self.keep, vs)):
             raise RuntimeError("the depth / mask / uncertainty tensor this graph was built from has been modified in place; "
@@ -360,10 +363,26 @@ class GraphBuilder:
         (additive) makes the kernel derive valid = isfinite & != nodata when no mask
         is given (scripts/inference_native.py:160)."""
         dev = self._device()
+        with torch.cuda.device(dev):
+            return self._build(*self._tile_cells(depth, valid_mask, uncertainty, resolution, nodata, dev))
+
+    def count_tile(self, depth, valid_mask=None, uncertainty=None, resolution=(1.0, 1.0), nodata=None, stream=None, scratch=None):
+        """`build_graph` in two steps for callers that pipeline tiles: `count_tile` (node / edge totals, host-synchronous on
+        `stream`) now, `emit_tile(pending)` later on the current stream.  `pending["N"]` is the tile's valid-cell count."""
+        dev = self._device()
+        with torch.cuda.device(dev):
+            return self._count(*self._tile_cells(depth, valid_mask, uncertainty, resolution, nodata, dev), stream=stream, scratch=scratch)
+
+    def emit_tile(self, pending) -> Data:
+        with torch.cuda.device(pending["dev"]):
+            return self._emit(pending)
+
+    def _tile_cells(self, depth, valid_mask, uncertainty, resolution, nodata, dev):
+        """The `bgnn_cells` descriptor of one tile (argument tuple of `_build` / `_count`)."""
         if getattr(depth, "ndim", 0) != 2:
             raise ValueError("depth must be a 2-D array")
         H, W = int(depth.shape[0]), int(depth.shape[1])
-        with torch.cuda.device(dev):
+        if True:
             d = _as_dev_f32(depth, dev)
 
             def same_view(t):       # a CUDA plane that shares the depth view's row stride is consumed in place
@@ -408,7 +427,7 @@ class GraphBuilder:
                 u = plane(uncertainty, torch.float32)
                 keep.append(u)
                 cells.unc = u.data_ptr()
-            return self._build(cells, keep, uncertainty is not None, (H, W), None, dev)
+            return cells, keep, uncertainty is not None, (H, W), None, dev
 
     def build_graph_batch(self, grids: Sequence[Tuple[np.ndarray, Optional[np.ndarray], Tuple[float, float]]],
                           nodata: Optional[float] = 1.0e6, use_uncertainty: bool = True) -> Data:
@@ -515,13 +534,31 @@ class GraphBuilder:
         return g
 
     def _build(self, cells, keep, has_unc, grid_shape, meta, dev, shapes=None) -> Data:
+        return self._emit(self._count(cells, keep, has_unc, grid_shape, meta, dev, shapes))
+
+    def _count(self, cells, keep, has_unc, grid_shape, meta, dev, shapes=None, stream=None, scratch=None):
+        """First half of a build: validity + neighbour counts + scans on `stream` (default: the current stream) and the
+        host-synchronous read-back of (N, E) -- the only host round trip of the path.  The survey driver issues it for tile
+        t + 1 on a side stream while tile t computes, so the GPU never waits for the host (survey.py)."""
         cfg, F = _graph_cfg(self.neighbor_offsets, self.node_features, has_unc, self.edge_features)
         n_cells = int(cells.n_cells)
-        scratch = torch.empty(max(int(lib.bgnn_graph_scratch_bytes(n_cells, cfg.n_offsets)), 256), dtype=torch.uint8, device=dev)
+        need = max(int(lib.bgnn_graph_scratch_bytes(n_cells, cfg.n_offsets)), 256)
+        borrowed = scratch is not None
+        if borrowed and scratch.numel() < need:
+            raise ValueError(f"scratch buffer too small: {scratch.numel()} < {need} bytes")
+        if scratch is None:
+            scratch = torch.empty(need, dtype=torch.uint8, device=dev)
         totals = (C.c_int64 * 2)()
-        st = stream_ptr()
+        st = stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
         check(lib.bgnn_graph_count(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), totals, st))
-        N, E = int(totals[0]), int(totals[1])
+        return dict(cells=cells, keep=keep, has_unc=has_unc, grid_shape=grid_shape, meta=meta, dev=dev, shapes=shapes, cfg=cfg,
+                    F=F, scratch=scratch, N=int(totals[0]), E=int(totals[1]), n_cells=n_cells, borrowed=borrowed)
+
+    def _emit(self, pending) -> Data:
+        """Second half of a build (current stream): ids, node features, edge features of a counted cell space."""
+        cells, keep, grid_shape, meta, dev, shapes = (pending[k] for k in ("cells", "keep", "grid_shape", "meta", "dev", "shapes"))
+        cfg, F, scratch, N, E, n_cells = (pending[k] for k in ("cfg", "F", "scratch", "N", "E", "n_cells"))
+        st = stream_ptr()
         if N == 0:
             logger.warning("No valid cells in grid")
             g = self._empty()
@@ -537,6 +574,7 @@ class GraphBuilder:
         dg = _DeviceGraph()
         dg.cells, dg.cfg, dg.scratch, dg.keep, dg.device, dg.grid_meta = cells, cfg, scratch, keep, dev, meta
         dg.keep_versions = [t._version for t in keep]
+        dg.scratch_borrowed = bool(pending.get("borrowed"))
         dg.N, dg.E, dg.n_cells = N, E, n_cells
         dg.node_id = torch.empty(n_cells, dtype=torch.int32, device=dev)
         dg.node_cell = torch.empty(N, dtype=torch.int32, device=dev)

@@ -42,7 +42,9 @@ METRIC = "depth cells/sec (graph build+GNN fwd)"
 UNIT = "cells/s"
 
 SLOT_NAMES = {0: "gb_count", 1: "gb_scan", 2: "gb_ids", 3: "gb_emit", 4: "gb_coo", 10: "mlp0", 11: "mlp1",
-              60: "heads_gemm", 61: "heads_finish", 70: "scatter_tile", 75: "vr_apply_results", 76: "sidecar_add"}
+              60: "heads_gemm", 61: "heads_finish", 70: "scatter_tile", 71: "stitch_add_tile", 72: "stitch_finalize", 73: "apply_corrections",
+              74: "graph_to_grid", 75: "vr_apply_results", 76: "sidecar_add", 77: "survey_emit", 78: "stitch_add_tile_nodes",
+              80: "csr_aggregate", 81: "linear"}
 for _l in range(16):
     SLOT_NAMES[20 + _l] = f"proj_l{_l}"
     SLOT_NAMES[40 + _l] = f"agg_l{_l}"

@@ -383,7 +383,7 @@ int bgnn_test_proj_bf16(const uint16_t* A_dev, int64_t M, int K, const uint16_t*
  * launching stream around every kernel the library launches.  Off by default; the record list is mutex-guarded.
  * Slot ids: 0 gb_count, 1 gb_scan, 2 gb_ids, 3 gb_emit, 4 gb_coo, 10 mlp0, 11 mlp1,
  * 20+l projection of layer l, 40+l aggregation of layer l, 60 heads gemm, 61 heads finish,
- * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit, 80 csr_aggregate, 81 linear,
+ * 70 scatter_tile, 71 stitch_add_tile, 72 stitch_finalize, 73 apply_corrections, 74 graph_to_grid, 77 survey_emit, 78 stitch_add_tile_nodes, 80 csr_aggregate, 81 linear,
  * 75 vr_apply_results, 76 sidecar_add.
  * ------------------------------------------------------------------------------------------ */
 int bgnn_profile_enable(int on);                               /* also clears recorded events */
