@@ -10,6 +10,11 @@ configs[1] -- a 2048x2048 fp32 tile (8-connected, F=7, hidden 64, 4 heads, 4
 layers) cut from a synthetic 3968^2 field; for N > 1 every rank processes its own
 tile (tiles are independent: no collective on the data path; weak scaling).
 
+The same line carries `survey` = BASELINE configs[2]: the 60 000 x 60 000 synthetic survey sharded as bands of tile-rows
+over the N ranks (STRONG scaling), timed from pinned host input to pinned host output (H2D + tiles + stitch + seam hand-over +
+finalize + corrections + D2H, see `survey_leg`), and at N = 1 `ragged` (configs[3], incl. the reference's own batching API)
+and `wide` (configs[4], fp32 and bf16 side by side).
+
 Prints ONE JSON line (rank 0).  `value` = depth cells/s with the tile resident in
 HBM; `e2e` = the same through the public API (`GraphBuilder.build_graph` +
 `BathymetricGNN.predict`) with pinned HOST buffers, H2D of depth+mask and D2H of
@@ -381,6 +386,22 @@ def run_ours(args):
         except (RuntimeError, MemoryError) as e:        # e.g. not enough pinned host memory on this box: say so, keep the line
             survey = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
+    # ---- BASELINE configs[3] (ragged VR grids, incl. the reference's own batching API) and configs[4] (wide variant, fp32 and
+    #      bf16 side by side): secondary objects of the same line, one GPU only (both are per-GPU workloads without exchange)
+    extra = {}
+    if world == 1 and not args.no_extra:
+        torch.cuda.empty_cache()
+        import copy
+        for name, fn, over in (("ragged", run_ragged, dict(grids=100000, api_grids=10000)), ("wide", run_wide, dict(steps=5, warmup=2))):
+            a2 = copy.copy(args)
+            for k_, v_ in over.items():
+                setattr(a2, k_, v_)
+            try:
+                extra[name] = fn(a2, embed=True)
+            except (RuntimeError, MemoryError) as e:
+                extra[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -393,7 +414,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "survey": survey}
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "survey": survey, "ragged": extra.get("ragged"),
+                "wide": extra.get("wide")}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -535,7 +557,7 @@ def run_survey(args):
         dist.destroy_process_group()
 
 
-def run_ragged(args):
+def run_ragged(args, embed=False):
     """BASELINE.json configs[3]: native VR BAG refinement grids (sides 3..50, 10 % nodata) batched as ONE ragged
     block-diagonal graph per chunk of <= ~8 M cells; grids are sharded contiguously across ranks (no collective).
     Secondary workload; `value` = valid cells / slowest rank's device time (packed buffers resident in HBM)."""
@@ -605,12 +627,15 @@ def run_ragged(args):
     if rank == 0 and not args.no_api:
         api = native_api_leg(args, model, builder, dev)
     if rank == 0:
-        print(json.dumps({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),
+        line = ({"metric": "depth cells/sec (graph build+GNN fwd), ragged VR grids", "value": world * nodes / (ms * 1e-3),
                           "unit": UNIT, "n_gpus": world, "ms_total": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"configs[3]: {args.grids} refinement grids, sides U{{3..50}}, 10% nodata, "
                                                  f"{len(chunks)} ragged chunks of <= {args.chunk_cells} cells per rank",
                                      "valid_cells_rank0": nodes, "note": "rank-0 time (ranks are independent; no collective)"},
-                          "kernels_ms_one_chunk": kernels, "vr_post_one_chunk": post, "reference_api": api}))
+                          "kernels_ms_one_chunk": kernels, "vr_post_one_chunk": post, "reference_api": api})
+        if embed:
+            return line
+        print(json.dumps(line))
 
 
 def native_api_leg(args, model, builder, dev):
@@ -703,7 +728,7 @@ def vr_post_row(g, out, chunk, dev):
             "cpu_port": {"grids": ns, "cells": int(off[ns]), "seconds": round(cpu_s, 4), "cells_per_s": int(off[ns]) / cpu_s, "cores": 1}}
 
 
-def run_wide(args):
+def run_wide(args, embed=False):
     """BASELINE.json configs[4]: wide variant -- 5x5 neighbourhood (k = 24), hidden 128 x 4 heads x 4 attention layers, one
     2048^2 tile per GPU, fp32 parity mode AND bf16 mode (bgnn_model_set_precision).  Secondary workload: one JSON line with
     both precisions, the per-kernel device times of one step each, and the bf16-vs-fp32 output differences on this tile."""
@@ -780,7 +805,7 @@ def run_wide(args):
     diff["label_disagreement_frac"] = float((outs["bf16"]["predicted_class"] != outs["fp32"]["predicted_class"]).float().mean())
     diff["logit_scale"] = float(outs["fp32"]["class_logits"].abs().max())
     if rank == 0:
-        print(json.dumps({"metric": METRIC + ", wide variant", "value": world * T * T / (float(t[1]) * 1e-3), "unit": UNIT,
+        line = ({"metric": METRIC + ", wide variant", "value": world * T * T / (float(t[1]) * 1e-3), "unit": UNIT,
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[1]),
                           "higher_is_better": True, "scaling": "weak", "dtype": "bf16 storage / f32 accumulate", "data": "synthetic",
                           "config": {"workload": f"configs[4]: one {T}x{T} tile per GPU, 24-connected (5x5), F=7, GAT hidden 128 x 4 heads "
@@ -789,7 +814,10 @@ def run_wide(args):
                           "fp32": {"ms_per_step": float(t[0]), "cells_per_s": world * T * T / (float(t[0]) * 1e-3), "kernels_ms": res["fp32"]["kernels_ms"],
                                    "roofline": res["fp32"]["roofline"]},
                           "bf16": {"ms_per_step": float(t[1]), "kernels_ms": res["bf16"]["kernels_ms"], "roofline": res["bf16"]["roofline"]},
-                          "bf16_vs_fp32_max_abs_diff": diff}))
+                          "bf16_vs_fp32_max_abs_diff": diff})
+        if embed:
+            return line
+        print(json.dumps(line))
 
 
 def cpu_oracle_sample(depth_np, mask_np, cfg, sd, crop=512, threads=None):
@@ -854,6 +882,7 @@ def main():
     ap.add_argument("--chunk-cells", type=int, default=8000000)
     ap.add_argument("--survey-size", type=int, default=60000, help="side of the configs[2] survey (the `survey` object of the default line)")
     ap.add_argument("--no-survey", action="store_true", help="default line without the configs[2] survey leg")
+    ap.add_argument("--no-extra", action="store_true", help="default line without the configs[3] / configs[4] objects")
     ap.add_argument("--tile", type=int, default=2048)
     ap.add_argument("--overlap", type=int, default=128)
     ap.add_argument("--cpu-crop", type=int, default=1024, help="cpu_baseline sample: crop x crop corner (about 10-15 s of CPU work)")

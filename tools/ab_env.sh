@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 i=0
 for setting in "$@"; do
   i=$((i+1))
-  env $setting python bench.py --no-survey --no-cpu --steps 20 --warmup 5 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
+  env $setting python bench.py --no-survey --no-extra --no-cpu --steps 20 --warmup 5 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
   python - <<PY
 import json
 try:

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for rep in 1 2; do
   for v in on off; do
     if [ $v = off ]; then export $VAR=1; else unset $VAR; fi
-    python bench.py --no-survey --no-cpu --steps 20 --warmup 5 > gpurun_out/${TAG}_${v}_${rep}.json 2> gpurun_out/${TAG}_${v}_${rep}.err
+    python bench.py --no-survey --no-extra --no-cpu --steps 20 --warmup 5 > gpurun_out/${TAG}_${v}_${rep}.json 2> gpurun_out/${TAG}_${v}_${rep}.err
     python - <<PY
 import json
 j=json.load(open("gpurun_out/${TAG}_${v}_${rep}.json"))
