@@ -15,7 +15,7 @@ MAX_OFFSETS, MAX_NODE_FEATS, MAX_EDGE_FEATS = 24, 8, 4
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3, -4
 PREC_F32, PREC_BF16 = 0, 1
 AGG_GCN, AGG_MEAN, AGG_GIN = 0, 1, 2
-OPTIONS = dict(tensor_cores=0, presplit=1, window=2, tile5=3, tile5_window=4)
+OPTIONS = dict(tensor_cores=0, presplit=1, window=2, tile5=3, tile5_window=4, ragged_patches=5)
 
 NF_CODES = dict(depth=0, local_mean=1, local_std=2, gradient_x=3, gradient_y=4,
                 gradient_magnitude=5, curvature=6, uncertainty=7)
@@ -45,7 +45,8 @@ class ModelDesc(C.Structure):
 
 class GridTopo(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("node_id", C.c_void_p), ("n_offsets", C.c_int32),
-                ("off_dr", C.c_int32 * MAX_OFFSETS), ("off_dc", C.c_int32 * MAX_OFFSETS), ("grid_eattr", C.c_void_p)]
+                ("off_dr", C.c_int32 * MAX_OFFSETS), ("off_dc", C.c_int32 * MAX_OFFSETS), ("grid_eattr", C.c_void_p),
+                ("patches", C.c_void_p), ("n_patches", C.c_int32)]
 
 
 class Survey(C.Structure):
@@ -69,6 +70,7 @@ SYMBOLS = {
     "bgnn_graph_scratch_bytes": (SZ, [I64, I32]),
     "bgnn_graph_count": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, C.POINTER(I64), P]),
     "bgnn_graph_emit": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, P, P, P, P, P, P, P, P]),
+    "bgnn_graph_emit_bands": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, I32, P, P, P, P, P, P, P]),
     "bgnn_graph_coo": (C.c_int, [C.POINTER(Cells), C.POINTER(GraphCfg), P, SZ, P, I64, P, P, P]),
     "bgnn_model_param_floats": (I64, [C.POINTER(ModelDesc)]),
     "bgnn_model_create": (C.c_int, [C.POINTER(ModelDesc), P, I64, C.c_int, C.POINTER(P)]),

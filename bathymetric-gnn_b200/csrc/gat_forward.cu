@@ -34,6 +34,7 @@ struct ModelOpts {
     bool window = true;             // ragged batches: windowed shared-memory CSR aggregation
     bool tile5 = true;              // 5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation
     bool tile5_window = true;       // full 5x5 stencil: sliding register window variant
+    bool ragged_patches = true;     // ragged batches with a band-patch table: tiled aggregation per band of grid rows
 };
 static ModelOpts default_opts() {
     ModelOpts o;
@@ -41,6 +42,7 @@ static ModelOpts default_opts() {
     o.window = getenv("BGNN_NO_WINDOW") == nullptr;
     o.tile5 = getenv("BGNN_NO_TILE5") == nullptr;
     o.tile5_window = getenv("BGNN_NO_TILE5_WINDOW") == nullptr;
+    o.ragged_patches = getenv("BGNN_NO_RAGGED_PATCHES") == nullptr;
     return o;
 }
 #ifdef BGNN_AGG_TIMING
@@ -1059,6 +1061,325 @@ int launch_agg_tile_t(const LayerDev& L, const float* h, const float* alpha, con
 }
 
 
+static bool tile_supported(const TopoDev& T, int H, int C, int ED, const float* grid_eattr, bool* conn4);
+
+// ------------------------------------------------------------------------------------------ ragged band-patch aggregation
+// Ragged batches (BASELINE configs[3]: thousands of small refinement grids packed end to end) with the TILE kernel's data
+// flow: a patch is a band of rows of ONE grid over its full width (geometry per patch from a table the host plans:
+// (rows + 2) x (width + 2) <= 324 halo slots, rows x width <= 256 destinations), so a halo row is again a run of cells with
+// consecutive node ids = one bulk copy per head, absent cells are zero rows, and warp w walks patch rows w, w + 8, ... with the
+// 3 x 3 sliding register window (3 new LDS.64 per destination).  The windowed CSR kernel this replaces staged a node-id WINDOW
+// (1.8x read amplification at width 50) and gathered nine rows per destination from shared memory by source id: 6.1 ms per
+// H = 4 layer of a 7.2 M-node chunk = 39 % of its byte roofline.  Same arithmetic and edge order as gat_aggregate_tile.
+struct RagPatch { long long cell_off; int gh, gw, r0, nr; };       // grid cell offset, grid rows / cols, first row, rows of the band
+
+template <int H, int C> struct RagCfg {
+    static constexpr int NSLOT = 324, NT = 256, AST = 12, RUNS = 256;
+    static constexpr size_t SMEM = (size_t)(NSLOT * C + NSLOT + NSLOT * H + NT * AST + BGNN_MAX_EDGE_FEATS * H + 3 * H * C + 2 * RUNS + 64) * 4 + 32;
+    static constexpr bool ALPHA_BULK = (2 * H * 4) % 16 == 0 && NSLOT * 2 * H <= NT * AST;
+};
+
+template <int H, int C, bool CONN4>
+__global__ void __launch_bounds__(256, 2)
+gat_aggregate_ragged(const float* __restrict__ h, const float* __restrict__ alpha, const int32_t* __restrict__ node_id,
+                     const RagPatch* __restrict__ patches, const TopoDev T, const float* __restrict__ grid_eattr, int ED,
+                     const float* __restrict__ Medge, const float* __restrict__ bias, const float* __restrict__ bn_a,
+                     const float* __restrict__ bn_b, int relu, float slope, float* __restrict__ out, int64_t n_nodes,
+                     const SplitOut SO) {
+    using G = RagCfg<H, C>;
+    using O = EdgeOrder<CONN4>;
+    constexpr int NSLOT = G::NSLOT, NT = G::NT, AST = G::AST;
+    constexpr int VEC = C / 32, HC = H * C;
+    static_assert(VEC == 2, "lane <-> 2 channels");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* rows = reinterpret_cast<float*>(smem_raw);          // [NSLOT][C]   source rows of the current head
+    int* ids = reinterpret_cast<int*>(rows + NSLOT * C);       // [NSLOT]      node id per halo cell (-1 invalid)
+    float* asrc = reinterpret_cast<float*>(ids + NSLOT);       // [H][NSLOT]   alpha_src per halo cell
+    float* a_sm = asrc + NSLOT * H;                            // [NT][AST]    3x3 attention weights of the current head
+    float* al_sm = a_sm;                                       // [NSLOT][2H]  landing area of the alpha bulk copies (setup only)
+    float* M_s = a_sm + NT * AST;                              // [ED_MAX][H]
+    float* s_bn = M_s + BGNN_MAX_EDGE_FEATS * H;               // [3][HC]
+    int* run_tab = reinterpret_cast<int*>(s_bn + 3 * HC);      // [RUNS][2]    (start << 16 | length, node id), `cap` entries per halo row
+    int* run_cnt = run_tab + 2 * G::RUNS;                      // [64]         runs per halo row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(run_cnt + 64); // [0] source rows, [1] alpha
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const RagPatch pt = patches[blockIdx.x];
+    const int W = pt.gw, PH = pt.nr, HWr = W + 2, HRr = PH + 2, nslot = HRr * HWr, ndest = PH * W, cap = HWr / 2 + 1;
+    const float sA = SO.hi ? operand_scale(SO.amax_src, SO.mul, SO.add) : 1.f;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(NT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar + 1)), "r"(HRr));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int sl = tid; sl < nslot; sl += NT) {
+        const int r = pt.r0 - 1 + sl / HWr, c = sl % HWr - 1;
+        int id = -1;
+        if (r >= 0 && r < pt.gh && c >= 0 && c < W) id = __ldg(node_id + pt.cell_off + (long long)r * W + c);
+        ids[sl] = id;
+    }
+    for (int i = tid; i < HC; i += NT) { s_bn[i] = __ldg(bias + i); s_bn[HC + i] = __ldg(bn_a + i); s_bn[2 * HC + i] = __ldg(bn_b + i); }
+    if (tid < BGNN_MAX_EDGE_FEATS * H) M_s[tid] = (tid / H) < ED ? __ldg(Medge + tid) : 0.f;
+    const bool has_dest = tid < ndest;
+    const int dr_ = has_dest ? tid / W : 0, dc_ = has_dest ? tid - dr_ * W : 0;
+    const int cs = (dr_ + 1) * HWr + (dc_ + 1);
+    float ea[8][BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ea[k][d] = 0.f;
+    if (has_dest && ED > 0) {
+        const float* ge = grid_eattr + (pt.cell_off + (long long)(pt.r0 + dr_) * W + dc_) * (T.K * ED);
+        if (T.K == 8 && ED == 3) {
+            float v[24];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(ge) + q);
+                v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) ea[k][d] = v[k * 3 + d];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d)
+                    if (k < T.K && d < ED) ea[k][d] = __ldg(ge + k * ED + d);
+        }
+    }
+    __syncthreads();
+
+    if (tid < HRr) {                               // runs of valid cells of halo row tid
+        const int s0 = tid * HWr;
+        int run = -1, n = 0;
+        for (int c = 0; c <= HWr; ++c) {
+            const int id = c < HWr ? ids[s0 + c] : -1;
+            if (id >= 0 && run < 0) run = c;
+            if (id < 0 && run >= 0) {
+                run_tab[2 * (tid * cap + n)] = (run << 16) | (c - run);
+                run_tab[2 * (tid * cap + n) + 1] = ids[s0 + run];
+                ++n;
+                run = -1;
+            }
+        }
+        run_cnt[tid] = n;
+    }
+    auto issue_rows = [&](int hh) {
+        if (tid < HRr) {
+            const float* hp = h + (int64_t)hh * n_nodes * C;
+            const int s0 = tid * HWr, n = run_cnt[tid];
+            for (int i = 0; i < n; ++i) {
+                const int sl = run_tab[2 * (tid * cap + i)], id = run_tab[2 * (tid * cap + i) + 1];
+                bulk_g2s(rows + (s0 + (sl >> 16)) * C, hp + (int64_t)id * C, (uint32_t)(sl & 0xffff) * C * 4, bar);
+            }
+        }
+    };
+    if (G::ALPHA_BULK && tid < HRr) {
+        const int s0 = tid * HWr, n = run_cnt[tid];
+        for (int i = 0; i < n; ++i) {
+            const int sl = run_tab[2 * (tid * cap + i)], id = run_tab[2 * (tid * cap + i) + 1];
+            bulk_g2s(al_sm + (s0 + (sl >> 16)) * 2 * H, alpha + (int64_t)id * 2 * H, (uint32_t)(sl & 0xffff) * 2 * H * 4, bar + 1);
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar + 1)) : "memory");
+    }
+    issue_rows(0);
+
+    const int myid = has_dest ? ids[cs] : -1;
+    float lsum[BGNN_MAX_EDGE_FEATS], ad[H];
+    unsigned nbv = 0;
+#pragma unroll
+    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ad[hh] = 0.f;
+    if (myid >= 0) {
+        int deg = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < T.K && ids[cs - T.dr[k] * HWr - T.dc[k]] >= 0) {
+                nbv |= 1u << k;
+                ++deg;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] += ea[k][d];
+            }
+#pragma unroll
+        for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) lsum[d] = lsum[d] / (float)(deg > 0 ? deg : 1);
+    }
+    for (int sl = tid; sl < nslot; sl += NT)
+        if (ids[sl] < 0) {
+#pragma unroll
+            for (int q = 0; q < C / 4; ++q) *reinterpret_cast<float4*>(rows + sl * C + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    if (G::ALPHA_BULK) {
+        mbar_wait_parity(bar + 1, 0);
+        for (int sl = tid; sl < nslot; sl += NT)
+            if (ids[sl] >= 0) {
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + sl] = al_sm[sl * 2 * H + hh];
+            }
+        if (myid >= 0) {
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) ad[hh] = al_sm[cs * 2 * H + H + hh];
+        }
+    } else {
+        for (int sl = tid; sl < nslot; sl += NT) {
+            const int id = ids[sl];
+            if (id >= 0) {
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) asrc[hh * NSLOT + sl] = __ldg(alpha + (int64_t)id * (2 * H) + hh);
+            }
+        }
+        if (myid >= 0) {
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) ad[hh] = __ldg(alpha + (int64_t)myid * (2 * H) + H + hh);
+        }
+    }
+    __syncthreads();                 // asrc complete; the alpha landing area (aliases a_sm) is free
+    int wpos[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wpos[k] = (1 - T.dr[k]) * 3 + (1 - T.dc[k]);
+
+#pragma unroll 1
+    for (int hh = 0; hh < H; ++hh) {
+        if (hh > 0) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            issue_rows(hh);
+        }
+        {
+            float4* az = reinterpret_cast<float4*>(a_sm + tid * AST);
+            az[0] = make_float4(0.f, 0.f, 0.f, 0.f); az[1] = make_float4(0.f, 0.f, 0.f, 0.f); az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (myid >= 0) {
+            float Mh[BGNN_MAX_EDGE_FEATS], adh = ad[0];
+#pragma unroll
+            for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) Mh[d] = M_s[d * H + hh];
+#pragma unroll
+            for (int q = 1; q < H; ++q) adh = (q == hh) ? ad[q] : adh;
+            float sc[9], mx = -CUDART_INF_F;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sc[k] = 0.f;
+                if ((nbv >> k) & 1u) {
+                    float ae = 0.f;
+#pragma unroll
+                    for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(ea[k][d], Mh[d], ae);
+                    float v = (asrc[hh * NSLOT + cs - T.dr[k] * HWr - T.dc[k]] + adh) + ae;
+                    v = v > 0.f ? v : v * slope;
+                    sc[k] = v;
+                    mx = fmaxf(mx, v);
+                }
+            }
+            {
+                float ae = 0.f;
+#pragma unroll
+                for (int d = 0; d < BGNN_MAX_EDGE_FEATS; ++d) ae = fmaf(lsum[d], Mh[d], ae);
+                float v = (asrc[hh * NSLOT + cs] + adh) + ae;
+                v = v > 0.f ? v : v * slope;
+                sc[8] = v;
+                mx = fmaxf(mx, v);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((nbv >> k) & 1u) { sc[k] = expf(sc[k] - mx); sum += sc[k]; }
+            sc[8] = expf(sc[8] - mx);
+            sum += sc[8];
+            sum += 1e-16f;
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((nbv >> k) & 1u) a_sm[tid * AST + wpos[k]] = sc[k] * inv;
+            a_sm[tid * AST + 4] = sc[8] * inv;
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+        mbar_wait_parity(bar, (uint32_t)(hh & 1));
+        float bs[VEC], ba[VEC], bb[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int ch = hh * C + lane * VEC + v;
+            bs[v] = s_bn[ch]; ba[v] = s_bn[HC + ch] * sA; bb[v] = s_bn[2 * HC + ch] * sA;
+        }
+        // work units = (patch row, segment of <= 16 columns): wide grids have few rows per band (4 at width 50), so whole rows per
+        // warp would leave half the warps idle and the others with 50 serial steps; 16-column segments give every warp ~32 steps
+        const int nseg = (W + 15) >> 4, units = PH * nseg;
+#pragma unroll 1
+        for (int u = warp; u < units; u += NT / 32) {
+            const int pr = u / nseg, c0 = (u - pr * nseg) << 4;             // patch row (halo rows pr .. pr + 2), first column
+            const float* base = rows + (pr * HWr + c0) * C + lane * VEC;
+            float2 win[3][3];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                win[dy][1] = *reinterpret_cast<const float2*>(base + (dy * HWr + 0) * C);
+                win[dy][2] = *reinterpret_cast<const float2*>(base + (dy * HWr + 1) * C);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = c0 + j;
+                if (c >= W) break;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    win[dy][0] = win[dy][1]; win[dy][1] = win[dy][2];
+                    win[dy][2] = *reinterpret_cast<const float2*>(base + (dy * HWr + j + 2) * C);
+                }
+                const int t2 = pr * W + c;
+                const float4 a0 = *reinterpret_cast<const float4*>(a_sm + t2 * AST);
+                const float4 a1 = *reinterpret_cast<const float4*>(a_sm + t2 * AST + 4);
+                const float aw[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a_sm[t2 * AST + 8]};
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < O::N; ++q) {
+                    const int pz = O::pos(q);
+                    acc0 = fmaf(aw[pz], win[pz / 3][pz % 3].x, acc0);
+                    acc1 = fmaf(aw[pz], win[pz / 3][pz % 3].y, acc1);
+                }
+                const int id2 = ids[(pr + 1) * HWr + c + 1];
+                float y0 = fmaf(acc0 + bs[0], ba[0], bb[0]), y1 = fmaf(acc1 + bs[1], ba[1], bb[1]);
+                if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                if (SO.hi) {
+                    const __half2 hi2 = __floats2half2_rn(y0, y1);                 // already scaled by sA
+                    const float2 hf = __half22float2(hi2);
+                    const __half2 lo2 = __floats2half2_rn((y0 - hf.x) * 2048.f, (y1 - hf.y) * 2048.f);
+                    if (id2 >= 0) {
+                        uint16_t* prow = SO.hi + (int64_t)id2 * (2 * HC) + hh * C + lane * VEC;
+                        *reinterpret_cast<__half2*>(prow) = hi2;
+                        *reinterpret_cast<__half2*>(prow + HC) = lo2;
+                    }
+                } else if (id2 >= 0) {
+                    *reinterpret_cast<float2*>(out + (int64_t)id2 * HC + hh * C + lane * VEC) = make_float2(y0, y1);
+                }
+            }
+        }
+        __syncthreads();                     // every warp is done with rows / a_sm before the next head overwrites them
+    }
+}
+
+// returns 1 when the band-patch kernel does not apply
+int launch_agg_ragged(const LayerDev& L, const float* h, const float* alpha, const int32_t* node_id, const void* patches,
+                      int n_patches, const TopoDev& T, const float* grid_eattr, int ED, int relu, float slope, float* out,
+                      int64_t n_nodes, const SplitOut& SO, cudaStream_t s) {
+    bool is4 = false;
+    TopoDev T1 = T; T1.rows = 1; T1.cols = 1;
+    if (L.C != 64 || !(L.H == 1 || L.H == 2 || L.H == 4) || ED > BGNN_MAX_EDGE_FEATS || !grid_eattr || !patches || !node_id) return 1;
+    if (!tile_supported(T1, L.H, L.C, ED, grid_eattr, &is4)) return 1;
+    if (n_patches == 0) return BGNN_OK;
+#define RLAUNCH(H_, C4_)                                                                                                \
+    do {                                                                                                                \
+        using G = RagCfg<H_, 64>;                                                                                       \
+        static_assert(G::SMEM <= 115000, "two CTAs per SM");                                                            \
+        auto kern = gat_aggregate_ragged<H_, 64, C4_>;                                                                  \
+        BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));               \
+        kern<<<(unsigned)n_patches, 256, G::SMEM, s>>>(h, alpha, node_id, reinterpret_cast<const RagPatch*>(patches), T, grid_eattr,  \
+                                                       ED, L.Medge, L.bias, L.bn_a, L.bn_b, relu, slope, out, n_nodes, SO); \
+    } while (0)
+    if (is4) { if (L.H == 4) RLAUNCH(4, true); else if (L.H == 2) RLAUNCH(2, true); else RLAUNCH(1, true); }
+    else { if (L.H == 4) RLAUNCH(4, false); else if (L.H == 2) RLAUNCH(2, false); else RLAUNCH(1, false); }
+#undef RLAUNCH
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+}
+
 // ------------------------------------------------------------------------------------------ windowed CSR aggregation
 // Ragged batches (scripts/inference_native.py:249-342: thousands of small refinement grids packed end to end) have no
 // single grid to tile, but their edges are LOCAL in node-id space: nodes are numbered in raster order per grid, so every
@@ -1940,6 +2261,7 @@ extern "C" int bgnn_model_set_option(bgnn_model* m, int option, int value) {
         case BGNN_OPT_WINDOW: m->opt.window = on; break;
         case BGNN_OPT_TILE5: m->opt.tile5 = on; break;
         case BGNN_OPT_TILE5_WINDOW: m->opt.tile5_window = on; break;
+        case BGNN_OPT_RAGGED_PATCHES: m->opt.ragged_patches = on; break;
         default: BGNN_CHECK_ARG(false, "unknown option %d", option);
     }
     return BGNN_OK;
@@ -1986,7 +2308,7 @@ extern "C" size_t bgnn_gat_workspace_bytes(const bgnn_model* m, int64_t n_nodes)
 }
 
 static bool topo_to_dev(const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
-    if (!(topo && topo->node_id && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0)) return false;
+    if (!(topo && topo->rows > 0 && topo->node_id && topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0)) return false;
     T.rows = topo->rows; T.cols = topo->cols; T.node_id = topo->node_id; T.K = topo->n_offsets;
     for (int k = 0; k < 8; ++k) {
         T.dr[k] = k < T.K ? topo->off_dr[k] : 0;
@@ -1996,8 +2318,26 @@ static bool topo_to_dev(const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
     return true;
 }
 
+// ragged batch with a band-patch table (bgnn_grid_topo::patches): stencil of the reference's 4 / 8 offsets, dense edge features
+static bool ragged_to_dev(const bgnn_model* m, const bgnn_grid_topo* topo, int64_t E, TopoDev& T) {
+    if (!(m && m->opt.ragged_patches && topo && topo->rows == 0 && topo->patches && topo->n_patches > 0 && topo->node_id &&
+          topo->n_offsets >= 1 && topo->n_offsets <= 8 && E > 0)) return false;
+    T.rows = 1; T.cols = 1; T.node_id = topo->node_id; T.K = topo->n_offsets;
+    for (int k = 0; k < 8; ++k) {
+        T.dr[k] = k < T.K ? topo->off_dr[k] : 0;
+        T.dc[k] = k < T.K ? topo->off_dc[k] : 0;
+    }
+    return true;
+}
+
 extern "C" int bgnn_gat_grid_path(const bgnn_model* m, const bgnn_grid_topo* topo, int64_t n_edges) {
     TopoDev T;
+    if (m && m->precision == BGNN_PREC_F32 && ragged_to_dev(m, topo, n_edges, T)) {
+        for (const LayerDev& L : m->layers)
+            if (L.C != 64 || !(L.H == 1 || L.H == 2 || L.H == 4) ||
+                !tile_supported(T, L.H, L.C, m->d.edge_dim, topo->grid_eattr, nullptr)) return 0;
+        return 1;
+    }
     if (!m || m->precision != BGNN_PREC_F32 || !topo_to_dev(topo, n_edges, T)) return 0;
     for (const LayerDev& L : m->layers)
         if (!tile_supported(T, L.H, L.C, m->d.edge_dim, topo->grid_eattr, nullptr)) return 0;
@@ -2122,6 +2462,8 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
     // grid path: radius-1 stencil (4-/8-connected) on a single tile
     TopoDev T;
     const bool tiled = topo_to_dev(topo, E, T);
+    TopoDev TR;
+    const bool ragged = !tiled && ragged_to_dev(m, topo, E, TR);
     Topo5Dev T5;
     const bool tiled5 = m->opt.tile5 && topo5_to_dev(topo, E, T5);
     T5.window = m->opt.tile5_window;
@@ -2221,10 +2563,12 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           SplitOut SO = {};
           bool want_split = false;
           const bool win_l = windowed && L.C == 64 && (L.H == 1 || L.H == 2 || L.H == 4);
-          if ((tile_ok0 || (win_l && m->opt.use_umma && m->opt.presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
+          const bool rag_l = ragged && L.C == 64 && (L.H == 1 || L.H == 2 || L.H == 4) &&
+                             tile_supported(TR, L.H, L.C, d.edge_dim, topo->grid_eattr, nullptr);
+          if ((tile_ok0 || ((win_l || rag_l) && m->opt.use_umma && m->opt.presplit)) && l + 1 < d.layers && L.C % 64 == 0) {
               const LayerDev& Ln = m->layers[l + 1];
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
-                           (win_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));
+                           (win_l || rag_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));
               if (want_split) {
                   SO.hi = reinterpret_cast<uint16_t*>(nxt);
                   SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
@@ -2233,6 +2577,11 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
           cur_split = false;
           if (rc == 1 && tiled) {
               rc = launch_agg_tile(L, hsrc, al, T, topo->grid_eattr, d.edge_dim, relu, d.negative_slope, nxt, N, SO, s);
+              if (rc == 0 && want_split) cur_split = true;
+          }
+          if (rc == 1 && rag_l) {
+              rc = launch_agg_ragged(L, hsrc, al, topo->node_id, topo->patches, topo->n_patches, TR, topo->grid_eattr, d.edge_dim, relu,
+                                     d.negative_slope, nxt, N, SO, s);
               if (rc == 0 && want_split) cur_split = true;
           }
           if (rc == 1 && win_l) {

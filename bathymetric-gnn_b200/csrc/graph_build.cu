@@ -524,6 +524,192 @@ __global__ void __launch_bounds__(TP_H * TP_W) gb_emit_tile(const GraphParams P,
     }
 }
 
+// ---------------------------------------------------------------- banded emit (ragged batches, the reference's 8 offsets)
+// gb_emit_tile's data flow for a ragged batch of small grids: one CTA per BAND PATCH (a band of rows of one grid over its
+// full width, <= 256 cells; the table the host plans for the band-patch aggregation, include/bgnn.h: bgnn_grid_topo::patches).
+// The generic gb_emit finds every cell's grid with a 20-step binary search and recomputes 5x5 boxes and eight fp64 atans
+// per cell from global memory: 2.3 ms per 8 M-cell chunk; here depth + validity of the band (halo 3) are staged once in shared
+// memory, the grid comes with the patch, and each cell computes the four FORWARD slopes only (the reverse ones are their
+// exact negations, as in gb_emit_tile).  Same arithmetic and fp64 summation order as gb_emit.
+struct BandPatch { long long cell_off; int gh, gw, r0, nr; };
+constexpr int BP_CELLS = 1024, BP_INNER = 324, BP_HALO = 3;
+
+__global__ void __launch_bounds__(256) gb_emit_bands(const GraphParams P, const BandPatch* __restrict__ patches,
+                                                     const int32_t* __restrict__ node_id, float* __restrict__ xout,
+                                                     float* __restrict__ local_std, float* __restrict__ grid_eattr) {
+    __shared__ float s_d[BP_CELLS];                 // depth (0 outside the grid), (nr + 6) x (W + 6)
+    __shared__ unsigned char s_v[BP_CELLS];         // validity
+    __shared__ float s_f[BP_INNER];                 // depth_filled on the halo-1 region, (nr + 2) x (W + 2)
+    __shared__ __align__(16) float s_s[BP_INNER][4];   // forward slopes of rows -1 .. nr-1, cols -1 .. W
+    const bgnn_cells& cs = P.cells;
+    const BandPatch pt = patches[blockIdx.x];
+    const int H = pt.gh, W = pt.gw, nr = pt.nr, r0 = pt.r0;
+    const int SW = W + 2 * BP_HALO, SH = nr + 2 * BP_HALO, FW = W + 2;
+    const int tid = threadIdx.x;
+    const int g = (int)0;
+    (void)g;
+    // per-grid resolution: found from the packed offset (one binary search per CTA, by one thread)
+    __shared__ double s_res[2];
+    if (tid == 0) {
+        int lo = 0, hi = cs.n_grids;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(cs.cell_off + mid) <= pt.cell_off) lo = mid; else hi = mid; }
+        s_res[0] = __ldg(cs.grid_res + 2 * lo); s_res[1] = __ldg(cs.grid_res + 2 * lo + 1);
+    }
+    for (int q = tid; q < SH * SW; q += 256) {
+        const int lr = q / SW, lc = q - lr * SW;
+        const int r = r0 - BP_HALO + lr, c = lc - BP_HALO;
+        float d = 0.f; bool v = false;
+        if (r >= 0 && r < H && c >= 0 && c < W) {
+            const int64_t di = pt.cell_off + (int64_t)r * W + c;
+            d = __ldg(cs.depth + di);
+            v = cs.mask ? (__ldg(cs.mask + di) != 0) : (isfinite(d) && (!cs.use_nodata || d != cs.nodata));
+        }
+        s_d[q] = d; s_v[q] = v ? 1 : 0;
+    }
+    __syncthreads();
+    auto box = [&](int lr, int lc, float& mean, float& stdv) {     // halo coordinates; zero outside the grid (invalid there)
+        double S = 0.0, Q = 0.0; int C = 0;
+#pragma unroll
+        for (int dr = -2; dr <= 2; ++dr)
+#pragma unroll
+            for (int dc = -2; dc <= 2; ++dc) {
+                const int q = (lr + dr) * SW + lc + dc;
+                if (s_v[q]) { const double d = (double)s_d[q]; S += d; Q += d * d; ++C; }
+            }
+        const double n = C > 0 ? (double)C : 1.0;
+        const double mu = S / n;
+        double var = Q / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean = (float)mu; stdv = (float)sqrt(var);
+    };
+    for (int q = tid; q < (nr + 2) * FW; q += 256) {               // depth_filled on the halo-1 region
+        const int fr = q / FW, fc = q - fr * FW;
+        const int lr = fr + BP_HALO - 1, lc = fc + BP_HALO - 1;
+        const int r = r0 - 1 + fr, c = fc - 1;
+        float f = 0.f;
+        if (r >= 0 && r < H && c >= 0 && c < W) {
+            if (s_v[lr * SW + lc]) f = s_d[lr * SW + lc];
+            else { float m, sd; box(lr, lc, m, sd); f = m; }
+            f = nan_to_num_f32(f);
+        }
+        s_f[q] = f;
+    }
+    const double rx = s_res[0], ry = s_res[1];
+    for (int q = tid; q < (nr + 1) * FW; q += 256) {               // forward slopes of rows -1 .. nr-1, cols -1 .. W
+        const int sr = q / FW, sc = q - sr * FW;
+        const int lr = sr + BP_HALO - 1, lc = sc + BP_HALO - 1;
+        float out4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s_v[lr * SW + lc]) {
+            const float dB = s_d[lr * SW + lc];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int dr = P.dr[4 + f], dc = P.dc[4 + f];
+                if (!s_v[(lr + dr) * SW + lc + dc]) continue;
+                const double dx = (double)dc * rx, dy = (double)dr * ry;
+                const double dist = sqrt(dx * dx + dy * dy);
+                const float dz = s_d[(lr + dr) * SW + lc + dc] - dB;
+                double sl = 0.0;
+                if (dist > 0.0) sl = atan((double)dz / dist) * (180.0 / 3.14159265358979323846);
+                if (isnan(sl)) sl = 0.0;
+                out4[f] = (float)sl;
+            }
+        }
+        *reinterpret_cast<float4*>(&s_s[q][0]) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    }
+    __syncthreads();
+
+    if (tid >= nr * W) return;
+    const int pr = tid / W, pc = tid - pr * W;
+    const int r = r0 + pr, c = pc;
+    const int lr = pr + BP_HALO, lc = pc + BP_HALO;
+    if (!s_v[lr * SW + lc]) return;
+    const int64_t t = pt.cell_off + (int64_t)r * W + c;
+    const int id = node_id[t];
+    const float d = s_d[lr * SW + lc];
+    if (xout || local_std) {
+        float mean, stdv;
+        box(lr, lc, mean, stdv);
+        if (local_std) local_std[id] = nan_to_num_f32(stdv);
+        if (xout) {
+            const float f0 = nan_to_num_f32(d);
+            const float up = r > 0 ? s_f[pr * FW + pc + 1] : f0;
+            const float dn = r < H - 1 ? s_f[(pr + 2) * FW + pc + 1] : f0;
+            const float lf = c > 0 ? s_f[(pr + 1) * FW + pc] : f0;
+            const float rt = c < W - 1 ? s_f[(pr + 1) * FW + pc + 2] : f0;
+            float gy = 0.f, gx = 0.f;
+            if (H >= 2) gy = r == 0 ? dn - f0 : (r == H - 1 ? f0 - up : (dn - up) / 2.0f);
+            if (W >= 2) gx = c == 0 ? rt - f0 : (c == W - 1 ? f0 - lf : (rt - lf) / 2.0f);
+            const float gm = sqrtf(gx * gx + gy * gy);
+            const double t0 = (double)f0 * -2.0 + ((double)up + (double)dn);
+            const double t1 = (double)f0 * -2.0 + ((double)lf + (double)rt);
+            float lap = (float)t0 + (float)t1;
+            int cnt3 = 0;
+#pragma unroll
+            for (int a = -1; a <= 1; ++a)
+#pragma unroll
+                for (int b = -1; b <= 1; ++b) cnt3 += s_v[(lr + a) * SW + lc + b];
+            if (cnt3 < 3) lap = 0.0f;
+            float* row = xout + (int64_t)id * P.F;
+            for (int j = 0; j < P.F; ++j) {
+                float v;
+                switch (P.nf[j]) {
+                    case BGNN_NF_DEPTH: v = d; break;
+                    case BGNN_NF_LOCAL_MEAN: v = mean; break;
+                    case BGNN_NF_LOCAL_STD: v = stdv; break;
+                    case BGNN_NF_GRAD_X: v = gx; break;
+                    case BGNN_NF_GRAD_Y: v = gy; break;
+                    case BGNN_NF_GRAD_MAG: v = gm; break;
+                    case BGNN_NF_CURVATURE: v = lap; break;
+                    default: v = cs.unc ? __ldg(cs.unc + t) : 0.0f;
+                }
+                row[j] = nan_to_num_f32(v);
+            }
+        }
+    }
+    if (grid_eattr) {
+        float gev[8 * BGNN_MAX_EDGE_FEATS];
+#pragma unroll
+        for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q) gev[q] = 0.0f;
+        const float4 mine = *reinterpret_cast<const float4*>(&s_s[(pr + 1) * FW + pc + 1][0]);
+        const float ms[4] = {mine.x, mine.y, mine.z, mine.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int jr = lr - P.dr[k], jc = lc - P.dc[k];          // source = i - off_k
+            if (!s_v[jr * SW + jc]) continue;
+            const double dx = (double)P.dc[k] * rx, dy = (double)P.dr[k] * ry;
+            double dist = sqrt(dx * dx + dy * dy);
+            const float dz = d - s_d[jr * SW + jc];
+            const float slope = k < 4 ? 0.0f - ms[3 - k] : s_s[(pr + 1 - P.dr[k]) * FW + pc + 1 - P.dc[k]][k - 4];   // 0 - x: no -0.0
+#pragma unroll
+            for (int e = 0; e < BGNN_MAX_EDGE_FEATS; ++e) {
+                if (e >= P.ED) continue;
+                float v;
+                switch (P.ef[e]) {
+                    case BGNN_EF_DISTANCE: { double dd = dist; if (isnan(dd)) dd = 0.0; v = (float)dd; break; }
+                    case BGNN_EF_DEPTH_DIFF: v = nan_to_num_f32(dz); break;
+                    case BGNN_EF_SLOPE: v = slope; break;
+                    default: v = 0.0f;
+                }
+                if (P.ED == 3) gev[k * 3 + e] = v;
+                else if (P.ED == 4) gev[k * 4 + e] = v;
+                else if (P.ED == 2) gev[k * 2 + e] = v;
+                else gev[k + e] = v;
+            }
+        }
+        float* ge = grid_eattr + t * (int64_t)(8 * P.ED);
+        const int n = 8 * P.ED;
+        if ((n & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (4 * q < n) reinterpret_cast<float4*>(ge)[q] = make_float4(gev[4 * q], gev[4 * q + 1], gev[4 * q + 2], gev[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8 * BGNN_MAX_EDGE_FEATS; ++q)
+                if (q < n) ge[q] = gev[q];
+        }
+    }
+}
+
 // reference COO: offset-major, node-minor (graph_construction.py:196-241)
 __global__ void __launch_bounds__(GB_THREADS) gb_coo(const GraphParams P, const int32_t* __restrict__ table,
                                                      const int32_t* __restrict__ node_id, int64_t E,
@@ -654,7 +840,7 @@ extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cf
     BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
     BGNN_CHECK_ARG(node_id, "node_id is required");
     BGNN_CHECK_ARG(rowptr || !(csr_src || csr_eattr), "rowptr is required for CSR outputs");
-    BGNN_CHECK_ARG(!grid_eattr || (P.K <= 8 && cells->n_grids == 1), "grid_eattr needs a single grid and at most 8 offsets");
+    BGNN_CHECK_ARG(!grid_eattr || P.K <= 8, "grid_eattr needs at most 8 offsets");
     BGNN_CHECK_ARG(!(x && P.F == 0), "x requested with zero node features");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int32_t* table = (const int32_t*)scratch;
@@ -674,6 +860,30 @@ extern "C" int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cf
         }
         BGNN_LAUNCH_CHECK();
     }
+    return BGNN_OK;
+}
+
+extern "C" int bgnn_graph_emit_bands(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch, size_t scratch_bytes,
+                                     const void* patches, int32_t n_patches, int32_t* node_id, int32_t* node_cell, float* x,
+                                     float* local_std, int32_t* rowptr, float* grid_eattr, void* stream_) {
+    GraphParams P;
+    int rc = make_params(cells, cfg, P);
+    if (rc) return rc;
+    if (cells->n_cells == 0) return BGNN_OK;
+    BGNN_CHECK_ARG(scratch && scratch_bytes >= bgnn_graph_scratch_bytes(cells->n_cells, P.K), "scratch too small");
+    BGNN_CHECK_ARG(node_id && patches && n_patches > 0 && cells->n_grids > 1, "ragged batch with a band-patch table required");
+    static const int r8[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, c8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    bool std8 = P.K == 8;
+    for (int k = 0; k < 8 && std8; ++k) std8 = P.dr[k] == r8[k] && P.dc[k] == c8[k];
+    BGNN_CHECK_ARG(std8, "the banded emit covers the reference's 8-connected offset list");
+    BGNN_CHECK_ARG(!(x && P.F == 0), "x requested with zero node features");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int32_t* table = (const int32_t*)scratch;
+    { ProfScope ps(2, stream); gb_ids<<<(unsigned)P.nblocks, GB_THREADS, 0, stream>>>(P, table, node_id, node_cell, rowptr); }
+    BGNN_LAUNCH_CHECK();
+    { ProfScope ps(3, stream);
+      gb_emit_bands<<<(unsigned)n_patches, 256, 0, stream>>>(P, reinterpret_cast<const BandPatch*>(patches), node_id, x, local_std, grid_eattr); }
+    BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }
 

@@ -388,8 +388,14 @@ class BathymetricGNN(nn.Module):
                     topo = _lib.GridTopo()
                     topo.rows, topo.cols, topo.node_id, topo.grid_eattr = 0, 0, None, None
                     topo.n_offsets = int(dg.cfg.n_offsets)
+                    for k in range(topo.n_offsets):
+                        topo.off_dr[k], topo.off_dc[k] = dg.cfg.off_dr[k], dg.cfg.off_dc[k]
+                    if getattr(dg, "rag_patches", None) is not None and dg.node_id is not None and dg.grid_eattr is not None:
+                        # band patches planned by the builder: tiled aggregation per band of grid rows
+                        topo.node_id, topo.grid_eattr = dg.node_id.data_ptr(), dg.grid_eattr.data_ptr()
+                        topo.patches, topo.n_patches = dg.rag_patches.data_ptr(), int(dg.n_rag_patches)
                 rowptr = dg.rowptr
-                if topo is not None and topo.rows > 0 and lib.bgnn_gat_grid_path(h, C.byref(topo), E) == 1:
+                if topo is not None and (topo.rows > 0 or topo.n_patches > 0) and lib.bgnn_gat_grid_path(h, C.byref(topo), E) == 1:
                     src, ea = None, None            # every layer runs the tiled kernel: the CSR payload is never read
                 else:
                     src, ea = dg.csr_src, dg.csr_eattr

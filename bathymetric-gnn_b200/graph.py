@@ -74,7 +74,7 @@ class _DeviceGraph:
     `csr_eattr`) is emitted on first access: the tiled aggregation of a single tile reads
     the dense per-cell `grid_eattr` instead and never needs it."""
     __slots__ = ("cells", "cfg", "scratch", "keep", "node_id", "node_cell", "rowptr", "_csr_src",
-                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta", "keep_versions", "scratch_borrowed")
+                 "_csr_eattr", "grid_eattr", "x", "local_std", "N", "E", "n_cells", "device", "grid_meta", "keep_versions", "scratch_borrowed", "rag_patches", "n_rag_patches")
 
     def check_sources_unchanged(self):
         """`build_graph` consumes CUDA planes IN PLACE (no tile copy) and the lazily emitted arrays (`edge_index`, `edge_attr`,
@@ -281,6 +281,31 @@ class Batch(Data):
         out.batch = torch.cat(batch_vec) if batch_vec else torch.zeros(0, dtype=torch.long)
         out.num_graphs = len(data_list)
         return out
+
+
+RAG_PATCH_DTYPE = np.dtype([("cell_off", np.int64), ("gh", np.int32), ("gw", np.int32), ("r0", np.int32), ("nr", np.int32)])
+
+
+def _ragged_patches(cell_off: np.ndarray, rows: np.ndarray, cols: np.ndarray) -> Optional[np.ndarray]:
+    """Band patches of a ragged batch (include/bgnn.h: bgnn_grid_topo::patches): every grid is cut into bands of `nr` rows over
+    its full width with (nr + 2)(cols + 2) <= 324 halo slots, nr * cols <= 256 destinations and nr <= 62.  None when a grid is
+    too wide for one band row (cols > 106): the forward then uses the windowed CSR kernel."""
+    rows = np.asarray(rows, np.int64); cols = np.asarray(cols, np.int64)
+    if rows.size == 0 or int(cols.max()) > 106:
+        return None
+    ph = np.minimum(np.minimum(256 // cols, 324 // (cols + 2) - 2), 62)
+    ph = np.maximum(np.minimum(ph, rows), 1)
+    nb = (rows + ph - 1) // ph
+    total = int(nb.sum())
+    g = np.repeat(np.arange(rows.size), nb)
+    first = np.zeros(rows.size, np.int64); np.cumsum(nb[:-1], out=first[1:])
+    band = np.arange(total, dtype=np.int64) - first[g]
+    t = np.empty(total, RAG_PATCH_DTYPE)
+    t["cell_off"] = np.asarray(cell_off, np.int64)[:-1][g]
+    t["gh"], t["gw"] = rows[g], cols[g]
+    t["r0"] = band * ph[g]
+    t["nr"] = np.minimum(ph[g], rows[g] - band * ph[g])
+    return t
 
 
 def _graph_cfg(offsets, node_feats: Sequence[str], has_unc: bool, edge_feats: Sequence[str]) -> Tuple[_lib.GraphCfg, int]:
@@ -585,14 +610,29 @@ class GraphBuilder:
         # single tile with a radius-1 stencil: also emit the dense per-cell edge features the tiled aggregation reads
         radius1 = all(abs(cfg.off_dr[k]) <= 1 and abs(cfg.off_dc[k]) <= 1 for k in range(cfg.n_offsets))
         dg.grid_eattr = None
+        dg.rag_patches, dg.n_rag_patches = None, 0
         if meta is None and int(cells.n_grids) == 1 and radius1 and cfg.n_offsets <= 8 and ED > 0:
             dg.grid_eattr = torch.empty((n_cells, cfg.n_offsets, ED), dtype=torch.float32, device=dev)
+        elif meta is not None and radius1 and cfg.n_offsets in (4, 8) and ED > 0:
+            # ragged batch: the same dense per-cell edge features + a table of band patches, so that the aggregation runs as
+            # the tiled kernel per band of grid rows (gat_aggregate_ragged) and the CSR payload is never needed
+            table = _ragged_patches(meta["cell_off"], meta["rows"], meta["cols"])
+            if table is not None:
+                dg.grid_eattr = torch.empty((n_cells, cfg.n_offsets, ED), dtype=torch.float32, device=dev)
+                dg.rag_patches = torch.from_numpy(table.view(np.uint8)).to(dev, non_blocking=True)
+                dg.n_rag_patches = int(table.shape[0])
         if dg.grid_eattr is None:           # no grid path for this graph: the forward needs the CSR payload right away
             dg._csr_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
             dg._csr_eattr = torch.empty((max(E, 1), max(ED, 1)), dtype=torch.float32, device=dev)
-        check(lib.bgnn_graph_emit(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), ptr(dg.node_id),
-                                  ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std), ptr(dg.rowptr), ptr(dg._csr_src),
-                                  ptr(dg._csr_eattr) if ED > 0 else None, ptr(dg.grid_eattr), st))
+        if dg.rag_patches is not None and cfg.n_offsets == 8 and dg._csr_src is None and min(min(s_) for s_ in dims) >= 2:
+            # ragged batch on the reference's 8 offsets: one CTA per band patch (shared-memory staging, 4 atans per cell)
+            check(lib.bgnn_graph_emit_bands(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), ptr(dg.rag_patches),
+                                            dg.n_rag_patches, ptr(dg.node_id), ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std),
+                                            ptr(dg.rowptr), ptr(dg.grid_eattr), st))
+        else:
+            check(lib.bgnn_graph_emit(C.byref(cells), C.byref(cfg), ptr(scratch), scratch.numel(), ptr(dg.node_id),
+                                      ptr(dg.node_cell), ptr(dg.x), ptr(dg.local_std), ptr(dg.rowptr), ptr(dg._csr_src),
+                                      ptr(dg._csr_eattr) if ED > 0 else None, ptr(dg.grid_eattr), st))
         g = GridGraph()
         g.__dict__["_dev"] = dg
         g.x = dg.x

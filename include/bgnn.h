@@ -123,6 +123,14 @@ int bgnn_graph_emit(const bgnn_cells* cells, const bgnn_graph_cfg* cfg,
                     int32_t* node_id, int32_t* node_cell, float* x, float* local_std,
                     int32_t* rowptr, int32_t* csr_src, float* csr_eattr, float* grid_eattr, void* stream);
 
+/* The same second phase for a RAGGED batch whose grids are cut into band patches (bgnn_grid_topo::patches; the reference's
+ * 8-connected offsets): one CTA per band with depth + validity staged in shared memory, no per-cell grid search, four
+ * fp64 atans per cell instead of eight.  Writes node_id / node_cell / rowptr, x, local_std and the dense grid_eattr (the
+ * CSR payload stays available through bgnn_graph_emit).  Bit-identical to bgnn_graph_emit. */
+int bgnn_graph_emit_bands(const bgnn_cells* cells, const bgnn_graph_cfg* cfg, void* scratch, size_t scratch_bytes,
+                          const void* patches, int32_t n_patches, int32_t* node_id, int32_t* node_cell, float* x,
+                          float* local_std, int32_t* rowptr, float* grid_eattr, void* stream);
+
 /* Optional phase 3: the reference's API-visible COO (offset-major, node-minor; :196-241) and
  * per-edge features in that order.  edge_index int64 [2,E] (row 0 = src/centre, row 1 = tgt),
  * edge_attr f32 [E, n_edge_feats].  Needs the scratch of the SAME count call and node_id. */
@@ -197,6 +205,12 @@ typedef struct bgnn_grid_topo {
     int32_t        off_dr[BGNN_MAX_OFFSETS];
     int32_t        off_dc[BGNN_MAX_OFFSETS];
     const float*   grid_eattr;                   /* [dev] optional dense edge features from bgnn_graph_emit */
+    /* ragged batches (rows == 0) only: band patches planned by the host -- one entry per (grid, band of rows):
+     * { int64 cell_off; int32 grid_rows, grid_cols, first_row, n_rows } with (n_rows + 2) * (grid_cols + 2) <= 324,
+     * n_rows * grid_cols <= 256, n_rows <= 62.  With node_id (packed cell space) and grid_eattr set, the aggregation of a
+     * ragged batch runs as the tiled kernel per band instead of the windowed CSR kernel and the CSR payload is never read. */
+    const void*    patches;                      /* [dev] or NULL */
+    int32_t        n_patches;
 } bgnn_grid_topo;
 
 /* 1 if bgnn_gat_forward would run EVERY layer of `m` through the tiled grid kernel for this topology (then
@@ -360,8 +374,10 @@ int bgnn_sidecar_add(const bgnn_sidecar* sc, int32_t n_grids, const int64_t* cel
  *   BGNN_OPT_PRESPLIT      a tiled aggregation hands its output to the next tcgen05 projection as fp16 hi / lo planes
  *   BGNN_OPT_WINDOW        ragged batches: windowed shared-memory aggregation (off -> warp-per-destination CSR kernel)
  *   BGNN_OPT_TILE5         5x5 stencil / bf16 mode on a single grid: radius-2 tiled aggregation (off -> CSR kernel)
- *   BGNN_OPT_TILE5_WINDOW  full 5x5 stencil: sliding register window variant of the radius-2 kernel */
-enum { BGNN_OPT_TENSOR_CORES = 0, BGNN_OPT_PRESPLIT = 1, BGNN_OPT_WINDOW = 2, BGNN_OPT_TILE5 = 3, BGNN_OPT_TILE5_WINDOW = 4 };
+ *   BGNN_OPT_TILE5_WINDOW  full 5x5 stencil: sliding register window variant of the radius-2 kernel
+ *   BGNN_OPT_RAGGED_PATCHES ragged batches: tiled aggregation per band of grid rows (bgnn_grid_topo::patches; off -> windowed kernel) */
+enum { BGNN_OPT_TENSOR_CORES = 0, BGNN_OPT_PRESPLIT = 1, BGNN_OPT_WINDOW = 2, BGNN_OPT_TILE5 = 3, BGNN_OPT_TILE5_WINDOW = 4,
+       BGNN_OPT_RAGGED_PATCHES = 5 };
 int bgnn_model_set_option(bgnn_model* m, int option, int value);
 /* testing aid: C_dev[M,N] = A_dev[M,K] . W_host[N,K]^T through the tcgen05 path (host-synchronous);
  * alpha_dev (optional) [M, 2*heads] receives the per-head dot products with att_src / att_dst [N]. */

@@ -150,8 +150,8 @@ def test_state_dict_compat_and_errors():
     g = bg.GraphBuilder().build_graph(c["depth"], c["mask"], c["unc"], c["res"])     # 8 features
     with pytest.raises(RuntimeError, match="shapes cannot be multiplied"):          # docs/LESSONS_LEARNED.md:64
         m.cuda().eval()(g)
-    with pytest.raises(NotImplementedError):
-        bg.BathymetricGNN(7, gnn_type="GCN")
+    with pytest.raises(ValueError, match="Unknown GNN type"):                     # models/gnn.py:145-146
+        bg.BathymetricGNN(7, gnn_type="Transformer")
 
 
 def test_forward_deterministic_and_isolated_nodes():
@@ -324,3 +324,25 @@ def test_plain_backbones_ragged_batch_and_foreign_coo(gnn_type):
     foreign = bg.Data(x=g.x.clone(), edge_index=g.edge_index.clone(), edge_attr=g.edge_attr.clone())
     out_f = model(foreign)
     np.testing.assert_allclose(out_f["class_logits"].cpu().numpy(), out["class_logits"].cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("conn,heads,lo,hi,frac", [("8-connected", 4, 2, 50, 0.10), ("4-connected", 4, 2, 20, 0.30),
+                                                   ("8-connected", 2, 2, 9, 0.0), ("8-connected", 4, 40, 106, 0.05)])
+def test_ragged_band_patch_aggregation_equals_windowed_kernel(conn, heads, lo, hi, frac):
+    """Ragged batches: the tiled aggregation per band of grid rows (bgnn_grid_topo::patches) against the windowed CSR kernel
+    (same arithmetic and edge order => bit-identical) and against the oracle; grids from 2 x 2 to 106 wide, holes, both stencils."""
+    import bathymetric_gnn_b200 as bg
+    grids = synth.ragged_grids(60 if hi <= 50 else 8, seed=lo * 7 + hi, lo=lo, hi=hi, nodata_frac=frac)
+    cfg = mo.ModelCfg(in_channels=7, heads=heads)
+    sd = mo.init_state_dict(cfg, seed=13, randomize_bn=True)
+    m = make_model(cfg, sd)
+    g = bg.GraphBuilder(conn).build_graph_batch(grids, nodata=1.0e6, use_uncertainty=False)
+    assert g._dev.rag_patches is not None and g._dev.n_rag_patches >= len(grids)
+    a = m.set_option("ragged_patches", 1)._run(g, 0.85, 0.6, True, return_hidden=True)
+    assert g._dev._csr_src is None                           # the CSR payload was never materialised
+    b = m.set_option("ragged_patches", 0)._run(g, 0.85, 0.6, True, return_hidden=True)
+    for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
+        assert torch.equal(a[k], b[k]), k
+    ref = mo.forward(sd, cfg, g.x.cpu().numpy(), g.edge_index.cpu().numpy(), g.edge_attr.cpu().numpy())
+    np.testing.assert_allclose(a["class_logits"].cpu().numpy(), ref["class_logits"].numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(a["confidence"].cpu().numpy(), ref["confidence"].numpy(), rtol=RTOL, atol=ATOL)
