@@ -4,7 +4,7 @@ per-tile inference hot path (graph build -> GAT forward -> tile stitch).
 The directory name carries a hyphen (task layout); import it as
 `bathymetric_gnn_b200` (the sibling shim package extends its __path__ here).
 """
-from .graph import Data, Batch, GridGraph, GraphBuilder, MultiScaleGraphBuilder, OFFSETS_4, OFFSETS_8, OFFSETS_24  # noqa: F401
+from .graph import Data, Batch, GridGraph, HostGridGraph, GraphBuilder, MultiScaleGraphBuilder, OFFSETS_4, OFFSETS_8, OFFSETS_24  # noqa: F401
 from .gnn import (BathymetricGNN, LocalFeatureExtractor, GNNBackbone, ClassificationHead,  # noqa: F401
                   ConfidenceHead, CorrectionHead)
 

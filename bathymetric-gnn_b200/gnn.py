@@ -354,6 +354,8 @@ class BathymetricGNN(nn.Module):
         _lib.require_cuda()
         if self.training and self.dropout > 0:
             raise RuntimeError("BathymetricGNN (B200 build) is inference-only: call .eval() first")
+        if "_host" in data.__dict__:            # a deferred small host grid (graph.py::HostGridGraph): build it on the device now
+            data._materialise_host()
         dg = data.__dict__.get("_dev")
         if dg is not None and hasattr(data, "topology_overridden") and data.topology_overridden():
             dg = None               # caller-assigned edge_index / edge_attr: honour them (COO path)

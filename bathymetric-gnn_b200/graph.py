@@ -181,6 +181,65 @@ class GridGraph(Data):
         return any(k in self.__dict__ and self.__dict__[k] is not em.get(k) for k in ("edge_index", "edge_attr"))
 
 
+class HostGridGraph(GridGraph):
+    """A SMALL host grid (NumPy depth, <= GraphBuilder.DEFER_MAX_CELLS cells) whose device build is DEFERRED.
+
+    `scripts/inference_native.py` builds one graph per refinement grid (`_build_graph_for_grid`, :158-179), reads only
+    `graph.num_nodes`, and hands the list to `Batch.from_data_list` (:312).  One device build per 3x3 ... 50x50 grid costs a
+    host round trip each (~150 us per grid, far more than its kernels), so `build_graph` returns this object instead: the node
+    count comes from the mask on the host, and `Batch.from_data_list` then builds the WHOLE list as one ragged device graph
+    (`GraphBuilder.build_graph_batch`).  Anything else that is asked of it (`x`, `edge_index`, `edge_attr`, `local_std`, the
+    model's forward ...) triggers the ordinary single-grid device build first, so the object behaves exactly like the eager
+    `GridGraph`; `valid_rows` / `valid_cols` / `pos` come from the host mask (what the reference's CPU graph holds)."""
+
+    _DEV_NAMES = ("_dev", "x", "local_std", "edge_index", "edge_attr")
+
+    def _materialise_host(self):
+        h = self.__dict__.pop("_host")
+        g = h["builder"]._build_now(h["depth"], h["mask"], h["unc"], h["res"])
+        self.__dict__.update(g.__dict__)         # _dev, x, local_std, ... (a local_std slice handed over by a batch build is the same data)
+
+    def __getattr__(self, name):
+        d = self.__dict__
+        if "_host" in d:
+            if name in HostGridGraph._DEV_NAMES:
+                self._materialise_host()
+                if name in self.__dict__:
+                    return self.__dict__[name]
+            elif name in ("valid_rows", "valid_cols", "pos"):
+                rr, cc = np.nonzero(d["_host"]["mask"])
+                d["valid_rows"], d["valid_cols"] = torch.from_numpy(rr.astype(np.int64)), torch.from_numpy(cc.astype(np.int64))
+                d["pos"] = torch.from_numpy(np.stack([cc, rr], axis=1).astype(np.float32))
+                return d[name]
+        return super().__getattr__(name)
+
+    @property
+    def num_nodes(self) -> int:
+        h = self.__dict__.get("_host")
+        return int(h["n"]) if h is not None else super().num_nodes
+
+    @property
+    def num_edges(self) -> int:
+        if "_host" in self.__dict__:
+            self._materialise_host()
+        return super().num_edges
+
+    def _apply(self, fn):
+        if "_host" in self.__dict__:                 # nothing lives on a device yet: .to() / .cpu() are the identity
+            return self
+        return super()._apply(fn)
+
+    def keys(self):
+        if "_host" in self.__dict__:
+            self._materialise_host()
+        return super().keys()
+
+    def topology_overridden(self) -> bool:
+        if "_host" in self.__dict__:
+            return any(k in self.__dict__ for k in ("edge_index", "edge_attr"))
+        return super().topology_overridden()
+
+
 class Batch(Data):
     """`torch_geometric.data.Batch.from_data_list` replacement
     (scripts/inference_native.py:312): block-diagonal concatenation."""
@@ -188,6 +247,11 @@ class Batch(Data):
     _LAZY = GridGraph._LAZY
 
     def __getattr__(self, name):
+        rag = self.__dict__.get("_ragged")
+        if rag is not None and name in Batch._LAZY:          # built as ONE ragged device graph: its lazily emitted arrays
+            tgt = self.__dict__.get("_target_device", self.__dict__["_dev"].device)
+            self.__dict__[name] = getattr(rag, name).to(tgt)
+            return self.__dict__[name]
         parts = self.__dict__.get("_parts")
         if parts is not None and name in Batch._LAZY:
             tgt = self.__dict__.get("_target_device", self.__dict__["_dev"].device)
@@ -252,7 +316,37 @@ class Batch(Data):
         return out
 
     @classmethod
+    def _from_host_graphs(cls, graphs: List["HostGridGraph"]) -> "Batch":
+        """All members are deferred host grids of one builder: ONE ragged device build for the whole list (per-grid boundary
+        conditions, explicit masks), the windowed / band-patch aggregation runs on it directly."""
+        hs = [g.__dict__["_host"] for g in graphs]
+        b = hs[0]["builder"]
+        use_unc = all(h["unc"] is not None for h in hs)
+        rag = b.build_graph_batch([(h["depth"], h["unc"], h["res"]) for h in hs], nodata=None, use_uncertainty=use_unc,
+                                  masks=[h["mask"] for h in hs])
+        out = cls()
+        counts = np.array([h["n"] for h in hs], np.int64)
+        out.__dict__["_dev"], out.__dict__["_ragged"] = rag._dev, rag
+        out.x, out.local_std = rag.x, rag.local_std
+        out.batch = torch.from_numpy(np.repeat(np.arange(len(hs), dtype=np.int64), counts))
+        out.num_graphs = len(graphs)
+        out.num_valid_cells = [int(c) for c in counts]
+        out.grid_shape = [tuple(h["depth"].shape) for h in hs]
+        # the per-grid correction scale the script reads after unbatching (`graph.local_std`, inference_native.py:181-204):
+        # one read-back for the whole batch, handed to the members as views
+        ls = rag.local_std.cpu()
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for i, g in enumerate(graphs):
+            g.__dict__["local_std"] = ls[int(off[i]):int(off[i + 1])]
+        return out
+
+    @classmethod
     def from_data_list(cls, data_list: List[Data]) -> "Batch":
+        if data_list and all(isinstance(d, HostGridGraph) and "_host" in d.__dict__ and not d.topology_overridden()
+                             for d in data_list):
+            h0 = data_list[0].__dict__["_host"]
+            if all(d.__dict__["_host"]["builder"] is h0["builder"] for d in data_list):
+                return cls._from_host_graphs(list(data_list))
         if data_list and all(isinstance(d, GridGraph) and "_dev" in d.__dict__ and not d.topology_overridden()
                              and d.x is d._dev.x for d in data_list):
             d0 = data_list[0]._dev
@@ -387,9 +481,49 @@ class GraphBuilder:
         tensor (a strided 2-D view of a survey is consumed in place).  `nodata`
         (additive) makes the kernel derive valid = isfinite & != nodata when no mask
         is given (scripts/inference_native.py:160)."""
+        if (isinstance(depth, np.ndarray) and depth.ndim == 2 and 0 < depth.size <= self.DEFER_MAX_CELLS
+                and (valid_mask is None or isinstance(valid_mask, np.ndarray))
+                and (uncertainty is None or isinstance(uncertainty, np.ndarray))):
+            return self._build_deferred(depth, valid_mask, uncertainty, resolution, nodata)
         dev = self._device()
         with torch.cuda.device(dev):
             return self._build(*self._tile_cells(depth, valid_mask, uncertainty, resolution, nodata, dev))
+
+    DEFER_MAX_CELLS = 4096       # host grids up to 64 x 64 (native VR refinement grids are 3x3 ... 50x50) are built on first use
+
+    def _build_deferred(self, depth, valid_mask, uncertainty, resolution, nodata) -> Data:
+        """`build_graph` for a small host grid: everything the callers of scripts/inference_native.py:158-179, 249-269 read
+        right away (node count, grid_shape) comes from the host mask; the device build happens on first use of a device
+        array, or -- for a whole list at once -- in `Batch.from_data_list`.  Same errors as the eager path."""
+        _lib.require_cuda()
+        d = np.asarray(depth, np.float32)
+        if valid_mask is not None:
+            m = np.asarray(valid_mask).astype(bool)
+        else:
+            m = np.isfinite(d)                                     # graph_construction.py:110-111
+            if nodata is not None and not np.isnan(nodata):
+                m &= d != np.float32(nodata)
+        n = int(np.count_nonzero(m))
+        if n == 0:
+            logger.warning("No valid cells in grid")
+            return self._empty()
+        if min(d.shape) < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least (edge_order + 1) elements are required.")
+        g = HostGridGraph()
+        g.__dict__["_host"] = dict(depth=d, mask=m, unc=None if uncertainty is None else np.asarray(uncertainty, np.float32),
+                                   res=(float(resolution[0]), float(resolution[1])), builder=self, n=n)
+        g.grid_shape = tuple(d.shape)
+        g.num_valid_cells = n
+        if self.include_self_loops:
+            g.__dict__["_self_loops"] = True
+        return g
+
+    def _build_now(self, depth, mask, unc, res) -> Data:
+        """The eager single-grid device build (what `build_graph` does for large / device inputs)."""
+        dev = self._device()
+        with torch.cuda.device(dev):
+            return self._build(*self._tile_cells(depth, mask, unc, res, None, dev))
 
     def count_tile(self, depth, valid_mask=None, uncertainty=None, resolution=(1.0, 1.0), nodata=None, stream=None, scratch=None):
         """`build_graph` in two steps for callers that pipeline tiles: `count_tile` (node / edge totals, host-synchronous on
@@ -455,7 +589,8 @@ class GraphBuilder:
             return cells, keep, uncertainty is not None, (H, W), None, dev
 
     def build_graph_batch(self, grids: Sequence[Tuple[np.ndarray, Optional[np.ndarray], Tuple[float, float]]],
-                          nodata: Optional[float] = 1.0e6, use_uncertainty: bool = True) -> Data:
+                          nodata: Optional[float] = 1.0e6, use_uncertainty: bool = True,
+                          masks: Optional[Sequence[np.ndarray]] = None) -> Data:
         """Ragged batch of refinement grids as ONE block-diagonal graph: replaces the
         per-grid build_graph loop + Batch.from_data_list of
         scripts/inference_native.py:158-179, 249-269, 312.  valid = (depth != nodata)
@@ -477,19 +612,23 @@ class GraphBuilder:
             # 50 000-node budget a flush is ~0.3 ms of kernels, so five pageable copies per flush were the larger cost.
             # The staging memory is free again when this call returns (the node count is read back synchronously).
             planes = 2 if has_unc else 1
-            stage = self._staging(planes * n * 4 + (G + 1) * 8 + 2 * G * 8 + 2 * G * 4 + 64)
+            mbytes = (n + 7) // 8 * 8 if masks is not None else 0          # explicit validity masks (one byte per cell) behind the metadata
+            stage = self._staging(planes * n * 4 + (G + 1) * 8 + 2 * G * 8 + 2 * G * 4 + 64 + mbytes)
             cells_h = stage[:planes * n * 4].view(torch.float32).numpy()
             if n:
                 np.concatenate([np.asarray(g[0], np.float32).ravel() for g in grids], out=cells_h[:n])
                 if has_unc:
                     np.concatenate([np.asarray(g[1], np.float32).ravel() for g in grids], out=cells_h[n:])
             m0 = (planes * n * 4 + 7) // 8 * 8
-            meta_h = stage[m0:m0 + (G + 1) * 8 + 2 * G * 8 + 2 * G * 4]
+            meta_len = (G + 1) * 8 + 2 * G * 8 + 2 * G * 4
+            meta_h = stage[m0:m0 + (meta_len + 7) // 8 * 8 + mbytes]
             mh = meta_h.numpy()
+            if masks is not None and n:
+                np.concatenate([np.asarray(mk, bool).ravel() for mk in masks], out=mh[(meta_len + 7) // 8 * 8:][:n].view(bool))
             mh[:(G + 1) * 8].view(np.int64)[:] = off
             mh[(G + 1) * 8:(G + 1) * 8 + 2 * G * 8].view(np.float64)[:] = res.ravel()
             mh[(G + 1) * 8 + 2 * G * 8:(G + 1) * 8 + 2 * G * 8 + G * 4].view(np.int32)[:] = rows
-            mh[(G + 1) * 8 + 2 * G * 8 + G * 4:].view(np.int32)[:] = cols
+            mh[(G + 1) * 8 + 2 * G * 8 + G * 4:meta_len].view(np.int32)[:] = cols
             cells_d = torch.empty(max(planes * n, 1), dtype=torch.float32, device=dev)
             if n:
                 cells_d[:planes * n].copy_(stage[:planes * n * 4].view(torch.float32), non_blocking=True)
@@ -499,13 +638,15 @@ class GraphBuilder:
             t_off = meta_d[:(G + 1) * 8].view(torch.int64)
             t_res = meta_d[(G + 1) * 8:(G + 1) * 8 + 2 * G * 8].view(torch.float64)
             t_rows = meta_d[(G + 1) * 8 + 2 * G * 8:(G + 1) * 8 + 2 * G * 8 + G * 4].view(torch.int32)
-            t_cols = meta_d[(G + 1) * 8 + 2 * G * 8 + G * 4:].view(torch.int32)
+            t_cols = meta_d[(G + 1) * 8 + 2 * G * 8 + G * 4:meta_len].view(torch.int32)
             keep = [cells_d, meta_d]
             cells = _lib.Cells()
             cells.n_grids, cells.n_cells = G, n
             cells.cell_off, cells.grid_rows, cells.grid_cols, cells.grid_res = (t.data_ptr() for t in (t_off, t_rows, t_cols, t_res))
             cells.depth = d.data_ptr()
-            if nodata is not None and not np.isnan(nodata):
+            if masks is not None:
+                cells.mask = meta_d[(meta_len + 7) // 8 * 8:].data_ptr()
+            elif nodata is not None and not np.isnan(nodata):
                 cells.use_nodata, cells.nodata = 1, float(nodata)
             if has_unc:
                 cells.unc = cells_d[n:].data_ptr()
@@ -656,6 +797,15 @@ class GraphBuilder:
             raise ValueError("Data object missing grid_shape metadata")
         if node_values.dim() != 1:
             raise ValueError("For multi-channel node values, call graph_to_grid for each channel")
+        h = data.__dict__.get("_host")
+        if h is not None and not node_values.is_cuda:
+            # host values of a host grid asked back as a host grid (the per-grid unbatching of scripts/inference_native.py:
+            # 181-204, 320-340): an index assignment through the grid's own mask, no arithmetic and no device round trip
+            if int(node_values.shape[0]) != h["n"]:
+                raise IndexError(f"node_values has {int(node_values.shape[0])} entries for {h['n']} nodes")
+            grid = np.full(h["depth"].shape, fill_value, dtype=np.float32)
+            grid[h["mask"]] = node_values.detach().to(torch.float32).numpy()
+            return grid
         return self.graph_to_grid_device(data, node_values, fill_value).cpu().numpy()
 
     def graph_to_grid_device(self, data: Data, node_values: torch.Tensor, fill_value: float = np.nan) -> torch.Tensor:
