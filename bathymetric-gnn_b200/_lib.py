@@ -92,7 +92,8 @@ SYMBOLS = {
     "bgnn_stitch_blend_tile": (C.c_int, [P, I64, I64, I64, I64, I32, I32, P, P, P, P]),
     "bgnn_stitch_finalize": (C.c_int, [C.POINTER(Survey), P]),
     "bgnn_apply_corrections": (C.c_int, [P, P, I64, P, P, P, P, F32, P]),
-    "bgnn_survey_emit": (C.c_int, [C.POINTER(Survey), P, I32, F32, F32, P, P, P]),
+    "bgnn_survey_emit": (C.c_int, [C.POINTER(Survey), P, I32, F32, F32, P, P, I64, P]),
+    "bgnn_memcpy2d_async": (C.c_int, [P, SZ, P, SZ, SZ, SZ, C.c_int, P]),
     "bgnn_vr_apply_results": (C.c_int, [P, P, I64, F32, P, P, P, F32, P, P, P, P, P]),
     "bgnn_sidecar_init": (C.c_int, [C.POINTER(Sidecar), P]),
     "bgnn_sidecar_add": (C.c_int, [C.POINTER(Sidecar), I32, P, P, I64, P, P, P, P, F32, P]),

@@ -28,6 +28,17 @@ extern "C" int bgnn_device_info(int device, int* out3) {
     return BGNN_OK;
 }
 
+// 2-D strided copies between pinned host memory and the device (column blocks of survey planes: survey.py streams a band
+// up block by block and its results down block by block; torch's copy_ stages strided host copies through temporaries)
+extern "C" int bgnn_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                                   int kind, void* stream) {
+    BGNN_CHECK_ARG(dst && src && dpitch >= width_bytes && spitch >= width_bytes && (kind == 1 || kind == 2), "bad 2-D copy");
+    if (width_bytes == 0 || height == 0) return BGNN_OK;
+    BGNN_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                                kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return BGNN_OK;
+}
+
 // ---------------------------------------------------------------- per-kernel timing (bench aid)
 struct ProfRec { int slot; cudaEvent_t a, b; cudaStream_t s; bool open; };
 // The one piece of process-wide state in the library: a measurement aid, off by default, guarded by a mutex (launches from

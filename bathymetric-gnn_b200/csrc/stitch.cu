@@ -207,9 +207,11 @@ k_apply(const float* __restrict__ depth, const uint8_t* __restrict__ valid, int6
 // derived here instead of being read from a mask plane; the class plane leaves as uint8 (255 = NaN / never written).
 __global__ void __launch_bounds__(ST_THREADS)
 k_survey_emit(const bgnn_survey s, const float* __restrict__ depth, int use_nodata, float nodata, float thr,
-              float* __restrict__ cleaned, uint8_t* __restrict__ cls_u8) {
+              float* __restrict__ cleaned, uint8_t* __restrict__ cls_u8, int64_t pitch) {
     const int64_t n = s.rows * s.cols;
-    for (int64_t t = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * ST_THREADS) {
+    for (int64_t q = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; q < n; q += (int64_t)gridDim.x * ST_THREADS) {
+        int64_t t = q;
+        if (pitch != s.cols) { const int64_t r = q / s.cols; t = r * pitch + (q - r * s.cols); }      // a column block of wider planes
         float cf = s.cont[0][t];
         float cr = s.n_cont > 1 ? s.cont[1][t] : 0.0f;
         const float w0 = s.wsum[0][t];
@@ -233,15 +235,17 @@ k_survey_emit(const bgnn_survey s, const float* __restrict__ depth, int use_noda
 }  // namespace
 
 extern "C" int bgnn_survey_emit(const bgnn_survey* s, const float* depth, int32_t use_nodata, float nodata,
-                                float auto_correct_threshold, float* cleaned, uint8_t* class_u8, void* stream) {
+                                float auto_correct_threshold, float* cleaned, uint8_t* class_u8, int64_t pitch, void* stream) {
     BGNN_CHECK_ARG(s && depth, "null argument");
     BGNN_CHECK_ARG(s->n_cont >= 1 && s->n_cont <= 2 && s->cont[0] && s->wsum[0] && s->discrete && s->f64_mask == 0,
                    "survey must carry float32 confidence [+ correction] and class planes");
     BGNN_CHECK_ARG(s->n_cont == 1 || (s->cont[1] && s->wsum[1]), "null correction plane");
     if (s->rows * s->cols <= 0) return BGNN_OK;
     ProfScope ps(77, (cudaStream_t)stream);
+    BGNN_CHECK_ARG(pitch == 0 || pitch >= s->cols, "pitch smaller than the block width");
     k_survey_emit<<<grid_for(s->rows * s->cols), ST_THREADS, 0, (cudaStream_t)stream>>>(*s, depth, use_nodata, nodata,
-                                                                                     auto_correct_threshold, cleaned, class_u8);
+                                                                                     auto_correct_threshold, cleaned, class_u8,
+                                                                                     pitch > 0 ? pitch : s->cols);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
 }

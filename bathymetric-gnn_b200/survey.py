@@ -204,15 +204,40 @@ class BandStitcher:
         """Contiguous row slices [a, b) of the five planes (what one band hands to the next)."""
         return [p[a:b] for p in (self.conf, self.corr, self.wsum, self.cls, self.trk)]
 
-    def emit(self, a: int, b: int, depth: torch.Tensor, use_nodata: bool, nodata: float, thr: float, cls_u8: torch.Tensor):
-        """Rows [a, b): finalize + fill + corrections in place; `depth[a:b]` becomes the cleaned depth."""
-        if b <= a:
+    def emit(self, a: int, b: int, c0: int, c1: int, depth: torch.Tensor, use_nodata: bool, nodata: float, thr: float,
+             cls_u8: torch.Tensor):
+        """Rows [a, b) x columns [c0, c1): finalize + fill + corrections in place; that block of `depth` becomes the cleaned depth."""
+        if b <= a or c1 <= c0:
             return
-        check(lib.bgnn_survey_emit(C.byref(self._survey(a, b)), ptr(depth[a:b]), 1 if use_nodata else 0, float(nodata), float(thr),
-                                   ptr(depth[a:b]), ptr(cls_u8[a:b]), stream_ptr()))
+        s = self._survey(a, b)
+        s.cols = c1 - c0
+        for k in range(2):
+            s.cont[k] += c0 * 4
+            s.wsum[k] += c0 * 4
+        s.discrete += c0 * 4
+        s.tracker += c0 * 4
+        dptr = C.c_void_p(depth.data_ptr() + (a * self.cols + c0) * 4)
+        uptr = C.c_void_p(cls_u8.data_ptr() + a * self.cols + c0)
+        check(lib.bgnn_survey_emit(C.byref(s), dptr, 1 if use_nodata else 0, float(nodata), float(thr), dptr, uptr, self.cols, stream_ptr()))
 
 
 # ------------------------------------------------------------------------------------------------ the band loop
+def _copy_block(dst: torch.Tensor, src: torch.Tensor, r0: int, r1: int, c0: int, c1: int, stream):
+    """dst[r0:r1, c0:c1] <- src[r0:r1, c0:c1] on `stream` (2-D planes of one dtype, one of them on the device): full-width
+    blocks and device-to-device copies go through torch, column blocks between host and device through cudaMemcpy2DAsync."""
+    if r1 <= r0 or c1 <= c0:
+        return
+    full = c0 == 0 and c1 == dst.shape[1] == src.shape[1] and dst.stride(0) == dst.shape[1] and src.stride(0) == src.shape[1]
+    if full or (dst.is_cuda and src.is_cuda):
+        with torch.cuda.stream(stream):
+            dst[r0:r1, c0:c1].copy_(src[r0:r1, c0:c1], non_blocking=True)
+        return
+    esz = src.element_size()
+    check(lib.bgnn_memcpy2d_async(C.c_void_p(dst.data_ptr() + (r0 * dst.stride(0) + c0) * esz), dst.stride(0) * esz,
+                                  C.c_void_p(src.data_ptr() + (r0 * src.stride(0) + c0) * esz), src.stride(0) * esz,
+                                  (c1 - c0) * esz, r1 - r0, 1 if dst.is_cuda else 2, C.c_void_p(stream.cuda_stream)))
+
+
 def pinned_outputs(rows: int, cols: int) -> Dict[str, torch.Tensor]:
     mk = lambda dt: torch.empty((rows, cols), dtype=dt, pin_memory=bool(rows * cols))
     return dict(cleaned_depth=mk(torch.float32), classification=mk(torch.uint8), confidence=mk(torch.float32),
@@ -251,35 +276,44 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
         unc = None if src_u is None else torch.empty((bh, W), dtype=torch.float32, device=dev)
         cls_u8 = torch.empty((max(own_rows, 1), W), dtype=torch.uint8, device=dev)
         st = BandStitcher(tm, bh, W, dev)
-        # ---- host -> device, tile-row by tile-row, all queued now on the copy stream
-        ready, up_to = [], 0
+        # ---- host -> device in BLOCKS (rows new to a tile-row x the columns between two tile starts), all queued now on the
+        #      copy stream: the first tile starts after 16 MB have arrived, not after its whole tile-row (0.5 GB at 60 000 columns)
+        col_blocks, ready, up_to = [], [], 0
         s_in.wait_stream(main)
-        with torch.cuda.stream(s_in):
-            for row in plan.tile_rows:
-                need = max(s.row_end for s in row) - plan.r0
-                if need > up_to:
-                    depth[up_to:need].copy_(src_d[up_to:need], non_blocking=True)
-                    if unc is not None:
-                        unc[up_to:need].copy_(src_u[up_to:need], non_blocking=True)
-                    up_to = need
+        for row in plan.tile_rows:
+            edges = [s.col_start for s in row] + [W]
+            blk = [(edges[j], edges[j + 1]) for j in range(len(row))]
+            need = max(s.row_end for s in row) - plan.r0
+            evs = []
+            for (c0, c1) in blk:
+                _copy_block(depth, src_d, up_to, need, c0, c1, s_in)
+                if unc is not None:
+                    _copy_block(unc, src_u, up_to, need, c0, c1, s_in)
                 ev = torch.cuda.Event()
                 ev.record(s_in)
-                ready.append(ev)
-        done_events = []
+                evs.append(ev)
+            up_to = max(up_to, need)
+            col_blocks.append(blk)
+            ready.append(evs)
 
-        def emit_rows(a: int, b: int):
-            """band-local rows [a, b) are final: finalise on the main stream, copy out on the output stream"""
-            if b <= a:
+        def ready_for(ti, spec):
+            """the upload event of the last column block tile `spec` of tile-row ti reads (copies complete in issue order)"""
+            blk = col_blocks[ti]
+            j = max(i for i, (c0, _) in enumerate(blk) if c0 < spec.col_end)
+            return ready[ti][j]
+
+        def emit_block(a: int, b: int, c0: int, c1: int):
+            """band-local rows [a, b) x columns [c0, c1) are final: finalise on the main stream, copy out on the output stream"""
+            if b <= a or c1 <= c0:
                 return
-            st.emit(a, b, depth, use_nodata, nodata if use_nodata else 0.0, thr, cls_u8)
+            st.emit(a, b, c0, c1, depth, use_nodata, nodata if use_nodata else 0.0, thr, cls_u8)
             ev = torch.cuda.Event()
             ev.record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev)
-                out["cleaned_depth"][a:b].copy_(depth[a:b], non_blocking=True)
-                out["classification"][a:b].copy_(cls_u8[a:b], non_blocking=True)
-                out["confidence"][a:b].copy_(st.conf[a:b], non_blocking=True)
-                out["correction"][a:b].copy_(st.corr[a:b], non_blocking=True)
+            s_out.wait_event(ev)
+            _copy_block(out["cleaned_depth"], depth, a, b, c0, c1, s_out)
+            _copy_block(out["classification"], cls_u8, a, b, c0, c1, s_out)
+            _copy_block(out["confidence"], st.conf, a, b, c0, c1, s_out)
+            _copy_block(out["correction"], st.corr, a, b, c0, c1, s_out)
 
         top = plan.top_end - plan.r0                      # band-local end of the parked seam
         bottom = plan.bottom0 - plan.r0
@@ -302,7 +336,7 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
             ti, spec = flat[k]
             loc = local(spec)
             sl = (slice(loc.row_start, loc.row_end), slice(loc.col_start, loc.col_end))
-            s_cnt.wait_event(ready[ti])                   # the tile's rows have arrived
+            s_cnt.wait_event(ready_for(ti, spec))         # the tile's cells have arrived
             if k >= 2:
                 s_cnt.wait_event(tile_done[k - 2])        # scratch[k % 2] is free again; keeps the host <= 2 tiles ahead
             return gb.count_tile(depth[sl], None, None if unc is None else unc[sl], resolution,
@@ -314,7 +348,7 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
             park = max(0, min(top, loc.row_end) - loc.row_start)
             cur, n = pending, pending["N"]
             size = (loc.row_end - loc.row_start) * (loc.col_end - loc.col_start)
-            main.wait_event(ready[ti])
+            main.wait_event(ready_for(ti, spec))
             if n / size < tm.min_valid_ratio:              # tiling.py:200 (skip_empty)
                 stats["skipped"] += 1
             else:
@@ -331,13 +365,15 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
             ev.record(main)
             tile_done.append(ev)
             pending = count(k + 1) if k + 1 < len(flat) else None      # host blocks here while tile k computes
-            last_of_row = k + 1 == len(flat) or flat[k + 1][0] != ti
-            if last_of_row:
-                nxt = plan.tile_rows[ti + 1] if ti + 1 < len(plan.tile_rows) else None
-                final_to = min(min(s.row_start for s in nxt) - plan.r0, bottom) if nxt else bottom
-                if final_to > emitted:
-                    emit_rows(emitted, final_to)
-                    emitted = final_to
+            # rows that only this tile-row (and earlier ones) touch are final, column block by column block: once tile j is in,
+            # no later tile writes the columns [col_start_j, col_start_j+1), so they are finalised and sent home now -- the
+            # device->host stream runs one tile behind the compute instead of one tile-row behind
+            nxt = plan.tile_rows[ti + 1] if ti + 1 < len(plan.tile_rows) else None
+            final_to = min(min(s.row_start for s in nxt) - plan.r0, bottom) if nxt else bottom
+            j = plan.tile_rows[ti].index(spec)
+            emit_block(emitted, final_to, *col_blocks[ti][j])
+            if k + 1 == len(flat) or flat[k + 1][0] != ti:
+                emitted = max(emitted, final_to)
         # ---- seams: hand [bottom0, r1) down, take [r0, top_end) from above, replay the parked strips
         send = (plan.next_rank, st.seam_views(bottom, bh)) if plan.next_rank is not None and bh > bottom else None
         recv = (plan.prev_rank, st.seam_views(0, top)) if plan.prev_rank is not None and top > 0 else None
@@ -355,7 +391,7 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
                 if recv:
                     st.replay_parked()
         if top > 0:
-            emit_rows(0, min(top, bottom))
+            emit_block(0, min(top, bottom), 0, W)
         s_out.synchronize()
         main.synchronize()
     out["stats"] = stats

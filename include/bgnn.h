@@ -325,7 +325,13 @@ int bgnn_apply_corrections(const float* depth, const uint8_t* valid, int64_t n_c
  * describes a ROW RANGE of the survey (plane pointers offset to its first row), so rows can be emitted as soon as every
  * tile that touches them has been accumulated. */
 int bgnn_survey_emit(const bgnn_survey* s, const float* depth, int32_t use_nodata, float nodata,
-                     float auto_correct_threshold, float* cleaned, uint8_t* class_u8, void* stream);
+                     float auto_correct_threshold, float* cleaned, uint8_t* class_u8,
+                     int64_t pitch /* row pitch in elements of every plane; 0 = s->cols (a COLUMN BLOCK of wider planes otherwise) */,
+                     void* stream);
+/* cudaMemcpy2DAsync between pinned host memory and the device (kind 1 = host->device, 2 = device->host): column blocks of
+ * the survey planes go up / come down tile by tile (survey.py) */
+int bgnn_memcpy2d_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes,
+                        size_t height, int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Native VR-BAG post-processing on the packed ragged cell space (the step right behind the ragged
