@@ -490,12 +490,30 @@ def survey_leg(args, dev, rank, world, dist, model, S=None):
     torch.cuda.empty_cache()
     t_setup = time.perf_counter() - t_setup
     barrier()
+    diag = os.environ.get("BGNN_SURVEY_PROFILE") == "1" and rank == 0       # dev aid: device time per slot inside the timed pass
+    if diag:
+        from bathymetric_gnn_b200._lib import lib as _lib_
+        _lib_.bgnn_profile_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     res = sv.process_band(pipe, plan, band, None, synth.SURVEY_NODATA, RES, out, link)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    slot_ms = None
+    if diag:
+        n_ = _lib_.bgnn_profile_collect(0, None, None)
+        sl_ = (C.c_int32 * n_)(); tm_ = (C.c_float * n_)()
+        _lib_.bgnn_profile_collect(n_, sl_, tm_)
+        _lib_.bgnn_profile_enable(0)
+        slot_ms = {}
+        for a_, b_ in zip(sl_, tm_):
+            k_ = SLOT_NAMES.get(int(a_), str(int(a_)))
+            slot_ms[k_] = slot_ms.get(k_, 0.0) + float(b_)
+        nt_ = max(res["stats"]["tiles"], 1)
+        slot_ms = {k_: round(v_ / nt_, 3) for k_, v_ in slot_ms.items()}
+        slot_ms["device_sum_per_tile"] = round(sum(slot_ms.values()), 3)
+        slot_ms["wall_per_tile_rank0"] = round(ms / nt_, 3)
     per_rank = [ms]
     if dist is not None:
         t = torch.zeros(world, device=dev, dtype=torch.float64)
@@ -532,7 +550,7 @@ def survey_leg(args, dev, rank, world, dist, model, S=None):
                             "apply_corrections + D2H of cleaned/class(u8)/confidence/correction to pinned host",
             "h2d_bytes": S * S * 4 + seam_rows * S * 4, "d2h_bytes": S * S * 13, "seam_p2p_bytes": seam_rows * S * 20,
             "checksum": dict(zip(("cleaned_depth", "classification", "confidence", "correction"), sums)),
-            "per_rank_seconds": [round(v * 1e-3, 4) for v in per_rank], "setup_seconds_rank0_untimed": round(t_setup, 2),
+            "per_rank_seconds": [round(v * 1e-3, 4) for v in per_rank], "host_cores": os.cpu_count(), "rank0_ms_per_tile_by_slot": slot_ms, "setup_seconds_rank0_untimed": round(t_setup, 2),
             "bit_identical_to_one_rank": "by construction (parked seam strips replayed in reference tile order; "
                                          "tests/test_gpu_survey.py, tests/test_host_logic.py::test_exact_seam_protocol_gloo)"}
 
