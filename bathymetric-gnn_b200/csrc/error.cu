@@ -4,6 +4,8 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -47,7 +49,23 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_recs;
 static std::mutex g_prof_mu;
 
+// NVTX range per library launch site: the slot names of include/bgnn.h, so a timeline groups the kernels of a
+// step by stage.  Pushed / popped on the launching host thread around the launch call(s) of a ProfScope.
+static const char* slot_name(int slot) {
+    switch (slot) {
+        case 0: return "bgnn:gb_count"; case 1: return "bgnn:gb_scan"; case 2: return "bgnn:gb_ids"; case 3: return "bgnn:gb_emit";
+        case 4: return "bgnn:gb_coo"; case 10: return "bgnn:mlp0"; case 11: return "bgnn:mlp1";
+        case 60: return "bgnn:heads"; case 61: return "bgnn:heads_finish"; case 70: return "bgnn:scatter_tile";
+        case 71: return "bgnn:stitch_add_tile"; case 72: return "bgnn:stitch_finalize"; case 73: return "bgnn:apply_corrections";
+        case 74: return "bgnn:graph_to_grid"; case 75: return "bgnn:vr_apply_results"; case 76: return "bgnn:sidecar_add";
+        case 77: return "bgnn:survey_emit"; case 78: return "bgnn:stitch_add_tile_nodes"; case 80: return "bgnn:csr_aggregate";
+        case 81: return "bgnn:linear";
+        default: return slot >= 40 && slot < 60 ? "bgnn:aggregate_layer" : slot >= 20 && slot < 40 ? "bgnn:project_layer" : "bgnn:kernel";
+    }
+}
+
 void bgnn_prof_start(int slot, cudaStream_t s) {
+    nvtxRangePushA(slot_name(slot));
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r; r.slot = slot; r.s = s; r.open = true;
@@ -56,6 +74,7 @@ void bgnn_prof_start(int slot, cudaStream_t s) {
     g_recs.push_back(r);
 }
 void bgnn_prof_stop(cudaStream_t s) {
+    nvtxRangePop();
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto it = g_recs.rbegin(); it != g_recs.rend(); ++it)

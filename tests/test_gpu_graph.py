@@ -257,3 +257,36 @@ def test_lazy_arrays_refuse_a_survey_edited_after_the_build():
     g2 = bg.GraphBuilder().build_graph(d, None, None, (1.0, 1.0))
     assert torch.equal(g2.edge_index, bg.GraphBuilder().build_graph(d.clone(), None, None, (1.0, 1.0)).edge_index)
     assert not torch.equal(g2.edge_attr, ea0)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_small_grids_vs_oracle(seed):
+    """Seeded sweep over the shapes / masks / values the golden cases do not enumerate: 2 ... 40-sided grids, scattered and
+    blocky holes, masked-out NaN / +-inf / nodata cells, anisotropic resolutions, 4- / 8- / 24-offset stencils, with and
+    without the uncertainty column -- device graph (eager AND deferred build) vs the oracle (pinned bit-for-bit to the
+    reference by tests/test_oracle_golden.py)."""
+    import bathymetric_gnn_b200 as bg
+    rng = np.random.default_rng(1000 + seed)
+    H, W = int(rng.integers(2, 41)), int(rng.integers(2, 41))
+    d = (20.0 + rng.normal(0, 1.0, (H, W)) + 0.05 * np.arange(W)[None, :]).astype(np.float32)
+    mask = rng.random((H, W)) > rng.choice([0.0, 0.05, 0.3, 0.7])
+    if rng.random() < 0.5 and H > 4 and W > 4:
+        r, c = int(rng.integers(0, H - 2)), int(rng.integers(0, W - 2))
+        mask[r:r + int(rng.integers(1, 4)), c:c + int(rng.integers(1, 4))] = False
+    if not mask.any():
+        mask[0, 0] = True
+    bad = ~mask
+    d[bad] = rng.choice([np.nan, np.inf, -np.inf, 1.0e6], size=int(bad.sum())).astype(np.float32)   # never leaks: masked out
+    conn = ["8-connected", "4-connected", "24-connected"][seed % 3]
+    res = [(1.0, 1.0), (0.5, 0.5), (2.0, 0.5), (4.0, 4.0)][seed % 4]
+    unc = (0.1 + 0.05 * rng.random((H, W))).astype(np.float32) if seed % 2 else None
+    ref = go.build_graph(d, mask, unc, res, connectivity=conn)
+    b = bg.GraphBuilder(conn)
+    g_def = b.build_graph(d, mask, unc, res)                                   # NumPy input, <= 4096 cells: deferred build
+    assert isinstance(g_def, bg.HostGridGraph) and g_def.num_nodes == int(mask.sum())
+    check_graph(g_def, ref, d, has_holes=not mask.all())
+    g_now = b.build_graph(torch.from_numpy(d).cuda(), torch.from_numpy(mask).cuda(), None if unc is None else torch.from_numpy(unc).cuda(), res)
+    assert not isinstance(g_now, bg.HostGridGraph)
+    check_graph(g_now, ref, d, has_holes=not mask.all())
+    for k in ("x", "edge_index", "edge_attr", "local_std"):
+        assert torch.equal(getattr(g_def, k), getattr(g_now, k)), k
