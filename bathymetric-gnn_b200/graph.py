@@ -496,9 +496,9 @@ class GraphBuilder:
         right away (node count, grid_shape) comes from the host mask; the device build happens on first use of a device
         array, or -- for a whole list at once -- in `Batch.from_data_list`.  Same errors as the eager path."""
         _lib.require_cuda()
-        d = np.asarray(depth, np.float32)
-        if valid_mask is not None:
-            m = np.asarray(valid_mask).astype(bool)
+        d = np.array(depth, dtype=np.float32)                      # private copies: the caller may reuse its buffers before the
+        if valid_mask is not None:                                  # deferred device build runs (the eager path uploads right away)
+            m = np.array(valid_mask, dtype=bool)
         else:
             m = np.isfinite(d)                                     # graph_construction.py:110-111
             if nodata is not None and not np.isnan(nodata):
@@ -511,7 +511,7 @@ class GraphBuilder:
             raise ValueError("Shape of array too small to calculate a numerical gradient, "
                              "at least (edge_order + 1) elements are required.")
         g = HostGridGraph()
-        g.__dict__["_host"] = dict(depth=d, mask=m, unc=None if uncertainty is None else np.asarray(uncertainty, np.float32),
+        g.__dict__["_host"] = dict(depth=d, mask=m, unc=None if uncertainty is None else np.array(uncertainty, dtype=np.float32),
                                    res=(float(resolution[0]), float(resolution[1])), builder=self, n=n)
         g.grid_shape = tuple(d.shape)
         g.num_valid_cells = n

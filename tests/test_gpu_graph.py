@@ -290,3 +290,16 @@ def test_random_small_grids_vs_oracle(seed):
     check_graph(g_now, ref, d, has_holes=not mask.all())
     for k in ("x", "edge_index", "edge_attr", "local_std"):
         assert torch.equal(getattr(g_def, k), getattr(g_now, k)), k
+
+
+def test_edge_total_guard_refuses_a_cell_space_beyond_int32():
+    """node / edge ids are int32; a cell space whose edge count reaches 2^31 (268 M valid cells at K = 8,
+    89 M at K = 24) must be REFUSED by bgnn_graph_count (ValueError) instead of returning a wrapped total that would size the
+    CSR arrays wrongly.  9 600 x 9 600 valid cells with the 24-offset stencil: 2.2e9 edges."""
+    import bathymetric_gnn_b200 as bg
+    side = 9600
+    d = torch.zeros((side, side), dtype=torch.float32, device="cuda")
+    with pytest.raises(ValueError, match="does not fit int32"):
+        bg.GraphBuilder("24-connected").build_graph(d, None, None, (1.0, 1.0))
+    g = bg.GraphBuilder("8-connected").build_graph(d[:3000, :3000], None, None, (1.0, 1.0))      # the same plane, in range: fine
+    assert g.num_nodes == 9_000_000 and g.num_edges == 4 * 2999 * (2 * 3000 - 1)
