@@ -383,8 +383,10 @@ def run_ours(args):
         torch.cuda.empty_cache()
         try:
             survey = survey_leg(args, dev, rank, world, dist, model)
-        except (RuntimeError, MemoryError) as e:        # e.g. not enough pinned host memory on this box: say so, keep the line
+        except Exception as e:                          # e.g. not enough pinned host memory on this box: say so, keep the line
             survey = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            if dist is not None:                        # a rank that failed alone would leave the others in a barrier
+                raise
 
     # ---- BASELINE configs[3] (ragged VR grids, incl. the reference's own batching API) and configs[4] (wide variant, fp32 and
     #      bf16 side by side): secondary objects of the same line, one GPU only (both are per-GPU workloads without exchange)
@@ -398,7 +400,7 @@ def run_ours(args):
                 setattr(a2, k_, v_)
             try:
                 extra[name] = fn(a2, embed=True)
-            except (RuntimeError, MemoryError) as e:
+            except Exception as e:                      # secondary objects never take the headline line down
                 extra[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
             torch.cuda.empty_cache()
 
