@@ -23,6 +23,7 @@ apply corrections.  Here, per rank:
 from __future__ import annotations
 
 import ctypes as C
+import logging
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -33,6 +34,8 @@ from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 from .config import CORRECTION_NORM_FLOOR
 from .tiling import TileSpec
+
+logger = logging.getLogger(__name__)
 
 CLASS_NAN_U8 = 255          # `classification` leaves the device as uint8; 255 = NaN (never written and not valid)
 
@@ -361,6 +364,8 @@ def process_band(pipe, plan: BandPlan, depth_host, uncertainty_host=None, nodata
                     del graph, out_t
                 stats["tiles"] += 1
                 stats["nodes"] += n
+            if (k + 1) % 10 == 0:                          # models/pipeline.py:184-185
+                logger.info("Processed %d/%d tiles", k + 1, len(flat))
             ev = torch.cuda.Event()
             ev.record(main)
             tile_done.append(ev)
