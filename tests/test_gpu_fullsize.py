@@ -238,3 +238,74 @@ def test_wide_variant_large_tile_tiled_kernel_equals_csr_kernel(prec):
     strict = (top2[:, 0] - top2[:, 1]) > (1e-4 if prec == "fp32" else 2e-2)
     assert bool((a["predicted_class"][strict] == b["predicted_class"][strict]).all())
     assert g.num_nodes > 700000
+
+
+def test_ragged_vr_chunk_at_bench_size_sampled_vs_oracle():
+    """BASELINE configs[3] at the size bench.py runs per chunk (12 000 refinement grids, sides 3..50, 10 % nodata, ~8 M
+    cells, ONE ragged graph through `build_graph_packed` -> band-patch aggregation): the oracle cannot finish 8 M cells in
+    seconds, but eval-mode graphs are independent (scripts/inference_native.py:249-342), so 32 sampled grids -- first, last,
+    the smallest and the largest included -- are rebuilt and forwarded ALONE by the oracle and compared with their slice
+    of the batch: ids / edges / depth bit-exact, outputs in the fp32 tolerance.  Whole-batch properties: node count ==
+    valid-cell count, per-grid node offsets == prefix sum of per-grid valid counts, edge count == in-grid 8-neighbour pairs."""
+    import bathymetric_gnn_b200 as bg
+    rng = np.random.default_rng(2024)
+    G = 12_000
+    rows = rng.integers(3, 51, G).astype(np.int32); cols = rng.integers(3, 51, G).astype(np.int32)
+    rows[5], cols[5], rows[6], cols[6] = 3, 3, 50, 50
+    res = rng.choice([0.5, 1.0, 2.0, 4.0], G); res2 = np.stack([res, res], 1)
+    size = rows.astype(np.int64) * cols
+    off = np.zeros(G + 1, np.int64); np.cumsum(size, out=off[1:])
+    n = int(off[-1])
+    depth = (30.0 + 0.5 * rng.standard_normal(n)).astype(np.float32)
+    depth[rng.random(n) < 0.10] = 1.0e6
+    valid = depth != 1.0e6
+    node_off = np.zeros(G + 1, np.int64); np.cumsum(np.add.reduceat(valid.astype(np.int64), off[:-1]), out=node_off[1:])
+
+    cfg = mo.ModelCfg(in_channels=7)
+    sd = mo.init_state_dict(cfg, seed=0, randomize_bn=True, head_gain=1.0)
+    model = bg.BathymetricGNN(7, 64, 4, "GAT", 4, 3, True, 0.0, 3)
+    model.load_state_dict(sd, strict=True); model = model.cuda().eval()
+    g = bg.GraphBuilder("8-connected").build_graph_packed(torch.from_numpy(depth).cuda(), off, rows, cols, res2, nodata=1.0e6)
+    assert g.num_nodes == int(valid.sum()) == int(node_off[-1]) > 7_000_000
+    out = model.predict(g)
+    assert np.array_equal(g.x[:, 0].cpu().numpy(), depth[valid])
+    rowptr = g._dev.rowptr.cpu().numpy().astype(np.int64)
+    assert rowptr[-1] == g.num_edges
+    ei = g.edge_index
+
+    sample = sorted(set([0, 5, 6, G - 1] + rng.choice(G, 28, replace=False).tolist()))
+    total_edges_checked = 0
+    for k in sample:
+        r, c = int(rows[k]), int(cols[k])
+        d = depth[off[k]:off[k + 1]].reshape(r, c)
+        m = valid[off[k]:off[k + 1]].reshape(r, c)
+        n0, n1 = int(node_off[k]), int(node_off[k + 1])
+        if n1 == n0:
+            continue
+        ref = go.build_graph(np.ascontiguousarray(d), np.ascontiguousarray(m), None, (float(res[k]),) * 2)
+        assert ref["x"].shape[0] == n1 - n0
+        # graph slice: edges of grid k are the contiguous CSR range of its nodes
+        e0, e1 = int(rowptr[n0]), int(rowptr[n1])
+        sel = ((ei[1] >= n0) & (ei[1] < n1)).nonzero().flatten()
+        assert sel.numel() == ref["edge_index"].shape[1] == e1 - e0
+        assert np.array_equal(ei[:, sel].cpu().numpy() - n0, ref["edge_index"])
+        ea = g.edge_attr[sel].cpu().numpy()
+        assert np.array_equal(ea[:, :2], ref["edge_attr"][:, :2])
+        assert np.all(np.abs(ea[:, 2].astype(np.float64) - ref["edge_attr"][:, 2]) <= np.spacing(np.abs(ref["edge_attr"][:, 2]).astype(np.float32)))
+        x = g.x[n0:n1].cpu().numpy()
+        assert np.array_equal(x[:, 0], ref["x"][:, 0])
+        np.testing.assert_allclose(x, ref["x"], rtol=0, atol=2e-5)
+        assert np.array_equal(g.valid_rows[n0:n1].cpu().numpy(), ref["valid_rows"])
+        assert np.array_equal(g.valid_cols[n0:n1].cpu().numpy(), ref["valid_cols"])
+        exp = mo.forward(sd, cfg, ref["x"], ref["edge_index"], ref["edge_attr"], torch.float32)
+        for key in ("class_logits", "confidence", "correction"):
+            np.testing.assert_allclose(out[key][n0:n1].cpu().numpy(), exp[key].numpy(), rtol=RTOL, atol=ATOL, err_msg=f"{key} grid {k} {r}x{c}")
+        total_edges_checked += e1 - e0
+    assert total_edges_checked > 100_000
+    # whole-batch edge count == in-grid 8-neighbour pairs, counted per grid shape class on the host for 400 more grids
+    for k in rng.choice(G, 400, replace=False).tolist():
+        r, c = int(rows[k]), int(cols[k])
+        m = valid[off[k]:off[k + 1]].reshape(r, c)
+        p = np.zeros((r + 2, c + 2), np.int64); p[1:-1, 1:-1] = m
+        nb = sum(p[1 + dr:1 + dr + r, 1 + dc:1 + dc + c] for dr in (-1, 0, 1) for dc in (-1, 0, 1) if (dr, dc) != (0, 0))
+        assert int((nb * m).sum()) == int(rowptr[node_off[k + 1]] - rowptr[node_off[k]]), k
