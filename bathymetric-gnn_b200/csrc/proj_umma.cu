@@ -60,9 +60,11 @@ extern "C" int bgnn_debug_umma_timing(unsigned long long* out8, int reset) {
     if (reset) { unsigned long long z[12] = {}; cudaMemcpyToSymbol(g_umma_t, z, sizeof(z)); }
     return 0;
 }
+#define UT_TICKP(slot) do { long long ut_now = clock64(); atomicAdd(&g_umma_t[slot], (unsigned long long)(ut_now - ut_prev)); ut_prev = ut_now; } while (0)
 #else
 #define UT_DECL()
 #define UT_TICK(slot)
+#define UT_TICKP(slot)
 #endif
 
 namespace {
@@ -806,6 +808,373 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     if (mc) cluster_sync_all();          // no CTA leaves while its peer may still arrive on its barriers
 }
 
+// =====================================================================================================================
+// cta_group::2 projection (PM_SPLIT operands, EM_PROJ epilogue, N = 256, K <= 256): the two CTAs of a cluster own ONE
+// 256 x 256 output tile.  CTA r stages its own 128 rows of A (fp16 plane chunks of 8 KB) and keeps its N half of the split
+// weights resident (128 KB); the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), for which each
+// SM reads only its own A rows and its own B half from shared memory: half the operand wavefronts per output of the
+// N = 2 x 128 multicast pair, whose tensor-core operand reads (46 % of the L1 data pipe) plus the epilogue's thread-per-row
+// stores (59 %) saturated that pipe (profiles/r2c_ncu_full_summary.csv).
+//   ONE accumulator per tile (256 TMEM columns, double-buffered: the epilogue of tile t overlaps the MMAs of tile t + 1).  The
+//   K extent is walked twice: pass 1 accumulates the two correction products a_lo*w_hi + a_hi*w_lo (both carry the 2^11 factor
+//   of the lo planes), pass 2 the main product a_hi*w_hi, whose FIRST instruction scales the accumulator by 2^-11
+//   (scale-input-d = 11: D = A*B + D * 2^-11) -- the same fp32 sum as main + corr * 2^-11 without a second accumulator.  The
+//   hi plane is therefore fetched twice (the second time from L2); the shared-memory fill per output still drops by 25 %.
+//   A ring: 5 units of [128 rows x 64] fp16 (128-byte rows, SWIZZLE_128B; the resident W keeps its 32-wide SWIZZLE_64B chunks --
+//   the two operand descriptors carry their own layout), filled by two loader threads that take alternate units.
+//   epilogue: tcgen05.ld of the next chunk is in flight while a chunk is finished; thread-per-row 256-bit stores (the L1 data
+//   pipe has room for them now; staging tiles for TMA stores would cost 32 KB = 2 of the 5 ring units: 2.24 vs 1.65 ms).
+//   measured (2048^2 tile, M = 4.1 M, K = N = 256): 1.65 ms vs 1.82 ms for the N = 2 x 128 multicast pair on the same box.
+//   barriers (same offsets in both CTAs; "leader" = cluster rank 0):
+//     FULL[u]    leader's, 2 arrivals (each CTA's loader: arrive.expect_tx 8 KB, remote for the peer); the TMA copies of both
+//                CTAs complete on it (cp.async.bulk.tensor ... cta_group::2)
+//     EMPTY[u]   own, 1 arrival: the leader's tcgen05.commit multicast to both CTAs when the MMAs reading the unit have retired
+//     TFULL[a]   own, 1 arrival: commit multicast after the last MMA of a tile
+//     TEMPTY[a]  leader's, 2 x 256 arrivals: every epilogue thread of both CTAs after its last tcgen05.ld of the tile
+//     WFULL      own (resident W landed); WPEER leader's: the peer's W loader arrives once its own WFULL completed
+namespace pairk {
+constexpr int THREADS = (EPI_WARPS + 4) * 32;      // 384: 8 epilogue warps | MMA issuer | 2 A loaders (alternate units) | W loader
+constexpr int NU = 5;                              // A ring: units of ONE plane chunk [128 rows x 64] fp16 = 16 KB
+constexpr int PN = 256, PHALF = 128;
+constexpr int KCA = 64;                            // K elements per A unit: 128-byte rows (SWIZZLE_128B), half the TMA row requests
+                                                   // of 64-byte rows
+constexpr int UNIT_B = TILE_M * KCA * 2;           // 16 KB
+constexpr int BT_B = PHALF * KC * 2;               // 8 KB: one split of this CTA's N half of a 32-wide W chunk
+constexpr int WSLOT_B = NSPLIT * BT_B;
+constexpr int MAXKC = 8;
+enum { B_FULL = 0, B_EMPTY = NU, B_TFULL = 2 * NU, B_TEMPTY = 2 * NU + 2, B_WFULL = 2 * NU + 4, B_WPEER, B_NUM };
+constexpr size_t BYTES = (size_t)NU * UNIT_B + (size_t)MAXKC * WSLOT_B + 3 * PN * sizeof(float) + B_NUM * 8 + 16;
+static_assert(BYTES <= 232448, "shared memory budget exceeded");
+}  // namespace pairk
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// (relaxed: a release at cluster scope costs a full memory fence per call -- measured 1 300 cycles per fetch in the loader
+//  thread -- and nothing is handed over through generic memory here: the data arrives with the TMA's own complete_tx)
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // arrivals may come from the peer CTA
+    uint32_t ok;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (128-byte rows, 1024 B between 8-row groups; layout type 2)
+__device__ __forceinline__ uint64_t make_desc128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A*B + D * 2^-11: folds the correction accumulator (which carries the 2^11 factor of the lo planes) into the main sum
+__device__ __forceinline__ void umma_f16_cg2_fold(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr));
+}
+
+__global__ void __launch_bounds__(pairk::THREADS, 1)
+proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA2) {
+    using namespace pairk;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* units = smem_raw;                                               // [NU] plane chunks of this CTA's 128 rows
+    unsigned char* wres = units + (size_t)NU * UNIT_B;                             // [nkc][hi half tile | lo half tile]
+    float* s_par = reinterpret_cast<float*>(wres + (size_t)MAXKC * WSLOT_B);       // att_src | att_dst | bias   [3][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 3 * PN);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + B_NUM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    const int64_t M = P.M;
+    const int nkc = P.K / KC, nkca = P.K / KCA;
+    const int64_t n_tiles = (M + 2 * TILE_M - 1) / (2 * TILE_M);
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    float out_scale = P.w_inv_scale;                 // (the operand scale sA was applied by the kernel that wrote the planes)
+    {
+        float bound = P.amax_add;
+        if (P.amax_src) bound = fmaf(P.amax_mul, __ldg(P.amax_src), P.amax_add);
+        const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);
+        const int es = 253 - e;
+        if (e > 0 && e < 255 && es >= 1 && es <= 253) out_scale *= __uint_as_float((uint32_t)(254 - es) << 23);
+    }
+    if (tid == 0) {
+        for (int u = 0; u < NU; ++u) { mbar_init(&bars[B_FULL + u], 1); mbar_init(&bars[B_EMPTY + u], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars[B_TFULL + a], 1); mbar_init(&bars[B_TEMPTY + a], 2 * EPI_WARPS * 32); }
+        mbar_init(&bars[B_WFULL], 1);
+        mbar_init(&bars[B_WPEER], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < PN; i += THREADS) {
+        s_par[i] = P.alpha ? __ldg(P.att_src + i) : 0.f;
+        s_par[PN + i] = P.alpha ? __ldg(P.att_dst + i) : 0.f;
+        s_par[2 * PN + i] = P.bias ? __ldg(P.bias + i) : 0.f;
+    }
+    if (warp == EPI_WARPS) {                       // the same warp of both CTAs allocates all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    cluster_sync_all();                            // the peer's barriers are initialised before anything arrives on them
+
+    if (warp == EPI_WARPS + 1 || warp == EPI_WARPS + 3) {
+        // ===================== A LOADERS (two threads per CTA, alternate units): own 128 rows; pass 1: hi, lo of every chunk;
+        // pass 2: hi again.  The LEADER's thread arms the unit's barrier for the bytes of both CTAs (the peer's copy may complete
+        // first: the transaction count then goes negative until the leader's arrive.expect_tx, the phase cannot complete before it)
+        if (lane == 0) {
+            const uint32_t me = warp == EPI_WARPS + 1 ? 0u : 1u;
+            const uint32_t full0 = mapa_u32(smem_u32(&bars[B_FULL]), 0);
+            uint32_t u = 0;
+            UT_DECL();
+            auto fetch = [&](const CUtensorMap* tm, int kc, int row0) {
+                if ((u & 1u) == me) {
+                    const int sl = u % NU;
+                    if (rank == 0 && me == 0) UT_TICKP(6);
+                    if (u >= (uint32_t)NU) mbar_wait(&bars[B_EMPTY + sl], ((u / NU) - 1) & 1);
+                    if (rank == 0 && me == 0) UT_TICKP(5);
+                    if (rank == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bars[B_FULL + sl])), "r"(2u * UNIT_B) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(smem_u32(units + (size_t)sl * UNIT_B)), "l"(tm), "r"(kc * KCA), "r"(row0), "r"(full0 + 8u * sl) : "memory");
+                }
+                ++u;
+            };
+            for (int64_t tile = pair; tile < n_tiles; tile += npairs) {
+                const int row0 = (int)(tile * 2 * TILE_M + rank * TILE_M);
+                for (int kc = 0; kc < nkca; ++kc) { fetch(&tmapA, kc, row0); fetch(&tmapA2, kc, row0); }
+                for (int kc = 0; kc < nkca; ++kc) fetch(&tmapA, kc, row0);
+            }
+        }
+    } else if (warp == EPI_WARPS + 2) {
+        // ===================== W LOADER (one thread per CTA): this CTA's N half of every chunk, once =====================
+        if (lane == 0) {
+            const uint32_t wbar = smem_u32(&bars[B_WFULL]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wbar), "r"((uint32_t)(nkc * WSLOT_B)) : "memory");
+            for (int kc = 0; kc < nkc; ++kc)
+#pragma unroll
+                for (int sp = 0; sp < NSPLIT; ++sp)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 ::"r"(smem_u32(wres + (size_t)kc * WSLOT_B + (size_t)sp * BT_B)),
+                                   "l"(reinterpret_cast<const unsigned char*>(P.Wsplit) + ((size_t)(kc * NSPLIT + sp) * 2 + rank) * BT_B),
+                                   "r"((uint32_t)BT_B), "r"(wbar)
+                                 : "memory");
+            if (rank != 0) {
+                mbar_wait(&bars[B_WFULL], 0);
+                mbar_arrive_remote(mapa_u32(smem_u32(&bars[B_WPEER]), 0));
+            }
+        }
+    } else if (warp == EPI_WARPS) {
+        // ===================== MMA ISSUER (one thread of the leader CTA) =====================
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor: D = F32, A = B = F16, both K-major, N = 256, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(PN >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
+            mbar_wait(&bars[B_WFULL], 0);
+            mbar_wait_cluster(&bars[B_WPEER], 0);
+            uint32_t u = 0, t = 0;
+            UT_DECL();
+#ifdef BGNN_AGG_TIMING
+            const long long ut_c0 = clock64();
+            unsigned long long ut_g0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ut_g0));
+#endif
+            for (int64_t tile = pair; tile < n_tiles; tile += npairs, ++t) {
+                const uint32_t as = t & 1u;
+                if (t >= 2) mbar_wait_cluster(&bars[B_TEMPTY + as], ((t >> 1) - 1) & 1);          // both epilogues drained this accumulator
+                UT_TICKP(0);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t d = tmem_base + as * (uint32_t)PN;
+                // pass 1: corr = a_lo * w_hi + a_hi * w_lo   (an A unit spans two 32-wide W chunks: k16 step ks <-> chunk 2 kca + ks / 2)
+                for (int kca = 0; kca < nkca; ++kca, u += 2) {
+                    const int s_hi = u % NU, s_lo = (u + 1) % NU;
+                    mbar_wait_cluster(&bars[B_FULL + s_hi], (u / NU) & 1);
+                    mbar_wait_cluster(&bars[B_FULL + s_lo], ((u + 1) / NU) & 1);
+                    UT_TICKP(1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a_hi = smem_u32(units + (size_t)s_hi * UNIT_B), a_lo = smem_u32(units + (size_t)s_lo * UNIT_B);
+                    const uint32_t b0 = smem_u32(wres + (size_t)(2 * kca) * WSLOT_B);
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks) {
+                        const uint32_t b_hi = b0 + (uint32_t)((ks >> 1) * WSLOT_B + (ks & 1) * 32);
+                        umma_f16_cg2(d, make_desc128(a_lo + ks * 32), make_desc(b_hi), idesc, (kca == 0 && ks == 0) ? 0u : 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks) {
+                        const uint32_t b_lo = b0 + (uint32_t)((ks >> 1) * WSLOT_B + BT_B + (ks & 1) * 32);
+                        umma_f16_cg2(d, make_desc128(a_hi + ks * 32), make_desc(b_lo), idesc, 1u);
+                    }
+                    umma_commit_cg2(&bars[B_EMPTY + s_hi], 3);       // the units are free in BOTH CTAs when these MMAs retire
+                    umma_commit_cg2(&bars[B_EMPTY + s_lo], 3);
+                    UT_TICKP(2);
+                }
+                // pass 2: main = a_hi * w_hi on top of corr * 2^-11
+                for (int kca = 0; kca < nkca; ++kca, ++u) {
+                    const int s_hi = u % NU;
+                    mbar_wait_cluster(&bars[B_FULL + s_hi], (u / NU) & 1);
+                    UT_TICKP(7);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a_hi = smem_u32(units + (size_t)s_hi * UNIT_B);
+                    const uint32_t b0 = smem_u32(wres + (size_t)(2 * kca) * WSLOT_B);
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks) {
+                        const uint32_t b_hi = b0 + (uint32_t)((ks >> 1) * WSLOT_B + (ks & 1) * 32);
+                        if (kca == 0 && ks == 0) umma_f16_cg2_fold(d, make_desc128(a_hi), make_desc(b_hi), idesc);
+                        else umma_f16_cg2(d, make_desc128(a_hi + ks * 32), make_desc(b_hi), idesc, 1u);
+                    }
+                    umma_commit_cg2(&bars[B_EMPTY + s_hi], 3);
+                    UT_TICKP(2);
+                }
+                umma_commit_cg2(&bars[B_TFULL + as], 3);             // accumulator complete (both CTAs' epilogues)
+            }
+#ifdef BGNN_AGG_TIMING
+            {
+                unsigned long long ut_g1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ut_g1));
+                atomicAdd(&g_umma_t[8], (unsigned long long)(clock64() - ut_c0));
+                atomicAdd(&g_umma_t[9], ut_g1 - ut_g0);
+            }
+#endif
+        }
+    } else {
+        // ===================== EPILOGUE (both CTAs): warp w <-> TMEM lanes 32*(w%4).., columns [128*(w/4), +128) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int cbeg = half * PHALF;
+        float cmax = 0.f;
+        uint32_t t = 0;
+        for (int64_t tile = pair; tile < n_tiles; tile += npairs, ++t) {
+            const uint32_t as = t & 1u;
+#ifdef BGNN_AGG_TIMING
+            long long ut_prev = clock64();
+#endif
+            mbar_wait(&bars[B_TFULL + as], (t >> 1) & 1);
+#ifdef BGNN_AGG_TIMING
+            if (warp == 0 && lane == 0 && rank == 0) UT_TICKP(3);
+#endif
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int64_t row = tile * 2 * TILE_M + rank * TILE_M + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)PN + (uint32_t)cbeg;
+            float as_acc = 0.f, ad_acc = 0.f;
+            uint32_t v[32];
+            tmem_ld32_issue(taddr, v);
+#pragma unroll 1
+            for (int cc = 0; cc < PHALF; cc += 32) {
+                const int c0 = cbeg + cc;
+                float x[32];
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                {
+                    const uint64_t sc2 = pk2(out_scale, out_scale);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) unpk2(fmul2(pk2u(v[j], v[j + 1]), sc2), x[j], x[j + 1]);
+                }
+                if (cc + 32 < PHALF) tmem_ld32_issue(taddr + (uint32_t)(cc + 32), v);          // next chunk in flight
+                else {
+                    // last chunk of this thread: its TMEM reads are complete -> the accumulator may be overwritten
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&bars[B_TEMPTY + as]), 0));
+                }
+                if (P.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_par + 2 * PN + c0 + j);
+                        unpk2(fadd2(pk2(x[j], x[j + 1]), b.x), x[j], x[j + 1]);
+                        unpk2(fadd2(pk2(x[j + 2], x[j + 3]), b.y), x[j + 2], x[j + 3]);
+                    }
+                }
+                if (P.cmax_out) {
+                    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        m0 = fmaxf(m0, fabsf(x[j])); m1 = fmaxf(m1, fabsf(x[j + 1]));
+                        m2 = fmaxf(m2, fabsf(x[j + 2])); m3 = fmaxf(m3, fabsf(x[j + 3]));
+                    }
+                    cmax = fmaxf(cmax, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                }
+                if (P.alpha) {
+                    float s0, s1, s2, s3, d0, d1, d2, d3;
+                    uint64_t s01 = 0ull, s23 = 0ull, d01 = 0ull, d23 = 0ull;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(s_par + c0 + j);
+                        const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(s_par + PN + c0 + j);
+                        const uint64_t x01 = pk2(x[j], x[j + 1]), x23 = pk2(x[j + 2], x[j + 3]);
+                        s01 = ffma2(x01, s4.x, s01); s23 = ffma2(x23, s4.y, s23);
+                        d01 = ffma2(x01, d4.x, d01); d23 = ffma2(x23, d4.y, d23);
+                    }
+                    unpk2(s01, s0, s1); unpk2(s23, s2, s3); unpk2(d01, d0, d1); unpk2(d23, d2, d3);
+                    as_acc += (s0 + s1) + (s2 + s3);
+                    ad_acc += (d0 + d1) + (d2 + d3);
+                    if (((c0 + 32) % P.CH) == 0) {          // a head's channels are complete
+                        if (row < M) {
+                            const int h = (c0 + 32) / P.CH - 1;
+                            P.alpha[row * (2 * P.Htot) + h] = as_acc;
+                            P.alpha[row * (2 * P.Htot) + P.Htot + h] = ad_acc;
+                        }
+                        as_acc = 0.f; ad_acc = 0.f;
+                    }
+                }
+                if (row < M) {           // thread-per-row 256-bit stores
+                    float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH) : P.Cout + row * PN + c0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
+                }
+            }
+#ifdef BGNN_AGG_TIMING
+            if (warp == 0 && lane == 0 && rank == 0) UT_TICKP(4);
+#endif
+        }
+        if (P.cmax_out) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(P.cmax_out), __float_as_uint(cmax));
+        }
+    }
+    // teardown: both CTAs are done with TMEM and with each other's barriers before either frees / leaves
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == EPI_WARPS) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -851,6 +1220,21 @@ int make_tmap_A16(const uint16_t* A, int64_t M, int K, int64_t ld, int box_rows,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for split A=%p M=%lld K=%d", (int)r, (const void*)A, (long long)M, K); return BGNN_E_CUDA; }
+    return BGNN_OK;
+}
+
+// the same plane with a [box_rows x 64] SWIZZLE_128B box (128 B inner extent; K % 64 == 0): proj_pair_kernel's A units
+int make_tmap_A16_wide(const uint16_t* A, int64_t M, int K, int64_t ld, int box_rows, CUtensorMap* out) {
+    EncodeTiledFn fn = nullptr;
+    { int rc = get_encode_fn(&fn); if (rc) return rc; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(uint16_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)pairk::KCA, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(A), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bgnn_set_error("cuTensorMapEncodeTiled failed (%d) for split A=%p M=%lld K=%d (128 B box)", (int)r, (const void*)A, (long long)M, K); return BGNN_E_CUDA; }
     return BGNN_OK;
 }
 
@@ -929,6 +1313,31 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
                        cudaGetErrorString(e));
         return BGNN_E_CUDA;
     }
+    return BGNN_OK;
+}
+
+// cta_group::2 pair kernel (PM_SPLIT + EM_PROJ, N = 256, K <= 256)
+int launch_pair(const UmmaArgs& a, int sms, cudaStream_t s) {
+    BGNN_CUDA(cudaFuncSetAttribute(proj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairk::BYTES));
+    BGNN_CHECK_ARG(a.A_hi && a.A_lo && ((reinterpret_cast<uintptr_t>(a.A_hi) | reinterpret_cast<uintptr_t>(a.A_lo)) & 15) == 0,
+                   "split A planes must be 16-byte aligned");
+    alignas(64) CUtensorMap tmap, tmap2;
+    memset(&tmap, 0, sizeof(tmap)); memset(&tmap2, 0, sizeof(tmap2));
+    const int64_t ld = a.a_ld > 0 ? a.a_ld : a.K;
+    int rc = make_tmap_A16_wide(a.A_hi, a.M, a.K, ld, TILE_M, &tmap);
+    if (!rc) rc = make_tmap_A16_wide(a.A_lo, a.M, a.K, ld, TILE_M, &tmap2);
+    if (rc) return rc;
+    BGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.Cout) & 31) == 0, "C must be 32-byte aligned");
+    const int64_t n_tiles = (a.M + 2 * TILE_M - 1) / (2 * TILE_M);
+    const int64_t pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (pairs > 0 ? pairs : 1))); cfg.blockDim = dim3(pairk::THREADS); cfg.dynamicSmemBytes = pairk::BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t el = cudaLaunchKernelEx(&cfg, proj_pair_kernel, a, tmap, tmap2);
+    if (el != cudaSuccess) { bgnn_set_error("cluster launch of proj_pair_kernel failed: %s", cudaGetErrorString(el)); return BGNN_E_CUDA; }
     return BGNN_OK;
 }
 
@@ -1040,6 +1449,7 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
 }
 
 static const bool g_mlp0_whole = getenv("BGNN_MLP0_WHOLE") != nullptr;       // dev switch: one 128 x 256 tile per CTA (1.30 vs 1.25 ms paired)
+static const bool g_pair_cg2 = getenv("BGNN_NO_CG2") == nullptr;             // on by default; dev switch back to the N = 2 x 128 multicast pair
 static const bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
 static const bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
                                                                          // 2-deep operand ring cannot hide the split latency)
@@ -1061,6 +1471,7 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
         switch (N) {
             case 64: return launch_t<64, PM_SPLIT, EM_PROJ>(a, sms, s);
             case 256:
+                if (g_pair_cg2 && a.K <= 8 * KC && a.K % pairk::KCA == 0 && (!a.alpha || 128 % a.CH == 0)) return launch_pair(a, sms, s);
                 if (!g_split_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_SPLIT, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_SPLIT, EM_PROJ>(a, sms, s);
         }

@@ -72,19 +72,35 @@ def test_umma_toggle_equivalence_in_forward():
 @pytest.mark.parametrize("M,K,N,heads", [(256, 256, 256, 4), (1000, 256, 256, 4), (70001, 256, 256, 4), (4099, 256, 64, 1),
                                          (513, 64, 64, 1), (50000, 64, 256, 4), (333, 128, 256, 8)])
 def test_umma_presplit_is_bit_identical(M, K, N, heads):
-    """A handed over as fp16 hi / lo planes (what the tiled aggregation writes) vs the in-kernel split of fp32 A: the same
-    operands reach the tensor cores in the same order, so C and alpha must match bit for bit."""
+    """A handed over as fp16 hi / lo planes (what the tiled aggregation writes) vs the in-kernel split of fp32 A.  N = 64: the
+    same operands reach the tensor cores in the same order, so C and alpha match bit for bit.  N = 256 (K % 64 == 0) runs the
+    cta_group::2 pair kernel, which folds the correction products into the ONE accumulator (D = A*B + D * 2^-11) instead of
+    adding a second accumulator in the epilogue: the same three fp16 products, another fp32 summation order -- agreement to
+    the accuracy both hold against fp64 (3.3e-7 * sum|a||w|, test_umma_matches_fp32_reference), rows past M untouched."""
     g = torch.Generator(device="cpu").manual_seed(M + K + N)
     A = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, 1, generator=g))).cuda()
     W = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
     att_s, att_d = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda()
     C0, a0 = run_umma(A, W, att_s, att_d, heads)
     C1, a1 = run_umma(A, W, att_s, att_d, heads, presplit=True)
-    assert torch.equal(C0, C1) and torch.equal(a0, a1)
+    if N == 256 and K % 64 == 0:
+        bound = A.abs().double() @ W.abs().double().T                       # sum_k |a||w| per output
+        assert bool(((C0.double() - C1.double()).abs() <= 4e-7 * bound + 1e-30).all())
+        ref = A.double() @ W.double().T
+        assert bool(((C1.double() - ref).abs() <= 4e-7 * bound + 1e-30).all())
+        CH = N // heads
+        for att, off in ((att_s, 0), (att_d, heads)):
+            ab = (bound.view(M, heads, CH) * att.abs().double().view(1, heads, CH)).sum(2)
+            d = (a0[:, off:off + heads].double() - a1[:, off:off + heads].double()).abs()
+            assert bool((d <= 1e-6 * ab + 1e-30).all())
+    else:
+        assert torch.equal(C0, C1) and torch.equal(a0, a1)
 
 
-def test_presplit_handover_is_bit_identical_in_forward():
-    """Whole forward with the fp16 hi / lo hand-over between aggregation and projection vs fp32 intermediates."""
+def test_presplit_handover_in_forward():
+    """Whole forward with the fp16 hi / lo hand-over between aggregation and projection vs fp32 intermediates: the last
+    projection (N = 64) consumes bit-identical operands either way; the N = 256 projections run the cta_group::2 pair kernel
+    on the hand-over path (other fp32 summation order, see above) -> agreement far inside the fp32 tolerance of the path."""
     import bathymetric_gnn_b200 as bg
     from bathymetric_gnn_b200._lib import lib
     from oracle import model_oracle as mo
@@ -99,8 +115,10 @@ def test_presplit_handover_is_bit_identical_in_forward():
     g = bg.GraphBuilder().build_graph(d, mask, None, (0.5, 0.5))
     a = m.set_option("presplit", 1)._run(g, 0.85, 0.6, True, return_hidden=True)
     b = m.set_option("presplit", 0)._run(g, 0.85, 0.6, True, return_hidden=True)
-    for k in ("hidden", "class_logits", "confidence", "correction", "predicted_class", "action"):
-        assert torch.equal(a[k], b[k]), k
+    for k in ("hidden", "class_logits", "confidence", "correction"):
+        np.testing.assert_allclose(a[k].cpu().numpy(), b[k].cpu().numpy(), rtol=2e-6, atol=2e-6, err_msg=k)
+    for k in ("predicted_class", "action"):
+        assert (a[k] != b[k]).float().mean().item() < 1e-3, k
 
 
 def test_adversarial_checkpoint_operand_scaling():
