@@ -820,11 +820,13 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 //   of the lo planes), pass 2 the main product a_hi*w_hi, whose FIRST instruction scales the accumulator by 2^-11
 //   (scale-input-d = 11: D = A*B + D * 2^-11) -- the same fp32 sum as main + corr * 2^-11 without a second accumulator.  The
 //   hi plane is therefore fetched twice (the second time from L2); the shared-memory fill per output still drops by 25 %.
-//   A ring: 5 units of [128 rows x 64] fp16 (128-byte rows, SWIZZLE_128B; the resident W keeps its 32-wide SWIZZLE_64B chunks --
+//   A ring: 6 units of [128 rows x 64] fp16 (128-byte rows, SWIZZLE_128B; the resident W keeps its 32-wide SWIZZLE_64B chunks --
 //   the two operand descriptors carry their own layout), filled by two loader threads that take alternate units.
 //   epilogue: tcgen05.ld of the next chunk is in flight while a chunk is finished; thread-per-row 256-bit stores (the L1 data
-//   pipe has room for them now; staging tiles for TMA stores would cost 32 KB = 2 of the 5 ring units: 2.24 vs 1.65 ms).
-//   measured (2048^2 tile, M = 4.1 M, K = N = 256): 1.65 ms vs 1.82 ms for the N = 2 x 128 multicast pair on the same box.
+//   pipe has room for them now; staging tiles for TMA stores would cost 32 KB = 2 ring units: 2.24 vs 1.65 ms).  The optional
+//   bias is read from global memory (warp-uniform, L1-resident): its 1 KB of shared memory is what lets the sixth unit fit.
+//   measured (2048^2 tile, M = 4.1 M, K = N = 256): 1.53 ms vs 1.78 ms for the N = 2 x 128 multicast pair on the same box (5 ring
+//   units: 1.65 ms; L2 prefetches of the pair's next tile: 1.56 ms -- the ring depth matters, the HBM -> L2 leg does not).
 //   barriers (same offsets in both CTAs; "leader" = cluster rank 0):
 //     FULL[u]    leader's, 2 arrivals (each CTA's loader: arrive.expect_tx 8 KB, remote for the peer); the TMA copies of both
 //                CTAs complete on it (cp.async.bulk.tensor ... cta_group::2)
@@ -834,7 +836,7 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 //     WFULL      own (resident W landed); WPEER leader's: the peer's W loader arrives once its own WFULL completed
 namespace pairk {
 constexpr int THREADS = (EPI_WARPS + 4) * 32;      // 384: 8 epilogue warps | MMA issuer | 2 A loaders (alternate units) | W loader
-constexpr int NU = 5;                              // A ring: units of ONE plane chunk [128 rows x 64] fp16 = 16 KB
+constexpr int NU = 6;                              // A ring: units of ONE plane chunk [128 rows x 64] fp16 = 16 KB
 constexpr int PN = 256, PHALF = 128;
 constexpr int KCA = 64;                            // K elements per A unit: 128-byte rows (SWIZZLE_128B), half the TMA row requests
                                                    // of 64-byte rows
@@ -843,7 +845,7 @@ constexpr int BT_B = PHALF * KC * 2;               // 8 KB: one split of this CT
 constexpr int WSLOT_B = NSPLIT * BT_B;
 constexpr int MAXKC = 8;
 enum { B_FULL = 0, B_EMPTY = NU, B_TFULL = 2 * NU, B_TEMPTY = 2 * NU + 2, B_WFULL = 2 * NU + 4, B_WPEER, B_NUM };
-constexpr size_t BYTES = (size_t)NU * UNIT_B + (size_t)MAXKC * WSLOT_B + 3 * PN * sizeof(float) + B_NUM * 8 + 16;
+constexpr size_t BYTES = (size_t)NU * UNIT_B + (size_t)MAXKC * WSLOT_B + 2 * PN * sizeof(float) + B_NUM * 8 + 16;
 static_assert(BYTES <= 232448, "shared memory budget exceeded");
 }  // namespace pairk
 
@@ -913,8 +915,8 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* units = smem_raw;                                               // [NU] plane chunks of this CTA's 128 rows
     unsigned char* wres = units + (size_t)NU * UNIT_B;                             // [nkc][hi half tile | lo half tile]
-    float* s_par = reinterpret_cast<float*>(wres + (size_t)MAXKC * WSLOT_B);       // att_src | att_dst | bias   [3][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 3 * PN);
+    float* s_par = reinterpret_cast<float*>(wres + (size_t)MAXKC * WSLOT_B);       // att_src | att_dst   [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 2 * PN);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + B_NUM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -943,7 +945,6 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     for (int i = tid; i < PN; i += THREADS) {
         s_par[i] = P.alpha ? __ldg(P.att_src + i) : 0.f;
         s_par[PN + i] = P.alpha ? __ldg(P.att_dst + i) : 0.f;
-        s_par[2 * PN + i] = P.bias ? __ldg(P.bias + i) : 0.f;
     }
     if (warp == EPI_WARPS) {                       // the same warp of both CTAs allocates all 512 columns
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "n"(512) : "memory");
@@ -1112,9 +1113,8 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 if (P.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_par + 2 * PN + c0 + j);
-                        unpk2(fadd2(pk2(x[j], x[j + 1]), b.x), x[j], x[j + 1]);
-                        unpk2(fadd2(pk2(x[j + 2], x[j + 3]), b.y), x[j + 2], x[j + 3]);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
+                        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
                     }
                 }
                 if (P.cmax_out) {
