@@ -832,21 +832,41 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 //                CTAs complete on it (cp.async.bulk.tensor ... cta_group::2)
 //     EMPTY[u]   own, 1 arrival: the leader's tcgen05.commit multicast to both CTAs when the MMAs reading the unit have retired
 //     TFULL[a]   own, 1 arrival: commit multicast after the last MMA of a tile
-//     TEMPTY[a]  leader's, 2 x 256 arrivals: every epilogue thread of both CTAs after its last tcgen05.ld of the tile
+//     TEMPTY[a]  leader's, 2 x 8 arrivals: lane 0 of every epilogue warp of both CTAs after the warp's last tcgen05.ld of the tile
 //     WFULL      own (resident W landed); WPEER leader's: the peer's W loader arrives once its own WFULL completed
 namespace pairk {
-constexpr int THREADS = (EPI_WARPS + 4) * 32;      // 384: 8 epilogue warps | MMA issuer | 2 A loaders (alternate units) | W loader
-constexpr int NU = 6;                              // A ring: units of ONE plane chunk [128 rows x 64] fp16 = 16 KB
 constexpr int PN = 256, PHALF = 128;
 constexpr int KCA = 64;                            // K elements per A unit: 128-byte rows (SWIZZLE_128B), half the TMA row requests
                                                    // of 64-byte rows
-constexpr int UNIT_B = TILE_M * KCA * 2;           // 16 KB
+constexpr int UNIT_B = TILE_M * KCA * 2;           // 16 KB: ONE plane chunk [128 rows x 64] fp16
 constexpr int BT_B = PHALF * KC * 2;               // 8 KB: one split of this CTA's N half of a 32-wide W chunk
 constexpr int WSLOT_B = NSPLIT * BT_B;
-constexpr int MAXKC = 8;
-enum { B_FULL = 0, B_EMPTY = NU, B_TFULL = 2 * NU, B_TEMPTY = 2 * NU + 2, B_WFULL = 2 * NU + 4, B_WPEER, B_NUM };
-constexpr size_t BYTES = (size_t)NU * UNIT_B + (size_t)MAXKC * WSLOT_B + 2 * PN * sizeof(float) + B_NUM * 8 + 16;
-static_assert(BYTES <= 232448, "shared memory budget exceeded");
+// MODE = PM_SPLIT: operands arrive as fp16 planes (two TMA loader threads); K <= 256, the hi plane is fetched for both passes
+// MODE = PM_MLP0:  four producer warps compute this CTA's 128 rows of relu(x W0^T + b0) straight into a {hi, lo} unit pair
+//                  (K = 64: one unit per plane holds the whole K extent and serves both passes); three tile slots; the
+//                  spare shared memory goes to staging tiles for TMA tensor stores
+template <int MODE> struct Cfg {
+    static constexpr bool MLP = MODE == PM_MLP0;
+    static constexpr int FEED_WARPS = MLP ? 4 : 2;
+#ifndef BGNN_PAIR_EPW_MLP
+#define BGNN_PAIR_EPW_MLP 16
+#endif
+    // epilogue warps: warp w <-> TMEM lanes 32 (w % 4).., columns [(w / 4) * 1024 / EPW, +1024 / EPW).  MLP: the epilogue IS the kernel
+    // (K = 64: 12 MMAs per tile), a chain of dependent instructions per warp -> four warps per scheduler instead of two
+#ifndef BGNN_PAIR_EPW_SPLIT
+#define BGNN_PAIR_EPW_SPLIT 8
+#endif
+    static constexpr int EPW = MLP ? BGNN_PAIR_EPW_MLP : BGNN_PAIR_EPW_SPLIT;
+    static constexpr int NCOLW = 4 * PN / EPW;                              // columns per epilogue warp: 128 or 64
+    static constexpr int THREADS = (EPW + 2 + FEED_WARPS) * 32;            // epilogue | MMA issuer | W loader | feeders
+    static constexpr int NU = 6;                                            // A ring (MLP: 3 tile slots x {hi, lo})
+    static constexpr int MAXKC = MLP ? 2 : 8;                               // resident W chunks of 32
+    static constexpr int STG_B = MLP ? EPW * 4096 : 0;                      // [32 x 32] fp32 staging tile per epilogue warp
+    static constexpr int PROD_F = MLP ? KCA * MLP0_FP + KCA : 0;            // W0 [64][8] | b0 [64]
+    static constexpr size_t BYTES = (size_t)NU * UNIT_B + (size_t)MAXKC * WSLOT_B + STG_B + (2 * PN + PROD_F) * sizeof(float) + 32 * 8 + 16;
+    static_assert(BYTES <= 232448, "shared memory budget exceeded");
+};
+enum { B_FULL = 0, B_EMPTY = 6, B_TFULL = 12, B_TEMPTY = 14, B_WFULL = 16, B_WPEER, B_NUM };
 }  // namespace pairk
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -861,6 +881,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 //  thread -- and nothing is handed over through generic memory here: the data arrives with the TMA's own complete_tx)
 __device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// default semantics (release at CTA scope): orders this CTA's own shared-memory writes, which its own SM's tensor core reads
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
@@ -909,14 +933,25 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t* v) {
         : "r"(addr));
 }
 
-__global__ void __launch_bounds__(pairk::THREADS, 1)
-proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA2) {
+#ifndef BGNN_EPI_SKIP
+#define BGNN_EPI_SKIP 0          /* dev: bit 0 skip alpha, bit 1 skip stores, bit 2 skip bias + cmax (timing experiments) */
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(pairk::Cfg<MODE>::THREADS, 1)
+proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA2,
+                 const __grid_constant__ CUtensorMap tmapC) {
     using namespace pairk;
+    using G = Cfg<MODE>;
+    constexpr bool MLP = G::MLP;
+    constexpr int NU = G::NU, THREADS = G::THREADS;
+    constexpr int EPW = G::EPW, MMA_W = EPW, W_WARP = EPW + 1, FEED_WARP0 = EPW + 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* units = smem_raw;                                               // [NU] plane chunks of this CTA's 128 rows
     unsigned char* wres = units + (size_t)NU * UNIT_B;                             // [nkc][hi half tile | lo half tile]
-    float* s_par = reinterpret_cast<float*>(wres + (size_t)MAXKC * WSLOT_B);       // att_src | att_dst   [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 2 * PN);
+    unsigned char* stg = wres + (size_t)G::MAXKC * WSLOT_B;                        // MLP: [8 warps][32 x 32 fp32, SWIZZLE_128B]
+    float* s_par = reinterpret_cast<float*>(stg + G::STG_B);                       // att_src | att_dst   [2][256]
+    float* s_prod = s_par + 2 * PN;                                                // MLP: W0 [64][8] (F padded with zeros) | b0 [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_prod + G::PROD_F);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + B_NUM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -927,17 +962,22 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     const int64_t n_tiles = (M + 2 * TILE_M - 1) / (2 * TILE_M);
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-    float out_scale = P.w_inv_scale;                 // (the operand scale sA was applied by the kernel that wrote the planes)
+    // power-of-two operand scale from the upper bound of max|A| (PM_SPLIT: applied by the kernel that wrote the planes)
+    float sA = 1.f, out_scale = P.w_inv_scale;
     {
         float bound = P.amax_add;
         if (P.amax_src) bound = fmaf(P.amax_mul, __ldg(P.amax_src), P.amax_add);
         const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);
         const int es = 253 - e;
-        if (e > 0 && e < 255 && es >= 1 && es <= 253) out_scale *= __uint_as_float((uint32_t)(254 - es) << 23);
+        if (e > 0 && e < 255 && es >= 1 && es <= 253) {
+            sA = __uint_as_float((uint32_t)es << 23);
+            out_scale *= __uint_as_float((uint32_t)(254 - es) << 23);
+        }
     }
     if (tid == 0) {
-        for (int u = 0; u < NU; ++u) { mbar_init(&bars[B_FULL + u], 1); mbar_init(&bars[B_EMPTY + u], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars[B_TFULL + a], 1); mbar_init(&bars[B_TEMPTY + a], 2 * EPI_WARPS * 32); }
+        // MLP: FULL[slot] collects one arrival per CTA (an elected producer thread, after the producers' own barrier)
+        for (int u = 0; u < NU; ++u) { mbar_init(&bars[B_FULL + u], MLP ? 2 : 1); mbar_init(&bars[B_EMPTY + u], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars[B_TFULL + a], 1); mbar_init(&bars[B_TEMPTY + a], 2 * EPW); }
         mbar_init(&bars[B_WFULL], 1);
         mbar_init(&bars[B_WPEER], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -946,7 +986,14 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         s_par[i] = P.alpha ? __ldg(P.att_src + i) : 0.f;
         s_par[PN + i] = P.alpha ? __ldg(P.att_dst + i) : 0.f;
     }
-    if (warp == EPI_WARPS) {                       // the same warp of both CTAs allocates all 512 columns
+    if (MLP) {
+        for (int i = tid; i < KCA * MLP0_FP; i += THREADS) {
+            const int kk = i / MLP0_FP, f = i % MLP0_FP;
+            s_prod[i] = f < P.F ? __ldg(P.W0 + kk * P.F + f) : 0.f;
+        }
+        for (int i = tid; i < KCA; i += THREADS) s_prod[KCA * MLP0_FP + i] = __ldg(P.b0 + i);
+    }
+    if (warp == MMA_W) {                       // the same warp of both CTAs allocates all 512 columns
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
     }
@@ -956,12 +1003,65 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     const uint32_t tmem_base = *s_tmem;
     cluster_sync_all();                            // the peer's barriers are initialised before anything arrives on them
 
-    if (warp == EPI_WARPS + 1 || warp == EPI_WARPS + 3) {
+    if (warp >= FEED_WARP0) {
+        if constexpr (MLP) {
+        // ===================== PRODUCERS (128 threads per CTA, thread <-> own row): relu(b0 + x W0^T) * sA -> fp16 hi / lo, written
+        // as 16-byte chunks of the K-major SWIZZLE_128B units (chunk c of row r at (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4))
+        const int r = tid - FEED_WARP0 * 32;
+        const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t full0 = mapa_u32(smem_u32(&bars[B_FULL]), 0);
+        uint32_t t = 0;
+        for (int64_t tile = pair; tile < n_tiles; tile += npairs, ++t) {
+            const int slot = t % 3;
+            const int64_t gr = tile * 2 * TILE_M + rank * TILE_M + r;
+            float xr[MLP0_FP];
+#pragma unroll
+            for (int q = 0; q < MLP0_FP; ++q) xr[q] = (gr < M && q < P.F) ? __ldg(P.x + gr * P.F + q) : 0.f;
+#ifdef BGNN_AGG_TIMING
+            long long ut_prev = clock64();
+#endif
+            if (t >= 3) mbar_wait(&bars[B_EMPTY + slot], ((t / 3) - 1) & 1);
+#ifdef BGNN_AGG_TIMING
+            if (r == 0 && rank == 0) UT_TICKP(5);
+#endif
+            unsigned char* u_hi = units + (size_t)(2 * slot) * UNIT_B + rowoff;
+            unsigned char* u_lo = u_hi + UNIT_B;
+#pragma unroll 2
+            for (int c = 0; c < KCA / 8; ++c) {
+                float o[8];
+#pragma unroll
+                for (int uu = 0; uu < 8; ++uu) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_prod + (c * 8 + uu) * MLP0_FP);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_prod + (c * 8 + uu) * MLP0_FP + 4);
+                    float acc = xr[0] * w0.x;
+                    acc = fmaf(xr[1], w0.y, acc); acc = fmaf(xr[2], w0.z, acc); acc = fmaf(xr[3], w0.w, acc);
+                    acc = fmaf(xr[4], w1.x, acc); acc = fmaf(xr[5], w1.y, acc); acc = fmaf(xr[6], w1.z, acc);
+                    acc = fmaf(xr[7], w1.w, acc);
+                    o[uu] = fmaxf(acc + s_prod[KCA * MLP0_FP + c * 8 + uu], 0.f);
+                }
+                uint2 h0, l0, h1, l1;
+                split4h(make_float4(o[0], o[1], o[2], o[3]), sA, h0, l0);
+                split4h(make_float4(o[4], o[5], o[6], o[7]), sA, h1, l1);
+                const uint32_t phys = (uint32_t)((c ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(u_hi + phys) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4*>(u_lo + phys) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+#ifdef BGNN_AGG_TIMING
+            if (r == 0 && rank == 0) UT_TICKP(6);
+#endif
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");                    // all rows of this CTA's units are written
+            if (r == 0) mbar_arrive_remote_cta(full0 + 8u * slot);                // one arrival per tile and CTA
+#ifdef BGNN_AGG_TIMING
+            if (r == 0 && rank == 0) UT_TICKP(7);
+#endif
+        }
+        } else {
         // ===================== A LOADERS (two threads per CTA, alternate units): own 128 rows; pass 1: hi, lo of every chunk;
         // pass 2: hi again.  The LEADER's thread arms the unit's barrier for the bytes of both CTAs (the peer's copy may complete
         // first: the transaction count then goes negative until the leader's arrive.expect_tx, the phase cannot complete before it)
-        if (lane == 0) {
-            const uint32_t me = warp == EPI_WARPS + 1 ? 0u : 1u;
+        if (lane == 0 && warp < FEED_WARP0 + 2) {
+            const uint32_t me = (uint32_t)(warp - FEED_WARP0);
             const uint32_t full0 = mapa_u32(smem_u32(&bars[B_FULL]), 0);
             uint32_t u = 0;
             UT_DECL();
@@ -984,7 +1084,8 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 for (int kc = 0; kc < nkca; ++kc) fetch(&tmapA, kc, row0);
             }
         }
-    } else if (warp == EPI_WARPS + 2) {
+        }
+    } else if (warp == W_WARP) {
         // ===================== W LOADER (one thread per CTA): this CTA's N half of every chunk, once =====================
         if (lane == 0) {
             const uint32_t wbar = smem_u32(&bars[B_WFULL]);
@@ -1002,7 +1103,7 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 mbar_arrive_remote(mapa_u32(smem_u32(&bars[B_WPEER]), 0));
             }
         }
-    } else if (warp == EPI_WARPS) {
+    } else if (warp == MMA_W) {
         // ===================== MMA ISSUER (one thread of the leader CTA) =====================
         if (lane == 0 && rank == 0) {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = 256, M = 256 (128 rows per CTA)
@@ -1022,6 +1123,29 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 UT_TICKP(0);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t d = tmem_base + as * (uint32_t)PN;
+                if constexpr (MLP) {
+                    // K = 64: the tile's {hi, lo} unit pair holds the whole K extent and serves both passes
+                    const int slot = t % 3;
+                    mbar_wait_cluster(&bars[B_FULL + slot], (t / 3) & 1);
+                    UT_TICKP(1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a_hi = smem_u32(units + (size_t)(2 * slot) * UNIT_B), a_lo = a_hi + (uint32_t)UNIT_B;
+                    const uint32_t b0 = smem_u32(wres);
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks)
+                        umma_f16_cg2(d, make_desc128(a_lo + ks * 32), make_desc(b0 + (uint32_t)((ks >> 1) * WSLOT_B + (ks & 1) * 32)), idesc, ks == 0 ? 0u : 1u);
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks)
+                        umma_f16_cg2(d, make_desc128(a_hi + ks * 32), make_desc(b0 + (uint32_t)((ks >> 1) * WSLOT_B + BT_B + (ks & 1) * 32)), idesc, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < KCA / 16; ++ks) {
+                        const uint32_t b_hi = b0 + (uint32_t)((ks >> 1) * WSLOT_B + (ks & 1) * 32);
+                        if (ks == 0) umma_f16_cg2_fold(d, make_desc128(a_hi), make_desc(b_hi), idesc);
+                        else umma_f16_cg2(d, make_desc128(a_hi + ks * 32), make_desc(b_hi), idesc, 1u);
+                    }
+                    umma_commit_cg2(&bars[B_EMPTY + slot], 3);       // the slot is free in BOTH CTAs when these MMAs retire
+                    UT_TICKP(2);
+                } else {
                 // pass 1: corr = a_lo * w_hi + a_hi * w_lo   (an A unit spans two 32-wide W chunks: k16 step ks <-> chunk 2 kca + ks / 2)
                 for (int kca = 0; kca < nkca; ++kca, u += 2) {
                     const int s_hi = u % NU, s_lo = (u + 1) % NU;
@@ -1062,6 +1186,7 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     umma_commit_cg2(&bars[B_EMPTY + s_hi], 3);
                     UT_TICKP(2);
                 }
+                }
                 umma_commit_cg2(&bars[B_TFULL + as], 3);             // accumulator complete (both CTAs' epilogues)
             }
 #ifdef BGNN_AGG_TIMING
@@ -1075,8 +1200,8 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         }
     } else {
         // ===================== EPILOGUE (both CTAs): warp w <-> TMEM lanes 32*(w%4).., columns [128*(w/4), +128) =====================
-        const int quarter = warp & 3, half = warp >> 2;
-        const int cbeg = half * PHALF;
+        const int quarter = warp & 3;
+        const int cbeg = (warp >> 2) * G::NCOLW;
         float cmax = 0.f;
         uint32_t t = 0;
         for (int64_t tile = pair; tile < n_tiles; tile += npairs, ++t) {
@@ -1093,31 +1218,35 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)PN + (uint32_t)cbeg;
             float as_acc = 0.f, ad_acc = 0.f;
             uint32_t v[32];
-            tmem_ld32_issue(taddr, v);
+            constexpr bool PREFETCH = G::EPW == 8;        // two warps per scheduler: keep the next chunk's tcgen05.ld in flight
+            if (PREFETCH) tmem_ld32_issue(taddr, v);
 #pragma unroll 1
-            for (int cc = 0; cc < PHALF; cc += 32) {
+            for (int cc = 0; cc < G::NCOLW; cc += 32) {
                 const int c0 = cbeg + cc;
                 float x[32];
+                if (!PREFETCH) tmem_ld32_issue(taddr + (uint32_t)cc, v);    // (four warps per scheduler hide the load; no prefetch registers)
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                 {
                     const uint64_t sc2 = pk2(out_scale, out_scale);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) unpk2(fmul2(pk2u(v[j], v[j + 1]), sc2), x[j], x[j + 1]);
                 }
-                if (cc + 32 < PHALF) tmem_ld32_issue(taddr + (uint32_t)(cc + 32), v);          // next chunk in flight
+                if (cc + 32 < G::NCOLW) { if (PREFETCH) tmem_ld32_issue(taddr + (uint32_t)(cc + 32), v); }          // next chunk in flight
                 else {
                     // last chunk of this thread: its TMEM reads are complete -> the accumulator may be overwritten
+                    // (tcgen05.wait::ld is warp-collective: all 32 lanes' reads are complete; ONE arrival per warp)
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                    mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&bars[B_TEMPTY + as]), 0));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&bars[B_TEMPTY + as]), 0));
                 }
-                if (P.bias) {
+                if (P.bias && !(BGNN_EPI_SKIP & 4)) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
                         x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
                     }
                 }
-                if (P.cmax_out) {
+                if (P.cmax_out && !(BGNN_EPI_SKIP & 4)) {
                     float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -1126,7 +1255,7 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                     }
                     cmax = fmaxf(cmax, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                 }
-                if (P.alpha) {
+                if (P.alpha && !(BGNN_EPI_SKIP & 1)) {
                     float s0, s1, s2, s3, d0, d1, d2, d3;
                     uint64_t s01 = 0ull, s23 = 0ull, d01 = 0ull, d23 = 0ull;
 #pragma unroll
@@ -1149,7 +1278,25 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                         as_acc = 0.f; ad_acc = 0.f;
                     }
                 }
-                if (row < M) {           // thread-per-row 256-bit stores
+                if (BGNN_EPI_SKIP & 2) { if (x[lane] == 123.456f) P.Cout[row] = x[0]; }
+                else if constexpr (MLP) {
+                    // chunk [32 rows x 32 cols] -> SWIZZLE_128B staging tile -> one TMA tensor store (rows >= M are clipped)
+                    unsigned char* tile_s = stg + (size_t)warp * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // previous store has read the tile
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(tile_s + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int cx = P.head_major ? (c0 % P.CH) : c0, cz = P.head_major ? (c0 / P.CH) : 0;
+                        const int cy = (int)(tile * 2 * TILE_M + rank * TILE_M + quarter * 32);
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n"
+                                     ::"l"(&tmapC), "r"(cx), "r"(cy), "r"(cz), "r"(smem_u32(tile_s)) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    }
+                } else if (row < M) {           // thread-per-row 256-bit stores
                     float* dst = P.head_major ? P.Cout + ((int64_t)(c0 / P.CH) * M + row) * P.CH + (c0 % P.CH) : P.Cout + row * PN + c0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, x + 8 * j);
@@ -1159,6 +1306,7 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
             if (warp == 0 && lane == 0 && rank == 0) UT_TICKP(4);
 #endif
         }
+        if (MLP && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");     // all tensor stores done
         if (P.cmax_out) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
@@ -1169,7 +1317,7 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     cluster_sync_all();
-    if (warp == EPI_WARPS) {
+    if (warp == MMA_W) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
     }
@@ -1316,28 +1464,36 @@ int launch_t(const UmmaArgs& a, int sms, cudaStream_t s) {
     return BGNN_OK;
 }
 
-// cta_group::2 pair kernel (PM_SPLIT + EM_PROJ, N = 256, K <= 256)
+// cta_group::2 pair kernel (EM_PROJ, N = 256): PM_SPLIT (K <= 256, K % 64 == 0) or PM_MLP0 (K == 64)
+template <int MODE>
 int launch_pair(const UmmaArgs& a, int sms, cudaStream_t s) {
-    BGNN_CUDA(cudaFuncSetAttribute(proj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairk::BYTES));
-    BGNN_CHECK_ARG(a.A_hi && a.A_lo && ((reinterpret_cast<uintptr_t>(a.A_hi) | reinterpret_cast<uintptr_t>(a.A_lo)) & 15) == 0,
-                   "split A planes must be 16-byte aligned");
-    alignas(64) CUtensorMap tmap, tmap2;
-    memset(&tmap, 0, sizeof(tmap)); memset(&tmap2, 0, sizeof(tmap2));
-    const int64_t ld = a.a_ld > 0 ? a.a_ld : a.K;
-    int rc = make_tmap_A16_wide(a.A_hi, a.M, a.K, ld, TILE_M, &tmap);
-    if (!rc) rc = make_tmap_A16_wide(a.A_lo, a.M, a.K, ld, TILE_M, &tmap2);
-    if (rc) return rc;
+    using G = pairk::Cfg<MODE>;
+    auto kern = proj_pair_kernel<MODE>;
+    BGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES));
+    alignas(64) CUtensorMap tmap, tmap2, tmapC;
+    memset(&tmap, 0, sizeof(tmap)); memset(&tmap2, 0, sizeof(tmap2)); memset(&tmapC, 0, sizeof(tmapC));
     BGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.Cout) & 31) == 0, "C must be 32-byte aligned");
+    if (MODE == PM_SPLIT) {
+        BGNN_CHECK_ARG(a.A_hi && a.A_lo && ((reinterpret_cast<uintptr_t>(a.A_hi) | reinterpret_cast<uintptr_t>(a.A_lo)) & 15) == 0,
+                       "split A planes must be 16-byte aligned");
+        const int64_t ld = a.a_ld > 0 ? a.a_ld : a.K;
+        int rc = make_tmap_A16_wide(a.A_hi, a.M, a.K, ld, TILE_M, &tmap);
+        if (!rc) rc = make_tmap_A16_wide(a.A_lo, a.M, a.K, ld, TILE_M, &tmap2);
+        if (rc) return rc;
+    } else {
+        int rc = make_tmap_C(a.Cout, a.M, pairk::PN, a.CH, a.head_major, &tmapC);
+        if (rc) return rc;
+    }
     const int64_t n_tiles = (a.M + 2 * TILE_M - 1) / (2 * TILE_M);
     const int64_t pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * (pairs > 0 ? pairs : 1))); cfg.blockDim = dim3(pairk::THREADS); cfg.dynamicSmemBytes = pairk::BYTES; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(2 * (pairs > 0 ? pairs : 1))); cfg.blockDim = dim3(G::THREADS); cfg.dynamicSmemBytes = G::BYTES; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const cudaError_t el = cudaLaunchKernelEx(&cfg, proj_pair_kernel, a, tmap, tmap2);
-    if (el != cudaSuccess) { bgnn_set_error("cluster launch of proj_pair_kernel failed: %s", cudaGetErrorString(el)); return BGNN_E_CUDA; }
+    const cudaError_t el = cudaLaunchKernelEx(&cfg, kern, a, tmap, tmap2, tmapC);
+    if (el != cudaSuccess) { bgnn_set_error("cluster launch of proj_pair_kernel<%d> failed: %s", MODE, cudaGetErrorString(el)); return BGNN_E_CUDA; }
     return BGNN_OK;
 }
 
@@ -1449,6 +1605,8 @@ int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s
 }
 
 static const bool g_mlp0_whole = getenv("BGNN_MLP0_WHOLE") != nullptr;       // dev switch: one 128 x 256 tile per CTA (1.30 vs 1.25 ms paired)
+static const bool g_pair_mlp0 = getenv("BGNN_NO_CG2_MLP0") == nullptr && getenv("BGNN_NO_CG2") == nullptr;   // layer-0 projection (fused MLP) as a
+                                                                         // cta_group::2 pair: on by default (1.03 vs 1.38 ms)
 static const bool g_pair_cg2 = getenv("BGNN_NO_CG2") == nullptr;             // on by default; dev switch back to the N = 2 x 128 multicast pair
 static const bool g_split_whole = getenv("BGNN_SPLIT_WHOLE") != nullptr;     // dev switch: pre-split A, N = 256 as one 128 x 256 tile per CTA
 static const bool g_n256_halves = getenv("BGNN_N256_HALVES") != nullptr;     // dev switch (measured slower with fp32 A: 2.49 vs 2.13 ms; the
@@ -1471,7 +1629,7 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
         switch (N) {
             case 64: return launch_t<64, PM_SPLIT, EM_PROJ>(a, sms, s);
             case 256:
-                if (g_pair_cg2 && a.K <= 8 * KC && a.K % pairk::KCA == 0 && (!a.alpha || 128 % a.CH == 0)) return launch_pair(a, sms, s);
+                if (g_pair_cg2 && a.K <= 8 * KC && a.K % pairk::KCA == 0 && (!a.alpha || pairk::Cfg<PM_SPLIT>::NCOLW % a.CH == 0)) return launch_pair<PM_SPLIT>(a, sms, s);
                 if (!g_split_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_SPLIT, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_SPLIT, EM_PROJ>(a, sms, s);
         }
@@ -1480,6 +1638,7 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
             case 128: return launch_t<128, PM_MLP0, EM_PROJ>(a, sms, s);
             case 256:
                 // paired CTAs, N = 2 x 128 (TMA stores): the epilogue, which dominates at K = 64, overlaps the next tile's MLP + MMAs
+                if (g_pair_mlp0 && a.K == pairk::KCA && a.F <= MLP0_FP && (!a.alpha || pairk::Cfg<PM_MLP0>::NCOLW % a.CH == 0)) return launch_pair<PM_MLP0>(a, sms, s);
                 if (!g_mlp0_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_MLP0, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_MLP0, EM_PROJ>(a, sms, s);
         }

@@ -2,8 +2,8 @@
 built with -DBGNN_AGG_TIMING '-DBGNN_UT_FILTER=false' so that only the pair kernel's own counters tick)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["BGNN_LIB"] = os.path.join(ROOT, "tools", "libbgnn_timing.so")
-os.environ["BGNN_CG2"] = "1"
+os.environ.setdefault("BGNN_LIB", os.path.join(ROOT, "tools", "libbgnn_timing.so"))
+os.environ["BGNN_NO_CG2"] = "1"; os.environ["PAIR_MLP0_ONLY"] = "1"
 sys.path.insert(0, ROOT)
 import torch
 import bench
@@ -24,7 +24,7 @@ out = (C.c_ulonglong * 12)()
 lib.bgnn_debug_umma_timing(out, 0)
 names = ["mma: wait TEMPTY (epilogues)", "mma: wait FULL pass 1", "mma: issue", "epi w0: wait TFULL", "epi w0: drain + store",
          "loader: wait EMPTY", "loader: issue", "mma: wait FULL pass 2", "mma thread: total cycles", "mma thread: total ns"]
-n = 74 * 2        # leader CTAs x launches
+n = 74 * (1 if os.environ.get("PAIR_MLP0_ONLY") else 2)        # leader CTAs x launches
 for i, nm in enumerate(names):
     print(f"   {nm:34s} {out[i]/n/1e3:10.1f} kcycles per leader CTA and launch")
 print(f"   SM clock {out[8]/max(out[9],1):.3f} GHz; kernel time {out[9]/n/1e6:.3f} ms")
