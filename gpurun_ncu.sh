@@ -3,7 +3,7 @@
 # usage: gpurun_ncu.sh <tag> [kernel-regex]
 set -x
 TAG=${1:-r1}
-PAT=${2:-"gat_aggregate_tile|proj_umma|gb_emit"}
+PAT=${2:-"gat_aggregate_tile|proj_umma|proj_pair|gb_emit"}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --quick"
 $CMD > gpurun_out/plain.log 2>&1 &&

@@ -10,6 +10,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum"]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", ",".join(METRICS)], capture_output=True, text=True).stdout
@@ -43,7 +44,7 @@ for r in data:
         slot = f"agg_l{seq['agg']}"; seq["agg"] += 1
     elif "proj_umma" in name and tmpl_args(name)[2:3] == ["1"]:      # EMODE == EM_HEADS
         slot = "heads_gemm"
-    elif "proj_umma" in name:
+    elif "proj_umma" in name or "proj_pair" in name:      # (proj_pair_kernel<MODE>: the cta_group::2 pair, layers 0..2)
         slot = f"proj_l{seq['proj']}"; seq["proj"] += 1
     elif "gb_emit" in name:
         slot = "gb_emit"
