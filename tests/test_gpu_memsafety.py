@@ -12,7 +12,7 @@ so the checks SURVEY.md 5.2 asks for are done with guards of our own:
     (different CTA interleavings).
 
 Workloads cover every kernel family: graph build (tile, strided view, ragged), tiled / windowed / CSR / radius-2 aggregation,
-tcgen05 projections (MLP0 / SPLIT incl. the 2-CTA multicast pair / PLAIN / HEADS), bf16 mode, GCN / GraphSAGE / GIN, tile
+tcgen05 projections (the cta_group::2 CTA-pair kernel in its MLP0 and SPLIT modes, single-CTA SPLIT / PLAIN / HEADS), bf16 mode, GCN / GraphSAGE / GIN, tile
 scatter + stitch, survey bands with a seam hand-over, VR post-processing."""
 import numpy as np
 import pytest
