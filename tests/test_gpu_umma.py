@@ -69,7 +69,8 @@ def test_umma_toggle_equivalence_in_forward():
     assert torch.equal(a["predicted_class"], b["predicted_class"]) or (a["predicted_class"] != b["predicted_class"]).float().mean() < 1e-3
 
 
-@pytest.mark.parametrize("M,K,N,heads", [(256, 256, 256, 4), (1000, 256, 256, 4), (70001, 256, 256, 4), (4099, 256, 64, 1),
+@pytest.mark.parametrize("M,K,N,heads", [(1, 256, 256, 4), (129, 256, 256, 4), (257, 64, 256, 4), (383, 192, 256, 4),
+                                         (256, 256, 256, 4), (1000, 256, 256, 4), (70001, 256, 256, 4), (4099, 256, 64, 1),
                                          (513, 64, 64, 1), (50000, 64, 256, 4), (333, 128, 256, 8)])
 def test_umma_presplit_is_bit_identical(M, K, N, heads):
     """A handed over as fp16 hi / lo planes (what the tiled aggregation writes) vs the in-kernel split of fp32 A.  N = 64: the
