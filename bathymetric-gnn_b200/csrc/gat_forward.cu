@@ -2569,10 +2569,15 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
               const LayerDev& Ln = m->layers[l + 1];
               want_split = Ln.Wsplit && Ln.in == L.HC && proj_umma_presplit_supported(Ln.HC, Ln.in, Ln.C, true) &&
                            (win_l || rag_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_));
-              if (want_split) {
-                  SO.hi = reinterpret_cast<uint16_t*>(nxt);
-                  SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
-              }
+          }
+          // last layer: the heads' tensor-core kernel takes the same hand-over (no converter stage; bit-identical products) unless
+          // the caller wants the fp32 hidden activations back
+          if ((tile_ok0 || ((win_l || rag_l) && m->opt.use_umma && m->opt.presplit)) && l + 1 == d.layers && L.HC == 64 && !hidden_out &&
+              m->hWsplit && proj_umma_heads_presplit_supported(C, m->hNpad))
+              want_split = win_l || rag_l || tile_supported(T, L.H, L.C, d.edge_dim, topo->grid_eattr, &is4_);
+          if (want_split) {
+              SO.hi = reinterpret_cast<uint16_t*>(nxt);
+              SO.amax_src = amax + 1 + l; SO.mul = L.out_mul; SO.add = L.out_add;
           }
           cur_split = false;
           if (rc == 1 && tiled) {
@@ -2601,13 +2606,14 @@ extern "C" int bgnn_gat_forward(const bgnn_model* m, int64_t N, int64_t E, const
         ProfScope ps(60, s);
         UmmaArgs a = {};
         a.A = cur; a.M = N; a.K = C; a.Wsplit = m->hWsplit; a.w_inv_scale = m->heads_inv;
+        if (cur_split) { a.A_hi = reinterpret_cast<const uint16_t*>(cur); a.A_lo = a.A_hi + C; a.a_ld = 2 * C; }
         const LayerDev& LL = m->layers[d.layers - 1];
         a.amax_src = amax + d.layers; a.amax_mul = LL.out_mul; a.amax_add = LL.out_add;
         a.hb0 = m->hb0; a.h2 = h2; a.nblk = nblk; a.ncls = d.num_classes;
         a.Wcls = m->Wcls; a.bcls = m->bcls; a.Wconf = m->Wconf; a.bconf = m->bconf; a.Wcorr = m->Wcorr; a.bcorr = m->bcorr;
         a.logits = logits; a.probs = probs; a.cls = cls; a.conf = conf; a.corr = corr; a.action = action;
         a.thr_auto = thr_auto; a.thr_review = thr_review;
-        return launch_umma(a, m->hNpad, PM_PLAIN, EM_HEADS, sms, s);
+        return launch_umma(a, m->hNpad, cur_split ? PM_SPLIT : PM_PLAIN, EM_HEADS, sms, s);
     }
     { ProfScope ps(60, s);
       if ((rc = launch_gemm(cur, C, m->hW0, C, N, nblk * h2, hbuf, nblk * h2, m->hb0, 1, C, 0, 0, 0, 0, s))) return rc; }

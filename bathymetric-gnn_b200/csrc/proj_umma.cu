@@ -842,12 +842,15 @@ constexpr int UNIT_B = TILE_M * KCA * 2;           // 16 KB: ONE plane chunk [12
 constexpr int BT_B = PHALF * KC * 2;               // 8 KB: one split of this CTA's N half of a 32-wide W chunk
 constexpr int WSLOT_B = NSPLIT * BT_B;
 // MODE = PM_SPLIT: operands arrive as fp16 planes (two TMA loader threads); K <= 256, the hi plane is fetched for both passes
-// MODE = PM_MLP0:  four producer warps compute this CTA's 128 rows of relu(x W0^T + b0) straight into a {hi, lo} unit pair
+// MODE = PM_MLP0:  eight producer warps compute this CTA's 128 rows of relu(x W0^T + b0) straight into a {hi, lo} unit pair
 //                  (K = 64: one unit per plane holds the whole K extent and serves both passes); three tile slots; the
 //                  spare shared memory goes to staging tiles for TMA tensor stores
 template <int MODE> struct Cfg {
     static constexpr bool MLP = MODE == PM_MLP0;
-    static constexpr int FEED_WARPS = MLP ? 4 : 2;
+#ifndef BGNN_PAIR_MLP_PRODW
+#define BGNN_PAIR_MLP_PRODW 8          /* producer warps of the MLP mode: 4 (thread <-> row) or 8 (thread <-> row, half of the hidden units: 1.01 vs 1.03 ms) */
+#endif
+    static constexpr int FEED_WARPS = MLP ? BGNN_PAIR_MLP_PRODW : 2;
 #ifndef BGNN_PAIR_EPW_MLP
 #define BGNN_PAIR_EPW_MLP 16
 #endif
@@ -1007,7 +1010,9 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
         if constexpr (MLP) {
         // ===================== PRODUCERS (128 threads per CTA, thread <-> own row): relu(b0 + x W0^T) * sA -> fp16 hi / lo, written
         // as 16-byte chunks of the K-major SWIZZLE_128B units (chunk c of row r at (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4))
-        const int r = tid - FEED_WARP0 * 32;
+        const int ptid = tid - FEED_WARP0 * 32;
+        const int r = ptid & (TILE_M - 1), chalf = ptid >> 7;                    // (8 producer warps: two threads share a row)
+        constexpr int NCH = (KCA / 8) / (G::FEED_WARPS / 4);                     // 16-byte chunks (8 hidden units) per thread
         const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const uint32_t full0 = mapa_u32(smem_u32(&bars[B_FULL]), 0);
         uint32_t t = 0;
@@ -1022,12 +1027,12 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 #endif
             if (t >= 3) mbar_wait(&bars[B_EMPTY + slot], ((t / 3) - 1) & 1);
 #ifdef BGNN_AGG_TIMING
-            if (r == 0 && rank == 0) UT_TICKP(5);
+            if (ptid == 0 && rank == 0) UT_TICKP(5);
 #endif
             unsigned char* u_hi = units + (size_t)(2 * slot) * UNIT_B + rowoff;
             unsigned char* u_lo = u_hi + UNIT_B;
 #pragma unroll 2
-            for (int c = 0; c < KCA / 8; ++c) {
+            for (int c = chalf * NCH; c < (chalf + 1) * NCH; ++c) {
                 float o[8];
 #pragma unroll
                 for (int uu = 0; uu < 8; ++uu) {
@@ -1047,13 +1052,13 @@ proj_pair_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
                 *reinterpret_cast<uint4*>(u_lo + phys) = make_uint4(l0.x, l0.y, l1.x, l1.y);
             }
 #ifdef BGNN_AGG_TIMING
-            if (r == 0 && rank == 0) UT_TICKP(6);
+            if (ptid == 0 && rank == 0) UT_TICKP(6);
 #endif
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");                    // all rows of this CTA's units are written
-            if (r == 0) mbar_arrive_remote_cta(full0 + 8u * slot);                // one arrival per tile and CTA
+            asm volatile("bar.sync 1, %0;\n" ::"n"(G::FEED_WARPS * 32) : "memory");      // all rows of this CTA's units are written
+            if (ptid == 0) mbar_arrive_remote_cta(full0 + 8u * slot);                // one arrival per tile and CTA
 #ifdef BGNN_AGG_TIMING
-            if (r == 0 && rank == 0) UT_TICKP(7);
+            if (ptid == 0 && rank == 0) UT_TICKP(7);
 #endif
         }
         } else {
@@ -1595,6 +1600,8 @@ bool proj_umma_heads_supported(int K, int h2, int nblk, int ncls, int* Npad) {
     return h2 % 32 == 0 && h2 <= HEADS_MAXH2 && real <= 256 && ncls >= 1 && ncls <= 8 && K % KC == 0 && K >= KC;
 }
 
+bool proj_umma_heads_presplit_supported(int K, int Npad) { return Npad == 128 && K % KC == 0 && K >= KC; }
+
 int launch_absmax(const float* v, int64_t n, float* out, int sms, cudaStream_t s) {
     if (n <= 0) return BGNN_OK;
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
@@ -1641,6 +1648,10 @@ int launch_umma(const UmmaArgs& a, int N, int pmode, int emode, int sms, cudaStr
                 if (g_pair_mlp0 && a.K == pairk::KCA && a.F <= MLP0_FP && (!a.alpha || pairk::Cfg<PM_MLP0>::NCOLW % a.CH == 0)) return launch_pair<PM_MLP0>(a, sms, s);
                 if (!g_mlp0_whole && a.K <= 8 * KC && (!a.alpha || 64 % a.CH == 0)) return launch_t<128, PM_MLP0, EM_PROJ, 2>(a, sms, s);
                 return launch_t<256, PM_MLP0, EM_PROJ>(a, sms, s);
+        }
+    } else if (pmode == PM_SPLIT && emode == EM_HEADS) {
+        switch (N) {
+            case 128: return launch_t<128, PM_SPLIT, EM_HEADS>(a, sms, s);
         }
     } else if (pmode == PM_PLAIN && emode == EM_HEADS) {
         switch (N) {

@@ -36,6 +36,7 @@ bool proj_umma_supported(int N, int K, int CH, bool want_alpha);
 bool proj_umma_presplit_supported(int N, int K, int CH, bool want_alpha);   // PM_SPLIT + EM_PROJ
 bool proj_umma_mlp0_supported(int N, int K, int F);               // PM_MLP0 + EM_PROJ
 bool proj_umma_heads_supported(int K, int h2, int nblk, int ncls, int* Npad);   // PM_PLAIN + EM_HEADS
+bool proj_umma_heads_presplit_supported(int K, int Npad);                       // PM_SPLIT + EM_HEADS (A handed over as fp16 hi / lo planes)
 // host: W [N,K] fp32 -> 2 x fp16 split of W*s, [K/32][2][N x 32 swizzled tile] (2*N*K uint16); returns 1/s
 float proj_umma_split_weights(const float* W, int N, int K, uint16_t* out);
 // max |v| over n floats, atomicMax into *out (float bits; zero it first)
