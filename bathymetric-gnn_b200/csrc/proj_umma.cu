@@ -809,8 +809,8 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 }
 
 // =====================================================================================================================
-// cta_group::2 projection (PM_SPLIT operands, EM_PROJ epilogue, N = 256, K <= 256): the two CTAs of a cluster own ONE
-// 256 x 256 output tile.  CTA r stages its own 128 rows of A (fp16 plane chunks of 8 KB) and keeps its N half of the split
+// cta_group::2 projection (EM_PROJ epilogue, N = 256; operands PM_SPLIT with K <= 256, or PM_MLP0 with K = 64 -- see Cfg below):
+// the two CTAs of a cluster own ONE 256 x 256 output tile.  CTA r stages its own 128 rows of A (fp16 plane chunks of 16 KB) and keeps its N half of the split
 // weights resident (128 KB); the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), for which each
 // SM reads only its own A rows and its own B half from shared memory: half the operand wavefronts per output of the
 // N = 2 x 128 multicast pair, whose tensor-core operand reads (46 % of the L1 data pipe) plus the epilogue's thread-per-row
@@ -822,17 +822,18 @@ proj_umma_kernel(const __grid_constant__ UmmaArgs P, const __grid_constant__ CUt
 //   hi plane is therefore fetched twice (the second time from L2); the shared-memory fill per output still drops by 25 %.
 //   A ring: 6 units of [128 rows x 64] fp16 (128-byte rows, SWIZZLE_128B; the resident W keeps its 32-wide SWIZZLE_64B chunks --
 //   the two operand descriptors carry their own layout), filled by two loader threads that take alternate units.
-//   epilogue: tcgen05.ld of the next chunk is in flight while a chunk is finished; thread-per-row 256-bit stores (the L1 data
-//   pipe has room for them now; staging tiles for TMA stores would cost 32 KB = 2 ring units: 2.24 vs 1.65 ms).  The optional
+//   epilogue (PM_SPLIT: 8 warps x 128 columns): tcgen05.ld of the next chunk is in flight while a chunk is finished; thread-per-row
+//   256-bit stores (staging tiles for TMA stores would cost 32 KB = 2 ring units: 2.24 vs 1.65 ms; PM_MLP0 has the room).  The optional
 //   bias is read from global memory (warp-uniform, L1-resident): its 1 KB of shared memory is what lets the sixth unit fit.
 //   measured (2048^2 tile, M = 4.1 M, K = N = 256): 1.53 ms vs 1.78 ms for the N = 2 x 128 multicast pair on the same box (5 ring
 //   units: 1.65 ms; L2 prefetches of the pair's next tile: 1.56 ms -- the ring depth matters, the HBM -> L2 leg does not).
 //   barriers (same offsets in both CTAs; "leader" = cluster rank 0):
-//     FULL[u]    leader's, 2 arrivals (each CTA's loader: arrive.expect_tx 8 KB, remote for the peer); the TMA copies of both
-//                CTAs complete on it (cp.async.bulk.tensor ... cta_group::2)
+//     FULL[u]    leader's.  PM_SPLIT: 1 arrival -- the leader's loader arms it for the bytes of BOTH CTAs (arrive.expect_tx 32 KB), the
+//                TMA copies of both CTAs complete on it (cp.async.bulk.tensor ... cta_group::2).  PM_MLP0: 2 arrivals -- one
+//                elected producer thread per CTA after the producers' own named barrier (remote arrive for the peer)
 //     EMPTY[u]   own, 1 arrival: the leader's tcgen05.commit multicast to both CTAs when the MMAs reading the unit have retired
 //     TFULL[a]   own, 1 arrival: commit multicast after the last MMA of a tile
-//     TEMPTY[a]  leader's, 2 x 8 arrivals: lane 0 of every epilogue warp of both CTAs after the warp's last tcgen05.ld of the tile
+//     TEMPTY[a]  leader's, 2 x EPW arrivals: lane 0 of every epilogue warp of both CTAs after the warp's last tcgen05.ld of the tile
 //     WFULL      own (resident W landed); WPEER leader's: the peer's W loader arrives once its own WFULL completed
 namespace pairk {
 constexpr int PN = 256, PHALF = 128;
