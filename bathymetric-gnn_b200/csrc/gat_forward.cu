@@ -1615,7 +1615,10 @@ int launch_agg_tile(const LayerDev& L, const float* h, const float* alpha, const
     if (L.H == H_ && L.C == C_)                                                                                         \
         return is4 ? launch_agg_tile_t<H_, C_, PH_, true>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, SO, s)   \
                    : launch_agg_tile_t<H_, C_, PH_, false>(L, h, alpha, T, grid_eattr, ED, relu, slope, out, n_nodes, SO, s)
-    TCASE(4, 64, 16); TCASE(1, 64, 8); TCASE(2, 64, 16); TCASE(8, 64, 16);      // (H = 1: 8 x 16 patches, three CTAs per SM: 0.62 -> 0.60 ms)
+#ifndef BGNN_AGG_PH_H4
+#define BGNN_AGG_PH_H4 16              /* patch height of the H = 4, C = 64 instantiation (8: three CTAs of four warps per SM: 1.90-1.97 vs 1.90 ms on one box, not kept) */
+#endif
+    TCASE(4, 64, BGNN_AGG_PH_H4); TCASE(1, 64, 8); TCASE(2, 64, 16); TCASE(8, 64, 16);      // (H = 1: 8 x 16 patches, three CTAs per SM: 0.62 -> 0.60 ms)
     TCASE(1, 32, 16); TCASE(2, 32, 16); TCASE(4, 32, 16); TCASE(8, 32, 16);
     TCASE(1, 128, 8); TCASE(2, 128, 8); TCASE(4, 128, 8);
 #undef TCASE
